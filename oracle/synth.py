@@ -1,0 +1,210 @@
+"""Deterministic synthetic weights and inputs shared by the oracle, the golden-vector
+generator, the GPU parity tests and bench.py.  TEST / MEASUREMENT INFRASTRUCTURE.
+
+Weights are drawn from numpy's PCG64 stream (stable across numpy versions) so the very
+same tensors can be rebuilt on the GPU box without shipping 50 MB fixtures.  Key names
+and shapes are the reference's state_dict (checked against the real reference modules by
+oracle/make_golden.py).  Input distributions follow SURVEY.md section 8d.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .trimodal_oracle import HotPathConfig
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def _bn(sd, rng, name, c):
+    sd[name + '.weight'] = torch.from_numpy((1.0 + 0.1 * rng.standard_normal(c)).astype(np.float32))
+    sd[name + '.bias'] = torch.from_numpy((0.1 * rng.standard_normal(c)).astype(np.float32))
+    sd[name + '.running_mean'] = torch.from_numpy((0.05 * rng.standard_normal(c)).astype(np.float32))
+    sd[name + '.running_var'] = torch.from_numpy((1.0 + 0.2 * rng.random(c)).astype(np.float32))
+    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.int64)
+
+
+def _lin(sd, rng, name, shape, fan_in, bias=True, scale=1.0):
+    s = scale / np.sqrt(fan_in)
+    sd[name + '.weight'] = torch.from_numpy((s * rng.standard_normal(shape)).astype(np.float32))
+    if bias:
+        sd[name + '.bias'] = torch.from_numpy((s * rng.standard_normal(shape[0])).astype(np.float32))
+
+
+def _gru(sd, rng, prefix, in_size, hidden, layers):
+    s = 1.0 / np.sqrt(hidden)
+    for l in range(layers):
+        for suf in ('', '_reverse'):
+            isz = in_size if l == 0 else 2 * hidden
+            sd[f'{prefix}.weight_ih_l{l}{suf}'] = torch.from_numpy((s * rng.standard_normal((3 * hidden, isz))).astype(np.float32))
+            sd[f'{prefix}.weight_hh_l{l}{suf}'] = torch.from_numpy((s * rng.standard_normal((3 * hidden, hidden))).astype(np.float32))
+            sd[f'{prefix}.bias_ih_l{l}{suf}'] = torch.from_numpy((s * rng.standard_normal(3 * hidden)).astype(np.float32))
+            sd[f'{prefix}.bias_hh_l{l}{suf}'] = torch.from_numpy((s * rng.standard_normal(3 * hidden)).astype(np.float32))
+
+
+def generator_state_dict(cfg: HotPathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of PoseGenerator (multimodal_context_net.py:64-104) in reference key order."""
+    rng = _rng(1000 + seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    p = 'audio_encoder.feat_extractor'
+    _lin(sd, rng, p + '.0', (16, 1, 15), 15)
+    _bn(sd, rng, p + '.1', 16)
+    _lin(sd, rng, p + '.3', (32, 16, 15), 16 * 15)
+    _bn(sd, rng, p + '.4', 32)
+    _lin(sd, rng, p + '.6', (64, 32, 15), 32 * 15)
+    _bn(sd, rng, p + '.7', 64)
+    _lin(sd, rng, p + '.9', (32, 64, 15), 64 * 15)
+    E, Hh = cfg.wordembed_dim, cfg.hidden_size
+    sd['text_encoder.embedding.weight'] = torch.from_numpy(rng.standard_normal((cfg.n_words, E)).astype(np.float32))
+    for i in range(cfg.n_layers):
+        cin = E if i == 0 else Hh
+        q = f'text_encoder.tcn.network.{i}'
+        for j, ci in ((1, cin), (2, Hh)):
+            v = (rng.standard_normal((Hh, ci, 2)) / np.sqrt(2 * ci)).astype(np.float32)
+            g = (np.linalg.norm(v.reshape(Hh, -1), axis=1) * (1.0 + 0.2 * rng.standard_normal(Hh))).astype(np.float32)
+            sd[f'{q}.conv{j}.bias'] = torch.from_numpy((0.05 * rng.standard_normal(Hh)).astype(np.float32))
+            sd[f'{q}.conv{j}.weight_g'] = torch.from_numpy(g.reshape(Hh, 1, 1))
+            sd[f'{q}.conv{j}.weight_v'] = torch.from_numpy(v)
+        if cin != Hh:
+            _lin(sd, rng, q + '.downsample', (Hh, cin, 1), cin)
+    _lin(sd, rng, 'text_encoder.decoder', (32, Hh), Hh)
+    sd['speaker_embedding.0.weight'] = torch.from_numpy(rng.standard_normal((cfg.n_speakers, cfg.z_size)).astype(np.float32))
+    _lin(sd, rng, 'speaker_embedding.1', (cfg.z_size, cfg.z_size), cfg.z_size)
+    _lin(sd, rng, 'speaker_mu', (cfg.z_size, cfg.z_size), cfg.z_size)
+    _lin(sd, rng, 'speaker_logvar', (cfg.z_size, cfg.z_size), cfg.z_size)
+    _gru(sd, rng, 'gru', cfg.gru_in, Hh, cfg.n_layers)
+    _lin(sd, rng, 'out.0', (Hh // 2, Hh), Hh)
+    _lin(sd, rng, 'out.2', (cfg.pose_dim, Hh // 2), Hh // 2)
+    return sd
+
+
+def discriminator_state_dict(cfg: HotPathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of ConvDiscriminator (multimodal_context_net.py:207-226)."""
+    rng = _rng(2000 + seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    _lin(sd, rng, 'pre_conv.0', (16, cfg.pose_dim, 3), cfg.pose_dim * 3)
+    _bn(sd, rng, 'pre_conv.1', 16)
+    _lin(sd, rng, 'pre_conv.3', (8, 16, 3), 48)
+    _bn(sd, rng, 'pre_conv.4', 8)
+    _lin(sd, rng, 'pre_conv.6', (8, 8, 3), 24)
+    _gru(sd, rng, 'gru', 8, cfg.d_hidden, cfg.d_layers)
+    _lin(sd, rng, 'out', (1, cfg.d_hidden), cfg.d_hidden)
+    _lin(sd, rng, 'out2', (1, cfg.n_poses - 6), cfg.n_poses - 6)
+    return sd
+
+
+def embedding_net_state_dict(cfg: HotPathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of EmbeddingNet(mode='pose') (embedding_net.py:42-82,165-217,262-273)."""
+    rng = _rng(3000 + seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    d = cfg.pose_dim
+    p = 'pose_encoder'
+    for i, (ci, co, k) in enumerate(((d, 32, 3), (32, 64, 3), (64, 64, 4))):
+        _lin(sd, rng, f'{p}.net.{i}.0', (co, ci, k), ci * k, scale=1.7)
+        _bn(sd, rng, f'{p}.net.{i}.1', co)
+    _lin(sd, rng, f'{p}.net.3', (32, 64, 3), 64 * 3, scale=1.7)
+    _lin(sd, rng, f'{p}.out_net.0', (256, 384), 384, scale=1.7)
+    _bn(sd, rng, f'{p}.out_net.1', 256)
+    _lin(sd, rng, f'{p}.out_net.3', (128, 256), 256, scale=1.7)
+    _bn(sd, rng, f'{p}.out_net.4', 128)
+    _lin(sd, rng, f'{p}.out_net.6', (32, 128), 128, scale=1.7)
+    _lin(sd, rng, f'{p}.fc_mu', (32, 32), 32, scale=1.7)
+    _lin(sd, rng, f'{p}.fc_logvar', (32, 32), 32)
+    q = 'decoder'
+    _lin(sd, rng, f'{q}.pre_net.0', (64, 32), 32)
+    _bn(sd, rng, f'{q}.pre_net.1', 64)
+    _lin(sd, rng, f'{q}.pre_net.3', (136, 64), 64)
+    _lin(sd, rng, f'{q}.net.0', (4, 32, 3), 12)          # ConvTranspose1d weight: [Cin, Cout, k]
+    sd[f'{q}.net.0.bias'] = torch.from_numpy((0.1 * rng.standard_normal(32)).astype(np.float32))
+    _bn(sd, rng, f'{q}.net.1', 32)
+    _lin(sd, rng, f'{q}.net.3', (32, 32, 3), 96)
+    _bn(sd, rng, f'{q}.net.4', 32)
+    _lin(sd, rng, f'{q}.net.6', (32, 32, 3), 96)
+    _lin(sd, rng, f'{q}.net.7', (d, 32, 3), 96)
+    return sd
+
+
+def make_inputs(cfg: HotPathConfig, batch: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic TED-shaped clips: audio 0.1*N(0,1) clipped, mostly-PAD word ids
+    with 5-9 word-onset frames, random-walk direction vectors, speaker ids U{1..n_spk-1}."""
+    rng = _rng(4000 + seed)
+    audio = np.clip(0.1 * rng.standard_normal((batch, cfg.audio_len)), -1, 1).astype(np.float32)
+    text = np.zeros((batch, cfg.n_poses), dtype=np.int64)
+    for b in range(batch):
+        n = int(rng.integers(5, 10))
+        frames = rng.choice(cfg.n_poses, size=n, replace=False)
+        text[b, frames] = rng.integers(4, cfg.n_words, size=n)
+    walk = np.cumsum(0.02 * rng.standard_normal((batch, cfg.n_poses, cfg.pose_dim)), axis=1)
+    target = (walk + 0.1 * rng.standard_normal((batch, 1, cfg.pose_dim))).astype(np.float32)
+    vid = rng.integers(1, cfg.n_speakers, size=batch).astype(np.int64)
+    return {'in_audio': torch.from_numpy(audio), 'in_text': torch.from_numpy(text),
+            'target': torch.from_numpy(target), 'vid': torch.from_numpy(vid)}
+
+
+def make_noise(cfg: HotPathConfig, batch: int, seed: int = 0, dropout: bool = False):
+    """All random draws of one train_iter_gan call (see trimodal_oracle.StepNoise)."""
+    from .trimodal_oracle import StepNoise
+    rng = _rng(5000 + seed)
+    eps = [torch.from_numpy(rng.standard_normal((batch, cfg.z_size)).astype(np.float32)) for _ in range(3)]
+    perm = torch.from_numpy(rng.permutation(batch).astype(np.int64))
+    noise = StepNoise(eps=eps, perm=perm)
+    if dropout:
+        noise.g_masks = [generator_masks(cfg, batch, rng) for _ in range(3)]
+        noise.d_masks = [discriminator_masks(cfg, batch, rng) for _ in range(3)]
+    return noise
+
+
+def _mask(rng, shape, p):
+    keep = (rng.random(shape) >= p).astype(np.float32) / (1.0 - p)
+    return torch.from_numpy(keep)
+
+
+def generator_masks(cfg: HotPathConfig, batch: int, rng) -> Dict[str, torch.Tensor]:
+    T, H = cfg.n_poses, cfg.hidden_size
+    m = {'emb': _mask(rng, (batch, T, cfg.wordembed_dim), cfg.emb_dropout)}
+    for i in range(cfg.n_layers):
+        m[f'tcn{i}_1'] = _mask(rng, (batch, H, T), cfg.dropout_prob)     # oracle layout [B,C,T]
+        m[f'tcn{i}_2'] = _mask(rng, (batch, H, T), cfg.dropout_prob)
+    for l in range(cfg.n_layers - 1):
+        m[f'gru{l}'] = _mask(rng, (batch, T, 2 * H), cfg.dropout_prob)
+    return m
+
+
+def discriminator_masks(cfg: HotPathConfig, batch: int, rng) -> Dict[str, torch.Tensor]:
+    T = cfg.n_poses - 6
+    return {f'gru{l}': _mask(rng, (batch, T, 2 * cfg.d_hidden), 0.3) for l in range(cfg.d_layers - 1)}
+
+
+def zeros_like_opt(sd: Dict[str, torch.Tensor]):
+    keys = [k for k in sd if not k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))]
+    return {'m': {k: torch.zeros_like(sd[k]) for k in keys}, 'v': {k: torch.zeros_like(sd[k]) for k in keys}}
+
+
+def golden_noise(cfg: HotPathConfig, batch: int, seed: int, use_masks: bool):
+    """Noise of the train_e11 / train_e0 golden fixtures: embedding + TCN dropout masks are
+    injected, GRU inter-layer dropout is off (the reference GRU cannot take a mask)."""
+    noise = make_noise(cfg, batch, seed=seed, dropout=use_masks)
+    if use_masks:
+        for m in noise.g_masks:
+            for l in range(cfg.n_layers - 1):
+                m.pop(f'gru{l}', None)
+        noise.d_masks = [None, None, None]
+    return noise
+
+
+def with_tcn_aliases(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The reference TemporalBlock registers conv1/conv2 a second time inside ``self.net``
+    (tcn.py:30-31), so its state_dict carries ``net.0.*`` / ``net.4.*`` duplicates of
+    ``conv1.*`` / ``conv2.*``.  Adds those alias keys (same tensors) for strict loading."""
+    out = OrderedDict(sd)
+    for k, v in sd.items():
+        if '.tcn.network.' in k and '.conv1.' in k:
+            out[k.replace('.conv1.', '.net.0.')] = v
+        if '.tcn.network.' in k and '.conv2.' in k:
+            out[k.replace('.conv2.', '.net.4.')] = v
+    return out

@@ -1,0 +1,99 @@
+"""CPU: pins the oracle (oracle/trimodal_oracle.py) against fixtures produced by the real
+reference modules (oracle/make_golden.py -> tests/golden/*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import trimodal_oracle as O
+from oracle.make_golden import digest, golden_cfg
+from conftest import GOLDEN, rel_l2
+
+# Conv biases feeding a train-mode BatchNorm have an analytically ZERO gradient; what autograd
+# produces is fp32 round-off, and Adam turns any non-zero round-off into a +-lr step.  Their
+# post-step values are therefore noise in the reference itself and are excluded from parity.
+ZERO_GRAD_KEYS = ('audio_encoder.feat_extractor.0.bias', 'audio_encoder.feat_extractor.3.bias',
+                  'audio_encoder.feat_extractor.6.bias', 'pre_conv.0.bias', 'pre_conv.3.bias')
+TOL = 2e-5          # fp32 CPU oracle vs fp32 CPU reference (different op order only)
+
+
+def _digest_close(a, ref, tol):
+    a = np.asarray(a); ref = np.asarray(ref)
+    scale = max(abs(ref[0]), 1e-12)          # l2 norm of the tensor
+    if scale < 1e-3:                          # analytically-zero grads (conv bias in front of BN): fp32 noise
+        assert abs(a[0]) < 1e-3
+        return
+    assert abs(a[0] - ref[0]) <= tol * scale + 1e-9
+    n = max(len(ref) - 2, 1)
+    assert np.abs(a[2:] - ref[2:]).max() <= tol * 50 * scale / np.sqrt(n) + 5e-7
+
+
+def _post_close(a, ref, lr, noisy=False):
+    """Post-Adam weights.  On the first Adam step every element moves by ~lr*sign(g) whatever
+    |g| is, so an element whose gradient is round-off noise may legitimately land 2*lr away;
+    the bulk (median) must agree tightly.  Gradients themselves are checked tightly above."""
+    d = np.abs(np.asarray(a)[2:] - np.asarray(ref)[2:])
+    assert d.max() <= 2.2 * lr + 1e-6
+    assert noisy or np.median(d) <= 2e-6 + 1e-5 * np.abs(np.asarray(ref)[2:]).max()
+
+
+def test_forward_eval_matches_reference():
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_eval.npz'))
+    inp = synth.make_inputs(cfg, 3, seed=1)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0]
+    gsd = synth.generator_state_dict(cfg)
+    dsd = synth.discriminator_state_dict(cfg)
+    with torch.no_grad():
+        poses, z, mu, logvar = O.pose_generator_forward(gsd, cfg, pre, inp['in_text'], inp['in_audio'], inp['vid'], eps)
+        audio = O.wav_encoder(gsd, 'audio_encoder', inp['in_audio'], False)
+        text = O.text_encoder_tcn(gsd, 'text_encoder', inp['in_text'], cfg.n_layers)
+        d_real = O.conv_discriminator_forward(dsd, cfg, inp['target'])
+        d_fake = O.conv_discriminator_forward(dsd, cfg, poses)
+    assert rel_l2(poses, g['poses']) < TOL
+    assert rel_l2(audio, g['audio_feat']) < TOL
+    assert rel_l2(text, g['text_feat']) < TOL
+    assert rel_l2(z, g['z']) < TOL and rel_l2(mu, g['mu']) < TOL and rel_l2(logvar, g['logvar']) < TOL
+    assert rel_l2(d_real, g['d_real']) < TOL and rel_l2(d_fake, g['d_fake']) < TOL
+
+
+@pytest.mark.parametrize('tag,epoch,use_masks', [('train_e11', 11, True), ('train_e0', 0, False)])
+def test_train_iter_matches_reference(tag, epoch, use_masks):
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, tag + '.npz'))
+    inp = synth.make_inputs(cfg, 3, seed=1)
+    noise = synth.golden_noise(cfg, 3, 2, use_masks)
+    gsd = synth.generator_state_dict(cfg)
+    dsd = synth.discriminator_state_dict(cfg)
+    ret = O.train_iter_gan_oracle(cfg, epoch, gsd, dsd, synth.zeros_like_opt(gsd), synth.zeros_like_opt(dsd), 1,
+                                  inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], noise)
+    for k, v in ret['losses'].items():
+        ref = float(g['loss_' + k])
+        assert abs(v - ref) <= 1e-4 * abs(ref) + 1e-6, (k, v, ref)
+    assert set('loss_' + k for k in ret['losses']) == set(k for k in g.files if k.startswith('loss_'))
+    for k, gr in ret['g_grads'].items():
+        _digest_close(digest(gr), g['ggrad/' + k], 2e-4)
+    for k, v in ret['g_sd'].items():
+        _post_close(digest(v), g['gpost/' + k], cfg.learning_rate, k in ZERO_GRAD_KEYS)
+    for k, v in ret['d_sd'].items():
+        _post_close(digest(v), g['dpost/' + k], cfg.learning_rate * cfg.discriminator_lr_weight, k in ZERO_GRAD_KEYS)
+
+
+def test_embedding_net_and_fgd_match_reference():
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'embedding_fgd.npz'))
+    esd = synth.embedding_net_state_dict(cfg)
+    rng = np.random.Generator(np.random.PCG64(77))
+    real = torch.from_numpy((0.5 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim))).astype(np.float32))
+    fake = torch.from_numpy((1.0 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim)) + 0.3).astype(np.float32))
+    with torch.no_grad():
+        rf, rrec = O.embedding_net_pose_forward(esd, real)
+        ff, frec = O.embedding_net_pose_forward(esd, fake)
+    assert rel_l2(rf, g['real_feat']) < TOL and rel_l2(ff, g['fake_feat']) < TOL
+    _digest_close(digest(rrec), g['real_recon'], 2e-5)
+    fgd, fdist = O.fgd_scores(ff.numpy(), rf.numpy())
+    assert abs(fgd - float(g['fgd'])) <= 1e-3 * abs(float(g['fgd']))
+    assert abs(fdist - float(g['feat_dist'])) <= 1e-4 * abs(float(g['feat_dist']))
