@@ -16,7 +16,7 @@ from conftest import GOLDEN, rel_l2
 # post-step values are therefore noise in the reference itself and are excluded from parity.
 ZERO_GRAD_KEYS = ('audio_encoder.feat_extractor.0.bias', 'audio_encoder.feat_extractor.3.bias',
                   'audio_encoder.feat_extractor.6.bias', 'pre_conv.0.bias', 'pre_conv.3.bias',
-                  'pre_conv.1.bias')   # D: BN bias -> identity 'LeakyReLU(True)' -> conv -> train-mode BN
+                  'pre_conv.1.bias', 'pre_conv.1.running_mean', 'pre_conv.4.running_mean')   # D: BN bias -> identity 'LeakyReLU(True)' -> conv -> train-mode BN
 TOL = 2e-5          # fp32 CPU oracle vs fp32 CPU reference (different op order only)
 
 
