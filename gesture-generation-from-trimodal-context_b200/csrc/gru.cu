@@ -1,0 +1,380 @@
+// Persistent bidirectional-GRU recurrence, strict-fp32 path (nn.GRU, multimodal_context_net.py:98-99,155,221-222,241).
+//
+// One cooperative launch per layer covers both directions and all T steps.  CTA (chunk c, batch group y, dir d) keeps
+// the W_hh rows of its `u` hidden units (3u gate rows x H) resident in shared memory for the whole sequence, computes
+// gh = W_hh h_{t-1} for its rows and its batch tile as a register-tiled outer-product GEMM, applies the gate
+// non-linearities and writes h_t for its units.  The UC chunk-CTAs of one (batch group, direction) exchange h_t through
+// L2 (st.global + fence, ld.global.cg) and step together with a release/acquire counter - no grid-wide barrier, no
+// kernel launch per time step.  The backward kernel mirrors it: every CTA multiplies its own dgh rows with the same
+// resident W_hh slice into a partial dh_{t-1}[all H], partials are summed by the owner of each unit after the barrier.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RP = 128;        // padded gate rows per CTA (3*u <= RP)
+constexpr int UMAX = 42;
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void group_wait(const int* counter, int target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire(counter) < target) { __nanosleep(20); }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void group_signal(int* counter) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(counter, 1);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct GruFwdP {
+  const float* gi;          // [B*T, 6H]
+  const float* whhT[2];     // [H, 3H] per direction (transposed W_hh)
+  const float* bhh[2];      // [3H]
+  float* out;               // [B, T, 2H]
+  float* saved;             // [4][..] planes of [B*T, 2H], may be null
+  long long saved_qstride;
+  int* sync;
+  int B, T, H, u, UC, NB, ntiles;
+};
+
+template <int BT>
+__global__ void __launch_bounds__(256, 1) gru_fwd_kernel(const GruFwdP p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int BC = BT / 16;
+  constexpr int HS = BT + 1;
+  float* Ws = smem;                       // [H][RP]
+  float* hs = smem + (size_t)p.H * RP;    // [H][HS]   (aliased by ghs [RP][HS] after the k loop)
+  float* ghs = hs;
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x, by = blockIdx.y, dir = blockIdx.z;
+  const int H = p.H, T = p.T, u = p.u;
+  const int u0 = c * u;
+  int* counter = p.sync + dir * p.NB + by;
+
+  // resident weights: Ws[k][g*u + jj] = W_hh[g*H + u0 + jj][k] = whhT[k][g*H + u0 + jj]
+  const float* wT = p.whhT[dir];
+  for (int i = tid; i < H * RP; i += 256) {
+    const int k = i / RP, lr = i - k * RP;
+    const int g = lr / u, jj = lr - g * u;
+    float v = 0.f;
+    if (g < 3 && u0 + jj < H) v = __ldg(wT + (long long)k * 3 * H + g * H + u0 + jj);
+    Ws[i] = v;
+  }
+  __syncthreads();
+
+  const int rg = tid >> 4, bcol = tid & 15;
+  const float* bhh = p.bhh[dir];
+  const long long row2H = 2ll * H;
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    if (s > 0) group_wait(counter, p.UC * s);
+    for (int tile = by; tile < p.ntiles; tile += p.NB) {
+      const int b0 = tile * BT;
+      if (s > 0) {
+        // h_{t-1} tile, transposed into hs[k][bb]
+        for (int i = tid; i < BT * H; i += 256) {
+          const int bb = i / H, k = i - bb * H;
+          const int b = b0 + bb;
+          float v = 0.f;
+          if (b < p.B) v = __ldcg(p.out + ((long long)b * T + tp) * row2H + dir * H + k);
+          hs[k * HS + bb] = v;
+        }
+        __syncthreads();
+        float acc[8][BC];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < BC; ++q) acc[i][q] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * RP + rg * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * RP + rg * 8 + 4);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float hv[BC];
+#pragma unroll
+          for (int q = 0; q < BC; ++q) hv[q] = hs[k * HS + bcol + 16 * q];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int q = 0; q < BC; ++q) acc[i][q] = fmaf(w[i], hv[q], acc[i][q]);
+        }
+        __syncthreads();   // everyone done reading hs before it is overwritten as ghs
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < BC; ++q) ghs[(rg * 8 + i) * HS + bcol + 16 * q] = acc[i][q];
+        __syncthreads();
+      }
+      // gates for (bb, jj): lanes along units -> coalesced global traffic
+      for (int i = tid; i < BT * u; i += 256) {
+        const int bb = i / u, jj = i - bb * u;
+        const int b = b0 + bb, unit = u0 + jj;
+        if (b >= p.B || unit >= H) continue;
+        float ghr = bhh[unit], ghz = bhh[H + unit], ghn = bhh[2 * H + unit];
+        float hprev = 0.f;
+        if (s > 0) {
+          ghr += ghs[jj * HS + bb]; ghz += ghs[(u + jj) * HS + bb]; ghn += ghs[(2 * u + jj) * HS + bb];
+          hprev = __ldcg(p.out + ((long long)b * T + tp) * row2H + dir * H + unit);
+        }
+        const long long row = (long long)b * T + t;
+        const float* gip = p.gi + row * 6 * H + dir * 3 * H + unit;
+        const float r = sigmoidf_(__ldg(gip) + ghr);
+        const float z = sigmoidf_(__ldg(gip + H) + ghz);
+        const float n = tanhf(__ldg(gip + 2 * H) + r * ghn);
+        const float h = (1.f - z) * n + z * hprev;
+        const long long o = row * row2H + dir * H + unit;
+        p.out[o] = h;
+        if (p.saved) {
+          p.saved[o] = r; p.saved[p.saved_qstride + o] = z; p.saved[2 * p.saved_qstride + o] = n;
+          p.saved[3 * p.saved_qstride + o] = ghn;
+        }
+      }
+      __syncthreads();
+    }
+    if (s + 1 < T) group_signal(counter);
+  }
+}
+
+struct GruBwdP {
+  const float* dout;        // [B, T, 2H]
+  const float* out;         // [B, T, 2H]
+  const float* saved; long long saved_qstride;
+  const float* whh[2];      // [3H, H]
+  float* dgi;               // [B*T, 6H]
+  float* dgh;               // [B*T, 6H]
+  float* partial;           // [2 parity][2 dir][B][UC][HP]
+  int* sync;
+  int B, T, H, u, UC, NB, ntiles, HP, tiles_per_cta;
+};
+
+template <int BT>
+__global__ void __launch_bounds__(256, 1) gru_bwd_kernel(const GruBwdP p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NBC = BT / 8;
+  constexpr int DS = BT + 1;
+  const int H = p.H, T = p.T, u = p.u, HP = p.HP;
+  float* Wb = smem;                             // [RP][HP]
+  float* ds = Wb + (size_t)RP * HP;             // [RP][DS]
+  float* dhc = ds + (size_t)RP * DS;            // [tiles_per_cta][BT][u]
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x, by = blockIdx.y, dir = blockIdx.z;
+  const int u0 = c * u;
+  int* counter = p.sync + dir * p.NB + by;
+
+  const float* W = p.whh[dir];
+  for (int i = tid; i < RP * HP; i += 256) {
+    const int lr = i / HP, k = i - lr * HP;
+    const int g = lr / u, jj = lr - g * u;
+    float v = 0.f;
+    if (g < 3 && u0 + jj < H && k < H) v = __ldg(W + (long long)(g * H + u0 + jj) * H + k);
+    Wb[i] = v;
+  }
+  for (int i = tid; i < RP * DS; i += 256) ds[i] = 0.f;
+  for (int i = tid; i < p.tiles_per_cta * BT * u; i += 256) dhc[i] = 0.f;
+  __syncthreads();
+
+  const int kg = tid & 31, bg = tid >> 5;
+  const long long row2H = 2ll * H;
+  const long long pstride_parity = 2ll * p.B * p.UC * HP;
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    const bool tp_ok = tp >= 0 && tp < T;
+    if (s > 0) group_wait(counter, p.UC * s);
+    const float* Pin = p.partial + (long long)((s - 1) & 1) * pstride_parity + (long long)dir * p.B * p.UC * HP;
+    float* Pout = p.partial + (long long)(s & 1) * pstride_parity + (long long)dir * p.B * p.UC * HP;
+    int tl = 0;
+    for (int tile = by; tile < p.ntiles; tile += p.NB, ++tl) {
+      const int b0 = tile * BT;
+      float* dh_t = dhc + (size_t)tl * BT * u;
+      for (int i = tid; i < BT * u; i += 256) {
+        const int bb = i / u, jj = i - bb * u;
+        const int b = b0 + bb, unit = u0 + jj;
+        float drp = 0.f, dzp = 0.f, dnr = 0.f;
+        if (b < p.B && unit < H) {
+          float carry = 0.f;
+          if (s > 0) {
+            carry = dh_t[i];
+            const float* pp = Pin + ((long long)b * p.UC) * HP + unit;
+            for (int cc = 0; cc < p.UC; ++cc) carry += __ldcg(pp + (long long)cc * HP);
+          }
+          const long long row = (long long)b * T + t;
+          const long long o = row * row2H + dir * H + unit;
+          const float dh = __ldg(p.dout + o) + carry;
+          const float r = __ldg(p.saved + o), z = __ldg(p.saved + p.saved_qstride + o);
+          const float n = __ldg(p.saved + 2 * p.saved_qstride + o), hn = __ldg(p.saved + 3 * p.saved_qstride + o);
+          const float hprev = tp_ok ? __ldg(p.out + ((long long)b * T + tp) * row2H + dir * H + unit) : 0.f;
+          const float dn = dh * (1.f - z) * (1.f - n * n);
+          dzp = dh * (hprev - n) * z * (1.f - z);
+          drp = dn * hn * r * (1.f - r);
+          dnr = dn * r;
+          float* gp = p.dgi + row * 6 * H + dir * 3 * H + unit;
+          gp[0] = drp; gp[H] = dzp; gp[2 * H] = dn;
+          float* hp = p.dgh + row * 6 * H + dir * 3 * H + unit;
+          hp[0] = drp; hp[H] = dzp; hp[2 * H] = dnr;
+          dh_t[i] = dh * z;
+        }
+        ds[jj * DS + bb] = drp; ds[(u + jj) * DS + bb] = dzp; ds[(2 * u + jj) * DS + bb] = dnr;
+      }
+      __syncthreads();
+      if (s + 1 < T) {
+        // partial dh_{prev}[bb, k] = sum_{own rows i} dgh[bb, i] * W_hh[i, k]
+        float acc[12][NBC];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+          for (int q = 0; q < NBC; ++q) acc[i][q] = 0.f;
+        const int nrows = 3 * u;
+        for (int i = 0; i < nrows; ++i) {
+          float w[12];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int col = kg * 4 + 128 * q;
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < HP) w4 = *reinterpret_cast<const float4*>(Wb + (size_t)i * HP + col);
+            w[q * 4] = w4.x; w[q * 4 + 1] = w4.y; w[q * 4 + 2] = w4.z; w[q * 4 + 3] = w4.w;
+          }
+          float d[NBC];
+#pragma unroll
+          for (int q = 0; q < NBC; ++q) d[q] = ds[i * DS + bg + 8 * q];
+#pragma unroll
+          for (int e = 0; e < 12; ++e)
+#pragma unroll
+            for (int q = 0; q < NBC; ++q) acc[e][q] = fmaf(w[e], d[q], acc[e][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NBC; ++q) {
+          const int b = b0 + bg + 8 * q;
+          if (b >= p.B) continue;
+          float* po = Pout + ((long long)b * p.UC + c) * HP;
+#pragma unroll
+          for (int qq = 0; qq < 3; ++qq) {
+            const int col = kg * 4 + 128 * qq;
+            if (col < HP)
+              __stcg(reinterpret_cast<float4*>(po + col),
+                     make_float4(acc[qq * 4][q], acc[qq * 4 + 1][q], acc[qq * 4 + 2][q], acc[qq * 4 + 3][q]));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (s + 1 < T) group_signal(counter);
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(long long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+struct GruPlan { int u, UC, BT, ntiles, NB, tiles_per_cta; };
+
+static int make_plan(int B, int H, GruPlan* pl, const char* name) {
+  TG_REQUIRE(H > 0 && H <= 384 && B > 0, name);
+  pl->UC = tg_ceil_div(H, UMAX);
+  pl->u = tg_ceil_div(H, pl->UC);
+  const int sms = tg_num_sms();
+  int max_nb = sms / (2 * pl->UC);
+  if (max_nb < 1) max_nb = 1;
+  // smallest batch tile whose tile count fits the co-resident grid; otherwise the widest tile and several tiles per CTA
+  int bt = 16;
+  while (bt < 48 && tg_ceil_div(B, bt) > max_nb) bt += 16;
+  pl->BT = bt;
+  pl->ntiles = tg_ceil_div(B, bt);
+  pl->NB = pl->ntiles < max_nb ? pl->ntiles : max_nb;
+  pl->tiles_per_cta = tg_ceil_div(pl->ntiles, pl->NB);
+  return 0;
+}
+
+template <typename K, typename P>
+static int coop_launch(K kernel, const P& params, dim3 grid, size_t smem, cudaStream_t s, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { tg_set_error("%s: smem attr (%zu B): %s", name, smem, cudaGetErrorString(e)); return -3; }
+  void* args[] = {(void*)&params};
+  e = cudaLaunchCooperativeKernel((const void*)kernel, grid, dim3(256), args, smem, s);
+  if (e != cudaSuccess) { tg_set_error("%s: cooperative launch grid (%u,%u,%u) smem %zu: %s", name, grid.x, grid.y, grid.z, smem,
+                                       cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream) {
+  dim3 grid(tg_ceil_div(C, 32), tg_ceil_div(R, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, R, C);
+  TG_CHECK_LAUNCH("tg_transpose_f32");
+  return 0;
+}
+
+extern "C" int tg_gru_sync_ints(int B, int H) {
+  GruPlan pl;
+  if (make_plan(B, H, &pl, "tg_gru_sync_ints")) return -1;
+  return 2 * pl.NB;
+}
+
+extern "C" int tg_gru_layer_fwd(const float* gi, const float* whhT_f, const float* whhT_r, const float* bhh_f, const float* bhh_r,
+                                float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream) {
+  TG_REQUIRE(gi && whhT_f && whhT_r && bhh_f && bhh_r && out && sync && T > 0, "tg_gru_layer_fwd");
+  GruPlan pl;
+  if (make_plan(B, H, &pl, "tg_gru_layer_fwd")) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd: memset: %s", cudaGetErrorString(e)); return -2; }
+  GruFwdP p;
+  p.gi = gi; p.whhT[0] = whhT_f; p.whhT[1] = whhT_r; p.bhh[0] = bhh_f; p.bhh[1] = bhh_r;
+  p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.sync = sync;
+  p.B = B; p.T = T; p.H = H; p.u = pl.u; p.UC = pl.UC; p.NB = pl.NB; p.ntiles = pl.ntiles;
+  dim3 grid(pl.UC, pl.NB, 2);
+  const size_t smem = ((size_t)H * RP + (size_t)(H > RP ? H : RP) * (pl.BT + 1)) * sizeof(float);
+  TG_REQUIRE(smem <= (size_t)tg_max_smem_optin(), "tg_gru_layer_fwd");
+  if (pl.BT == 16) return coop_launch(gru_fwd_kernel<16>, p, grid, smem, s, "tg_gru_layer_fwd");
+  if (pl.BT == 32) return coop_launch(gru_fwd_kernel<32>, p, grid, smem, s, "tg_gru_layer_fwd");
+  return coop_launch(gru_fwd_kernel<48>, p, grid, smem, s, "tg_gru_layer_fwd");
+}
+
+extern "C" size_t tg_gru_bwd_scratch_floats(int B, int H) {
+  GruPlan pl;
+  if (make_plan(B, H, &pl, "tg_gru_bwd_scratch_floats")) return 0;
+  const int HP = (H + 3) & ~3;
+  return (size_t)2 * 2 * B * pl.UC * HP;
+}
+
+extern "C" int tg_gru_layer_bwd(const float* dout, const float* out, const float* saved, long long saved_qstride,
+                                const float* whh_f, const float* whh_r, float* dgi, float* dgh, float* partial, int* sync,
+                                int B, int T, int H, tg_stream stream) {
+  TG_REQUIRE(dout && out && saved && whh_f && whh_r && dgi && dgh && partial && sync && T > 0, "tg_gru_layer_bwd");
+  GruPlan pl;
+  if (make_plan(B, H, &pl, "tg_gru_layer_bwd")) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd: memset: %s", cudaGetErrorString(e)); return -2; }
+  GruBwdP p;
+  p.dout = dout; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.whh[0] = whh_f; p.whh[1] = whh_r;
+  p.dgi = dgi; p.dgh = dgh; p.partial = partial; p.sync = sync;
+  p.B = B; p.T = T; p.H = H; p.u = pl.u; p.UC = pl.UC; p.NB = pl.NB; p.ntiles = pl.ntiles;
+  p.HP = (H + 3) & ~3; p.tiles_per_cta = pl.tiles_per_cta;
+  dim3 grid(pl.UC, pl.NB, 2);
+  const size_t smem = ((size_t)RP * p.HP + (size_t)RP * (pl.BT + 1) + (size_t)pl.tiles_per_cta * pl.BT * pl.u) * sizeof(float);
+  TG_REQUIRE(smem <= (size_t)tg_max_smem_optin(), "tg_gru_layer_bwd");
+  if (pl.BT == 16) return coop_launch(gru_bwd_kernel<16>, p, grid, smem, s, "tg_gru_layer_bwd");
+  if (pl.BT == 32) return coop_launch(gru_bwd_kernel<32>, p, grid, smem, s, "tg_gru_layer_bwd");
+  return coop_launch(gru_bwd_kernel<48>, p, grid, smem, s, "tg_gru_layer_bwd");
+}

@@ -1,0 +1,112 @@
+"""EmbeddingNet(mode='pose') - the pose auto-encoder whose 32-d latent is the feature space of the Frechet Gesture
+Distance (reference: scripts/model/embedding_net.py:10-13, 16-39, 42-82, 165-217, 262-314).
+
+Parameter containers with the reference's names; the forward runs as 14 fused sm_100a GEMM launches with eval-mode
+BatchNorm folded into their epilogues (tgb200.engine.EmbeddingEngine).  Only what FGD needs is built: mode='pose',
+eval mode.  The joint-embedding baseline (ContextEncoder / PoseDecoderGRU / PoseDecoderFC, embedding_net.py:85-162,
+220-259) and training of the auto-encoder (train_feature_extractor.py) are outside the hot path."""
+import torch
+import torch.nn as nn
+
+from tgb200 import _lib, ops
+from tgb200.engine import EmbeddingEngine
+
+
+def reparameterize(mu, logvar):
+    """embedding_net.py:10-13: mu + eps*exp(0.5*logvar), eps from the Philox kernel (CUDA tensors only)."""
+    _lib.require_cuda()
+    mu_c, lv_c = mu.detach().contiguous().float(), logvar.detach().contiguous().float()
+    eps = torch.empty_like(mu_c)
+    off = torch.zeros(1, dtype=torch.int64, device=mu.device)
+    ops.philox_normal(eps, eps.numel(), int(torch.randint(0, 2 ** 62, (1,)).item()), off, 7)
+    z = torch.empty_like(mu_c)
+    ops.reparam_fwd(mu_c, lv_c, eps, z, z.numel())
+    return z
+
+
+def ConvNormRelu(in_channels, out_channels, downsample=False, padding=0, batchnorm=True):
+    k, s = (4, 2) if downsample else (3, 1)
+    conv_block = nn.Conv1d(in_channels, out_channels, kernel_size=k, stride=s, padding=padding)
+    if batchnorm:
+        return nn.Sequential(conv_block, nn.BatchNorm1d(out_channels), nn.LeakyReLU(0.2, True))
+    return nn.Sequential(conv_block, nn.LeakyReLU(0.2, True))
+
+
+class PoseEncoderConv(nn.Module):
+    def __init__(self, length, dim):
+        super().__init__()
+        self.net = nn.Sequential(ConvNormRelu(dim, 32, batchnorm=True), ConvNormRelu(32, 64, batchnorm=True),
+                                 ConvNormRelu(64, 64, True, batchnorm=True), nn.Conv1d(64, 32, 3))
+        self.out_net = nn.Sequential(nn.Linear(384, 256), nn.BatchNorm1d(256), nn.LeakyReLU(True),      # 384: 34-frame clips
+                                     nn.Linear(256, 128), nn.BatchNorm1d(128), nn.LeakyReLU(True), nn.Linear(128, 32))
+        self.fc_mu = nn.Linear(32, 32)
+        self.fc_logvar = nn.Linear(32, 32)
+
+    def forward(self, poses, variational_encoding):
+        raise RuntimeError('PoseEncoderConv holds parameters only; run EmbeddingNet.forward')
+
+
+class PoseDecoderConv(nn.Module):
+    def __init__(self, length, dim, use_pre_poses=False):
+        super().__init__()
+        assert not use_pre_poses, 'use_pre_poses=True is never constructed by the reference (embedding_net.py:273)'
+        self.use_pre_poses = use_pre_poses
+        feat_size = 32
+        if length == 64:
+            self.pre_net = nn.Sequential(nn.Linear(feat_size, 128), nn.BatchNorm1d(128), nn.LeakyReLU(True), nn.Linear(128, 256))
+        elif length == 34:
+            self.pre_net = nn.Sequential(nn.Linear(feat_size, 64), nn.BatchNorm1d(64), nn.LeakyReLU(True), nn.Linear(64, 136))
+        else:
+            assert False
+        self.net = nn.Sequential(nn.ConvTranspose1d(4, 32, 3), nn.BatchNorm1d(32), nn.LeakyReLU(0.2, True),
+                                 nn.ConvTranspose1d(32, 32, 3), nn.BatchNorm1d(32), nn.LeakyReLU(0.2, True),
+                                 nn.Conv1d(32, 32, 3), nn.Conv1d(32, dim, 3))
+
+    def forward(self, feat, pre_poses=None):
+        raise RuntimeError('PoseDecoderConv holds parameters only; run EmbeddingNet.forward')
+
+
+class EmbeddingNet(nn.Module):
+    def __init__(self, args, pose_dim, n_frames, n_words, word_embed_size, word_embeddings, mode):
+        super().__init__()
+        if mode != 'pose':
+            raise NotImplementedError("only EmbeddingNet(mode='pose') (the FGD feature extractor) is on the B200 hot path; the "
+                                      'joint-embedding baseline is out of scope (SURVEY.md 8 f4)')
+        self.context_encoder = None
+        self.pose_encoder = PoseEncoderConv(n_frames, pose_dim)
+        self.decoder = PoseDecoderConv(n_frames, pose_dim)
+        self.mode = mode
+        self._engine = None
+
+    def engine(self) -> EmbeddingEngine:
+        if self._engine is None:
+            self._engine = EmbeddingEngine(self)
+        return self._engine
+
+    def forward(self, in_text, in_audio, pre_poses, poses, input_mode=None, variational_encoding=False):
+        _lib.require_cuda()
+        if input_mode is None:
+            assert self.mode is not None
+            input_mode = self.mode
+        assert input_mode == 'pose', "EmbeddingNet(mode='pose') has no context encoder (embedding_net.py:270-273,282)"
+        if self.training:
+            raise RuntimeError('EmbeddingNet kernels implement the eval-mode (running-statistics) forward used by FGD; '
+                               'training the auto-encoder is outside the hot path')
+        if not poses.is_cuda and not _lib.TRACE_ONLY:
+            raise _lib.TgError('EmbeddingNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+        eng = self.engine().ensure(poses.device)
+        poses_c = poses.detach().contiguous().float()
+        eps = None
+        if variational_encoding:
+            eps = eng.ws.get('emb.eps', (poses.shape[0], 32))
+            off = eng.ws.get('emb.off', (1,), torch.int64, zero=True)
+            ops.philox_normal(eps, eps.numel(), int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF), off, 9)
+            ops.increment_i64(off, 1)
+        feat, mu, logvar, recon = eng.forward(poses_c, eps, variational_encoding, decode=True)
+        return None, None, None, feat.clone(), mu.clone(), logvar.clone(), recon.clone()
+
+    def freeze_pose_nets(self):
+        for param in self.pose_encoder.parameters():
+            param.requires_grad = False
+        for param in self.decoder.parameters():
+            param.requires_grad = False

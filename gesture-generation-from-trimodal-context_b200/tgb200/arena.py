@@ -1,0 +1,154 @@
+"""Flat parameter / gradient / Adam-state arenas.
+
+All trainable parameters of a module live in ONE contiguous fp32 buffer (each tensor 16-byte aligned); the
+nn.Parameters keep their reference names and shapes but become views into it, and `.grad` becomes a view into a
+second flat buffer.  That makes the optimiser one kernel launch (tg_adam_flat) and the data-parallel gradient
+exchange a handful of large NCCL all-reduces instead of ~90 small ones."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _ceil4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+class ParamArena:
+    def __init__(self, module: nn.Module, order: Optional[List[str]] = None):
+        self.module = module
+        named = dict(module.named_parameters())
+        names = list(order) if order is not None else list(named.keys())
+        assert set(names) == set(named.keys()), (set(names) ^ set(named.keys()))
+        self.names = [n for n in names if named[n].requires_grad]
+        self.params: Dict[str, nn.Parameter] = {n: named[n] for n in names}
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for n in self.names:
+            self.offsets[n] = off
+            off += _ceil4(named[n].numel())
+        self.numel = off
+        self.flat = self.grad = self.exp_avg = self.exp_avg_sq = None
+        self.step_dev = None
+        self.step = 0
+        self._bound_optim = None
+
+    # -- storage ------------------------------------------------------------------------------------------
+    def is_current(self) -> bool:
+        if self.flat is None:
+            return False
+        base = self.flat.data_ptr()
+        for n in (self.names[0], self.names[-1]):
+            if self.params[n].data_ptr() != base + 4 * self.offsets[n]:
+                return False
+        return True
+
+    def _grads_bound(self) -> bool:
+        for n in (self.names[0], self.names[-1]):
+            g = self.params[n].grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * self.offsets[n]:
+                return False
+        return True
+
+    def bind_grads(self):
+        """Points every .grad at its slice of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
+        for n in self.names:
+            p = self.params[n]
+            o, k = self.offsets[n], p.numel()
+            p.grad = self.grad[o:o + k].view(p.shape)
+
+    def ensure(self, device) -> 'ParamArena':
+        """(Re)builds the flat storage if the module was moved / re-created since the last call."""
+        if self.is_current():
+            if not self._grads_bound():
+                self.bind_grads()
+            return self
+        old_m, old_v = self.exp_avg, self.exp_avg_sq
+        self.flat = torch.zeros(self.numel, device=device, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        for n in self.names:
+            p = self.params[n]
+            assert p.dtype == torch.float32, (n, p.dtype)
+            o, k = self.offsets[n], p.numel()
+            self.flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + k].view(p.shape)
+            p.grad = self.grad[o:o + k].view(p.shape)
+        if old_m is not None and old_m.numel() == self.numel:
+            self.exp_avg, self.exp_avg_sq = old_m.to(device), old_v.to(device)
+        else:
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+        if self.step_dev is None or self.step_dev.device != self.flat.device:
+            self.step_dev = torch.full((1,), self.step, device=device, dtype=torch.int64)
+        self._bound_optim = None
+        return self
+
+    def view(self, name: str) -> torch.Tensor:
+        return self.params[name].data
+
+    def gview(self, name: str) -> torch.Tensor:
+        o = self.offsets[name]
+        p = self.params[name]
+        return self.grad[o:o + p.numel()].view(p.shape)
+
+    def adjacent(self, a: str, b: str) -> bool:
+        return self.offsets[b] == self.offsets[a] + self.params[a].numel()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    # -- optimiser ----------------------------------------------------------------------------------------
+    def bind_optimizer(self, optim: torch.optim.Optimizer):
+        """Makes a caller-constructed torch.optim.Adam (train.py:104-109) share our flat state so that its
+        state_dict() stays meaningful while the update itself is one tg_adam_flat launch."""
+        if self._bound_optim is optim:
+            return
+        assert isinstance(optim, torch.optim.Adam), 'train_iter_gan expects the torch.optim.Adam objects of train.py:104-109'
+        assert len(optim.param_groups) == 1
+        g = optim.param_groups[0]
+        assert g.get('weight_decay', 0) == 0 and not g.get('amsgrad', False) and not g.get('maximize', False)
+        ours = {id(self.params[n]) for n in self.names}
+        theirs = {id(p) for p in g['params'] if p.requires_grad}
+        assert ours == theirs, 'optimizer parameters differ from the module parameters'
+        steps = set()
+        for n in self.names:
+            p = self.params[n]
+            st = optim.state.get(p, None)
+            o, k = self.offsets[n], p.numel()
+            if st and 'exp_avg' in st and st['exp_avg'].data_ptr() != self.exp_avg.data_ptr() + 4 * o:
+                self.exp_avg[o:o + k].copy_(st['exp_avg'].reshape(-1))
+                self.exp_avg_sq[o:o + k].copy_(st['exp_avg_sq'].reshape(-1))
+                steps.add(int(st['step']))
+        if steps:
+            assert len(steps) == 1
+            self.step = steps.pop()
+            self.step_dev.fill_(self.step)
+        self._step_tensor = torch.tensor(float(self.step))
+        for n in self.names:
+            p = self.params[n]
+            o, k = self.offsets[n], p.numel()
+            optim.state[p] = {'step': self._step_tensor, 'exp_avg': self.exp_avg[o:o + k].view(p.shape),
+                              'exp_avg_sq': self.exp_avg_sq[o:o + k].view(p.shape)}
+        self._bound_optim = optim
+
+    def adam_step(self, optim: torch.optim.Optimizer, grad_scale: float = 1.0, host_step: bool = True):
+        """One Adam update of every parameter.  host_step=False: the caller advances step_dev on the device
+        (CUDA-graph replay) and calls note_steps() afterwards."""
+        self.bind_optimizer(optim)
+        g = optim.param_groups[0]
+        if host_step:
+            self.step += 1
+            self._step_tensor.fill_(float(self.step))
+            ops.increment_i64(self.step_dev, 1)
+        b1, b2 = g['betas']
+        ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.numel, float(g['lr']), float(b1), float(b2),
+                      float(g['eps']), float(grad_scale), self.step_dev)
+
+    def note_steps(self, n: int):
+        self.step += n
+        if getattr(self, '_step_tensor', None) is not None:
+            self._step_tensor.fill_(float(self.step))

@@ -1,0 +1,680 @@
+"""Launch plans for the hot path: PoseGenerator and ConvDiscriminator forward + hand-derived backward, expressed as
+sequences of C-ABI kernel launches (tgb200.ops) over pre-allocated workspaces.
+
+Layout: every activation is channels-last ([B, T, C] == row-major [B*T, C]); the reference's [B, C, T] conv layout,
+its chomp copy (tcn.py:13), its torch.cat / repeat of the GRU input (multimodal_context_net.py:139-153) and its
+per-parameter gradient tensors do not exist here.  Parameters live in a flat arena (tgb200.arena).
+
+Reference anchors: scripts/model/multimodal_context_net.py:9-28 (WavEncoder), :31-61 + scripts/model/tcn.py
+(TextEncoderTCN), :110-160 (PoseGenerator.forward), :207-252 (ConvDiscriminator)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .arena import ParamArena
+
+F32 = torch.float32
+BN_EPS = 1e-5
+BN_MOM = 0.1
+
+
+class Workspace:
+    """Named scratch tensors, allocated once per shape (so steady-state steps allocate nothing and can be graph-captured)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype=F32, zero=False):
+        shape = tuple(int(s) for s in shape)
+        t = self.t.get(name)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)
+            self.t[name] = t
+        return t
+
+    def __getitem__(self, name):
+        return self.t[name]
+
+
+def _conv_out(tin, k, stride, pad=0, dil=1):
+    return (tin + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def gru_arena_order(names: List[str]) -> List[str]:
+    """Arena order with weight_ih / bias_ih of both directions adjacent, so that one GEMM produces gi for fwd|rev."""
+    gru = [n for n in names if n.startswith('gru.')]
+    rest = [n for n in names if not n.startswith('gru.')]
+    layers = sorted({int(n.split('_l')[1].split('_')[0]) for n in gru})
+    out = []
+    for l in layers:
+        for kind in ('weight_ih', 'bias_ih', 'weight_hh', 'bias_hh'):
+            out += [f'gru.{kind}_l{l}', f'gru.{kind}_l{l}_reverse']
+    assert sorted(out) == sorted(gru)
+    return rest + out
+
+
+# =====================================================================================================================
+# shared bidirectional multi-layer GRU plan
+# =====================================================================================================================
+class GruPlan:
+    def __init__(self, arena: ParamArena, prefix: str, in_size: int, hidden: int, layers: int, ws: Workspace, tag: str):
+        self.a, self.pre, self.I, self.H, self.L, self.ws, self.tag = arena, prefix, in_size, hidden, layers, ws, tag
+        for l in range(layers):
+            for kind in ('weight_ih', 'bias_ih'):
+                assert arena.adjacent(f'{prefix}.{kind}_l{l}', f'{prefix}.{kind}_l{l}_reverse')
+
+    def _w(self, kind, l, rev=False):
+        return self.a.view(f'{self.pre}.{kind}_l{l}' + ('_reverse' if rev else ''))
+
+    def _g(self, kind, l, rev=False):
+        return self.a.gview(f'{self.pre}.{kind}_l{l}' + ('_reverse' if rev else ''))
+
+    def prep(self):
+        """W_hh^T for the forward recurrence kernel (weights change every optimiser step)."""
+        H = self.H
+        for l in range(self.L):
+            for d in (0, 1):
+                wt = self.ws.get(f'{self.tag}.whhT{l}_{d}', (H, 3 * H))
+                ops.transpose(self._w('weight_hh', l, bool(d)), wt, 3 * H, H)
+
+    def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool):
+        """x [B*T, I] -> out of the last layer [B*T, 2H].  masks[l] multiplies the output of layer l (l < L-1)."""
+        H, ws, tag = self.H, self.ws, self.tag
+        M = B * T
+        gi = ws.get(f'{tag}.gi', (M, 6 * H))
+        sync = ws.get(f'{tag}.sync', (max(ops.gru_sync_ints(B, H), 1),), torch.int32)
+        inp, K = x, self.I
+        for l in range(self.L):
+            ops.conv_gemm(inp, self._w('weight_ih', l), gi, B=1, Tin=M, Tout=M, N=6 * H, Cin=K, ldw=K, bias=self._w('bias_ih', l))
+            out = ws.get(f'{tag}.out{l}', (M, 2 * H))
+            saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
+            ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
+                              out, saved, M * 2 * H, sync, B, T, H)
+            if masks is not None and l < self.L - 1 and masks[l] is not None:
+                drop = ws.get(f'{tag}.drop{l}', (M, 2 * H))
+                ops.mul(out, masks[l], drop, M * 2 * H)
+                inp = drop
+            else:
+                inp = out
+            K = 2 * H
+        self._fwd_inputs = x
+        return inp
+
+    def backward(self, dout, x, B_all, lo, hi, T, masks, need_dx: bool):
+        """dout [(hi-lo)*T, 2H] = gradient of the last layer's output for clips [lo,hi) of a forward over B_all clips.
+        Accumulates all weight grads; returns d x [(hi-lo)*T, I] (or None)."""
+        H, ws, tag = self.H, self.ws, self.tag
+        Bb = hi - lo
+        Mb, M_all = Bb * T, B_all * T
+        r0, r1 = lo * T, hi * T
+        dgi = ws.get(f'{tag}.dgi', (Mb, 6 * H))
+        dgh = ws.get(f'{tag}.dgh', (Mb, 6 * H))
+        partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_scratch_floats(Bb, H), 1),))
+        sync = ws.get(f'{tag}.bsync', (max(ops.gru_sync_ints(Bb, H), 1),), torch.int32)
+        dx = None
+        for l in range(self.L - 1, -1, -1):
+            out = ws[f'{tag}.out{l}'][r0:r1]
+            saved = ws[f'{tag}.saved{l}'][:, r0:r1]          # plane stride stays M_all*2H
+            ops.gru_layer_bwd(dout, out, saved[0], M_all * 2 * H, self._w('weight_hh', l), self._w('weight_hh', l, True), dgi, dgh,
+                              partial, sync, Bb, T, H)
+            K = self.I if l == 0 else 2 * H
+            if l == 0:
+                inp = x[r0:r1]
+            elif masks is not None and masks[l - 1] is not None:
+                inp = ws[f'{tag}.drop{l - 1}'][r0:r1]
+            else:
+                inp = ws[f'{tag}.out{l - 1}'][r0:r1]
+            ops.conv_wgrad(inp, dgi, self._g('weight_ih', l), B=1, Tin=Mb, Tout=Mb, N=6 * H, Cin=K, ldw=K, dbias=self._g('bias_ih', l))
+            for d in (0, 1):
+                # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
+                ops.conv_wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, Tin=T, Tout=T, N=3 * H, Cin=H,
+                               taps=1, pad=(1 if d == 0 else -1), lda=2 * H, ldg=6 * H, ldw=H, dbias=self._g('bias_hh', l, bool(d)))
+            if l > 0 or need_dx:
+                dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
+                m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
+                ops.linear_dgrad(dgi, self._w('weight_ih', l), dx, M=Mb, K=K, N=6 * H, mask=m)
+                dout = dx
+            else:
+                dx = None
+        return dx
+
+
+# =====================================================================================================================
+# PoseGenerator
+# =====================================================================================================================
+class GeneratorEngine:
+    WAV = ((1, 16, 15, 5, 1600), (16, 32, 15, 6, 0), (32, 64, 15, 6, 0), (64, 32, 15, 6, 0))   # Cin, Cout, k, stride, pad
+
+    def __init__(self, module):
+        self.m = module
+        names = [n for n, _ in module.named_parameters()]
+        self.arena = ParamArena(module, gru_arena_order(names))
+        self.ws: Optional[Workspace] = None
+        self.gru: Optional[GruPlan] = None
+        self.slots = {}
+        self.use_audio = module.input_context in ('both', 'audio')
+        self.use_text = module.input_context in ('both', 'text')
+        self.z_mode = module.z_mode            # 'speaker' | 'random' | None
+        self.H = module.hidden_size
+        self.L = module.gru.num_layers
+        self.I = module.in_size
+        self.E = module.text_encoder.embedding.weight.shape[1]
+        self.n_tcn = len(module.text_encoder.tcn.network)
+        self.tcn_k = module.text_encoder.tcn.network[0].conv1.weight_v.shape[2]
+        self.p_emb = float(module.text_encoder.emb_dropout)
+        self.p_tcn = float(module.text_encoder.tcn.network[0].dropout1.p)
+        self.p_gru = float(module.gru.dropout)
+        self.bufs = dict(module.named_buffers())
+
+    # -------------------------------------------------------------------------------------------- setup
+    def ensure(self, device, slot='default'):
+        """Binds the flat arena and selects the workspace `slot` (distinct slots never share scratch memory, so a
+        CUDA graph captured on one slot stays valid while another slot is used with other shapes)."""
+        if not self.arena.is_current():
+            self.slots = {}
+        self.arena.ensure(device)
+        key = (slot, str(device))
+        if key not in self.slots:
+            w = Workspace(device)
+            self.slots[key] = (w, GruPlan(self.arena, 'gru', self.I, self.H, self.L, w, 'g'))
+        self.ws, self.gru = self.slots[key]
+        self.bufs = dict(self.m.named_buffers())
+        return self
+
+    def P(self, name):
+        return self.arena.params[name].data
+
+    def G(self, name):
+        return self.arena.gview(name)
+
+    def prep_weights(self):
+        """Per-optimiser-step derived weights: weight-norm'ed TCN filters and transposed recurrent matrices."""
+        ws = self.ws
+        if self.use_text:
+            for i in range(self.n_tcn):
+                for j in (1, 2):
+                    q = f'text_encoder.tcn.network.{i}.conv{j}'
+                    v = self.P(q + '.weight_v')
+                    N, K = v.shape[0], v.shape[1] * v.shape[2]
+                    ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (N, K)), ws.get(f'tcn.inv{i}_{j}', (N,)), N, K)
+        self.gru.prep()
+
+    def make_masks(self, Bt, T, seed, offset_dev, sid0=0):
+        """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel."""
+        ws, M = self.ws, Bt * T
+        masks = {}
+        sid = sid0
+        if self.use_text:
+            if self.p_emb > 0:
+                masks['emb'] = ws.get('mask.emb', (M, self.E)); ops.philox_dropout_mask(masks['emb'], M * self.E, self.p_emb, seed, offset_dev, sid)
+            sid += 1
+            for i in range(self.n_tcn):
+                for j in (1, 2):
+                    if self.p_tcn > 0:
+                        mk = ws.get(f'mask.tcn{i}_{j}', (M, self.H))
+                        ops.philox_dropout_mask(mk, M * self.H, self.p_tcn, seed, offset_dev, sid)
+                        masks[f'tcn{i}_{j}'] = mk
+                    sid += 1
+        for l in range(self.L - 1):
+            if self.p_gru > 0:
+                mk = ws.get(f'mask.gru{l}', (M, 2 * self.H))
+                ops.philox_dropout_mask(mk, M * 2 * self.H, self.p_gru, seed, offset_dev, sid)
+                masks[f'gru{l}'] = mk
+            sid += 1
+        return masks
+
+    # -------------------------------------------------------------------------------------------- WavEncoder
+    def wav_forward(self, audio, training: bool, n_updates: int = 1):
+        """multimodal_context_net.py:9-28.  audio [Ba, L] -> [Ba*T, 32].  BatchNorm+LeakyReLU(0.3) are never materialised:
+        they are applied as the next convolution's operand prologue."""
+        ws = self.ws
+        Ba, L = audio.shape
+        pre = 'audio_encoder.feat_extractor.'
+        self.wav_T = [L]
+        x = audio
+        scale = shift = None
+        for li, (cin, cout, k, s, pad) in enumerate(self.WAV):
+            conv = pre + str(3 * li)
+            tin = self.wav_T[-1]
+            tout = _conv_out(tin, k, s, pad)
+            self.wav_T.append(tout)
+            y = ws.get(f'wav.y{li}', (Ba * tout, cout))
+            if li == 0:
+                ops.conv1_direct(x, self.P(conv + '.weight'), self.P(conv + '.bias'), y, B=Ba, Tin=tin, Tout=tout, N=cout, taps=k, stride=s, pad=pad)
+            else:
+                ops.conv1d(x, self.P(conv + '.weight'), self.P(conv + '.bias'), y, B=Ba, Tin=tin, Cin=cin, N=cout, k=k, stride=s, pad=pad,
+                           pscale=scale, pshift=shift, pslope=0.3)
+            if li < 3:
+                bn = pre + str(3 * li + 1)
+                mean, rstd = ws.get(f'wav.mean{li}', (cout,)), ws.get(f'wav.rstd{li}', (cout,))
+                scale, shift = ws.get(f'wav.scale{li}', (cout,)), ws.get(f'wav.shift{li}', (cout,))
+                if training:
+                    sums = ws.get(f'wav.sums{li}', (2 * cout,), torch.float64)
+                    sums.zero_()
+                    ops.col_stats(y, cout, Ba * tout, cout, sums)
+                    ops.bn_finalize(sums, Ba * tout, cout, BN_EPS, BN_MOM, n_updates, self.P(bn + '.weight'), self.P(bn + '.bias'),
+                                    self.bufs[bn + '.running_mean'], self.bufs[bn + '.running_var'], self.bufs[bn + '.num_batches_tracked'],
+                                    mean, rstd, scale, shift)
+                else:
+                    ops.bn_eval_fold(self.P(bn + '.weight'), self.P(bn + '.bias'), self.bufs[bn + '.running_mean'],
+                                     self.bufs[bn + '.running_var'], BN_EPS, None, scale, shift, cout)
+            x = y
+        return x                                           # [Ba*34, 32]
+
+    def wav_backward(self, d_feat, audio):
+        """d_feat [Ba*T, 32] -> accumulates conv / BN grads (train-mode BN)."""
+        ws = self.ws
+        Ba = audio.shape[0]
+        pre = 'audio_encoder.feat_extractor.'
+        dy = d_feat
+        for li in (3, 2, 1, 0):
+            cin, cout, k, s, pad = self.WAV[li]
+            conv = pre + str(3 * li)
+            tin, tout = self.wav_T[li], self.wav_T[li + 1]
+            x = audio if li == 0 else ws[f'wav.y{li - 1}']
+            sc = ws[f'wav.scale{li - 1}'] if li > 0 else None
+            sh = ws[f'wav.shift{li - 1}'] if li > 0 else None
+            ops.conv1d_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k,
+                             stride=s, pad=pad, pscale=sc, pshift=sh, pslope=0.3)
+            if li == 0:
+                break
+            da = ws.get(f'wav.da{li - 1}', (Ba * tin, cin))
+            ops.conv1d_dgrad(dy, self.P(conv + '.weight'), da, B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s, pad=pad)
+            bn = pre + str(3 * (li - 1) + 1)
+            sums = ws.get(f'wav.bsums{li - 1}', (2 * cin,), torch.float64)
+            sums.zero_()
+            mean, rstd = ws[f'wav.mean{li - 1}'], ws[f'wav.rstd{li - 1}']
+            ops.bn_bwd_reduce(da, x, Ba * tin, cin, mean, rstd, sc, sh, 0.3, sums)
+            ops.bn_bwd_apply(da, x, da, Ba * tin, cin, mean, rstd, sc, sh, 0.3, self.P(bn + '.weight'), sums, self.G(bn + '.weight'),
+                             self.G(bn + '.bias'))
+            dy = da
+
+    # -------------------------------------------------------------------------------------------- TextEncoderTCN
+    def text_forward(self, in_text, Bt, T, masks):
+        """multimodal_context_net.py:57-61 + tcn.py:43-64.  in_text [Ba, T] int64 (read at row % (Ba*T)) -> [Bt*T, 32]."""
+        ws, H, E = self.ws, self.H, self.E
+        M = Bt * T
+        Ba = in_text.shape[0]
+        idx_mod = Ba * T if Bt != Ba else 0
+        emb = ws.get('txt.emb', (M, E))
+        ops.embedding_gather(self.P('text_encoder.embedding.weight'), in_text, idx_mod, masks.get('emb') if masks else None, emb, M, E)
+        x, cin = emb, E
+        k = self.tcn_k
+        for i in range(self.n_tcn):
+            d = 2 ** i
+            q = f'text_encoder.tcn.network.{i}'
+            assert cin == H, 'TemporalBlock.downsample (n_inputs != n_outputs) is not on the configured path (tcn.py:33)'
+            y1 = ws.get(f'txt.y1_{i}', (M, H)); y2 = ws.get(f'txt.y2_{i}', (M, H)); xo = ws.get(f'txt.x{i}', (M, H))
+            m1 = masks.get(f'tcn{i}_1') if masks else None
+            m2 = masks.get(f'tcn{i}_2') if masks else None
+            ops.conv1d(x, ws[f'tcn.w{i}_1'], self.P(q + '.conv1.bias'), y1, B=Bt, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d,
+                       act1=ops.ACT_RELU, mask=m1)
+            ops.conv1d(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), y2, B=Bt, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d,
+                       act1=ops.ACT_RELU, mask=m2)
+            ops.add(y2, x, xo, M * H, relu=True)
+            x, cin = xo, H
+        feat = ws.get('txt.feat', (M, 32))
+        ops.linear(x, self.P('text_encoder.decoder.weight'), self.P('text_encoder.decoder.bias'), feat, M=M, K=H, N=32)
+        return feat
+
+    def text_backward(self, d_feat, in_text, lo, hi, T, masks):
+        ws, H, E = self.ws, self.H, self.E
+        Bb = hi - lo
+        Mb = Bb * T
+        r0, r1 = lo * T, hi * T
+        k = self.tcn_k
+        sl = lambda t: t[r0:r1] if t is not None else None
+        xl = ws[f'txt.x{self.n_tcn - 1}'][r0:r1]
+        ops.linear_wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), self.G('text_encoder.decoder.bias'), M=Mb, K=H, N=32)
+        dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dc = ws.get('txt.dC', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
+        ops.linear_dgrad(d_feat, self.P('text_encoder.decoder.weight'), dx, M=Mb, K=H, N=32)
+        for i in range(self.n_tcn - 1, -1, -1):
+            d = 2 ** i
+            q = f'text_encoder.tcn.network.{i}'
+            xin = (ws[f'txt.x{i - 1}'] if i > 0 else ws['txt.emb'])[r0:r1]
+            cin = H if i > 0 else E
+            y1, y2, xo = ws[f'txt.y1_{i}'][r0:r1], ws[f'txt.y2_{i}'][r0:r1], ws[f'txt.x{i}'][r0:r1]
+            m1 = sl(masks.get(f'tcn{i}_1')) if masks else None
+            m2 = sl(masks.get(f'tcn{i}_2')) if masks else None
+            ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                      # through the block's final ReLU
+            ops.relu_mask_bwd(dpre, y2, m2, dc, Mb * H)                        # dropout2 + relu2
+            dw = ws.get('tcn.dw', (H, max(cin, H) * k)); dw.zero_()
+            ops.conv1d_wgrad(y1, dc, dw, self.G(q + '.conv2.bias'), B=Bb, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d)
+            ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
+                                self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H * k)
+            ops.conv1d_dgrad(dc, ws[f'tcn.w{i}_2'], dy1, B=Bb, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d)
+            ops.relu_mask_bwd(dy1, y1, m1, dc, Mb * H)                         # dropout1 + relu1
+            dw.zero_()
+            ops.conv1d_wgrad(xin, dc, dw, self.G(q + '.conv1.bias'), B=Bb, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d)
+            ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
+                                self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin * k)
+            # d x_in = conv1^T(dc) + residual branch (dpre)
+            ops.conv1d_dgrad(dc, ws[f'tcn.w{i}_1'], dx, B=Bb, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d, residual=dpre)
+        emb_p = self.arena.params['text_encoder.embedding.weight']
+        if emb_p.requires_grad:
+            Ba = in_text.shape[0]
+            assert Bb == Ba and lo % Ba == 0
+            ops.embedding_scatter_add(dx, in_text, sl(masks.get('emb')) if masks else None, self.G('text_encoder.embedding.weight'), Mb, E)
+
+    # -------------------------------------------------------------------------------------------- full forward
+    def forward(self, pre_seq, in_text, in_audio, vid, eps, Bt, training, masks=None, n_bn_updates=1, save=True):
+        """PoseGenerator.forward (multimodal_context_net.py:110-160) over Bt clips whose pre_seq/text/audio repeat with
+        period Ba = in_audio.shape[0] (train_iter_gan runs its three generator passes as ONE Bt = 3*Ba pass).
+        Returns views (poses [Bt,T,D], z, mu, logvar) into the workspace."""
+        ws, m = self.ws, self.m
+        Ba, T = pre_seq.shape[0], pre_seq.shape[1]
+        Dp = pre_seq.shape[2]
+        M = Bt * T
+        self.ctx = dict(Bt=Bt, Ba=Ba, T=T, masks=masks, pre_seq=pre_seq, in_text=in_text, in_audio=in_audio, vid=vid, eps=eps)
+        audio_feat = self.wav_forward(in_audio, training, n_bn_updates) if self.use_audio else None
+        text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
+        z = mu = logvar = None
+        Z = 0
+        if self.z_mode == 'speaker':
+            Z = 16
+            e0, e1 = ws.get('spk.e0', (Bt, Z)), ws.get('spk.e1', (Bt, Z))
+            mu, logvar, z = ws.get('spk.mu', (Bt, Z)), ws.get('spk.logvar', (Bt, Z)), ws.get('spk.z', (Bt, Z))
+            ops.embedding_gather(self.P('speaker_embedding.0.weight'), vid, 0, None, e0, Bt, Z)
+            ops.linear(e0, self.P('speaker_embedding.1.weight'), self.P('speaker_embedding.1.bias'), e1, M=Bt, K=Z, N=Z)
+            ops.linear(e1, self.P('speaker_mu.weight'), self.P('speaker_mu.bias'), mu, M=Bt, K=Z, N=Z)
+            ops.linear(e1, self.P('speaker_logvar.weight'), self.P('speaker_logvar.bias'), logvar, M=Bt, K=Z, N=Z)
+            ops.reparam_fwd(mu, logvar, eps, z, Bt * Z)
+        elif self.z_mode == 'random':
+            Z = 16
+            z = eps
+        in_data = ws.get('g.in', (M, self.I))
+        Da = 32 if self.use_audio else 0
+        Dt = 32 if self.use_text else 0
+        assert Dp + Da + Dt + Z == self.I
+        ops.gru_input_concat(pre_seq, audio_feat, text_feat, z, in_data, Bt, Ba, T, Dp, Da, Dt, Z)
+        gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
+        out = self.gru.forward(in_data, Bt, T, gmasks, save)
+        H = self.H
+        hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, H // 2)); poses = ws.get('g.poses', (M, m.pose_dim))
+        ops.sum_halves(out, hsum, M, H)
+        ops.linear(hsum, self.P('out.0.weight'), self.P('out.0.bias'), y1, M=M, K=H, N=H // 2)      # LeakyReLU(True) == identity
+        ops.linear(y1, self.P('out.2.weight'), self.P('out.2.bias'), poses, M=M, K=H // 2, N=m.pose_dim)
+        return poses.view(Bt, T, m.pose_dim), z, mu, logvar
+
+    def backward(self, d_poses, lo, hi, d_mu=None, d_logvar=None, d_z=None):
+        """Gradient of clips [lo,hi) of the last forward.  d_poses [(hi-lo),T,D]; d_mu/d_logvar/d_z [(hi-lo),16] optional
+        (d_mu / d_logvar are used as accumulators and overwritten).  Accumulates into the flat gradient arena."""
+        ws, m, c = self.ws, self.m, self.ctx
+        T, Ba, Bt, masks = c['T'], c['Ba'], c['Bt'], c['masks']
+        Bb = hi - lo
+        Mb = Bb * T
+        r0, r1 = lo * T, hi * T
+        H, D = self.H, m.pose_dim
+        d_poses = d_poses.reshape(Mb, D)
+        dy1 = ws.get('g.dy1', (Mb, H // 2)); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
+        ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
+        ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)
+        ops.linear_wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), self.G('out.0.bias'), M=Mb, K=H, N=H // 2)
+        ops.linear_dgrad(dy1, self.P('out.0.weight'), dhs, M=Mb, K=H, N=H // 2)
+        ops.dup_halves(dhs, dout, Mb, H)
+        gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
+        need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'
+        d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx)
+        if not need_dx:
+            return
+        Dp = c['pre_seq'].shape[2]
+        Da = 32 if self.use_audio else 0
+        Dt = 32 if self.use_text else 0
+        Z = 16 if self.z_mode else 0
+        d_audio = ws.get('g.daudio', (Mb, max(Da, 1))); d_text = ws.get('g.dtext', (Mb, max(Dt, 1))); dzc = ws.get('g.dz', (Bb, max(Z, 1)))
+        ops.gru_input_split_bwd(d_in, d_audio, d_text, dzc, Bb, T, Dp, Da, Dt, Z)
+        if self.z_mode == 'speaker':
+            Zs = 16
+            if d_z is not None:
+                ops.add(dzc, d_z, dzc, Bb * Zs)
+            dmu = d_mu if d_mu is not None else ws.get('spk.dmu', (Bb, Zs), zero=True)
+            dlv = d_logvar if d_logvar is not None else ws.get('spk.dlv', (Bb, Zs), zero=True)
+            if d_mu is None: dmu.zero_()
+            if d_logvar is None: dlv.zero_()
+            ops.reparam_bwd(dzc, ws['spk.logvar'][lo:hi], c['eps'][lo:hi], dmu, dlv, Bb * Zs)
+            e0, e1 = ws['spk.e0'][lo:hi], ws['spk.e1'][lo:hi]
+            de1, de0 = ws.get('spk.de1', (Bb, Zs)), ws.get('spk.de0', (Bb, Zs))
+            ops.linear_wgrad(e1, dmu, self.G('speaker_mu.weight'), self.G('speaker_mu.bias'), M=Bb, K=Zs, N=Zs)
+            ops.linear_wgrad(e1, dlv, self.G('speaker_logvar.weight'), self.G('speaker_logvar.bias'), M=Bb, K=Zs, N=Zs)
+            ops.linear_dgrad(dmu, self.P('speaker_mu.weight'), de1, M=Bb, K=Zs, N=Zs)
+            ops.linear_dgrad(dlv, self.P('speaker_logvar.weight'), de1, M=Bb, K=Zs, N=Zs, accumulate=True)
+            ops.linear_wgrad(e0, de1, self.G('speaker_embedding.1.weight'), self.G('speaker_embedding.1.bias'), M=Bb, K=Zs, N=Zs)
+            ops.linear_dgrad(de1, self.P('speaker_embedding.1.weight'), de0, M=Bb, K=Zs, N=Zs)
+            ops.embedding_scatter_add(de0, c['vid'][lo:hi], None, self.G('speaker_embedding.0.weight'), Bb, Zs)
+        if self.use_text:
+            self.text_backward(d_text, c['in_text'], lo, hi, T, masks)
+        if self.use_audio:
+            assert Bb == Ba and lo % Ba == 0
+            self.wav_backward(d_audio, c['in_audio'])
+
+
+# =====================================================================================================================
+# ConvDiscriminator
+# =====================================================================================================================
+class DiscriminatorEngine:
+    CONVS = (('pre_conv.0', 'pre_conv.1'), ('pre_conv.3', 'pre_conv.4'), ('pre_conv.6', None))
+
+    def __init__(self, module):
+        self.m = module
+        names = [n for n, _ in module.named_parameters()]
+        self.arena = ParamArena(module, gru_arena_order(names))
+        self.ws: Optional[Workspace] = None
+        self.gru: Optional[GruPlan] = None
+        self.slots = {}
+        self.H = module.hidden_size
+        self.L = module.gru.num_layers
+        self.p_gru = float(module.gru.dropout)
+
+    def ensure(self, device, slot='default'):
+        if not self.arena.is_current():
+            self.slots = {}
+        self.arena.ensure(device)
+        key = (slot, str(device))
+        if key not in self.slots:
+            w = Workspace(device)
+            self.slots[key] = (w, GruPlan(self.arena, 'gru', 8, self.H, self.L, w, 'd'))
+        self.ws, self.gru = self.slots[key]
+        self.bufs = dict(self.m.named_buffers())
+        return self
+
+    def P(self, name):
+        return self.arena.params[name].data
+
+    def G(self, name):
+        return self.arena.gview(name)
+
+    def prep_weights(self):
+        self.gru.prep()
+
+    def make_masks(self, B, T, seed, offset_dev, sid0=0, tag=''):
+        masks = {}
+        M = B * T
+        for l in range(self.L - 1):
+            if self.p_gru > 0:
+                mk = self.ws.get(f'mask{tag}.gru{l}', (M, 2 * self.H))
+                ops.philox_dropout_mask(mk, M * 2 * self.H, self.p_gru, seed, offset_dev, sid0 + l)
+                masks[f'gru{l}'] = mk
+        return masks
+
+    def forward(self, poses, training, masks=None, save=True):
+        """ConvDiscriminator.forward (multimodal_context_net.py:232-252): poses [B,34,27] -> sigmoid [B,1]."""
+        ws = self.ws
+        B, T0, D = poses.shape
+        self.ctx = dict(B=B, T0=T0, D=D, masks=masks, poses=poses, training=training)
+        x, tin, cin = poses, T0, D
+        scale = shift = None
+        self.Ts = [T0]
+        for li, (conv, bn) in enumerate(self.CONVS):
+            w = self.P(conv + '.weight')
+            cout, k = w.shape[0], w.shape[2]
+            tout = tin - k + 1
+            y = ws.get(f'd.y{li}', (B * tout, cout))
+            ops.conv1d(x, w, self.P(conv + '.bias'), y, B=B, Tin=tin, Cin=cin, N=cout, k=k, pscale=scale, pshift=shift, pslope=1.0)
+            if bn is not None:
+                mean, rstd = ws.get(f'd.mean{li}', (cout,)), ws.get(f'd.rstd{li}', (cout,))
+                scale, shift = ws.get(f'd.scale{li}', (cout,)), ws.get(f'd.shift{li}', (cout,))
+                if training:
+                    sums = ws.get(f'd.sums{li}', (2 * cout,), torch.float64); sums.zero_()
+                    ops.col_stats(y, cout, B * tout, cout, sums)
+                    ops.bn_finalize(sums, B * tout, cout, BN_EPS, BN_MOM, 1, self.P(bn + '.weight'), self.P(bn + '.bias'),
+                                    self.bufs[bn + '.running_mean'], self.bufs[bn + '.running_var'], self.bufs[bn + '.num_batches_tracked'],
+                                    mean, rstd, scale, shift)
+                else:
+                    ops.bn_eval_fold(self.P(bn + '.weight'), self.P(bn + '.bias'), self.bufs[bn + '.running_mean'],
+                                     self.bufs[bn + '.running_var'], BN_EPS, None, scale, shift, cout)
+            x, tin, cin = y, tout, cout
+            self.Ts.append(tout)
+        T = tin
+        M = B * T
+        H = self.H
+        gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
+        out = self.gru.forward(x, B, T, gmasks, save)
+        hsum = ws.get('d.hsum', (M, H)); o1 = ws.get('d.o1', (M, 1)); prob = ws.get('d.prob', (B, 1))
+        ops.sum_halves(out, hsum, M, H)
+        ops.linear(hsum, self.P('out.weight'), self.P('out.bias'), o1, M=M, K=H, N=1)
+        ops.linear(o1, self.P('out2.weight'), self.P('out2.bias'), prob, M=B, K=T, N=1, act1=ops.ACT_SIGMOID)
+        self.ctx['T'] = T
+        return prob
+
+    def backward(self, dlogit, need_dposes: bool, param_grads: bool = True):
+        """dlogit [B,1] = d loss / d (pre-sigmoid output).  Returns d poses [B,34,27] if requested."""
+        ws, c = self.ws, self.ctx
+        B, T, H = c['B'], c['T'], self.H
+        M = B * T
+        masks = c['masks']
+        do1 = ws.get('d.do1', (M, 1)); dhs = ws.get('d.dhs', (M, H)); dout = ws.get('d.dout', (M, 2 * H))
+        ops.linear_wgrad(ws['d.o1'], dlogit, self.G('out2.weight'), self.G('out2.bias'), M=B, K=T, N=1)
+        ops.linear_dgrad(dlogit, self.P('out2.weight'), do1, M=B, K=T, N=1)
+        ops.linear_wgrad(ws['d.hsum'], do1, self.G('out.weight'), self.G('out.bias'), M=M, K=H, N=1)
+        ops.linear_dgrad(do1, self.P('out.weight'), dhs, M=M, K=H, N=1)
+        ops.dup_halves(dhs, dout, M, H)
+        gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
+        dy = self.gru.backward(dout, ws['d.y2'], B, 0, B, T, gmasks, True)
+        dposes = None
+        for li in (2, 1, 0):
+            conv, _ = self.CONVS[li]
+            w = self.P(conv + '.weight')
+            cout, cin, k = w.shape
+            tin, tout = self.Ts[li], self.Ts[li + 1]
+            x = c['poses'] if li == 0 else ws[f'd.y{li - 1}']
+            sc = ws[f'd.scale{li - 1}'] if li > 0 else None
+            sh = ws[f'd.shift{li - 1}'] if li > 0 else None
+            ops.conv1d_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k,
+                             pscale=sc, pshift=sh, pslope=1.0)
+            if li == 0 and not need_dposes:
+                break
+            da = ws.get(f'd.da{li}', (B * tin, cin))
+            ops.conv1d_dgrad(dy, w, da, B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k)
+            if li == 0:
+                dposes = da.view(B, tin, cin)
+                break
+            bn = self.CONVS[li - 1][1]
+            sums = ws.get(f'd.bsums{li - 1}', (2 * cin,), torch.float64); sums.zero_()
+            mean, rstd = ws[f'd.mean{li - 1}'], ws[f'd.rstd{li - 1}']
+            assert c['training'], 'backward through eval-mode BatchNorm is not on the hot path'
+            ops.bn_bwd_reduce(da, x, B * tin, cin, mean, rstd, sc, sh, 1.0, sums)
+            ops.bn_bwd_apply(da, x, da, B * tin, cin, mean, rstd, sc, sh, 1.0, self.P(bn + '.weight'), sums, self.G(bn + '.weight'),
+                             self.G(bn + '.bias'))
+            dy = da
+        return dposes
+
+
+# =====================================================================================================================
+# EmbeddingNet (mode='pose'), eval mode: the feature extractor behind FGD
+# =====================================================================================================================
+class EmbeddingEngine:
+    """PoseEncoderConv + PoseDecoderConv forward (embedding_net.py:42-82,165-217) with eval-mode BatchNorm folded into
+    each producing GEMM's epilogue (scale/shift per output channel)."""
+
+    def __init__(self, module):
+        self.m = module
+        self.ws: Optional[Workspace] = None
+
+    def ensure(self, device):
+        if self.ws is None or self.ws.device != device:
+            self.ws = Workspace(device)
+        self.p = {k: v.data for k, v in self.m.named_parameters()}
+        self.b = dict(self.m.named_buffers())
+        return self
+
+    def _fold(self, tag, bn, conv_bias, C):
+        sc, sh = self.ws.get(tag + '.sc', (C,)), self.ws.get(tag + '.sh', (C,))
+        ops.bn_eval_fold(self.p[bn + '.weight'], self.p[bn + '.bias'], self.b[bn + '.running_mean'], self.b[bn + '.running_var'],
+                         BN_EPS, conv_bias, sc, sh, C)
+        return sc, sh
+
+    def forward(self, poses, eps=None, variational=False, decode=True):
+        """poses [B,T,D] -> (feat [B,32], mu, logvar, recon [B,T,D] or None)"""
+        ws, p = self.ws, self.p
+        B, T, D = poses.shape
+        x, tin, cin = poses, T, D
+        e = 'pose_encoder.'
+        for i, (k, s) in enumerate(((3, 1), (3, 1), (4, 2))):
+            w = p[f'{e}net.{i}.0.weight']
+            cout = w.shape[0]
+            sc, sh = self._fold(f'e{i}', f'{e}net.{i}.1', p[f'{e}net.{i}.0.bias'], cout)
+            tout = _conv_out(tin, k, s)
+            y = ws.get(f'emb.e{i}', (B * tout, cout))
+            ops.conv1d(x, w, sh, y, B=B, Tin=tin, Cin=cin, N=cout, k=k, stride=s, escale=sc, act1=ops.ACT_LRELU, slope1=0.2)
+            x, tin, cin = y, tout, cout
+        w = p[e + 'net.3.weight']
+        cout, k = w.shape[0], w.shape[2]
+        tout = _conv_out(tin, k, 1)
+        y = ws.get('emb.e3', (B * tout, cout))
+        ops.conv1d(x, w, p[e + 'net.3.bias'], y, B=B, Tin=tin, Cin=cin, N=cout, k=k)
+        # flatten is channel-major in the reference ([B,32,12] -> 384): read the Linear weight with (tap=t, chan=c) strides
+        w0 = p[e + 'out_net.0.weight']
+        n0 = w0.shape[0]
+        assert w0.shape[1] == cout * tout, 'PoseEncoderConv.out_net is hard-wired to 34-frame clips (embedding_net.py:54-55)'
+        sc, sh = self._fold('o0', e + 'out_net.1', p[e + 'out_net.0.bias'], n0)
+        h0 = ws.get('emb.h0', (B, n0))
+        ops.conv_gemm(y, w0, h0, B=B, Tin=tout, Tout=1, N=n0, Cin=cout, taps=tout, ldw=cout * tout, wsj=1, wsc=tout, escale=sc, bias=sh)
+        w1 = p[e + 'out_net.3.weight']; n1 = w1.shape[0]
+        sc, sh = self._fold('o1', e + 'out_net.4', p[e + 'out_net.3.bias'], n1)
+        h1 = ws.get('emb.h1', (B, n1))
+        ops.linear(h0, w1, sh, h1, M=B, K=n0, N=n1, escale=sc)
+        w2 = p[e + 'out_net.6.weight']; n2 = w2.shape[0]
+        h2 = ws.get('emb.h2', (B, n2))
+        ops.linear(h1, w2, p[e + 'out_net.6.bias'], h2, M=B, K=n1, N=n2)
+        mu = ws.get('emb.mu', (B, 32)); logvar = ws.get('emb.logvar', (B, 32))
+        ops.linear(h2, p[e + 'fc_mu.weight'], p[e + 'fc_mu.bias'], mu, M=B, K=n2, N=32)
+        ops.linear(h2, p[e + 'fc_logvar.weight'], p[e + 'fc_logvar.bias'], logvar, M=B, K=n2, N=32)
+        feat = mu
+        if variational:
+            feat = ws.get('emb.z', (B, 32))
+            ops.reparam_fwd(mu, logvar, eps, feat, B * 32)
+        if not decode:
+            return feat, mu, logvar, None
+        d = 'decoder.'
+        wp = p[d + 'pre_net.0.weight']; c0 = wp.shape[0]
+        sc, sh = self._fold('d0', d + 'pre_net.1', p[d + 'pre_net.0.bias'], c0)
+        g0 = ws.get('emb.g0', (B, c0))
+        ops.linear(feat, wp, sh, g0, M=B, K=32, N=c0, escale=sc)
+        wq = p[d + 'pre_net.3.weight']; c1 = wq.shape[0]
+        g1 = ws.get('emb.g1', (B, c1))
+        ops.linear(g0, wq, p[d + 'pre_net.3.bias'], g1, M=B, K=c0, N=c1)
+        # view [B,4,L] channel-major -> read as channels-last through A strides (row stride 1, channel stride L)
+        ch, L = 4, c1 // 4
+        x, tin, cin = g1, L, ch
+        a_kw = dict(lda=1, asc=L, a_bstride=c1)
+        for i, idx in enumerate((0, 3)):                                   # two ConvTranspose1d(k=3) + BN + LeakyReLU(0.2)
+            w = p[f'{d}net.{idx}.weight']                                  # [Cin, Cout, k]
+            cout, k = w.shape[1], w.shape[2]
+            sc, sh = self._fold(f't{i}', f'{d}net.{idx + 1}', p[f'{d}net.{idx}.bias'], cout)
+            tout = tin + k - 1
+            y = ws.get(f'emb.t{i}', (B * tout, cout))
+            ops.conv_gemm(x, w, y, B=B, Tin=tin, Tout=tout, N=cout, Cin=cin, taps=k, dil=-1, pad=0, ldw=k, wsj=1, wsc=cout * k,
+                          escale=sc, bias=sh, act1=ops.ACT_LRELU, slope1=0.2, **a_kw)
+            x, tin, cin, a_kw = y, tout, cout, {}
+        for i, idx in enumerate((6, 7)):
+            w = p[f'{d}net.{idx}.weight']
+            cout, k = w.shape[0], w.shape[2]
+            tout = tin - k + 1
+            y = ws.get(f'emb.c{i}', (B * tout, cout))
+            ops.conv1d(x, w, p[f'{d}net.{idx}.bias'], y, B=B, Tin=tin, Cin=cin, N=cout, k=k)
+            x, tin, cin = y, tout, cout
+        return feat, mu, logvar, x.view(B, tin, cin)

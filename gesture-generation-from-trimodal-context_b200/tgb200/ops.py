@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI (include/tg_b200.h).  Every function enqueues hand-written sm_100a kernels on
+torch's current CUDA stream; torch is used only for memory (tensors) and streams.  CUDA tensors only - no fallback."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemm, ConvWgrad, check
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+
+_launches = 0           # kernel launches issued through this module (bench.py reports it as gpu_launches)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _L():
+    return _lib.load()
+
+
+def _s():
+    if _lib.TRACE_ONLY:
+        return 0
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda and not _lib.TRACE_ONLY:
+        raise _lib.TgError('tgb200 ops take CUDA tensors only (no CPU fallback)')
+    return t.data_ptr()
+
+
+def _f32(t: torch.Tensor):
+    assert t.dtype == torch.float32, t.dtype
+    return t
+
+
+def device_info():
+    out = (ctypes.c_int * 2)()
+    _L().tg_device_info(out)
+    return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------ implicit GEMM
+def conv_gemm(A, W, Y, *, B, Tin, Tout, N, Cin, taps=1, stride=1, dil=1, pad=0, lda=None, ldw=None, wsj=0, wsc=1, ldc=None,
+              ToutFull=None, ostride=1, ooff=0, pscale=None, pshift=None, pslope=1.0, escale=None, bias=None, act1=0,
+              slope1=0.0, mask=None, ldmask=None, residual=None, ldres=None, act2=0, accumulate=False, asc=1, a_bstride=0,
+              w_off=0):
+    g = ConvGemm()
+    g.A = _p(_f32(A)); g.lda = Cin if lda is None else lda; g.asc = asc; g.a_bstride = a_bstride
+    g.W = _p(_f32(W)) + 4 * w_off; g.ldw = taps * Cin if ldw is None else ldw; g.wsj = wsj; g.wsc = wsc
+    g.Y = _p(_f32(Y)); g.ldc = N if ldc is None else ldc
+    g.B, g.Tout, g.Tin, g.N, g.Cin, g.taps, g.stride, g.dil, g.pad = B, Tout, Tin, N, Cin, taps, stride, dil, pad
+    g.ToutFull = Tout if ToutFull is None else ToutFull; g.ostride = ostride; g.ooff = ooff
+    g.pscale = _p(pscale); g.pshift = _p(pshift); g.pslope = pslope
+    g.escale = _p(escale); g.bias = _p(bias); g.act1 = act1; g.slope1 = slope1
+    g.mask = _p(mask); g.ldmask = (N if ldmask is None else ldmask)
+    g.residual = _p(residual); g.ldres = (N if ldres is None else ldres)
+    g.act2 = act2; g.accumulate = 1 if accumulate else 0
+    check(_L().tg_conv_gemm_f32(ctypes.byref(g), _s()), 'tg_conv_gemm_f32')
+    _count()
+
+
+def conv_wgrad(A, G, dW, *, B, Tin, Tout, N, Cin, taps=1, stride=1, dil=1, pad=0, lda=None, ldg=None, ldw=None, wsj=0, wsc=1,
+               pscale=None, pshift=None, pslope=1.0, dbias=None, dw_off=0):
+    g = ConvWgrad()
+    g.A = _p(_f32(A)); g.lda = Cin if lda is None else lda
+    g.G = _p(_f32(G)); g.ldg = N if ldg is None else ldg
+    g.dW = _p(_f32(dW)) + 4 * dw_off; g.ldw = taps * Cin if ldw is None else ldw; g.wsj = wsj; g.wsc = wsc
+    g.B, g.Tout, g.Tin, g.N, g.Cin, g.taps, g.stride, g.dil, g.pad = B, Tout, Tin, N, Cin, taps, stride, dil, pad
+    g.pscale = _p(pscale); g.pshift = _p(pshift); g.pslope = pslope
+    g.dbias = _p(dbias)
+    check(_L().tg_conv_wgrad_f32(ctypes.byref(g), _s()), 'tg_conv_wgrad_f32')
+    _count()
+
+
+def linear(x, W, bias, out, *, M, K, N, **kw):
+    """out[M,N] = x[M,K] @ W[N,K]^T + bias (nn.Linear)."""
+    conv_gemm(x, W, out, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=K, wsc=1, bias=bias, **kw)
+
+
+def linear_dgrad(dy, W, dx, *, M, K, N, **kw):
+    """dx[M,K] = dy[M,N] @ W[N,K]."""
+    conv_gemm(dy, W, dx, B=1, Tin=M, Tout=M, N=K, Cin=N, taps=1, ldw=1, wsc=K, **kw)
+
+
+def linear_wgrad(x, dy, dW, dbias, *, M, K, N, **kw):
+    conv_wgrad(x, dy, dW, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=K, wsc=1, dbias=dbias, **kw)
+
+
+def conv1d(x, W, bias, y, *, B, Tin, Cin, N, k, stride=1, dil=1, pad=0, **kw):
+    """nn.Conv1d on channels-last x [B,Tin,Cin] with the reference weight layout W [N,Cin,k]; y [B,Tout,N]."""
+    Tout = (Tin + 2 * pad - dil * (k - 1) - 1) // stride + 1 if 'Tout' not in kw else kw.pop('Tout')
+    conv_gemm(x, W, y, B=B, Tin=Tin, Tout=Tout, N=N, Cin=Cin, taps=k, stride=stride, dil=dil, pad=pad, ldw=Cin * k, wsj=1, wsc=k,
+              bias=bias, **kw)
+    return Tout
+
+
+def conv1d_wgrad(x, dy, dW, dbias, *, B, Tin, Tout, Cin, N, k, stride=1, dil=1, pad=0, **kw):
+    conv_wgrad(x, dy, dW, B=B, Tin=Tin, Tout=Tout, N=N, Cin=Cin, taps=k, stride=stride, dil=dil, pad=pad, ldw=Cin * k, wsj=1, wsc=k,
+               dbias=dbias, **kw)
+
+
+def conv1d_dgrad(dy, W, dx, *, B, Tin, Tout, Cin, N, k, stride=1, dil=1, pad=0, **kw):
+    """dx [B,Tin,Cin] = conv-transpose of dy [B,Tout,N] with W [N,Cin,k]; `stride` dense phases for a strided conv."""
+    if stride == 1:
+        conv_gemm(dy, W, dx, B=B, Tin=Tout, Tout=Tin, N=Cin, Cin=N, taps=k, stride=1, dil=-dil, pad=-pad, ldw=k, wsj=1,
+                  wsc=Cin * k, **kw)
+        return
+    assert dil == 1
+    for r in range(min(stride, Tin)):
+        j0 = (r + pad) % stride
+        q_r = (Tin - r + stride - 1) // stride
+        if j0 >= k:
+            # no tap reaches these positions: gradient is zero
+            dx.view(B, Tin, Cin)[:, r::stride].zero_()
+            continue
+        taps_r = (k - j0 + stride - 1) // stride
+        off = (r + pad - j0) // stride
+        conv_gemm(dy, W, dx, B=B, Tin=Tout, Tout=q_r, N=Cin, Cin=N, taps=taps_r, stride=1, dil=-1, pad=-off, ldw=k, wsj=stride,
+                  wsc=Cin * k, w_off=j0, ToutFull=Tin, ostride=stride, ooff=r, **kw)
+
+
+def conv1_direct(x, w, bias, y, *, B, Tin, Tout, N, taps, stride, pad):
+    check(_L().tg_conv1_direct_f32(_p(x), _p(w), _p(bias), _p(y), B, Tin, Tout, N, taps, stride, pad, _s()), 'tg_conv1_direct_f32')
+    _count()
+
+
+# ------------------------------------------------------------------------------------------ batch norm
+def col_stats(x, ld, M, C, sums):
+    check(_L().tg_col_stats_f64(_p(x), ld, M, C, _p(sums), _s()), 'tg_col_stats_f64'); _count()
+
+
+def bn_finalize(sums, M, C, eps, momentum, n_updates, gamma, beta, rm, rv, nbt, mean, rstd, scale, shift):
+    check(_L().tg_bn_finalize(_p(sums), M, C, eps, momentum, n_updates, _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), _p(mean),
+                              _p(rstd), _p(scale), _p(shift), _s()), 'tg_bn_finalize'); _count()
+
+
+def bn_eval_fold(gamma, beta, rm, rv, eps, conv_bias, scale, shift, C):
+    check(_L().tg_bn_eval_fold(_p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(conv_bias), _p(scale), _p(shift), C, _s()),
+          'tg_bn_eval_fold'); _count()
+
+
+def affine_lrelu(x, y, M, C, scale, shift, slope):
+    check(_L().tg_affine_lrelu(_p(x), _p(y), M, C, _p(scale), _p(shift), slope, _s()), 'tg_affine_lrelu'); _count()
+
+
+def bn_bwd_reduce(dy, x, M, C, mean, rstd, scale, shift, slope, sums):
+    check(_L().tg_bn_bwd_reduce(_p(dy), _p(x), M, C, _p(mean), _p(rstd), _p(scale), _p(shift), slope, _p(sums), _s()),
+          'tg_bn_bwd_reduce'); _count()
+
+
+def bn_bwd_apply(dy, x, dx, M, C, mean, rstd, scale, shift, slope, gamma, sums, dgamma, dbeta):
+    check(_L().tg_bn_bwd_apply(_p(dy), _p(x), _p(dx), M, C, _p(mean), _p(rstd), _p(scale), _p(shift), slope, _p(gamma), _p(sums),
+                               _p(dgamma), _p(dbeta), _s()), 'tg_bn_bwd_apply'); _count()
+
+
+# ------------------------------------------------------------------------------------------ embedding / weight norm / misc
+def embedding_gather(table, idx, idx_mod, mask, out, M, E):
+    assert idx.dtype == torch.int64
+    check(_L().tg_embedding_gather(_p(table), _p(idx), idx_mod, _p(mask), _p(out), M, E, _s()), 'tg_embedding_gather'); _count()
+
+
+def embedding_scatter_add(dout, idx, mask, dtable, M, E):
+    assert idx.dtype == torch.int64
+    check(_L().tg_embedding_scatter_add(_p(dout), _p(idx), _p(mask), _p(dtable), M, E, _s()), 'tg_embedding_scatter_add'); _count()
+
+
+def weight_norm_fwd(v, g, w, inv_norm, N, K):
+    check(_L().tg_weight_norm_fwd(_p(v), _p(g), _p(w), _p(inv_norm), N, K, _s()), 'tg_weight_norm_fwd'); _count()
+
+
+def weight_norm_bwd(dw, v, g, inv_norm, dv, dg, N, K):
+    check(_L().tg_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv_norm), _p(dv), _p(dg), N, K, _s()), 'tg_weight_norm_bwd'); _count()
+
+
+def mul(a, b, out, n):
+    check(_L().tg_mul(_p(a), _p(b), _p(out), n, _s()), 'tg_mul'); _count()
+
+
+def add(a, b, out, n, relu=False):
+    check(_L().tg_add(_p(a), _p(b), _p(out), n, 1 if relu else 0, _s()), 'tg_add'); _count()
+
+
+def relu_mask_bwd(dy, y, mask, dx, n):
+    check(_L().tg_relu_mask_bwd(_p(dy), _p(y), _p(mask), _p(dx), n, _s()), 'tg_relu_mask_bwd'); _count()
+
+
+def sum_halves(x, out, M, H):
+    check(_L().tg_sum_halves(_p(x), _p(out), M, H, _s()), 'tg_sum_halves'); _count()
+
+
+def dup_halves(d, dx, M, H):
+    check(_L().tg_dup_halves(_p(d), _p(dx), M, H, _s()), 'tg_dup_halves'); _count()
+
+
+def reparam_fwd(mu, logvar, eps, z, n):
+    check(_L().tg_reparam_fwd(_p(mu), _p(logvar), _p(eps), _p(z), n, _s()), 'tg_reparam_fwd'); _count()
+
+
+def reparam_bwd(dz, logvar, eps, dmu, dlogvar, n):
+    check(_L().tg_reparam_bwd(_p(dz), _p(logvar), _p(eps), _p(dmu), _p(dlogvar), n, _s()), 'tg_reparam_bwd'); _count()
+
+
+def make_pre_seq(target, pre, B, T, D, n_pre):
+    check(_L().tg_make_pre_seq(_p(target), _p(pre), B, T, D, n_pre, _s()), 'tg_make_pre_seq'); _count()
+
+
+def gru_input_concat(pre, audio, text, z, out, B, Ba, T, Dp, Da, Dt, Dz):
+    check(_L().tg_gru_input_concat(_p(pre), _p(audio), _p(text), _p(z), _p(out), B, Ba, T, Dp, Da, Dt, Dz, _s()),
+          'tg_gru_input_concat'); _count()
+
+
+def gru_input_split_bwd(din, daudio, dtext, dz, B, T, Dp, Da, Dt, Dz):
+    check(_L().tg_gru_input_split_bwd(_p(din), _p(daudio), _p(dtext), _p(dz), B, T, Dp, Da, Dt, Dz, _s()),
+          'tg_gru_input_split_bwd'); _count()
+
+
+def transpose(x, out, R, C):
+    check(_L().tg_transpose_f32(_p(x), _p(out), R, C, _s()), 'tg_transpose_f32'); _count()
+
+
+# ------------------------------------------------------------------------------------------ GRU
+def gru_sync_ints(B, H):
+    return _L().tg_gru_sync_ints(B, H)
+
+
+def gru_bwd_scratch_floats(B, H):
+    return _L().tg_gru_bwd_scratch_floats(B, H)
+
+
+def gru_layer_fwd(gi, whhT_f, whhT_r, bhh_f, bhh_r, out, saved, saved_qstride, sync, B, T, H):
+    check(_L().tg_gru_layer_fwd(_p(gi), _p(whhT_f), _p(whhT_r), _p(bhh_f), _p(bhh_r), _p(out), _p(saved), saved_qstride, _p(sync),
+                                B, T, H, _s()), 'tg_gru_layer_fwd'); _count(2)
+
+
+def gru_layer_bwd(dout, out, saved, saved_qstride, whh_f, whh_r, dgi, dgh, partial, sync, B, T, H):
+    check(_L().tg_gru_layer_bwd(_p(dout), _p(out), _p(saved), saved_qstride, _p(whh_f), _p(whh_r), _p(dgi), _p(dgh), _p(partial),
+                                _p(sync), B, T, H, _s()), 'tg_gru_layer_bwd'); _count(2)
+
+
+# ------------------------------------------------------------------------------------------ losses / optimiser / rng
+def gen_losses(out, target, out_rand, z, z_rand, mu, logvar, B, TD, Z, w_reg, w_div, w_kld, scalars, d_out, dmu, dlogvar):
+    check(_L().tg_gen_losses(_p(out), _p(target), _p(out_rand), _p(z), _p(z_rand), _p(mu), _p(logvar), B, TD, Z, w_reg, w_div, w_kld,
+                             _p(scalars), _p(d_out), _p(dmu), _p(dlogvar), _s()), 'tg_gen_losses'); _count()
+
+
+def bce_sigmoid(p, n, s, o, w, scalar, dlogit):
+    check(_L().tg_bce_sigmoid(_p(p), n, s, o, w, _p(scalar), _p(dlogit), _s()), 'tg_bce_sigmoid'); _count()
+
+
+def adam_flat(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step_dev):
+    check(_L().tg_adam_flat(_p(p), _p(g), _p(m), _p(v), n, lr, b1, b2, eps, grad_scale, _p(step_dev), _s()), 'tg_adam_flat'); _count()
+
+
+def increment_i64(x, by=1):
+    check(_L().tg_increment_i64(_p(x), by, _s()), 'tg_increment_i64'); _count()
+
+
+def philox_normal(out, n, seed, offset_dev, stream_id):
+    check(_L().tg_philox_normal(_p(out), n, seed, _p(offset_dev), stream_id, _s()), 'tg_philox_normal'); _count()
+
+
+def philox_dropout_mask(out, n, p, seed, offset_dev, stream_id):
+    check(_L().tg_philox_dropout_mask(_p(out), n, p, seed, _p(offset_dev), stream_id, _s()), 'tg_philox_dropout_mask'); _count()
+
+
+def philox_randperm(out, n, seed, offset_dev, stream_id):
+    check(_L().tg_philox_randperm(_p(out), n, seed, _p(offset_dev), stream_id, _s()), 'tg_philox_randperm'); _count()
+
+
+def gather_i64(src, idx, out, n):
+    check(_L().tg_gather_i64(_p(src), _p(idx), _p(out), n, _s()), 'tg_gather_i64'); _count()
+
+
+def feature_stats(feat, n, F, acc):
+    check(_L().tg_feature_stats_f64(_p(feat), n, F, _p(acc), _s()), 'tg_feature_stats_f64'); _count()
+
+
+def l1_dist(a, b, n, acc):
+    check(_L().tg_l1_dist_f64(_p(a), _p(b), n, _p(acc), _s()), 'tg_l1_dist_f64'); _count()

@@ -1,0 +1,216 @@
+"""train_iter_gan - one adversarial G+D iteration, drop-in for scripts/train_eval/train_gan.py:13-103.
+
+Same signature, same arithmetic, same returned dict of python floats ('loss', 'KLD', 'DIV_REG', 'gen', 'dis').
+What differs is the schedule on the device (B200-first, results identical):
+  * the generator weights do not change between the reference's three generator forwards of one iteration
+    (train_gan.py:30,50,67; the D step in between only updates D), so the three forwards run as ONE pass over
+    3*B clips - a third of the sequential GRU steps; each pass still draws its own dropout masks and noise, and
+    BatchNorm running statistics receive the same number of momentum updates;
+  * the WavEncoder features of that pass are computed once (the three passes see the same audio, same weights and
+    train-mode batch statistics, hence bit-identical features);
+  * every loss term and its gradient come from two fused kernels, the optimiser is one flat Adam launch per
+    network, and the five logged scalars leave the device in a single copy (the reference syncs 7 times);
+  * with torch.distributed initialised (one process per GPU), gradients are averaged with NCCL all-reduce over
+    the flat gradient arena before Adam - the data-parallel equivalent of nn.DataParallel (train.py:93-96).
+"""
+from typing import Dict, Optional
+
+import torch
+
+from tgb200 import _lib, ops
+
+
+def add_noise(data):
+    """train_gan.py:8-10 (unused by the reference: use_noisy_target=False at :17)."""
+    return data + torch.randn_like(data) * 0.1
+
+
+def _unwrap(m):
+    return m.module if hasattr(m, 'module') and isinstance(m, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel)) else m
+
+
+class StepNoise:
+    """Optional injection of every random draw of one iteration (tests): eps [n_pass][B,16], perm [B] int64,
+    g_masks / d_masks lists of channels-last keep-mask dicts (or None)."""
+
+    def __init__(self, eps=None, perm=None, g_masks=None, d_masks=None):
+        self.eps, self.perm, self.g_masks, self.d_masks = eps, perm, g_masks, d_masks
+
+
+_injected_noise: Optional[StepNoise] = None
+
+
+def inject_noise(noise: Optional[StepNoise]):
+    global _injected_noise
+    _injected_noise = noise
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def _allreduce_grads(arena, bucket_floats=4 << 20):
+    """Bucketed NCCL all-reduce (sum) of the flat gradient arena; averaging is folded into Adam's grad_scale."""
+    import torch.distributed as dist
+    works = []
+    n = arena.numel
+    for o in range(0, n, bucket_floats):
+        works.append(dist.all_reduce(arena.grad[o:min(n, o + bucket_floats)], op=dist.ReduceOp.SUM, async_op=True))
+    for w in works:
+        w.wait()
+
+
+def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, pose_decoder, discriminator, pose_dec_optim, dis_optim):
+    _lib.require_cuda()
+    global _injected_noise
+    noise, _injected_noise = _injected_noise, None
+    G, D = _unwrap(pose_decoder), _unwrap(discriminator)
+    dev = target_poses.device
+    if not target_poses.is_cuda and not _lib.TRACE_ONLY:
+        raise _lib.TgError('train_iter_gan runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+    B, T, Dm = target_poses.shape
+    after = epoch > args.loss_warmup
+    do_d = after and args.loss_gan_weight > 0.0
+    z_type = getattr(args, 'z_type', 'speaker')
+    do_div = z_type in ('speaker', 'random') and args.loss_reg_weight > 0.0
+    do_kld = do_div and z_type == 'speaker'
+    world = _dist_world()
+
+    ge = G.engine().ensure(dev, 'train_%d' % B)
+    de = D.engine().ensure(dev, 'train_%d' % B)
+    ws = ge.ws
+    target = target_poses.contiguous().float()
+    in_text = in_text.contiguous()
+    in_audio = in_audio.contiguous().float()
+
+    # ---- pass list: [D-step forward] + G-step forward + [permuted-speaker forward]
+    passes = (['d'] if do_d else []) + ['g'] + (['r'] if do_div else [])
+    n_pass = len(passes)
+    Bt = n_pass * B
+    ig = passes.index('g')
+    pre_seq = ws.get('ti.pre', (B, T, Dm + 1))
+    ops.make_pre_seq(target, pre_seq, B, T, Dm, args.n_pre_poses)
+
+    off = G._noise.offset_dev(dev)
+    seed = G._noise.seed
+    vid_all = eps_all = None
+    if ge.z_mode is not None:
+        eps_all = ws.get('ti.eps', (Bt, 16))
+        if noise is not None and noise.eps is not None:
+            for i, e in enumerate(noise.eps[-n_pass:] if len(noise.eps) > n_pass else noise.eps):
+                eps_all[i * B:(i + 1) * B].copy_(e)
+        else:
+            ops.philox_normal(eps_all, Bt * 16, seed, off, 1000)
+    if ge.z_mode == 'speaker':
+        vid = vid_indices.contiguous()
+        vid_all = ws.get('ti.vid', (Bt,), torch.int64)
+        for i, p in enumerate(passes):
+            if p == 'r':
+                perm = ws.get('ti.perm', (B,), torch.int64)
+                if noise is not None and noise.perm is not None:
+                    perm.copy_(noise.perm)
+                else:
+                    ops.philox_randperm(perm, B, seed, off, 1001)
+                ops.gather_i64(vid, perm, vid_all[i * B:(i + 1) * B], B)
+            else:
+                vid_all[i * B:(i + 1) * B].copy_(vid)
+    g_masks = None
+    if G.training:
+        if noise is not None and noise.g_masks is not None:
+            g_masks = _stack_masks(ws, noise.g_masks[-n_pass:] if len(noise.g_masks) > n_pass else noise.g_masks, B * T)
+        else:
+            g_masks = ge.make_masks(Bt, T, seed, off)
+    G._noise.advance()
+
+    def d_masks_for(i):
+        if not D.training:
+            return None
+        if noise is not None and noise.d_masks is not None:
+            return noise.d_masks[i]
+        m = de.make_masks(B, T - 6, D._noise.seed, D._noise.offset_dev(dev), sid0=16 * i)
+        return m
+
+    # ---- all generator passes in one sweep
+    ge.prep_weights()
+    poses, z, mu, logvar = ge.forward(pre_seq, in_text, in_audio, vid_all, eps_all, Bt, G.training, g_masks, n_bn_updates=n_pass)
+    sc = ws.get('ti.scalars', (8,), torch.float64)
+    sc.zero_()
+    dlogit = ws.get('ti.dlogit', (B, 1))
+
+    # ---- train D (train_gan.py:24-43)
+    de.prep_weights()
+    if do_d:
+        de.arena.zero_grad()
+        p_real = de.forward(target, D.training, d_masks_for(0))
+        ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
+        de.backward(dlogit, need_dposes=False)
+        p_fake = de.forward(poses[0:B], D.training, d_masks_for(1))          # generator output of the D-step pass (detached)
+        ops.bce_sigmoid(p_fake, B, -1.0, 1.0, 1.0, sc[5:], dlogit)
+        de.backward(dlogit, need_dposes=False)
+        if world > 1:
+            _allreduce_grads(de.arena)
+        de.arena.adam_step(dis_optim, grad_scale=1.0 / world)
+        de.prep_weights()
+
+    # ---- train G (train_gan.py:45-92)
+    ge.arena.zero_grad()
+    out = poses[ig * B:(ig + 1) * B]
+    p_gen = de.forward(out, D.training, d_masks_for(2))                       # runs in warm-up too (updates D's BN statistics)
+    if D.training:
+        D._noise.advance()
+    d_out = ws.get('ti.dout', (B, T, Dm))
+    dmu = ws.get('ti.dmu', (B, 16)); dlv = ws.get('ti.dlv', (B, 16))
+    ir = passes.index('r') if do_div else None
+    ops.gen_losses(out, target, poses[ir * B:(ir + 1) * B] if do_div else None,
+                   z[ig * B:(ig + 1) * B] if do_div else None, z[ir * B:(ir + 1) * B] if do_div else None,
+                   mu[ig * B:(ig + 1) * B] if do_kld else None, logvar[ig * B:(ig + 1) * B] if do_kld else None,
+                   B, T * Dm, 16, float(args.loss_regression_weight), float(args.loss_reg_weight) if do_div else 0.0,
+                   float(args.loss_kld_weight) if do_kld else 0.0, sc, d_out, dmu if do_kld else None, dlv if do_kld else None)
+    ops.bce_sigmoid(p_gen, B, 1.0, 0.0, float(args.loss_gan_weight), sc[3:], dlogit)
+    if after:
+        dposes = de.backward(dlogit, need_dposes=True)                        # D's own (stale) grads accumulate as in the reference
+        ops.add(d_out, dposes, d_out, B * T * Dm)
+    ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
+    if world > 1:
+        _allreduce_grads(ge.arena)
+    ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world)
+
+    # ---- one device->host copy for the logged scalars (train_gan.py:94-102)
+    s = sc.cpu().tolist()
+    huber = s[0] / (B * T * Dm)
+    ret: Dict[str, float] = {'loss': args.loss_regression_weight * huber}
+    if do_kld:
+        kld = -0.5 * s[2] / (B * 16)
+        if kld:
+            ret['KLD'] = args.loss_kld_weight * kld
+    if do_div:
+        div = s[1] / B
+        if div:
+            ret['DIV_REG'] = args.loss_reg_weight * div
+    if do_d:
+        ret['gen'] = args.loss_gan_weight * s[3]
+        ret['dis'] = s[4] + s[5]
+    return ret
+
+
+def _stack_masks(ws, per_pass, rows_per_pass):
+    """Concatenates per-pass mask dicts ([B*T, C] each) into one dict of [n_pass*B*T, C] tensors."""
+    out = {}
+    keys = set()
+    for m in per_pass:
+        if m:
+            keys |= set(m.keys())
+    for k in keys:
+        ref = next(m[k] for m in per_pass if m and k in m)
+        C = ref.shape[-1]
+        buf = ws.get('ti.mask.' + k, (len(per_pass) * rows_per_pass, C))
+        for i, m in enumerate(per_pass):
+            if m and k in m:
+                buf[i * rows_per_pass:(i + 1) * rows_per_pass].copy_(m[k].reshape(rows_per_pass, C))
+            else:
+                buf[i * rows_per_pass:(i + 1) * rows_per_pass].fill_(1.0)
+        out[k] = buf
+    return out

@@ -1,0 +1,203 @@
+/* tg_b200.h — C ABI of libtg_b200.so: hand-written sm_100a kernels for the trimodal-gesture hot path.
+ *
+ * The reference (ai4r/Gesture-Generation-from-Trimodal-Context) has no FFI of its own: every FLOP of its hot
+ * path is a stock PyTorch op.  Each entry point below therefore cites the reference call site
+ * (scripts/... file:line) whose PyTorch op(s) it replaces.  Conventions:
+ *   - plain C types only; device pointers are borrowed (never freed, never retained after the call returns);
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately:
+ *     no allocation, no synchronisation, safe under CUDA-graph capture;
+ *   - return value 0 = ok, negative = error; tg_last_error() gives a thread-local message;
+ *   - activations are "channels-last": a [B, T, C] clip tensor is a row-major matrix of B*T rows x C columns.
+ */
+#ifndef TG_B200_H
+#define TG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tg_stream;
+
+const char* tg_last_error(void);
+int tg_version(void);
+/* device properties the host side sizes persistent grids with: out[0]=SM count, out[1]=max opt-in smem/block */
+int tg_device_info(int* out2);
+/* out[0] = sizeof(tg_conv_gemm_t), out[1] = sizeof(tg_conv_wgrad_t): lets a foreign-language binding verify its layout */
+int tg_struct_sizes(int* out2);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer, fp32 SIMT ("strict fp32" mode).
+ *   Y[orow(b,t), n] = epi( sum_{j<taps} sum_{c<Cin} pro(A[b*Tin + t*stride + j*dil - pad, c]) * W(n,j,c) )
+ * with m = b*Tout + t, out-of-range input rows reading as zero (causal left pad of tcn.py:7-13,19-31; the
+ * pad=1600 of multimodal_context_net.py:13).  W(n,j,c) = W[n*ldw + j*wsj + c*wsc] so that nn.Conv1d weights
+ * [N,Cin,k] (wsj=1, wsc=k), nn.Linear weights [N,K] (taps=1, wsc=1) and transposed views are read in place.
+ * Output row orow = b*ToutFull + t*ostride + ooff lets a strided-conv dgrad be issued as `stride` dense phases.
+ * Replaces: nn.Conv1d / nn.Linear / F.conv_transpose1d forward and input-gradient at
+ *   multimodal_context_net.py:12-23,48,60,88-93,100-104,213-226; tcn.py:19-31; embedding_net.py:46-65,188-206.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A;  int lda;                 /* input rows, pitch in floats */
+  int asc;                                  /* channel stride of A in floats (0 or 1 = contiguous channels) */
+  long long a_bstride;                      /* floats between clips of A (0 = Tin*lda) */
+  const float* W;  int ldw, wsj, wsc;
+  float* Y;        int ldc;
+  int B, Tout, Tin, N, Cin, taps, stride, dil, pad;
+  int ToutFull, ostride, ooff;
+  /* prologue on A (in-range elements only): a' = lrelu(a*pscale[c] + pshift[c], pslope); NULL = identity */
+  const float* pscale; const float* pshift; float pslope;
+  /* epilogue: v = acc*escale[n] + bias[n]; act1; v *= mask[orow, n]; v += residual[orow, n]; act2; (+= Y if accumulate) */
+  const float* escale; const float* bias;
+  int act1; float slope1;                   /* 0 none, 1 relu, 2 leaky-relu(slope1), 3 sigmoid */
+  const float* mask;   int ldmask;
+  const float* residual; int ldres;
+  int act2;
+  int accumulate;
+} tg_conv_gemm_t;
+int tg_conv_gemm_f32(const tg_conv_gemm_t* p, tg_stream stream);
+
+/* Weight gradient of the same operator: dW(n,j,c) += sum_m G[m*ldg + n] * pro(A[row(m,j), c]); atomically accumulated
+ * (grads accumulate across backward calls exactly like torch .grad does).  Replaces the autograd of the ops above. */
+typedef struct {
+  const float* A;  int lda;
+  const float* G;  int ldg;
+  float* dW;       int ldw, wsj, wsc;
+  int B, Tout, Tin, N, Cin, taps, stride, dil, pad;
+  const float* pscale; const float* pshift; float pslope;
+  float* dbias;                             /* optional: dbias[n] += sum_m G[m,n] */
+} tg_conv_wgrad_t;
+int tg_conv_wgrad_f32(const tg_conv_wgrad_t* p, tg_stream stream);
+
+/* Direct strided convolution for a single input channel (WavEncoder conv1: Conv1d(1,16,15,stride 5,pad 1600),
+ * multimodal_context_net.py:13).  HBM-bound: x [B,Tin] -> y [B,Tout,N] channels-last, N <= 32, taps <= 32. */
+int tg_conv1_direct_f32(const float* x, const float* w, const float* bias, float* y,
+                        int B, int Tin, int Tout, int N, int taps, int stride, int pad, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm1d, train mode (multimodal_context_net.py:14,17,20,214,217) over a [M,C] channels-last matrix.
+ * --------------------------------------------------------------------------------------------------------- */
+/* sums[0..C) += column sums, sums[C..2C) += column sums of squares (fp64 accumulators, caller zeroes them) */
+int tg_col_stats_f64(const float* x, int ld, long long M, int C, double* sums, tg_stream stream);
+/* from the fp64 sums: mean/rstd (biased var, eps), fused scale = gamma*rstd, shift = beta - mean*scale, and
+ * `n_updates` momentum updates of running_mean/running_var (unbiased var) + num_batches_tracked += n_updates */
+int tg_bn_finalize(const double* sums, long long M, int C, float eps, float momentum, int n_updates,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   long long* num_batches_tracked, float* mean, float* rstd, float* scale, float* shift, tg_stream stream);
+/* eval-mode BatchNorm folded to an affine map: scale = gamma/sqrt(rv+eps), shift = beta + (conv_bias - rm)*scale
+ * (conv_bias may be NULL = 0).  Used as conv prologue (WavEncoder) or epilogue (EmbeddingNet). */
+int tg_bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                    const float* conv_bias, float* scale, float* shift, int C, tg_stream stream);
+/* y = lrelu(x*scale[c] + shift[c], slope) */
+int tg_affine_lrelu(const float* x, float* y, long long M, int C, const float* scale, const float* shift, float slope,
+                    tg_stream stream);
+/* backward of y = lrelu(bn(x)): pass 1 accumulates sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat (dz = dy*lrelu') */
+int tg_bn_bwd_reduce(const float* dy, const float* x, long long M, int C, const float* mean, const float* rstd,
+                     const float* scale, const float* shift, float slope, double* sums, tg_stream stream);
+/* pass 2: dx = gamma*rstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); dgamma += sum dz*xhat; dbeta += sum dz */
+int tg_bn_bwd_apply(const float* dy, const float* x, float* dx, long long M, int C, const float* mean, const float* rstd,
+                    const float* scale, const float* shift, float slope, const float* gamma, const double* sums,
+                    float* dgamma, float* dbeta, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Embedding (multimodal_context_net.py:40-43,58,88) with optional dropout mask; dense scatter-add backward.
+ * idx_mod > 0 reads idx[m % idx_mod] (the three generator passes of one train_iter_gan share in_text).
+ * --------------------------------------------------------------------------------------------------------- */
+int tg_embedding_gather(const float* table, const long long* idx, int idx_mod, const float* mask, float* out,
+                        long long M, int E, tg_stream stream);
+int tg_embedding_scatter_add(const float* dout, const long long* idx, const float* mask, float* dtable,
+                             long long M, int E, tg_stream stream);
+
+/* torch.nn.utils.weight_norm, dim=0 (tcn.py:19-25): w = g*v/||v|| per output row; backward to g and v. */
+int tg_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, tg_stream stream);
+int tg_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg,
+                       int N, int K, tg_stream stream);
+
+/* elementwise helpers: out = a*b ; out = a+b ; dx = dy*mask*(y>0) (ReLU+dropout backward, tcn.py:22-23,28-29,46) */
+int tg_mul(const float* a, const float* b, float* out, long long n, tg_stream stream);
+/* out = a + b, optionally followed by ReLU (TemporalBlock residual, tcn.py:46) */
+int tg_add(const float* a, const float* b, float* out, long long n, int relu, tg_stream stream);
+int tg_relu_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, tg_stream stream);
+/* out[m, 0..H) = x[m, 0..H) + x[m, H..2H)  (sum of GRU directions, multimodal_context_net.py:156,243) and its backward */
+int tg_sum_halves(const float* x, float* out, long long M, int H, tg_stream stream);
+int tg_dup_halves(const float* d, float* dx, long long M, int H, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Speaker style sampling (multimodal_context_net.py:125-131, embedding_net.py:10-13): z = mu + eps*exp(0.5*logvar)
+ * and GRU-input assembly cat(pre_seq, audio, text, repeat(z)) (multimodal_context_net.py:139-153).
+ * --------------------------------------------------------------------------------------------------------- */
+int tg_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, long long n, tg_stream stream);
+/* dmu += dz ; dlogvar += dz*eps*0.5*exp(0.5*logvar) */
+int tg_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar, long long n,
+                   tg_stream stream);
+/* seed-pose conditioning input of train_iter_gan (train_gan.py:20-22): pre [B,T,D+1] = target for t < n_pre with a
+ * constraint bit 1 in the last channel, zero elsewhere */
+int tg_make_pre_seq(const float* target, float* pre, int B, int T, int D, int n_pre, tg_stream stream);
+/* pre and audio have Ba <= B clips and are read at b % Ba (the generator passes of one train_iter_gan share them).
+ * Widths: pre Dp, audio Da, text Dt, z Dz (any may be 0). */
+int tg_gru_input_concat(const float* pre, const float* audio, const float* text, const float* z, float* out,
+                        int B, int Ba, int T, int Dp, int Da, int Dt, int Dz, tg_stream stream);
+/* split d_in -> d_audio[B,T,Da], d_text[B,T,Dt], d_z[B,Dz] (= sum over T) */
+int tg_gru_input_split_bwd(const float* din, float* daudio, float* dtext, float* dz,
+                           int B, int T, int Dp, int Da, int Dt, int Dz, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Bidirectional GRU layer recurrence (nn.GRU at multimodal_context_net.py:98-99,155,221-222,241; gate order r,z,n).
+ * gi = x W_ih^T + b_ih for both directions is a tg_conv_gemm_f32 call ([B*T, 6H]: fwd r,z,n | rev r,z,n); the
+ * sequential part runs as ONE persistent cooperative kernel per layer: W_hh slices stay resident in shared memory
+ * across (unit-chunk x batch-tile x direction) CTAs which exchange h_t through L2 with release/acquire counters.
+ *   out   [B,T,2H]  (fwd | rev)
+ *   saved [4][B*T][2H] = r, z, n, hn (= W_hn h + b_hn) for the backward; may be NULL (inference)
+ *   sync  int[tg_gru_sync_ints(B,H)] scratch, zeroed by the call
+ * --------------------------------------------------------------------------------------------------------- */
+/* whhT_* = transposed recurrent weights [H, 3H] (tg_transpose_f32 of weight_hh_l*), saved_qstride = floats between
+ * the r/z/n/hn planes of `saved` (lets a backward run on a batch slice of a larger forward). */
+int tg_gru_layer_fwd(const float* gi, const float* whhT_f, const float* whhT_r, const float* bhh_f, const float* bhh_r,
+                     float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream);
+/* BPTT: dout [B,T,2H] -> dgi [B*T,6H] (grad of gi = x W_ih^T + b_ih) and dgh [B*T,6H] (grad of gh = h W_hh^T + b_hh);
+ * the weight grads are then tg_conv_wgrad_f32 calls (dW_hh uses A = out shifted by one step, pad = +1 / -1).
+ * whh_* = weight_hh [3H, H] as stored.  partial: float scratch of tg_gru_bwd_scratch_floats(B,H). */
+size_t tg_gru_bwd_scratch_floats(int B, int H);
+int tg_gru_sync_ints(int B, int H);
+int tg_gru_layer_bwd(const float* dout, const float* out, const float* saved, long long saved_qstride,
+                     const float* whh_f, const float* whh_r, float* dgi, float* dgh, float* partial, int* sync,
+                     int B, int T, int H, tg_stream stream);
+int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Losses of train_iter_gan (train_gan.py:41,53-56,67-82), forward value + gradient in one pass.
+ * scalars (fp64, caller zeroes): [0] sum huber(out,target;0.1)  [1] sum_i div_i  [2] sum (1+lv-mu^2-e^lv)
+ * d_out = w_reg/(B*T*D) * huber' + w_div/B * d div_i ; dmu/dlogvar = kld gradient * w_kld.
+ * --------------------------------------------------------------------------------------------------------- */
+int tg_gen_losses(const float* out, const float* target, const float* out_rand, const float* z, const float* z_rand,
+                  const float* mu, const float* logvar, int B, int TD, int Z, float w_reg, float w_div, float w_kld,
+                  double* scalars, float* d_out, float* dmu, float* dlogvar, tg_stream stream);
+/* NS-GAN terms on sigmoid outputs p[n]: loss += -sum log(s*p + o + 1e-8)/n (s=+1,o=0 for "real"/generator,
+ * s=-1,o=1 for "fake"); dlogit = w * d loss/d p * p(1-p).  scalar[0] += loss (fp64). */
+int tg_bce_sigmoid(const float* p, int n, float s, float o, float w, double* scalar, float* dlogit, tg_stream stream);
+
+/* torch.optim.Adam (train.py:104-109; no weight decay / amsgrad) over a flat arena.  step_dev: device int64 holding
+ * the 1-based step count of THIS update (host bumps it or a graph-resident kernel does). grad_scale multiplies g. */
+int tg_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                 float grad_scale, const long long* step_dev, tg_stream stream);
+int tg_increment_i64(long long* x, long long by, tg_stream stream);
+
+/* Philox-4x32-10 counter RNG: standard normals (reparameterize noise) and scaled Bernoulli keep-masks (dropout).
+ * (seed, *offset_dev + stream_id) select the stream; offset_dev is a device int64 so CUDA-graph replays advance. */
+int tg_philox_normal(float* out, long long n, unsigned long long seed, const long long* offset_dev, int stream_id,
+                     tg_stream stream);
+int tg_philox_dropout_mask(float* out, long long n, float p, unsigned long long seed, const long long* offset_dev,
+                           int stream_id, tg_stream stream);
+/* random permutation of 0..n-1 (torch.randperm, train_gan.py:62), n <= 2048, one CTA bitonic sort of Philox keys */
+int tg_philox_randperm(long long* out, int n, unsigned long long seed, const long long* offset_dev, int stream_id,
+                       tg_stream stream);
+int tg_gather_i64(const long long* src, const long long* idx, long long* out, int n, tg_stream stream);
+
+/* FGD sufficient statistics (embedding_space_evaluator.py:79-80): acc[0]+=n, acc[1..1+F)+=sum x, acc[1+F..)+=sum x x^T */
+int tg_feature_stats_f64(const float* feat, long long n, int F, double* acc, tg_stream stream);
+/* sum_i sum_f |a-b| accumulated in fp64 (feat_dist, embedding_space_evaluator.py:95-99) */
+int tg_l1_dist_f64(const float* a, const float* b, long long n, double* acc, tg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tg_b200.h declares; the drop-in nn.Modules carry the
+reference's state_dict keys and shapes; host-side bookkeeping (flat arena ordering) is sound.  No kernel is launched."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import synth
+from oracle.make_golden import golden_cfg
+
+
+def test_library_exports_every_header_symbol():
+    from tgb200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.tg_version() >= 100
+    sizes = (ctypes.c_int * 2)()
+    loaded.tg_struct_sizes(sizes)
+    assert sizes[0] == ctypes.sizeof(_lib.ConvGemm) and sizes[1] == ctypes.sizeof(_lib.ConvWgrad)
+
+
+def test_header_has_no_torch_types():
+    from tgb200 import _lib
+    import re
+    src = open(_lib.HEADER).read()
+    code = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)          # signatures only, comments stripped
+    assert 'torch' not in code.lower() and 'at::' not in code and 'Tensor' not in code and 'extern "C"' in code
+
+
+def test_modules_have_reference_state_dict_keys():
+    from gpu_util import build_ours
+    cfg = golden_cfg()
+    args, G, D, gsd, dsd = build_ours(cfg, None)            # strict=True load inside
+    assert set(G.state_dict().keys()) == set(synth.with_tcn_aliases(gsd).keys())
+    assert list(D.state_dict().keys()) == list(dsd.keys())
+    from model.embedding_net import EmbeddingNet
+    from gpu_util import make_args
+    E = EmbeddingNet(make_args(cfg), cfg.pose_dim, cfg.n_poses, cfg.n_words, cfg.wordembed_dim, None, 'pose')
+    E.load_state_dict(synth.embedding_net_state_dict(cfg), strict=True)
+    assert G.z_obj is not None and G.pre_length == 4 and G.gen_length == 30 and G.in_size == 108 and G.hidden_size == 300
+
+
+def test_arena_order_puts_gru_directions_adjacent():
+    from gpu_util import build_ours
+    from tgb200.arena import ParamArena
+    from tgb200.engine import gru_arena_order
+    cfg = golden_cfg()
+    args, G, D, _, _ = build_ours(cfg, None)
+    for m in (G, D):
+        names = [n for n, _ in m.named_parameters()]
+        a = ParamArena(m, gru_arena_order(names))
+        for l in range(4):
+            assert a.adjacent(f'gru.weight_ih_l{l}', f'gru.weight_ih_l{l}_reverse')
+            assert a.adjacent(f'gru.bias_ih_l{l}', f'gru.bias_ih_l{l}_reverse')
+        a.ensure(torch.device('cpu'))                      # flat storage is plain torch memory: works without a GPU
+        p = dict(m.named_parameters())['gru.weight_ih_l1']
+        assert p.data_ptr() == a.flat.data_ptr() + 4 * a.offsets['gru.weight_ih_l1']
+        assert p.grad is not None and p.grad.data_ptr() == a.grad.data_ptr() + 4 * a.offsets['gru.weight_ih_l1']
+    sd = G.state_dict()
+    assert sd['gru.weight_ih_l1'].shape == (900, 600)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gesture-generation-from-trimodal-context_b200')
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dp, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_no_cpu_fallback_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from tgb200 import _lib
+    from train_eval.train_gan import train_iter_gan
+    with pytest.raises(_lib.TgError):
+        train_iter_gan(None, 0, None, None, torch.zeros(1, 34, 27), None, None, None, None, None)

@@ -1,0 +1,231 @@
+"""GPU parity proper: OUR nn.Modules / train_iter_gan (hand-written sm_100a kernels through the C ABI) against
+(1) the golden fixtures produced by the unmodified reference modules (tests/golden, oracle/make_golden.py) and
+(2) the oracle (oracle/trimodal_oracle.py, float64) on identical seeded inputs at the benchmark batch size.
+Tolerance: north_star fp32 mode = 1e-4 relative L2 on poses and losses."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from gpu_util import build_ours, masks_to_ours, to_dev
+from oracle import synth
+from oracle import trimodal_oracle as O
+from oracle.make_golden import digest, golden_cfg
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+ZERO_GRAD_KEYS = ('audio_encoder.feat_extractor.0.bias', 'audio_encoder.feat_extractor.3.bias', 'audio_encoder.feat_extractor.6.bias',
+                  'pre_conv.0.bias', 'pre_conv.3.bias', 'pre_conv.1.bias', 'pre_conv.1.running_mean', 'pre_conv.4.running_mean')
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def test_forward_eval_vs_reference_golden(dev):
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_eval.npz'))
+    args, G, D, _, _ = build_ours(cfg, dev)
+    G.eval(); D.eval()
+    inp = to_dev(synth.make_inputs(cfg, 3, seed=1), dev)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0].to(dev)
+    with torch.no_grad():
+        G.set_noise(eps=eps)
+        poses, z, mu, logvar = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
+        d_real = D(inp['target'])
+        d_fake = D(poses)
+    ws = G.engine().ws
+    assert rel_l2(ws['wav.y3'].view(3, 34, 32), g['audio_feat']) < TOL
+    assert rel_l2(ws['txt.feat'].view(3, 34, 32), g['text_feat']) < TOL
+    assert rel_l2(z, g['z']) < TOL and rel_l2(mu, g['mu']) < TOL and rel_l2(logvar, g['logvar']) < TOL
+    assert rel_l2(poses, g['poses']) < TOL, rel_l2(poses, g['poses'])
+    assert rel_l2(d_real, g['d_real']) < TOL and rel_l2(d_fake, g['d_fake']) < TOL
+
+
+def _digest_close(a, ref, tol):
+    a = np.asarray(a); ref = np.asarray(ref)
+    scale = max(abs(ref[0]), 1e-12)
+    if scale < 1e-3:
+        assert abs(a[0]) < 1e-3
+        return
+    assert abs(a[0] - ref[0]) <= tol * scale + 1e-9, (a[0], ref[0])
+    n = max(len(ref) - 2, 1)
+    assert np.abs(a[2:] - ref[2:]).max() <= tol * 50 * scale / np.sqrt(n) + 5e-7
+
+
+def _post_close(a, ref, lr, noisy=False):
+    d = np.abs(np.asarray(a)[2:] - np.asarray(ref)[2:])
+    assert d.max() <= 2.2 * lr + 1e-6
+    assert noisy or np.median(d) <= 2e-6 + 1e-5 * np.abs(np.asarray(ref)[2:]).max()
+
+
+@pytest.mark.parametrize('tag,epoch,use_masks', [('train_e11', 11, True), ('train_e0', 0, False)])
+def test_train_iter_vs_reference_golden(dev, tag, epoch, use_masks):
+    """Full train_iter_gan (3 G fwd, G bwd, 3 D fwd/bwd, both Adam steps) vs the reference's own run."""
+    from train_eval import train_gan as TG
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, tag + '.npz'))
+    args, G, D, _, _ = build_ours(cfg, dev)
+    G.train(); D.train()
+    inp = to_dev(synth.make_inputs(cfg, 3, seed=1), dev)
+    noise = synth.golden_noise(cfg, 3, 2, use_masks)
+    g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=[e.to(dev) for e in noise.eps], perm=noise.perm.to(dev),
+                                 g_masks=[masks_to_ours(m, dev) if m else {} for m in noise.g_masks],
+                                 d_masks=[{}, {}, {}]))
+    ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+    assert set('loss_' + k for k in ret) == set(k for k in g.files if k.startswith('loss_'))
+    for k, v in ret.items():
+        ref = float(g['loss_' + k])
+        assert abs(v - ref) <= TOL * abs(ref) + 1e-6, (k, v, ref)
+    for k, p in G.named_parameters():
+        _digest_close(digest(p.grad.cpu()), g['ggrad/' + k], 3e-4)
+    gsd = G.state_dict()
+    for k in g.files:
+        if k.startswith('gpost/'):
+            _post_close(digest(gsd[k[6:]].cpu()), g[k], cfg.learning_rate, k[6:] in ZERO_GRAD_KEYS)
+    dsd = D.state_dict()
+    for k in g.files:
+        if k.startswith('dpost/'):
+            _post_close(digest(dsd[k[6:]].cpu()), g[k], cfg.learning_rate * cfg.discriminator_lr_weight, k[6:] in ZERO_GRAD_KEYS)
+    assert g_opt.state_dict()['state'][0]['exp_avg'].abs().sum() > 0      # torch optimiser sees our flat Adam state
+
+
+def _oracle_step(cfg, epoch, gsd, dsd, inp, noise, dev):
+    """float64 oracle on the GPU (fast): the accuracy yard-stick at full batch size."""
+    f64 = lambda sd: {k: (v.to(dev).double() if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
+    g64, d64 = f64(gsd), f64(dsd)
+    n64 = O.StepNoise(eps=[e.to(dev).double() for e in noise.eps], perm=noise.perm.to(dev),
+                      g_masks=[({k: v.to(dev).double() for k, v in m.items()} if m else None) for m in noise.g_masks],
+                      d_masks=[({k: v.to(dev).double() for k, v in m.items()} if m else None) for m in noise.d_masks])
+    i64 = {k: (v.double() if v.is_floating_point() else v) for k, v in inp.items()}
+    return O.train_iter_gan_oracle(cfg, epoch, g64, d64, synth.zeros_like_opt(g64), synth.zeros_like_opt(d64), 1,
+                                   i64['in_text'], i64['in_audio'], i64['target'], i64['vid'], n64)
+
+
+@pytest.mark.parametrize('B,epoch', [(128, 11), (16, 0)])
+def test_train_iter_full_size_vs_oracle(dev, B, epoch):
+    """BASELINE.json configs[1]: batch 128, every dropout mask injected (incl. GRU inter-layer masks, which the
+    reference itself cannot take - hence the oracle)."""
+    from train_eval import train_gan as TG
+    cfg = O.HotPathConfig(n_words=2000, n_speakers=50)
+    args, G, D, gsd, dsd = build_ours(cfg, dev)
+    G.train(); D.train()
+    inp = to_dev(synth.make_inputs(cfg, B, seed=3), dev)
+    noise = synth.make_noise(cfg, B, seed=4, dropout=True)
+    ref = _oracle_step(cfg, epoch, gsd, dsd, inp, noise, dev)
+    g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=[e.to(dev) for e in noise.eps], perm=noise.perm.to(dev),
+                                 g_masks=[masks_to_ours(m, dev) for m in noise.g_masks],
+                                 d_masks=[masks_to_ours(m, dev) for m in noise.d_masks]))
+    ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+    assert set(ret) == set(ref['losses'])
+    for k, v in ret.items():
+        r = ref['losses'][k]
+        assert abs(v - r) <= TOL * abs(r) + 1e-7, (k, v, r)
+    ig = 1 if epoch > cfg.loss_warmup else 0
+    out = G.engine().ws['g.poses'].view(-1, cfg.n_poses, cfg.pose_dim)[ig * B:(ig + 1) * B]
+    assert rel_l2(out, ref['out']) < TOL, rel_l2(out, ref['out'])
+    worst = ('', 0.0)
+    for k, p in G.named_parameters():
+        r = ref['g_grads'][k]
+        if r.norm() < 1e-6:
+            assert p.grad.norm() < 1e-3, k
+            continue
+        e = rel_l2(p.grad, r)
+        worst = max(worst, (k, e), key=lambda t: t[1])
+    assert worst[1] < 1e-3, worst
+    if ref['d_grads'] is not None:
+        # D.grad after the call = D-step grads + (stale) G-step grads, like the reference; compare BN running stats instead
+        pass
+    for k, v in D.state_dict().items():
+        if 'running' in k and k not in ZERO_GRAD_KEYS:
+            assert rel_l2(v, ref['d_sd'][k]) < 1e-4, k
+    for k, v in G.state_dict().items():
+        if 'running' in k:
+            assert rel_l2(v, ref['g_sd'][k]) < 1e-4, k
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == int(ref['g_sd'][k])
+
+
+def test_module_api_autograd_matches_oracle(dev):
+    """Reference-style usage: our modules under torch autograd (loss.backward()), p=0 dropout."""
+    cfg = O.HotPathConfig(n_words=300, n_speakers=12, dropout_prob=0.0, emb_dropout=0.0)
+    args, G, D, gsd, dsd = build_ours(cfg, dev, dropout_prob=0.0)
+    G.text_encoder.drop.p = 0.0; G.text_encoder.emb_dropout = 0.0
+    D.gru.dropout = 0.0
+    G._engine = None; D._engine = None
+    G.train(); D.train()
+    B = 5
+    inp = to_dev(synth.make_inputs(cfg, B, seed=7), dev)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, B, seed=8).eps[0].to(dev)
+    G.set_noise(eps=eps, masks={})
+    poses, z, mu, logvar = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
+    D.set_noise(masks={})
+    prob = D(poses)
+    loss = (poses ** 2).mean() + prob.log().mean() + (mu ** 2).mean() + 0.1 * logvar.mean() + z.sum() * 0.01
+    loss.backward()
+    f64 = lambda sd: {k: (v.to(dev).double().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.to(dev)) for k, v in sd.items()}
+    g64, d64 = f64(gsd), f64(dsd)
+    po, zo, muo, lvo = O.pose_generator_forward(g64, cfg, pre.double(), inp['in_text'], inp['in_audio'].double(), inp['vid'], eps.double(), True, None, {})
+    pr = O.conv_discriminator_forward(d64, cfg, po, True, None, {})
+    lo = (po ** 2).mean() + pr.log().mean() + (muo ** 2).mean() + 0.1 * lvo.mean() + zo.sum() * 0.01
+    lo.backward()
+    assert rel_l2(poses, po) < TOL and rel_l2(prob, pr) < TOL
+    for k, p in G.named_parameters():
+        r = g64[k].grad
+        if r is None or r.norm() < 1e-7:
+            continue
+        assert rel_l2(p.grad, r) < 1e-3, (k, rel_l2(p.grad, r))
+    for k, p in D.named_parameters():
+        r = d64[k].grad
+        if r is None or r.norm() < 1e-7:
+            continue
+        assert rel_l2(p.grad, r) < 1e-3, (k, rel_l2(p.grad, r))
+
+
+def test_embedding_net_and_fgd_vs_reference_golden(dev):
+    from model.embedding_net import EmbeddingNet
+    from model.embedding_space_evaluator import EmbeddingSpaceEvaluator
+    from gpu_util import make_args
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'embedding_fgd.npz'))
+    E = EmbeddingNet(make_args(cfg), cfg.pose_dim, cfg.n_poses, cfg.n_words, cfg.wordembed_dim, None, 'pose')
+    E.load_state_dict(synth.embedding_net_state_dict(cfg), strict=True)
+    E = E.to(dev).eval()
+    rng = np.random.Generator(np.random.PCG64(77))
+    real = torch.from_numpy((0.5 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim))).astype(np.float32)).to(dev)
+    fake = torch.from_numpy((1.0 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim)) + 0.3).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        _, _, _, rf, _, _, rrec = E(None, None, None, real, 'pose', variational_encoding=False)
+        _, _, _, ff, _, _, frec = E(None, None, None, fake, 'pose', variational_encoding=False)
+    assert rel_l2(rf, g['real_feat']) < TOL and rel_l2(ff, g['fake_feat']) < TOL
+    _digest_close(digest(rrec.cpu()), g['real_recon'], 1e-4)
+    _digest_close(digest(frec.cpu()), g['fake_recon'], 1e-4)
+    ev = EmbeddingSpaceEvaluator.from_net(E, cfg.n_pre_poses, dev)
+    for i in range(0, 256, 64):                      # four pushes, like four validation batches
+        ev.push_samples(None, None, fake[i:i + 64], real[i:i + 64])
+    fgd, feat_dist = ev.get_scores()
+    assert abs(fgd - float(g['fgd'])) <= 0.01 * abs(float(g['fgd'])), (fgd, float(g['fgd']))          # north_star: FGD within 1 %
+    assert abs(feat_dist - float(g['feat_dist'])) <= 1e-4 * abs(float(g['feat_dist']))
+
+
+def test_cpu_tensors_fail_loudly(dev):
+    """No CPU fallback: the product path refuses CPU tensors instead of silently computing with PyTorch."""
+    from tgb200 import _lib
+    cfg = golden_cfg()
+    args, G, D, _, _ = build_ours(cfg, None)
+    inp = synth.make_inputs(cfg, 2, seed=1)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    with pytest.raises(_lib.TgError):
+        G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
+    with pytest.raises(_lib.TgError):
+        D(inp['target'])
