@@ -73,7 +73,8 @@ class _NoiseSource:
         return self.offset
 
     def advance(self):
-        ops.increment_i64(self.offset, 1)
+        if self.offset is not None:
+            ops.increment_i64(self.offset, 1)
 
 
 def _module_seed():

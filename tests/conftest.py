@@ -18,8 +18,8 @@ def pytest_configure(config):
 
 def rel_l2(a, b):
     import torch
-    a = torch.as_tensor(a).double().flatten()
-    b = torch.as_tensor(b).double().flatten()
+    a = torch.as_tensor(a).detach().double().flatten().cpu()
+    b = torch.as_tensor(b).detach().double().flatten().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
