@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py - G+D adversarial training step of the trimodal gesture model (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference algorithm on the box's host cores)
+
+One "step" = one train_iter_gan call (epoch 11 > loss_warmup: 3 generator forwards, 1 generator backward, 3
+discriminator forward/backwards, two Adam updates) on a batch of 128 synthetic TED-shaped clips per GPU.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'gesture-generation-from-trimodal-context_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+N_WORDS, N_SPEAKERS, AUDIO_LEN, T, POSE_DIM = 20000, 1371, 36267, 34, 27
+FLOP_PER_SAMPLE_STEP = 2.735e9          # 5 x 521.7 MFLOP (3 G fwd + G bwd@2x) + 9 x 14.05 MFLOP
+FLOP_PER_CLIP_FWD = 521.7e6
+
+
+def make_args_ns():
+    return argparse.Namespace(n_pre_poses=4, n_poses=T, input_context='both', hidden_size=300, n_layers=4, dropout_prob=0.3,
+                              freeze_wordembed=False, z_type='speaker', loss_warmup=10, loss_gan_weight=5.0,
+                              loss_regression_weight=500.0, loss_kld_weight=0.1, loss_reg_weight=0.05, wordembed_dim=300)
+
+
+def synth_batch(batch, seed):
+    """Synthetic TED-shaped clips: audio 0.1*N(0,1) clipped, mostly-PAD word ids with 5-9 word frames,
+    random-walk direction vectors, speaker ids."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    audio = np.clip(0.1 * rng.standard_normal((batch, AUDIO_LEN)), -1, 1).astype(np.float32)
+    text = np.zeros((batch, T), dtype=np.int64)
+    for b in range(batch):
+        n = int(rng.integers(5, 10))
+        text[b, rng.choice(T, size=n, replace=False)] = rng.integers(4, N_WORDS, size=n)
+    walk = np.cumsum(0.02 * rng.standard_normal((batch, T, POSE_DIM)), axis=1)
+    target = (walk + 0.1 * rng.standard_normal((batch, 1, POSE_DIM))).astype(np.float32)
+    vid = rng.integers(1, N_SPEAKERS, size=batch).astype(np.int64)
+    return dict(in_text=torch.from_numpy(text), in_audio=torch.from_numpy(audio), target=torch.from_numpy(target),
+                vid=torch.from_numpy(vid))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement of the reference algorithm, pinned to the reference's own
+# modules by tests/test_oracle_golden.py) timed on the host cores.  The only place bench.py touches oracle/.
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, batch, budget_s):
+    from oracle import synth
+    from oracle import trimodal_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.HotPathConfig(n_words=N_WORDS, n_speakers=N_SPEAKERS)
+    gsd, dsd = synth.generator_state_dict(cfg), synth.discriminator_state_dict(cfg)
+    g_opt, d_opt = synth.zeros_like_opt(gsd), synth.zeros_like_opt(dsd)
+
+    def one(bs, it):
+        inp = synth_batch(bs, 100 + it)
+        noise = synth.make_noise(cfg, bs, seed=it, dropout=True)
+        t0 = time.perf_counter()
+        O.train_iter_gan_oracle(cfg, 11, gsd, dsd, g_opt, d_opt, 1, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], noise)
+        return time.perf_counter() - t0
+    bs = batch
+    t_probe = one(min(bs, 16), 0)                     # also warms the thread pool
+    est = t_probe * bs / min(bs, 16)
+    while bs > 8 and est * (steps + warmup) > budget_s:
+        bs //= 2
+        est /= 2
+    for i in range(warmup):
+        one(bs, i + 1)
+    ts = [one(bs, 50 + i) for i in range(steps)]
+    return dict(batch=bs, ms=1e3 * float(np.mean(ts)), cores=torch.get_num_threads())
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_reference_run(a.steps, a.warmup, a.batch, budget_s=150.0)
+    val = r['batch'] / (r['ms'] / 1e3)
+    sample = 'G+D step (epoch 11, all dropout masks) on a %d-clip sample of the %d-clip batch, %d timed steps' % (r['batch'], a.batch, a.steps)
+    line = {'impl': 'reference', 'metric': 'G+D train samples/s', 'value': val, 'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': r['ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(a, 1),
+            'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def workload_config(a, world):
+    return {'workload': 'multimodal_context G+D adversarial training step (train_iter_gan, epoch>loss_warmup), batch %d per GPU, '
+                        '34 frames x 27-d poses, 4 seed poses, 36267 audio samples, 34-word ids, n_words=20000, 1370 speakers' % a.batch,
+            'global_batch': a.batch * world, 'per_gpu_batch': a.batch, 'parallelism': 'dp%d' % world, 'mode': 'fp32 (CUDA-core FFMA kernels)',
+            'l2': 'per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; inputs rotate over 8 distinct batches'}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--batch', type=int, default=128, help='clips per GPU')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-profile', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        return run_reference(a)
+    a.warmup = max(a.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs CUDA devices; there is no CPU fallback for the product path'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    from model import vocab
+    from model.multimodal_context_net import ConvDiscriminator, PoseGenerator
+    from tgb200 import ops
+    from tgb200.profiler import KernelTimer
+    from train_eval.train_gan import train_iter_gan
+
+    torch.manual_seed(0)                                   # identical random-init weights on every rank
+    args = make_args_ns()
+    spk = vocab.Vocab('vid', insert_default_tokens=False)
+    while spk.n_words < N_SPEAKERS:
+        spk.index_word('s%d' % spk.n_words)
+    G = PoseGenerator(args, POSE_DIM, N_WORDS, 300, None, z_obj=spk).to(dev).train()
+    D = ConvDiscriminator(POSE_DIM).to(dev).train()
+    g_opt = torch.optim.Adam(G.parameters(), lr=5e-4, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=5e-4 * 0.2, betas=(0.5, 0.999))
+
+    n_pool = 8
+    host = [synth_batch(a.batch, 1000 * rank + i) for i in range(n_pool)]
+    pinned = [{k: v.pin_memory() for k, v in h.items()} for h in host]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step_resident(i):
+        b = resident[i % n_pool]
+        return train_iter_gan(args, 11, b['in_text'], b['in_audio'], b['target'], b['vid'], G, D, g_opt, d_opt)
+
+    def step_e2e(i):
+        p = pinned[i % n_pool]
+        b = {k: v.to(dev, non_blocking=True) for k, v in p.items()}
+        return train_iter_gan(args, 11, b['in_text'], b['in_audio'], b['target'], b['vid'], G, D, g_opt, d_opt)   # returns python floats (D2H)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launches()
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ops.launches() - l0, t0, t1
+
+    for i in range(a.warmup):
+        ret = step_resident(i)
+    assert all(np.isfinite(v) for v in ret.values()), ret
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    ms, launches, t0, t1 = timed(step_resident, a.steps)
+    clock_info = clocks.stop(t0, t1) if rank == 0 else None
+    value = world * a.batch * a.steps / (ms / 1e3)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _, _ = timed(step_e2e, a.steps)
+    e2e_value = world * a.batch * a.steps / (ms_e2e / 1e3)
+
+    # ---- PoseGenerator inference (the metric's "clips/s"): eval forward, batch 128 and batch 1, device-resident inputs
+    G.eval()
+    infer = {}
+    with torch.no_grad():
+        for bs in (a.batch, 1):
+            b = {k: v[:bs].contiguous() for k, v in resident[0].items()}
+            pre = torch.zeros(bs, T, POSE_DIM + 1, device=dev)
+            pre[:, :4, :-1] = b['target'][:, :4]; pre[:, :4, -1] = 1
+            f = lambda i: G(pre, b['in_text'], b['in_audio'], b['vid'])
+            for i in range(3):
+                f(i)
+            n_it = 20
+            ims, _, _, _ = timed(f, n_it)
+            infer['b%d' % bs] = world * bs * n_it / (ims / 1e3)
+    G.train()
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        roof = None
+        if not a.no_kernel_profile:
+            # per-launch CUDA-event timing of two more steps -> dominant kernel family and its achieved rate
+            with KernelTimer() as kt:
+                for i in range(2):
+                    step_resident(i)
+            agg = kt.summary()
+            total_ms = sum(v['ms'] for v in agg.values())
+            top = max(agg.items(), key=lambda kv: kv[1]['ms'])
+            name, v = top
+            tflops = v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] > 0 else 0.0
+            roof = {'bound': 'tensor', 'kernel': name, 'achieved': tflops, 'peak': peaks['tf_sust'], 'unit': 'TFLOP/s',
+                    'frac': tflops / peaks['tf_sust'], 'traffic': None, 'peak_source': peaks['src'] + ' bf16 dense sustained',
+                    'share_of_step': v['ms'] / total_ms, 'launches_per_step': v['calls'] / 2,
+                    'note': 'fp32 CUDA-core kernel measured against the bf16 tensor-pipe peak (strict-fp32 mode); whole-step fraction = '
+                            '%.4f' % (value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12)),
+                    'by_kernel_ms_per_step': {k: round(x['ms'] / 2, 4) for k, x in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:8]}}
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            r = cpu_reference_run(2, 1, a.batch, budget_s=45.0)
+            cpu = {'value': r['batch'] / (r['ms'] / 1e3), 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
+                   'sample': 'oracle G+D step on a %d-clip sample, 2 timed steps after 1 warm-up' % r['batch']}
+        line = {'metric': 'G+D train samples/s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+                'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': workload_config(a, world),
+                'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 64,
+                        'ms_per_step': ms_e2e / a.steps},
+                'gpu_launches': launches, 'clocks': clock_info, 'roofline': roof, 'cpu_baseline': cpu,
+                'step_roofline_frac': value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12),
+                'infer_clips_per_s': infer, 'last_losses': ret}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
