@@ -153,32 +153,46 @@ __global__ void embedding_scatter_kernel(const float* __restrict__ dout, const l
 }
 
 // ------------------------------------------------------------------ weight norm: one warp per output row
+// v [N, Cin, taps] (nn.Conv1d layout).  Effective weight is written TAP-MAJOR: w[tap][n][c] (each tap a K-contiguous
+// [N, Cin] GEMM operand) and optionally transposed per tap: wT[tap][c][n] (the data-gradient operand).
 __global__ void weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
-                                       float* __restrict__ inv_norm, int N, int K) {
+                                       float* __restrict__ wT, float* __restrict__ inv_norm, int N, int Cin, int taps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= N) return;
+  const int K = Cin * taps;
   const float* vr = v + (long long)row * K;
   float ss = 0.f;
   for (int k = lane; k < K; k += 32) ss += vr[k] * vr[k];
   ss = warp_sum(ss);
   const float inv = rsqrtf(ss);
   const float s = g[row] * inv;
-  for (int k = lane; k < K; k += 32) w[(long long)row * K + k] = vr[k] * s;
+  for (int k = lane; k < K; k += 32) {
+    const int c = k / taps, j = k - c * taps;
+    const float val = vr[k] * s;
+    w[((long long)j * N + row) * Cin + c] = val;
+    if (wT) wT[((long long)j * Cin + c) * N + row] = val;
+  }
   if (lane == 0) inv_norm[row] = inv;
 }
 __global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
-                                       const float* __restrict__ inv_norm, float* dv, float* dg, int N, int K) {
+                                       const float* __restrict__ inv_norm, float* dv, float* dg, int N, int Cin, int taps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= N) return;
+  const int K = Cin * taps;
   const float* vr = v + (long long)row * K;
-  const float* dwr = dw + (long long)row * K;
   float dot = 0.f;
-  for (int k = lane; k < K; k += 32) dot += dwr[k] * vr[k];
+  for (int k = lane; k < K; k += 32) {
+    const int c = k / taps, j = k - c * taps;
+    dot += dw[((long long)j * N + row) * Cin + c] * vr[k];
+  }
   dot = warp_sum(dot);
   const float inv = inv_norm[row], gg = g[row];
   // w = g v / |v| : dg = dot/|v| ; dv = g/|v| * (dw - v * dot / |v|^2)
   const float c1 = gg * inv, c2 = dot * inv * inv;
-  for (int k = lane; k < K; k += 32) dv[(long long)row * K + k] += c1 * (dwr[k] - vr[k] * c2);
+  for (int k = lane; k < K; k += 32) {
+    const int c = k / taps, j = k - c * taps;
+    dv[(long long)row * K + k] += c1 * (dw[((long long)j * N + row) * Cin + c] - vr[k] * c2);
+  }
   if (lane == 0) dg[row] += dot * inv;
 }
 
@@ -492,16 +506,17 @@ extern "C" int tg_embedding_scatter_add(const float* dout, const long long* idx,
   TG_CHECK_LAUNCH("tg_embedding_scatter_add");
   return 0;
 }
-extern "C" int tg_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, tg_stream stream) {
-  TG_REQUIRE(v && g && w && inv_norm, "tg_weight_norm_fwd");
-  weight_norm_fwd_kernel<<<tg_ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(v, g, w, inv_norm, N, K);
+extern "C" int tg_weight_norm_fwd(const float* v, const float* g, float* w, float* wT, float* inv_norm, int N, int Cin, int taps,
+                                  tg_stream stream) {
+  TG_REQUIRE(v && g && w && inv_norm && taps > 0, "tg_weight_norm_fwd");
+  weight_norm_fwd_kernel<<<tg_ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(v, g, w, wT, inv_norm, N, Cin, taps);
   TG_CHECK_LAUNCH("tg_weight_norm_fwd");
   return 0;
 }
 extern "C" int tg_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int N,
-                                  int K, tg_stream stream) {
-  TG_REQUIRE(dw && v && g && inv_norm && dv && dg, "tg_weight_norm_bwd");
-  weight_norm_bwd_kernel<<<tg_ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, N, K);
+                                  int Cin, int taps, tg_stream stream) {
+  TG_REQUIRE(dw && v && g && inv_norm && dv && dg && taps > 0, "tg_weight_norm_bwd");
+  weight_norm_bwd_kernel<<<tg_ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, N, Cin, taps);
   TG_CHECK_LAUNCH("tg_weight_norm_bwd");
   return 0;
 }

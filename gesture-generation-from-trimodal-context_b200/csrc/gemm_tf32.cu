@@ -1,0 +1,258 @@
+// Tensor-core GEMM for the "fast" mode: tcgen05.mma kind::tf32 (fp32 operands read straight from the fp32 activations
+// and weights by TMA - no conversion pass, 10-bit-mantissa products, fp32 accumulation in TMEM).
+//
+//   C[m, n] = epi( sum_tap sum_k A[m + shift_tap, k] * B[tap*N + n, k] )        A, B row-major (K contiguous)
+//
+// 128 x BN tile per CTA, BK = 32 floats (one 128-byte swizzle atom), NSTAGE-deep TMA->MMA mbarrier pipeline,
+// warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
+// (tcgen05.ld 32x32b, one TMEM lane = one output row per thread).
+// Two-tap mode (the TCN's causal dilated convolution, tcn.py:19-31, and its anti-causal data gradient): the shifted
+// tap accumulates in a second TMEM accumulator and is masked per row in the epilogue (t + shift outside the clip),
+// so the shifted operand is a plain 2-D TMA load with a row offset - no im2col, no padded copy, no chomp.
+#include <cudaTypedefs.h>
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int BM = 128, BKF = 32;            // BKF floats = 128 bytes
+constexpr int A_STAGE_BYTES = BM * 128;
+
+struct GemmP {
+  float* C; int ldc;
+  int M, N, K, taps, shift0, T;
+  const float* escale; const float* bias; int act1; float slope1;
+  const float* mask; int ldmask; const float* residual; int ldres; int act2; int accumulate;
+};
+
+template <int BN, int NSTAGE>
+__global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                           const GemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tmem_full_bar = empty_bar + NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nkb = (p.K + BKF - 1) / BKF;
+  const int iters = nkb * p.taps;
+  constexpr uint32_t TMEM_COLS_1 = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS_2 = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  const uint32_t tmem_cols = p.taps == 2 ? TMEM_COLS_2 : TMEM_COLS_1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = it / nkb, kb = it - tap * nkb;
+        const int shift = (p.taps == 2 && tap == 0) ? p.shift0 : 0;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(sa, &tmA, &full_bar[s], kb * BKF, m0 + shift);
+        tma_load_2d(sb, &tmB, &full_bar[s], kb * BKF, tap * p.N + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(BM, BN, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const int tap = it / nkb, kb = it - tap * nkb;
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t dcol = tmem_base + (uint32_t)(tap * BN);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t ad = smem_desc_sw128(sa + k4 * 32, 16, 1024);
+          const uint64_t bd = smem_desc_sw128(sb + k4 * 32, 16, 1024);
+          mma_tf32(dcol, ad, bd, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    bool tap0_ok = true;
+    if (p.taps == 2) {
+      const int t = m % p.T;
+      const int ts = t + p.shift0;
+      tap0_ok = ts >= 0 && ts < p.T;
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                        (!p.mask || ((p.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) &&
+                        (!p.residual || ((p.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (p.taps == 2) {
+        float v0[32];
+        tmem_ld32(lane_addr + (uint32_t)c0, v0);
+        tmem_ld32(lane_addr + (uint32_t)(BN + c0), v);
+        tmem_ld_wait();
+        if (tap0_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v0[j];
+        }
+      } else {
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+      }
+      const int nb = n0 + c0;
+      if (row_ok && nb < p.N) {
+      float* crow = p.C + (long long)m * p.ldc + nb;
+      const float* mrow = p.mask ? p.mask + (long long)m * p.ldmask + nb : nullptr;
+      const float* rrow = p.residual ? p.residual + (long long)m * p.ldres + nb : nullptr;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        if (nb + j4 >= p.N) break;
+        const bool full4 = vec_ok && (nb + j4 + 3 < p.N);
+        float o[4];
+        float mk[4] = {1.f, 1.f, 1.f, 1.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full4) {
+          if (mrow) { const float4 t4 = *reinterpret_cast<const float4*>(mrow + j4); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
+          if (rrow) { const float4 t4 = *reinterpret_cast<const float4*>(rrow + j4); rs[0] = t4.x; rs[1] = t4.y; rs[2] = t4.z; rs[3] = t4.w; }
+          if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(crow + j4); old[0] = t4.x; old[1] = t4.y; old[2] = t4.z; old[3] = t4.w; }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (nb + j4 + e < p.N) {
+              if (mrow) mk[e] = mrow[j4 + e];
+              if (rrow) rs[e] = rrow[j4 + e];
+              if (p.accumulate) old[e] = crow[j4 + e];
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = nb + j4 + e;
+          float x = v[j4 + e];
+          if (n < p.N) {
+            if (p.escale) x *= __ldg(p.escale + n);
+            if (p.bias) x += __ldg(p.bias + n);
+          }
+          x = tg_act(x, p.act1, p.slope1);
+          x = x * mk[e] + rs[e];
+          x = tg_act(x, p.act2, 0.f);
+          o[e] = x + old[e];
+        }
+        if (full4) {
+          *reinterpret_cast<float4*>(crow + j4) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (nb + j4 + e < p.N) crow[j4 + e] = o[e];
+        }
+      }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// row-major fp32 matrix [rows, cols], pitch ld floats; box = 32 floats x box_rows, 128-byte swizzle, zero OOB fill
+int make_map_2d(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_rows, const char* name) {
+  auto enc = get_encode();
+  if (!enc) { tg_set_error("%s: cuTensorMapEncodeTiled unavailable", name); return -4; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 4) & 15)) { tg_set_error("%s: TMA needs 16-byte aligned base and pitch (ld=%lld)", name, ld); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { tg_set_error("%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", name, (int)r, rows, cols, ld); return -4; }
+  return 0;
+}
+
+template <int BN, int NSTAGE>
+int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  int rc = make_map_2d(&ta, g.A, g.a_rows, g.K, g.lda, BM, "tg_gemm_tf32(A)");
+  if (rc) return rc;
+  rc = make_map_2d(&tb, g.Bw, (long long)g.taps * g.N, g.K, g.ldb, BN, "tg_gemm_tf32(B)");
+  if (rc) return rc;
+  GemmP p;
+  p.C = g.C; p.ldc = g.ldc; p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.shift0 = g.shift0; p.T = g.T > 0 ? g.T : 1;
+  p.escale = g.escale; p.bias = g.bias; p.act1 = g.act1; p.slope1 = g.slope1; p.mask = g.mask; p.ldmask = g.ldmask;
+  p.residual = g.residual; p.ldres = g.ldres; p.act2 = g.act2; p.accumulate = g.accumulate;
+  constexpr size_t smem = (size_t)NSTAGE * (A_STAGE_BYTES + BN * 128) + (2 * NSTAGE + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
+    attr_done = true;
+  }
+  dim3 grid(tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN));
+  gemm_tf32_kernel<BN, NSTAGE><<<grid, 192, smem, s>>>(ta, tb, p);
+  TG_CHECK_LAUNCH("tg_gemm_tf32");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
+  const tg_gemm_tf32_t& g = *gp;
+  TG_REQUIRE(g.A && g.Bw && g.C && g.M > 0 && g.N > 0 && g.K > 0, "tg_gemm_tf32");
+  TG_REQUIRE(g.taps == 1 || g.taps == 2, "tg_gemm_tf32");
+  cudaStream_t s = (cudaStream_t)stream;
+  // tile width: minimise padded N, prefer wider tiles on ties (fewer A re-reads)
+  int bn;
+  if (g.N <= 32) bn = 32;
+  else if (g.N <= 64) bn = 64;
+  else {
+    const int p128 = tg_ceil_div(g.N, 128) * 128, p160 = tg_ceil_div(g.N, 160) * 160;
+    bn = (p160 < p128) ? 160 : 128;
+  }
+  if (bn == 32) return launch<32, 6>(g, s);
+  if (bn == 64) return launch<64, 6>(g, s);
+  if (bn == 128) return launch<128, 5>(g, s);
+  return launch<160, 5>(g, s);
+}

@@ -45,6 +45,20 @@ class ConvWgrad(ctypes.Structure):
                 ('dbias', ctypes.c_void_p)]
 
 
+class GemmTf32(ctypes.Structure):
+    """tg_gemm_tf32_t (include/tg_b200.h)."""
+    _fields_ = [('A', ctypes.c_void_p), ('lda', ctypes.c_int), ('a_rows', ctypes.c_longlong),
+                ('Bw', ctypes.c_void_p), ('ldb', ctypes.c_int),
+                ('C', ctypes.c_void_p), ('ldc', ctypes.c_int),
+                ('M', ctypes.c_int), ('N', ctypes.c_int), ('K', ctypes.c_int), ('taps', ctypes.c_int), ('shift0', ctypes.c_int),
+                ('T', ctypes.c_int),
+                ('escale', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+                ('act1', ctypes.c_int), ('slope1', ctypes.c_float),
+                ('mask', ctypes.c_void_p), ('ldmask', ctypes.c_int),
+                ('residual', ctypes.c_void_p), ('ldres', ctypes.c_int),
+                ('act2', ctypes.c_int), ('accumulate', ctypes.c_int)]
+
+
 def _ctype(decl: str):
     d = decl.strip()
     if '*' in d:

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import config, ops
 from .arena import ParamArena
 
 F32 = torch.float32
@@ -38,6 +38,28 @@ class Workspace:
 
     def __getitem__(self, name):
         return self.t[name]
+
+
+def _tf32_ok(A, lda, W, ldw, K):
+    """Operands a TMA descriptor can describe: 16-byte aligned base and pitch, K at least one 32-float swizzle atom."""
+    return (config.fast() and K >= 32 and lda % 4 == 0 and ldw % 4 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
+
+
+def mm_nt(A, W, C, *, M, N, K, lda=None, **epi):
+    """C[M,N] = epi(A[M,K] @ W[N,K]^T): tcgen05 TF32 GEMM in fast mode when the operands qualify, fp32 FFMA GEMM otherwise."""
+    lda = K if lda is None else lda
+    if _tf32_ok(A, lda, W, K, K):
+        ops.gemm_tf32(A, W, C, M=M, N=N, K=K, lda=lda, **epi)
+    else:
+        ops.conv_gemm(A, W, C, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, lda=lda, ldw=K, wsc=1, **epi)
+
+
+def mm_nn(dY, W, Wt, dX, *, M, N, K, **epi):
+    """dX[M,K] = epi(dY[M,N] @ W[N,K]).  Wt = W^T [K,N] (prepared in fast mode) feeds the tensor-core path."""
+    if Wt is not None and _tf32_ok(dY, N, Wt, N, N):
+        ops.gemm_tf32(dY, Wt, dX, M=M, N=K, K=N, **epi)
+    else:
+        ops.linear_dgrad(dY, W, dX, M=M, K=K, N=N, **epi)
 
 
 def _conv_out(tin, k, stride, pad=0, dil=1):
@@ -80,6 +102,10 @@ class GruPlan:
             for d in (0, 1):
                 wt = self.ws.get(f'{self.tag}.whhT{l}_{d}', (H, 3 * H))
                 ops.transpose(self._w('weight_hh', l, bool(d)), wt, 3 * H, H)
+            K = self.I if l == 0 else 2 * H
+            if config.fast() and l > 0:
+                # [6H, K] (both directions, adjacent in the arena) -> [K, 6H]: operand of the data-gradient GEMM
+                ops.transpose(self._w('weight_ih', l), self.ws.get(f'{self.tag}.wihT{l}', (K, 6 * H)), 6 * H, K)
 
     def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool):
         """x [B*T, I] -> out of the last layer [B*T, 2H].  masks[l] multiplies the output of layer l (l < L-1)."""
@@ -89,7 +115,7 @@ class GruPlan:
         sync = ws.get(f'{tag}.sync', (max(ops.gru_sync_ints(B, H), 1),), torch.int32)
         inp, K = x, self.I
         for l in range(self.L):
-            ops.conv_gemm(inp, self._w('weight_ih', l), gi, B=1, Tin=M, Tout=M, N=6 * H, Cin=K, ldw=K, bias=self._w('bias_ih', l))
+            mm_nt(inp, self._w('weight_ih', l), gi, M=M, N=6 * H, K=K, bias=self._w('bias_ih', l))
             out = ws.get(f'{tag}.out{l}', (M, 2 * H))
             saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
             ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
@@ -136,7 +162,8 @@ class GruPlan:
             if l > 0 or need_dx:
                 dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
                 m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
-                ops.linear_dgrad(dgi, self._w('weight_ih', l), dx, M=Mb, K=K, N=6 * H, mask=m)
+                wt = ws.t.get(f'{tag}.wihT{l}') if config.fast() else None
+                mm_nn(dgi, self._w('weight_ih', l), wt, dx, M=Mb, N=6 * H, K=K, mask=m)
                 dout = dx
             else:
                 dx = None
@@ -199,8 +226,16 @@ class GeneratorEngine:
                 for j in (1, 2):
                     q = f'text_encoder.tcn.network.{i}.conv{j}'
                     v = self.P(q + '.weight_v')
-                    N, K = v.shape[0], v.shape[1] * v.shape[2]
-                    ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (N, K)), ws.get(f'tcn.inv{i}_{j}', (N,)), N, K)
+                    N, Cin, k = v.shape
+                    wT = ws.get(f'tcn.wT{i}_{j}', (k, Cin, N)) if config.fast() else None
+                    ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (k, N, Cin)), wT, ws.get(f'tcn.inv{i}_{j}', (N,)),
+                                        N, Cin, k)
+        if config.fast():
+            for name in ('text_encoder.decoder.weight', 'out.0.weight', 'out.2.weight'):
+                if name.startswith('text') and not self.use_text:
+                    continue
+                w = self.P(name)
+                ops.transpose(w, ws.get('T.' + name, (w.shape[1], w.shape[0])), w.shape[0], w.shape[1])
         self.gru.prep()
 
     def make_masks(self, Bt, T, seed, offset_dev, sid0=0):
@@ -311,15 +346,31 @@ class GeneratorEngine:
             y1 = ws.get(f'txt.y1_{i}', (M, H)); y2 = ws.get(f'txt.y2_{i}', (M, H)); xo = ws.get(f'txt.x{i}', (M, H))
             m1 = masks.get(f'tcn{i}_1') if masks else None
             m2 = masks.get(f'tcn{i}_2') if masks else None
-            ops.conv1d(x, ws[f'tcn.w{i}_1'], self.P(q + '.conv1.bias'), y1, B=Bt, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d,
-                       act1=ops.ACT_RELU, mask=m1)
-            ops.conv1d(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), y2, B=Bt, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d,
-                       act1=ops.ACT_RELU, mask=m2)
+            self._tcn_conv(x, ws[f'tcn.w{i}_1'], self.P(q + '.conv1.bias'), y1, Bt, T, cin, H, k, d, act1=ops.ACT_RELU, mask=m1)
+            self._tcn_conv(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), y2, Bt, T, H, H, k, d, act1=ops.ACT_RELU, mask=m2)
             ops.add(y2, x, xo, M * H, relu=True)
             x, cin = xo, H
         feat = ws.get('txt.feat', (M, 32))
-        ops.linear(x, self.P('text_encoder.decoder.weight'), self.P('text_encoder.decoder.bias'), feat, M=M, K=H, N=32)
+        mm_nt(x, self.P('text_encoder.decoder.weight'), feat, M=M, N=32, K=H, bias=self.P('text_encoder.decoder.bias'))
         return feat
+
+    @staticmethod
+    def _tcn_conv(x, w_tap, bias, y, B, T, cin, cout, k, d, **epi):
+        """Causal dilated conv (tcn.py:19-31) on tap-major weights w_tap [k][cout][cin]; x [B*T, cin] -> y [B*T, cout]."""
+        if k == 2 and _tf32_ok(x, cin, w_tap, cin, cin):
+            ops.gemm_tf32(x, w_tap, y, M=B * T, N=cout, K=cin, taps=2, shift0=-d, T=T, bias=bias, **epi)
+        else:
+            ops.conv_gemm(x, w_tap, y, B=B, Tin=T, Tout=T, N=cout, Cin=cin, taps=k, dil=d, pad=(k - 1) * d, ldw=cin, wsj=cout * cin, wsc=1,
+                          bias=bias, **epi)
+
+    @staticmethod
+    def _tcn_dgrad(dy, w_tap, wT_tap, dx, B, T, cin, cout, k, d, **epi):
+        """Data gradient of _tcn_conv: dx[t] = sum_j dy[t + (k-1-j)*d] W_j (anti-causal)."""
+        if k == 2 and wT_tap is not None and _tf32_ok(dy, cout, wT_tap, cout, cout):
+            ops.gemm_tf32(dy, wT_tap, dx, M=B * T, N=cin, K=cout, taps=2, shift0=d, T=T, **epi)
+        else:
+            ops.conv_gemm(dy, w_tap, dx, B=B, Tin=T, Tout=T, N=cin, Cin=cout, taps=k, dil=-d, pad=-(k - 1) * d, ldw=1, wsj=cout * cin,
+                          wsc=cin, **epi)
 
     def text_backward(self, d_feat, in_text, lo, hi, T, masks):
         ws, H, E = self.ws, self.H, self.E
@@ -331,7 +382,8 @@ class GeneratorEngine:
         xl = ws[f'txt.x{self.n_tcn - 1}'][r0:r1]
         ops.linear_wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), self.G('text_encoder.decoder.bias'), M=Mb, K=H, N=32)
         dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dc = ws.get('txt.dC', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
-        ops.linear_dgrad(d_feat, self.P('text_encoder.decoder.weight'), dx, M=Mb, K=H, N=32)
+        mm_nn(d_feat, self.P('text_encoder.decoder.weight'), ws.t.get('T.text_encoder.decoder.weight') if config.fast() else None, dx,
+              M=Mb, N=32, K=H)
         for i in range(self.n_tcn - 1, -1, -1):
             d = 2 ** i
             q = f'text_encoder.tcn.network.{i}'
@@ -342,18 +394,21 @@ class GeneratorEngine:
             m2 = sl(masks.get(f'tcn{i}_2')) if masks else None
             ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                      # through the block's final ReLU
             ops.relu_mask_bwd(dpre, y2, m2, dc, Mb * H)                        # dropout2 + relu2
-            dw = ws.get('tcn.dw', (H, max(cin, H) * k)); dw.zero_()
-            ops.conv1d_wgrad(y1, dc, dw, self.G(q + '.conv2.bias'), B=Bb, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d)
+            dw = ws.get('tcn.dw', (k * H * max(cin, H),)); dw.zero_()                 # tap-major [k][H][cin]
+            wT = lambda j: ws.t.get(f'tcn.wT{i}_{j}') if config.fast() else None
+            ops.conv_wgrad(y1, dc, dw, B=Bb, Tin=T, Tout=T, N=H, Cin=H, taps=k, dil=d, pad=(k - 1) * d, ldw=H, wsj=H * H, wsc=1,
+                           dbias=self.G(q + '.conv2.bias'))
             ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
-                                self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H * k)
-            ops.conv1d_dgrad(dc, ws[f'tcn.w{i}_2'], dy1, B=Bb, Tin=T, Tout=T, Cin=H, N=H, k=k, dil=d, pad=(k - 1) * d)
+                                self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H, k)
+            self._tcn_dgrad(dc, ws[f'tcn.w{i}_2'], wT(2), dy1, Bb, T, H, H, k, d)
             ops.relu_mask_bwd(dy1, y1, m1, dc, Mb * H)                         # dropout1 + relu1
             dw.zero_()
-            ops.conv1d_wgrad(xin, dc, dw, self.G(q + '.conv1.bias'), B=Bb, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d)
+            ops.conv_wgrad(xin, dc, dw, B=Bb, Tin=T, Tout=T, N=H, Cin=cin, taps=k, dil=d, pad=(k - 1) * d, ldw=cin, wsj=H * cin, wsc=1,
+                           dbias=self.G(q + '.conv1.bias'))
             ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
-                                self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin * k)
+                                self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin, k)
             # d x_in = conv1^T(dc) + residual branch (dpre)
-            ops.conv1d_dgrad(dc, ws[f'tcn.w{i}_1'], dx, B=Bb, Tin=T, Tout=T, Cin=cin, N=H, k=k, dil=d, pad=(k - 1) * d, residual=dpre)
+            self._tcn_dgrad(dc, ws[f'tcn.w{i}_1'], wT(1), dx, Bb, T, cin, H, k, d, residual=dpre)
         emb_p = self.arena.params['text_encoder.embedding.weight']
         if emb_p.requires_grad:
             Ba = in_text.shape[0]
@@ -396,8 +451,8 @@ class GeneratorEngine:
         H = self.H
         hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, H // 2)); poses = ws.get('g.poses', (M, m.pose_dim))
         ops.sum_halves(out, hsum, M, H)
-        ops.linear(hsum, self.P('out.0.weight'), self.P('out.0.bias'), y1, M=M, K=H, N=H // 2)      # LeakyReLU(True) == identity
-        ops.linear(y1, self.P('out.2.weight'), self.P('out.2.bias'), poses, M=M, K=H // 2, N=m.pose_dim)
+        mm_nt(hsum, self.P('out.0.weight'), y1, M=M, N=H // 2, K=H, bias=self.P('out.0.bias'))      # LeakyReLU(True) == identity
+        mm_nt(y1, self.P('out.2.weight'), poses, M=M, N=m.pose_dim, K=H // 2, bias=self.P('out.2.bias'))
         return poses.view(Bt, T, m.pose_dim), z, mu, logvar
 
     def backward(self, d_poses, lo, hi, d_mu=None, d_logvar=None, d_z=None):
@@ -412,9 +467,9 @@ class GeneratorEngine:
         d_poses = d_poses.reshape(Mb, D)
         dy1 = ws.get('g.dy1', (Mb, H // 2)); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
         ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
-        ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)
+        ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)          # K = 27 reduction: fp32 kernel
         ops.linear_wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), self.G('out.0.bias'), M=Mb, K=H, N=H // 2)
-        ops.linear_dgrad(dy1, self.P('out.0.weight'), dhs, M=Mb, K=H, N=H // 2)
+        mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=H // 2, K=H)
         ops.dup_halves(dhs, dout, Mb, H)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'

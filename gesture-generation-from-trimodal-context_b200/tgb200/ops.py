@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ConvGemm, ConvWgrad, check
+from ._lib import ConvGemm, ConvWgrad, GemmTf32, check
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 
@@ -83,6 +83,22 @@ def conv_wgrad(A, G, dW, *, B, Tin, Tout, N, Cin, taps=1, stride=1, dil=1, pad=0
     g.pscale = _p(pscale); g.pshift = _p(pshift); g.pslope = pslope
     g.dbias = _p(dbias)
     check(_L().tg_conv_wgrad_f32(ctypes.byref(g), _s()), 'tg_conv_wgrad_f32')
+    _count()
+
+
+def gemm_tf32(A, Bw, C, *, M, N, K, lda=None, ldb=None, ldc=None, a_rows=None, taps=1, shift0=0, T=1, escale=None, bias=None, act1=0,
+              slope1=0.0, mask=None, ldmask=None, residual=None, ldres=None, act2=0, accumulate=False):
+    """C[M,N] = epi(A[M,K] @ Bw[N,K]^T) on the tcgen05 tensor cores (TF32 operands, fp32 accumulate); see tg_gemm_tf32_t."""
+    g = GemmTf32()
+    g.A = _p(_f32(A)); g.lda = K if lda is None else lda; g.a_rows = M if a_rows is None else a_rows
+    g.Bw = _p(_f32(Bw)); g.ldb = K if ldb is None else ldb
+    g.C = _p(_f32(C)); g.ldc = N if ldc is None else ldc
+    g.M, g.N, g.K, g.taps, g.shift0, g.T = M, N, K, taps, shift0, T
+    g.escale = _p(escale); g.bias = _p(bias); g.act1 = act1; g.slope1 = slope1
+    g.mask = _p(mask); g.ldmask = N if ldmask is None else ldmask
+    g.residual = _p(residual); g.ldres = N if ldres is None else ldres
+    g.act2 = act2; g.accumulate = 1 if accumulate else 0
+    check(_L().tg_gemm_tf32(ctypes.byref(g), _s()), 'tg_gemm_tf32')
     _count()
 
 
@@ -178,12 +194,12 @@ def embedding_scatter_add(dout, idx, mask, dtable, M, E):
     check(_L().tg_embedding_scatter_add(_p(dout), _p(idx), _p(mask), _p(dtable), M, E, _s()), 'tg_embedding_scatter_add'); _count()
 
 
-def weight_norm_fwd(v, g, w, inv_norm, N, K):
-    check(_L().tg_weight_norm_fwd(_p(v), _p(g), _p(w), _p(inv_norm), N, K, _s()), 'tg_weight_norm_fwd'); _count()
+def weight_norm_fwd(v, g, w, wT, inv_norm, N, Cin, taps):
+    check(_L().tg_weight_norm_fwd(_p(v), _p(g), _p(w), _p(wT), _p(inv_norm), N, Cin, taps, _s()), 'tg_weight_norm_fwd'); _count()
 
 
-def weight_norm_bwd(dw, v, g, inv_norm, dv, dg, N, K):
-    check(_L().tg_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv_norm), _p(dv), _p(dg), N, K, _s()), 'tg_weight_norm_bwd'); _count()
+def weight_norm_bwd(dw, v, g, inv_norm, dv, dg, N, Cin, taps):
+    check(_L().tg_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv_norm), _p(dv), _p(dg), N, Cin, taps, _s()), 'tg_weight_norm_bwd'); _count()
 
 
 def mul(a, b, out, n):

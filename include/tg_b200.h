@@ -68,6 +68,28 @@ typedef struct {
 } tg_conv_wgrad_t;
 int tg_conv_wgrad_f32(const tg_conv_wgrad_t* p, tg_stream stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * "Fast" mode GEMM on the 5th-generation tensor cores: tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM.
+ *   C[m, n] = epi( sum_{tap < taps} sum_k A[m + shift(tap), k] * Bw[tap*N + n, k] ),  shift(0) = shift0 if taps == 2 else 0
+ * A [a_rows, K] and Bw [taps*N, K] are row-major fp32 (pitches lda / ldb floats, 16-byte aligned); operands are read
+ * as TF32 (10-bit mantissa), accumulation is fp32.  taps == 2 is the TCN causal dilated convolution (tcn.py:19-31)
+ * and its data gradient: the shifted tap only contributes to rows whose clip-local time t = m % T satisfies
+ * 0 <= t + shift0 < T.  Epilogue as tg_conv_gemm_f32.  Same reference call sites as tg_conv_gemm_f32.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A;  int lda; long long a_rows;
+  const float* Bw; int ldb;
+  float* C;        int ldc;
+  int M, N, K, taps, shift0, T;
+  const float* escale; const float* bias;
+  int act1; float slope1;
+  const float* mask;   int ldmask;
+  const float* residual; int ldres;
+  int act2;
+  int accumulate;
+} tg_gemm_tf32_t;
+int tg_gemm_tf32(const tg_gemm_tf32_t* p, tg_stream stream);
+
 /* Direct strided convolution for a single input channel (WavEncoder conv1: Conv1d(1,16,15,stride 5,pad 1600),
  * multimodal_context_net.py:13).  HBM-bound: x [B,Tin] -> y [B,Tout,N] channels-last, N <= 32, taps <= 32. */
 int tg_conv1_direct_f32(const float* x, const float* w, const float* bias, float* y,
@@ -107,10 +129,13 @@ int tg_embedding_gather(const float* table, const long long* idx, int idx_mod, c
 int tg_embedding_scatter_add(const float* dout, const long long* idx, const float* mask, float* dtable,
                              long long M, int E, tg_stream stream);
 
-/* torch.nn.utils.weight_norm, dim=0 (tcn.py:19-25): w = g*v/||v|| per output row; backward to g and v. */
-int tg_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, tg_stream stream);
+/* torch.nn.utils.weight_norm, dim=0 (tcn.py:19-25): w = g*v/||v|| per output channel, v [N,Cin,taps] in nn.Conv1d
+ * layout.  The effective weight is emitted TAP-MAJOR, w[tap][n][c] (each tap a K-contiguous [N,Cin] GEMM operand), plus
+ * optionally its per-tap transpose wT[tap][c][n] (operand of the data gradient).  Backward reads dw tap-major. */
+int tg_weight_norm_fwd(const float* v, const float* g, float* w, float* wT, float* inv_norm, int N, int Cin, int taps,
+                       tg_stream stream);
 int tg_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg,
-                       int N, int K, tg_stream stream);
+                       int N, int Cin, int taps, tg_stream stream);
 
 /* elementwise helpers: out = a*b ; out = a+b ; dx = dy*mask*(y>0) (ReLU+dropout backward, tcn.py:22-23,28-29,46) */
 int tg_mul(const float* a, const float* b, float* out, long long n, tg_stream stream);

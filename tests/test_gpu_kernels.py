@@ -18,6 +18,14 @@ def dev():
     return torch.device('cuda:0')
 
 
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    from tgb200 import config
+    old = config.set_mode('fp32')
+    yield
+    config.set_mode(old)
+
+
 def _rand(*shape, dev, seed=0, scale=1.0):
     g = torch.Generator(device='cpu').manual_seed(seed + sum(shape))
     return (scale * torch.randn(*shape, generator=g)).to(dev)
@@ -205,14 +213,16 @@ def test_embedding_weightnorm_misc(dev):
     assert rel_l2(dt, ref) < 1e-6
     N, K = 300, 600
     v = _rand(N, K, dev=dev, seed=5).requires_grad_(True); g = (_rand(N, dev=dev, seed=6).abs() + 0.5).requires_grad_(True)
-    w = torch.empty(N, K, device=dev); inv = torch.empty(N, device=dev)
-    ops.weight_norm_fwd(v.data, g.data, w, inv, N, K)
-    ref = O.weight_norm_weight(g.view(N, 1, 1), v.view(N, K // 2, 2)).reshape(N, K)
-    assert rel_l2(w, ref) < 1e-6
-    dw = _rand(N, K, dev=dev, seed=7)
-    ref.backward(dw)
+    Cin, k = K // 2, 2
+    w = torch.empty(k, N, Cin, device=dev); wT = torch.empty(k, Cin, N, device=dev); inv = torch.empty(N, device=dev)
+    ops.weight_norm_fwd(v.data, g.data, w, wT, inv, N, Cin, k)
+    ref = O.weight_norm_weight(g.view(N, 1, 1), v.view(N, Cin, k))           # [N, Cin, k]
+    assert rel_l2(w, ref.permute(2, 0, 1)) < 1e-6                            # tap-major [k][N][Cin]
+    assert rel_l2(wT, ref.permute(2, 1, 0)) < 1e-6
+    dw = _rand(k, N, Cin, dev=dev, seed=7)
+    ref.backward(dw.permute(1, 2, 0))
     dv = torch.zeros(N, K, device=dev); dg = torch.zeros(N, device=dev)
-    ops.weight_norm_bwd(dw, v.data, g.data, inv, dv, dg, N, K)
+    ops.weight_norm_bwd(dw, v.data, g.data, inv, dv, dg, N, Cin, k)
     assert rel_l2(dv, v.grad) < 1e-5 and rel_l2(dg, g.grad) < 1e-5
 
 

@@ -15,7 +15,8 @@ from oracle import trimodal_oracle as O
 from oracle.make_golden import digest, golden_cfg
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+TOL = 1e-4            # fp32 mode (north_star)
+TOL_FAST = 1e-2       # tf32 mode (north_star: "bf16/tf32 mode is held to a stated 1e-2 tolerance")
 ZERO_GRAD_KEYS = ('audio_encoder.feat_extractor.0.bias', 'audio_encoder.feat_extractor.3.bias', 'audio_encoder.feat_extractor.6.bias',
                   'pre_conv.0.bias', 'pre_conv.3.bias', 'pre_conv.1.bias', 'pre_conv.1.running_mean', 'pre_conv.4.running_mean')
 
@@ -24,6 +25,15 @@ ZERO_GRAD_KEYS = ('audio_encoder.feat_extractor.0.bias', 'audio_encoder.feat_ext
 def dev():
     assert torch.cuda.is_available()
     return torch.device('cuda:0')
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    """Every test in this file runs the strict fp32 kernels unless it switches the mode itself."""
+    from tgb200 import config
+    old = config.set_mode('fp32')
+    yield
+    config.set_mode(old)
 
 
 def test_forward_eval_vs_reference_golden(dev):
@@ -229,3 +239,61 @@ def test_cpu_tensors_fail_loudly(dev):
         G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
     with pytest.raises(_lib.TgError):
         D(inp['target'])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fast mode: tcgen05 TF32 tensor-core kernels, tolerance 1e-2 on poses and losses (north_star)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fast_mode_forward_eval_vs_reference_golden(dev):
+    from tgb200 import config
+    config.set_mode('tf32')
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_eval.npz'))
+    args, G, D, _, _ = build_ours(cfg, dev)
+    G.eval(); D.eval()
+    inp = to_dev(synth.make_inputs(cfg, 3, seed=1), dev)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0].to(dev)
+    with torch.no_grad():
+        G.set_noise(eps=eps)
+        poses, z, mu, logvar = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
+        d_fake = D(poses)
+    e = rel_l2(poses, g['poses'])
+    assert e < TOL_FAST, e
+    assert rel_l2(G.engine().ws['txt.feat'].view(3, 34, 32), g['text_feat']) < TOL_FAST
+    assert rel_l2(d_fake, g['d_fake']) < TOL_FAST
+
+
+@pytest.mark.parametrize('B,epoch', [(128, 11), (16, 0)])
+def test_fast_mode_train_iter_full_size_vs_oracle(dev, B, epoch):
+    from tgb200 import config
+    from train_eval import train_gan as TG
+    config.set_mode('tf32')
+    cfg = O.HotPathConfig(n_words=2000, n_speakers=50)
+    args, G, D, gsd, dsd = build_ours(cfg, dev)
+    G.train(); D.train()
+    inp = to_dev(synth.make_inputs(cfg, B, seed=3), dev)
+    noise = synth.make_noise(cfg, B, seed=4, dropout=True)
+    ref = _oracle_step(cfg, epoch, gsd, dsd, inp, noise, dev)
+    g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=[e.to(dev) for e in noise.eps], perm=noise.perm.to(dev),
+                                 g_masks=[masks_to_ours(m, dev) for m in noise.g_masks],
+                                 d_masks=[masks_to_ours(m, dev) for m in noise.d_masks]))
+    ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+    assert set(ret) == set(ref['losses'])
+    for k, v in ret.items():
+        r = ref['losses'][k]
+        assert abs(v - r) <= TOL_FAST * abs(r) + 1e-6, (k, v, r)
+    ig = 1 if epoch > cfg.loss_warmup else 0
+    out = G.engine().ws['g.poses'].view(-1, cfg.n_poses, cfg.pose_dim)[ig * B:(ig + 1) * B]
+    e = rel_l2(out, ref['out'])
+    assert e < TOL_FAST, e
+    worst = ('', 0.0)
+    for k, p in G.named_parameters():
+        r = ref['g_grads'][k]
+        if r.norm() < 1e-6:
+            continue
+        worst = max(worst, (k, rel_l2(p.grad, r)), key=lambda t: t[1])
+    print('fast-mode pose rel-L2 %.2e, worst gradient rel-L2 %s %.2e' % (e, worst[0], worst[1]))
+    assert worst[1] < 5e-2, worst

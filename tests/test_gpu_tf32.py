@@ -1,0 +1,63 @@
+"""GPU: tcgen05 / TMA / TMEM kernels of the fast (TF32) mode against float64 torch.  TF32 keeps a 10-bit mantissa, so a
+K-long dot product is accurate to ~1e-3 relative; the stated fast-mode tolerance on poses/losses is 1e-2 (north_star)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 2e-3
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def _rand(*shape, dev, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed + sum(shape))
+    return (scale * torch.randn(*shape, generator=g)).to(dev)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 32, 32), (4352, 1800, 600), (4352, 1800, 108), (13056, 300, 300), (102, 150, 300), (4352, 32, 300),
+                                   (1000, 64, 960), (4352, 600, 1800), (300, 28, 64)])
+def test_gemm_tf32_plain(dev, M, N, K):
+    from tgb200 import ops
+    a = _rand(M, K, dev=dev); w = _rand(N, K, dev=dev, seed=1, scale=K ** -0.5); b = _rand(N, dev=dev, seed=2)
+    c = torch.full((M, N), float('nan'), device=dev)
+    ops.gemm_tf32(a, w, c, M=M, N=N, K=K, bias=b)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t() + b.double()
+    assert rel_l2(c, ref) < TF32_TOL, rel_l2(c, ref)
+    # epilogue: relu, mask, residual, second relu, accumulate
+    mask = (torch.rand(M, N, device=dev) > 0.3).float() / 0.7
+    res = _rand(M, N, dev=dev, seed=3)
+    c2 = torch.ones(M, N, device=dev)
+    ops.gemm_tf32(a, w, c2, M=M, N=N, K=K, bias=b, act1=ops.ACT_RELU, mask=mask, residual=res, act2=ops.ACT_RELU, accumulate=True)
+    ref2 = torch.relu(torch.relu(ref) * mask.double() + res.double()) + 1.0
+    assert rel_l2(c2, ref2) < TF32_TOL, rel_l2(c2, ref2)
+
+
+@pytest.mark.parametrize('d', [1, 2, 4, 8])
+@pytest.mark.parametrize('B', [3, 128])
+def test_gemm_tf32_causal_two_tap(dev, B, d):
+    """TCN conv (k=2, dilation d, causal) and its anti-causal data gradient as two-accumulator GEMMs."""
+    from tgb200 import ops
+    T, C = 34, 300
+    x = _rand(B, T, C, dev=dev); w = _rand(C, C, 2, dev=dev, seed=1, scale=(2 * C) ** -0.5); b = _rand(C, dev=dev, seed=2)
+    wt = w.permute(2, 0, 1).contiguous()                       # [tap][N][Cin]
+    y = torch.full((B * T, C), float('nan'), device=dev)
+    ops.gemm_tf32(x.view(B * T, C), wt.view(2 * C, C), y, M=B * T, N=C, K=C, taps=2, shift0=-d, T=T, bias=b, act1=ops.ACT_RELU)
+    xr = x.double().transpose(1, 2).requires_grad_(True)
+    ref = torch.relu(F.conv1d(xr, w.double(), b.double(), padding=d, dilation=d)[:, :, :-d])
+    assert rel_l2(y.view(B, T, C), ref.transpose(1, 2)) < TF32_TOL
+    dy = _rand(B, T, C, dev=dev, seed=3)
+    ref.backward(dy.double().transpose(1, 2))
+    dc = (dy * (ref.transpose(1, 2) > 0)).float().contiguous()
+    # dx[t] = dc[t+d] W0 + dc[t] W1 : B operand = W_tap^T  ([tap][Cin][N])
+    wtt = w.permute(2, 1, 0).contiguous()
+    dx = torch.full((B * T, C), float('nan'), device=dev)
+    ops.gemm_tf32(dc.view(B * T, C), wtt.view(2 * C, C), dx, M=B * T, N=C, K=C, taps=2, shift0=d, T=T)
+    assert rel_l2(dx.view(B, T, C), xr.grad.transpose(1, 2)) < 2 * TF32_TOL
