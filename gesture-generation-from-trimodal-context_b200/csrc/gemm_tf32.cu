@@ -28,7 +28,7 @@ struct GemmP {
 };
 
 template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                            const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
@@ -251,8 +251,11 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
     const int p128 = tg_ceil_div(g.N, 128) * 128, p160 = tg_ceil_div(g.N, 160) * 160;
     bn = (p160 < p128) ? 160 : 128;
   }
-  if (bn == 32) return launch<32, 6>(g, s);
-  if (bn == 64) return launch<64, 6>(g, s);
-  if (bn == 128) return launch<128, 5>(g, s);
-  return launch<160, 5>(g, s);
+  // 3-4 stages keep two CTAs resident per SM (shared memory and 2 x 256 TMEM columns), so one CTA's epilogue overlaps
+  // the other's main loop; the two-accumulator mode is limited to BN <= 128 for the same reason (2 x 2 x 128 = 512 columns)
+  if (g.taps == 2 && bn == 160) bn = 128;
+  if (bn == 32) return launch<32, 4>(g, s);
+  if (bn == 64) return launch<64, 4>(g, s);
+  if (bn == 128) return launch<128, 3>(g, s);
+  return launch<160, 3>(g, s);
 }

@@ -271,6 +271,172 @@ __global__ void __launch_bounds__(256, 1) gru_bwd_kernel(const GruBwdP p) {
   }
 }
 
+
+// =====================================================================================================================
+// Small hidden size (H <= 64: the ConvDiscriminator's GRU, multimodal_context_net.py:221-222).  The whole W_hh of one
+// direction fits in one CTA's shared memory, so a CTA owns a 16-clip batch tile for all T steps: no inter-CTA exchange,
+// only __syncthreads per step; gi / saved-gate loads of step s are issued before the matmul of that step so their
+// latency hides behind the FFMA loop.
+// =====================================================================================================================
+constexpr int SB = 4;             // clips per CTA: B/4 x 2 CTAs spread the (transcendental-heavy) gate math over the chip
+constexpr int SBP = SB + 1;
+constexpr int KS = 4;             // the per-step matmul reduction is split 4 ways across the 256 threads
+
+struct GruSmallFwdP {
+  const float* gi; const float* whhT[2]; const float* bhh[2]; float* out; float* saved; long long saved_qstride;
+  int B, T, H;
+};
+
+__global__ void __launch_bounds__(256) gru_small_fwd_kernel(const GruSmallFwdP p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, T = p.T, G3 = 3 * H;
+  const int WS = ((G3 + 3) & ~3) + 4;                 // row pitch of Ws (floats), multiple of 4
+  float* Ws = smem;                                   // [H][WS]    Ws[k][g*H + unit]
+  float* hs = Ws + (size_t)H * WS;                    // [H][SBP]   h_{t-1}
+  float* ghp = hs + (size_t)H * SBP;                  // [KS][192][SBP] partial gh per reduction slice
+  const int tid = threadIdx.x;
+  const int dir = blockIdx.y, b0 = blockIdx.x * SB;
+  const float* wT = p.whhT[dir];
+  for (int i = tid; i < H * G3; i += 256) { const int k = i / G3, r = i - k * G3; Ws[k * WS + r] = __ldg(wT + i); }
+  for (int i = tid; i < H * SBP; i += 256) hs[i] = 0.f;
+  __syncthreads();
+  const int ks = tid >> 6, w = tid & 63;
+  const int rg = w >> 2, bcol = w & 3;                // matmul: rows rg*12 .. +11, clip bcol, k in [ks*KQ, +KQ)
+  const int KQ = (H + KS - 1) / KS;
+  const float* bhh = p.bhh[dir];
+  const long long row2H = 2ll * H;
+  // the (clip, unit) pair this thread owns in the gate phase (H <= 64 -> SB*H <= 256 pairs)
+  const int pbb = tid / H, punit = tid - pbb * H;
+  const int pb = b0 + pbb;
+  const bool pok = tid < SB * H && pb < p.B;
+  float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+  if (pok) { b_r = __ldg(bhh + punit); b_z = __ldg(bhh + H + punit); b_n = __ldg(bhh + 2 * H + punit); }
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    float gir = 0.f, giz = 0.f, gin = 0.f;            // input projections: issued now, consumed after the matmul
+    if (pok) {
+      const float* gp = p.gi + ((long long)pb * T + t) * 6 * H + dir * 3 * H + punit;
+      gir = __ldg(gp); giz = __ldg(gp + H); gin = __ldg(gp + 2 * H);
+    }
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    if (s > 0 && rg * 12 < G3) {
+      const int k1 = min(H, (ks + 1) * KQ);
+#pragma unroll 4
+      for (int k = ks * KQ; k < k1; ++k) {
+        const float hv = hs[k * SBP + bcol];
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12 + 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12 + 8);
+        acc[0] = fmaf(w0.x, hv, acc[0]); acc[1] = fmaf(w0.y, hv, acc[1]); acc[2] = fmaf(w0.z, hv, acc[2]); acc[3] = fmaf(w0.w, hv, acc[3]);
+        acc[4] = fmaf(w1.x, hv, acc[4]); acc[5] = fmaf(w1.y, hv, acc[5]); acc[6] = fmaf(w1.z, hv, acc[6]); acc[7] = fmaf(w1.w, hv, acc[7]);
+        acc[8] = fmaf(w2.x, hv, acc[8]); acc[9] = fmaf(w2.y, hv, acc[9]); acc[10] = fmaf(w2.z, hv, acc[10]); acc[11] = fmaf(w2.w, hv, acc[11]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ghp[(ks * 192 + rg * 12 + i) * SBP + bcol] = acc[i];
+    __syncthreads();
+    if (pok) {
+      float ghr = b_r, ghz = b_z, ghn = b_n;
+#pragma unroll
+      for (int q = 0; q < KS; ++q) {
+        ghr += ghp[(q * 192 + punit) * SBP + pbb];
+        ghz += ghp[(q * 192 + H + punit) * SBP + pbb];
+        ghn += ghp[(q * 192 + 2 * H + punit) * SBP + pbb];
+      }
+      const float hprev = hs[punit * SBP + pbb];
+      const float r = sigmoidf_(gir + ghr);
+      const float z = sigmoidf_(giz + ghz);
+      const float n = tanhf(gin + r * ghn);
+      const float h = (1.f - z) * n + z * hprev;
+      hs[punit * SBP + pbb] = h;
+      const long long o = ((long long)pb * T + t) * row2H + dir * H + punit;
+      p.out[o] = h;
+      if (p.saved) {
+        p.saved[o] = r; p.saved[p.saved_qstride + o] = z; p.saved[2 * p.saved_qstride + o] = n; p.saved[3 * p.saved_qstride + o] = ghn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct GruSmallBwdP {
+  const float* dout; const float* out; const float* saved; long long saved_qstride; const float* whh[2];
+  float* dgi; float* dgh; int B, T, H;
+};
+
+__global__ void __launch_bounds__(256) gru_small_bwd_kernel(const GruSmallBwdP p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, T = p.T, G3 = 3 * H;
+  const int WP = H + 4;
+  float* Wb = smem;                                   // [3H][WP]   W_hh rows as stored
+  float* ds = Wb + (size_t)G3 * WP;                   // [3H][SBP]  dgh of the tile
+  float* dhp = ds + (size_t)G3 * SBP;                 // [KS][SB][H+1] partial dh carried to the previous step
+  const int tid = threadIdx.x;
+  const int dir = blockIdx.y, b0 = blockIdx.x * SB;
+  const float* W = p.whh[dir];
+  for (int i = tid; i < G3 * H; i += 256) { const int r = i / H, k = i - r * H; Wb[r * WP + k] = __ldg(W + i); }
+  for (int i = tid; i < G3 * SBP; i += 256) ds[i] = 0.f;
+  for (int i = tid; i < KS * SB * (H + 1); i += 256) dhp[i] = 0.f;
+  __syncthreads();
+  const int ks = tid >> 6, w = tid & 63;
+  const int kq = w & 15, mb = w >> 4;                 // matmul: columns kq*4..+3, clip mb, rows i in [ks*IQ, +IQ)
+  const int IQ = (G3 + KS - 1) / KS;
+  const long long row2H = 2ll * H;
+  const int pbb = tid / H, punit = tid - pbb * H;
+  const int pb = b0 + pbb;
+  const bool pin = tid < SB * H;
+  const bool pok = pin && pb < p.B;
+  float dhz = 0.f;                                    // dh * z carried by the owner of the (clip, unit) pair
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    const bool tp_ok = tp >= 0 && tp < T;
+    if (pin) {
+      float drp = 0.f, dzp = 0.f, dnr = 0.f;
+      if (pok) {
+        const long long row = (long long)pb * T + t;
+        const long long o = row * row2H + dir * H + punit;
+        // all six operand loads are issued back to back
+        const float l_do = __ldg(p.dout + o), r = __ldg(p.saved + o), z = __ldg(p.saved + p.saved_qstride + o);
+        const float n = __ldg(p.saved + 2 * p.saved_qstride + o), hn = __ldg(p.saved + 3 * p.saved_qstride + o);
+        const float hprev = tp_ok ? __ldg(p.out + ((long long)pb * T + tp) * row2H + dir * H + punit) : 0.f;
+        float dh = l_do + dhz;
+#pragma unroll
+        for (int q = 0; q < KS; ++q) dh += dhp[(q * SB + pbb) * (H + 1) + punit];
+        const float dn = dh * (1.f - z) * (1.f - n * n);
+        dzp = dh * (hprev - n) * z * (1.f - z);
+        drp = dn * hn * r * (1.f - r);
+        dnr = dn * r;
+        dhz = dh * z;
+        float* gp = p.dgi + row * 6 * H + dir * 3 * H + punit;
+        gp[0] = drp; gp[H] = dzp; gp[2 * H] = dn;
+        float* hp = p.dgh + row * 6 * H + dir * 3 * H + punit;
+        hp[0] = drp; hp[H] = dzp; hp[2 * H] = dnr;
+      }
+      ds[punit * SBP + pbb] = drp; ds[(H + punit) * SBP + pbb] = dzp; ds[(2 * H + punit) * SBP + pbb] = dnr;
+    }
+    __syncthreads();
+    if (s + 1 < T) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kq * 4 < H) {
+        const int i1 = min(G3, (ks + 1) * IQ);
+#pragma unroll 4
+        for (int i = ks * IQ; i < i1; ++i) {
+          const float d = ds[i * SBP + mb];
+          const float4 wv = *reinterpret_cast<const float4*>(Wb + i * WP + kq * 4);
+          acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]); acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kq * 4 + e < H) dhp[(ks * SB + mb) * (H + 1) + kq * 4 + e] = acc[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -333,9 +499,21 @@ extern "C" int tg_gru_sync_ints(int B, int H) {
 extern "C" int tg_gru_layer_fwd(const float* gi, const float* whhT_f, const float* whhT_r, const float* bhh_f, const float* bhh_r,
                                 float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream) {
   TG_REQUIRE(gi && whhT_f && whhT_r && bhh_f && bhh_r && out && sync && T > 0, "tg_gru_layer_fwd");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (H <= 64 && (H & 3) == 0) {
+    GruSmallFwdP q;
+    q.gi = gi; q.whhT[0] = whhT_f; q.whhT[1] = whhT_r; q.bhh[0] = bhh_f; q.bhh[1] = bhh_r; q.out = out; q.saved = saved;
+    q.saved_qstride = saved_qstride; q.B = B; q.T = T; q.H = H;
+    const int WS = ((3 * H + 3) & ~3) + 4;
+    const size_t smem = ((size_t)H * WS + (size_t)H * SBP + (size_t)KS * 192 * SBP) * sizeof(float);
+    cudaError_t e2 = cudaFuncSetAttribute(gru_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) { tg_set_error("tg_gru_layer_fwd(small): smem attr: %s", cudaGetErrorString(e2)); return -3; }
+    gru_small_fwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), 256, smem, s>>>(q);
+    TG_CHECK_LAUNCH("tg_gru_layer_fwd(small)");
+    return 0;
+  }
   GruPlan pl;
   if (make_plan(B, H, &pl, "tg_gru_layer_fwd")) return -1;
-  cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd: memset: %s", cudaGetErrorString(e)); return -2; }
   GruFwdP p;
@@ -361,9 +539,20 @@ extern "C" int tg_gru_layer_bwd(const float* dout, const float* out, const float
                                 const float* whh_f, const float* whh_r, float* dgi, float* dgh, float* partial, int* sync,
                                 int B, int T, int H, tg_stream stream) {
   TG_REQUIRE(dout && out && saved && whh_f && whh_r && dgi && dgh && partial && sync && T > 0, "tg_gru_layer_bwd");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (H <= 64 && (H & 3) == 0) {
+    GruSmallBwdP q;
+    q.dout = dout; q.out = out; q.saved = saved; q.saved_qstride = saved_qstride; q.whh[0] = whh_f; q.whh[1] = whh_r;
+    q.dgi = dgi; q.dgh = dgh; q.B = B; q.T = T; q.H = H;
+    const size_t smem = ((size_t)3 * H * (H + 4) + (size_t)3 * H * SBP + (size_t)KS * SB * (H + 1)) * sizeof(float);
+    cudaError_t e2 = cudaFuncSetAttribute(gru_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) { tg_set_error("tg_gru_layer_bwd(small): smem attr: %s", cudaGetErrorString(e2)); return -3; }
+    gru_small_bwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), 256, smem, s>>>(q);
+    TG_CHECK_LAUNCH("tg_gru_layer_bwd(small)");
+    return 0;
+  }
   GruPlan pl;
   if (make_plan(B, H, &pl, "tg_gru_layer_bwd")) return -1;
-  cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd: memset: %s", cudaGetErrorString(e)); return -2; }
   GruBwdP p;

@@ -114,9 +114,9 @@ class _TraceLib:
             if len(args) != len(self._protos[name][1]):
                 raise TypeError('%s: expected %d arguments, got %d' % (name, len(self._protos[name][1]), len(args)))
             trace.append(name)
-            if name == 'tg_gru_sync_ints':
+            if name in ('tg_gru_sync_ints', 'tg_gru_tf32_sync_ints'):
                 return 64
-            if name == 'tg_gru_bwd_scratch_floats':
+            if name in ('tg_gru_bwd_scratch_floats', 'tg_gru_bwd_tf32_scratch_floats'):
                 return 2 * 2 * args[0] * 8 * ((args[1] + 3) // 4 * 4)
             return 0
         return fn

@@ -89,6 +89,11 @@ class GruPlan:
             for kind in ('weight_ih', 'bias_ih'):
                 assert arena.adjacent(f'{prefix}.{kind}_l{l}', f'{prefix}.{kind}_l{l}_reverse')
 
+    def tc(self):
+        """Tensor-core recurrence kernels are used in fast mode for the hidden sizes they support."""
+        # H <= 64 (the discriminator) runs the single-CTA-per-tile fp32 kernels in both modes: no inter-CTA stepping at all
+        return config.fast() and self.H % 4 == 0 and 64 < self.H <= 384
+
     def _w(self, kind, l, rev=False):
         return self.a.view(f'{self.pre}.{kind}_l{l}' + ('_reverse' if rev else ''))
 
@@ -112,14 +117,19 @@ class GruPlan:
         H, ws, tag = self.H, self.ws, self.tag
         M = B * T
         gi = ws.get(f'{tag}.gi', (M, 6 * H))
-        sync = ws.get(f'{tag}.sync', (max(ops.gru_sync_ints(B, H), 1),), torch.int32)
+        tc = self.tc()
+        sync = ws.get(f'{tag}.sync', (max(ops.gru_tf32_sync_ints(B, H) if tc else ops.gru_sync_ints(B, H), 1),), torch.int32)
         inp, K = x, self.I
         for l in range(self.L):
             mm_nt(inp, self._w('weight_ih', l), gi, M=M, N=6 * H, K=K, bias=self._w('bias_ih', l))
             out = ws.get(f'{tag}.out{l}', (M, 2 * H))
             saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
-            ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
-                              out, saved, M * 2 * H, sync, B, T, H)
+            if tc:
+                ops.gru_layer_fwd_tf32(gi, self._w('weight_hh', l), self._w('weight_hh', l, True), self._w('bias_hh', l),
+                                       self._w('bias_hh', l, True), out, saved, M * 2 * H, sync, B, T, H)
+            else:
+                ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
+                                  out, saved, M * 2 * H, sync, B, T, H)
             if masks is not None and l < self.L - 1 and masks[l] is not None:
                 drop = ws.get(f'{tag}.drop{l}', (M, 2 * H))
                 ops.mul(out, masks[l], drop, M * 2 * H)
@@ -139,14 +149,19 @@ class GruPlan:
         r0, r1 = lo * T, hi * T
         dgi = ws.get(f'{tag}.dgi', (Mb, 6 * H))
         dgh = ws.get(f'{tag}.dgh', (Mb, 6 * H))
-        partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_scratch_floats(Bb, H), 1),))
-        sync = ws.get(f'{tag}.bsync', (max(ops.gru_sync_ints(Bb, H), 1),), torch.int32)
+        tc = self.tc()
+        partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_tf32_scratch_floats(Bb, H) if tc else ops.gru_bwd_scratch_floats(Bb, H), 1),))
+        sync = ws.get(f'{tag}.bsync', (max(ops.gru_tf32_sync_ints(Bb, H) if tc else ops.gru_sync_ints(Bb, H), 1),), torch.int32)
         dx = None
         for l in range(self.L - 1, -1, -1):
             out = ws[f'{tag}.out{l}'][r0:r1]
             saved = ws[f'{tag}.saved{l}'][:, r0:r1]          # plane stride stays M_all*2H
-            ops.gru_layer_bwd(dout, out, saved[0], M_all * 2 * H, self._w('weight_hh', l), self._w('weight_hh', l, True), dgi, dgh,
-                              partial, sync, Bb, T, H)
+            if tc:
+                ops.gru_layer_bwd_tf32(dout, out, saved[0], M_all * 2 * H, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], dgi, dgh,
+                                       partial, sync, Bb, T, H)
+            else:
+                ops.gru_layer_bwd(dout, out, saved[0], M_all * 2 * H, self._w('weight_hh', l), self._w('weight_hh', l, True), dgi, dgh,
+                                  partial, sync, Bb, T, H)
             K = self.I if l == 0 else 2 * H
             if l == 0:
                 inp = x[r0:r1]

@@ -267,6 +267,24 @@ def gru_layer_bwd(dout, out, saved, saved_qstride, whh_f, whh_r, dgi, dgh, parti
                                 _p(sync), B, T, H, _s()), 'tg_gru_layer_bwd'); _count(2)
 
 
+def gru_tf32_sync_ints(B, H):
+    return _L().tg_gru_tf32_sync_ints(B, H)
+
+
+def gru_bwd_tf32_scratch_floats(B, H):
+    return _L().tg_gru_bwd_tf32_scratch_floats(B, H)
+
+
+def gru_layer_fwd_tf32(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, sync, B, T, H):
+    check(_L().tg_gru_layer_fwd_tf32(_p(gi), _p(whh_f), _p(whh_r), _p(bhh_f), _p(bhh_r), _p(out), _p(saved), saved_qstride, _p(sync),
+                                     B, T, H, _s()), 'tg_gru_layer_fwd_tf32'); _count(2)
+
+
+def gru_layer_bwd_tf32(dout, out, saved, saved_qstride, whhT_f, whhT_r, dgi, dgh, partial, sync, B, T, H):
+    check(_L().tg_gru_layer_bwd_tf32(_p(dout), _p(out), _p(saved), saved_qstride, _p(whhT_f), _p(whhT_r), _p(dgi), _p(dgh), _p(partial),
+                                     _p(sync), B, T, H, _s()), 'tg_gru_layer_bwd_tf32'); _count(2)
+
+
 # ------------------------------------------------------------------------------------------ losses / optimiser / rng
 def gen_losses(out, target, out_rand, z, z_rand, mu, logvar, B, TD, Z, w_reg, w_div, w_kld, scalars, d_out, dmu, dlogvar):
     check(_L().tg_gen_losses(_p(out), _p(target), _p(out_rand), _p(z), _p(z_rand), _p(mu), _p(logvar), B, TD, Z, w_reg, w_div, w_kld,

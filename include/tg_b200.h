@@ -188,6 +188,18 @@ int tg_gru_layer_bwd(const float* dout, const float* out, const float* saved, lo
                      int B, int T, int H, tg_stream stream);
 int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream);
 
+/* Fast-mode recurrence: the same persistent kernels with the per-step product on tcgen05 tensor cores (TF32 operands,
+ * fp32 accumulate in TMEM, W_hh resident in shared memory via TMA).  NOTE the weight layouts are swapped with respect
+ * to the fp32 kernels: forward takes weight_hh as stored [3H,H], backward takes its transpose [H,3H].
+ * H % 4 == 0, 32 <= H <= 384.  sync: int[tg_gru_tf32_sync_ints(B,H)], partial: tg_gru_bwd_tf32_scratch_floats(B,H). */
+int tg_gru_tf32_sync_ints(int B, int H);
+size_t tg_gru_bwd_tf32_scratch_floats(int B, int H);
+int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
+                          float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream);
+int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const float* saved, long long saved_qstride,
+                          const float* whhT_f, const float* whhT_r, float* dgi, float* dgh, float* partial, int* sync,
+                          int B, int T, int H, tg_stream stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Losses of train_iter_gan (train_gan.py:41,53-56,67-82), forward value + gradient in one pass.
  * scalars (fp64, caller zeroes): [0] sum huber(out,target;0.1)  [1] sum_i div_i  [2] sum (1+lv-mu^2-e^lv)

@@ -61,3 +61,52 @@ def test_gemm_tf32_causal_two_tap(dev, B, d):
     dx = torch.full((B * T, C), float('nan'), device=dev)
     ops.gemm_tf32(dc.view(B * T, C), wtt.view(2 * C, C), dx, M=B * T, N=C, K=C, taps=2, shift0=d, T=T)
     assert rel_l2(dx.view(B, T, C), xr.grad.transpose(1, 2)) < 2 * TF32_TOL
+
+
+@pytest.mark.parametrize('B,T,I,H', [(3, 34, 108, 300), (128, 34, 108, 300), (384, 34, 40, 300), (128, 28, 8, 64), (5, 7, 16, 200), (600, 5, 16, 300)])
+def test_gru_layer_tensor_core_fwd_bwd(dev, B, T, I, H):
+    """tcgen05 recurrence kernels (W_hh resident in smem, TMEM accumulators) vs the float64 oracle cell."""
+    from oracle import trimodal_oracle as O
+    from test_gpu_kernels import _gru_params
+    from tgb200 import ops
+    p = _gru_params(I, H, dev)
+    x = _rand(B, T, I, dev=dev)
+    M = B * T
+    wih = torch.cat(p['wih'], 0).contiguous(); bih = torch.cat(p['bih'], 0).contiguous()
+    gi = torch.empty(M, 6 * H, device=dev)
+    ops.linear(x.view(M, I), wih, bih, gi, M=M, K=I, N=6 * H)
+    out = torch.full((M, 2 * H), float('nan'), device=dev)
+    saved = torch.empty(4, M, 2 * H, device=dev)
+    sync = torch.zeros(max(ops.gru_tf32_sync_ints(B, H), 1), dtype=torch.int32, device=dev)
+    ops.gru_layer_fwd_tf32(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, sync, B, T, H)
+    torch.cuda.synchronize()
+    xd = x.double().requires_grad_(True)
+    pd = {k: [t.double().requires_grad_(True) for t in v] for k, v in p.items()}
+    ref = torch.cat([O.gru_cell_sequence(xd, pd['wih'][d], pd['whh'][d], pd['bih'][d], pd['bhh'][d], bool(d)) for d in (0, 1)], dim=2)
+    e = rel_l2(out, ref)
+    assert e < TF32_TOL, e
+    lo, hi = (0, B) if B < 8 else (B // 4, B // 4 + max(B // 3, 1))
+    Bb = hi - lo
+    dout = _rand(B, T, 2 * H, dev=dev, seed=9)
+    dsel = torch.zeros_like(dout); dsel[lo:hi] = dout[lo:hi]
+    ref.backward(dsel.double())
+    Mb = Bb * T
+    dgi = torch.full((Mb, 6 * H), float('nan'), device=dev); dgh = torch.full((Mb, 6 * H), float('nan'), device=dev)
+    partial = torch.empty(max(ops.gru_bwd_tf32_scratch_floats(Bb, H), 1), device=dev)
+    bsync = torch.zeros(max(ops.gru_tf32_sync_ints(Bb, H), 1), dtype=torch.int32, device=dev)
+    whhT = [p['whh'][d].t().contiguous() for d in (0, 1)]
+    ops.gru_layer_bwd_tf32(dout[lo:hi].contiguous().view(Mb, 2 * H), out[lo * T:hi * T], saved[0, lo * T:hi * T], M * 2 * H, whhT[0], whhT[1],
+                           dgi, dgh, partial, bsync, Bb, T, H)
+    torch.cuda.synchronize()
+    dx = torch.empty(Mb, I, device=dev)
+    ops.linear_dgrad(dgi, wih, dx, M=Mb, K=I, N=6 * H)
+    e = rel_l2(dx, xd.grad[lo:hi].reshape(Mb, I))
+    assert e < 3 * TF32_TOL, e
+    o_sl = out[lo * T:hi * T]
+    for d in (0, 1):
+        dwhh = torch.zeros(3 * H, H, device=dev); dbhh = torch.zeros(3 * H, device=dev)
+        ops.conv_wgrad(o_sl[:, d * H:], dgh[:, d * 3 * H:], dwhh, B=Bb, Tin=T, Tout=T, N=3 * H, Cin=H, taps=1, pad=(1 if d == 0 else -1),
+                       lda=2 * H, ldg=6 * H, ldw=H, dbias=dbhh)
+        e = rel_l2(dwhh, pd['whh'][d].grad)
+        assert e < 3 * TF32_TOL, (d, e)
+        assert rel_l2(dbhh, pd['bhh'][d].grad) < 3 * TF32_TOL
