@@ -28,6 +28,37 @@ __device__ __forceinline__ void spin_until(const int* counter, int target) {
 }
 __device__ __forceinline__ void epi_bar512() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// optional per-step phase stamps of CTA (0,0,0) (tg_debug_gru_trace): trace[step*16 + slot] = %globaltimer
+__device__ __forceinline__ void stamp(long long* trace, int step, int slot) {
+  if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+    trace[step * 16 + slot] = (long long)t;
+  }
+}
+
+// Loads as volatile asm: the compiler may neither sink them to their first use nor move them across the (volatile) barrier
+// waits, so a batch of loads issued before a wait really is in flight during the wait.
+__device__ __forceinline__ float ldv_nc(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldv_cg(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldv_nc4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldv_cg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -45,6 +76,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 struct FwdP {
   const float* gi; const float* bhh[2]; float* out; float* saved; long long saved_qstride; int* sync;
   int B, T, H, u, UC, NB, ntiles, nkc;
+  long long* trace;
 };
 
 template <int BT>
@@ -107,7 +139,9 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
       for (int s = 1; s < T; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
         const int tp = dir == 0 ? t - 1 : t + 1;
+        stamp(p.trace, s, 0);
         spin_until(counter, p.UC * s);
+        stamp(p.trace, s, 1);
         fence_proxy_async_all();
         for (int tile = by; tile < p.ntiles; tile += p.NB, ++it) {
           if (it > 0) mbar_wait(epi_done, (uint32_t)((it - 1) & 1));
@@ -115,6 +149,7 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
             mbar_expect_tx(&h_full[kc], (uint32_t)H_CHUNK);
             tma_load_3d(Ht + (size_t)kc * H_CHUNK, tmH, &h_full[kc], kc * 32, tp, tile * BT);
           }
+          stamp(p.trace, s, 2);
         }
       }
     }
@@ -164,15 +199,16 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
             const int b = b0 + bb, unit = u0 + jj;
             if (b < p.B && unit < H) {
               const float* gip = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + unit;
-              gir[e] = __ldg(gip); giz[e] = __ldg(gip + H); gin[e] = __ldg(gip + 2 * H);
-              bhh_r_[e] = __ldg(bhh + unit); bhh_z_[e] = __ldg(bhh + H + unit); bhh_n_[e] = __ldg(bhh + 2 * H + unit);
-              if (s > 0) hpv[e] = __ldcg(p.out + ((long long)b * T + tp) * row2H + dir * H + unit);
+              gir[e] = ldv_nc(gip); giz[e] = ldv_nc(gip + H); gin[e] = ldv_nc(gip + 2 * H);
+              bhh_r_[e] = ldv_nc(bhh + unit); bhh_z_[e] = ldv_nc(bhh + H + unit); bhh_n_[e] = ldv_nc(bhh + 2 * H + unit);
+              if (s > 0) hpv[e] = ldv_cg(p.out + ((long long)b * T + tp) * row2H + dir * H + unit);
             }
           }
         }
         if (s > 0) {
           if (warp < 6) {
             mbar_wait(tmem_full, (uint32_t)(it & 1));
+            if (etid == 0) stamp(p.trace, s, 3);
             tc_fence_after();
             float v[BT];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -185,6 +221,7 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
             tc_fence_before();
           }
           epi_bar512();
+          if (etid == 0) stamp(p.trace, s, 4);
         }
         // pass 2: gates.  The global loads (gi, h_{t-1}) were issued in pass 1 (before the TMEM wait), so nothing
         // here depends on a fresh memory round trip.
@@ -203,10 +240,8 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
           const float h = (1.f - z) * n + z * hpv[e];
           const long long o = ((long long)b * T + t) * row2H + dir * H + unit;
           p.out[o] = h;
-          if (p.saved) {
-            p.saved[o] = r; p.saved[p.saved_qstride + o] = z; p.saved[2 * p.saved_qstride + o] = n;
-            p.saved[3 * p.saved_qstride + o] = ghn;
-          }
+          // r, z, n, hn are only needed by the backward pass: kept in registers, stored after h_t has been published
+          gir[e] = r; giz[e] = z; gin[e] = n; hpv[e] = ghn;
         }
         if (s > 0) {
           fence_proxy_async_smem();      // ghs (generic proxy) is about to be overwritten by the next TMA (async proxy)
@@ -214,12 +249,29 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
           if (etid == 0) mbar_arrive(epi_done);
           ++it;
         }
-      }
-      if (s + 1 < T) {
-        __threadfence();
-        fence_proxy_async_all();         // h_t is read by other CTAs through TMA (async proxy)
-        epi_bar512();
-        if (etid == 0) atomicAdd(counter, 1);
+        const bool last_tile = tile + p.NB >= p.ntiles;
+        if (last_tile && s + 1 < T) {
+          // publish h_t before the (off-critical-path) stores of the saved gates of this tile
+          if (etid == 0) stamp(p.trace, s, 5);
+          __threadfence();
+          fence_proxy_async_all();         // h_t is read by other CTAs through TMA (async proxy)
+          if (etid == 0) stamp(p.trace, s, 6);
+          epi_bar512();
+          if (etid == 0) { atomicAdd(counter, 1); stamp(p.trace, s, 7); }
+        }
+        if (p.saved) {
+#pragma unroll
+          for (int e = 0; e < NP; ++e) {
+            const int i = etid + 512 * e;
+            if (i >= BT * u) continue;
+            const int bb = i / u, jj = i - bb * u;
+            const int b = b0 + bb, unit = u0 + jj;
+            if (b >= p.B || unit >= H) continue;
+            const long long o = ((long long)b * T + t) * row2H + dir * H + unit;
+            p.saved[o] = gir[e]; p.saved[p.saved_qstride + o] = giz[e]; p.saved[2 * p.saved_qstride + o] = gin[e];
+            p.saved[3 * p.saved_qstride + o] = hpv[e];
+          }
+        }
       }
     }
   }
@@ -235,6 +287,7 @@ struct BwdP {
   const float* dout; const float* out; const float* saved; long long saved_qstride;
   float* dgi; float* dgh; float* partial; int* sync;
   int B, T, H, UC, NB, HP, nh, Nh;      // nh N-halves of Nh columns each (nh*Nh >= H)
+  long long* trace;
 };
 constexpr int BU = 32;                   // hidden units per CTA in the backward kernel (one 128-byte K chunk per gate)
 constexpr int MAXUC = 12;                // H <= 384
@@ -339,12 +392,12 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
       for (int g4 = 0; g4 < 4; ++g4) {
         ld_do[g4] = ld_r[g4] = ld_z[g4] = ld_n[g4] = ld_hn[g4] = ld_hp[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b_ok && g4 * 4 < nu) {
-          ld_do[g4] = __ldg(reinterpret_cast<const float4*>(p.dout + o) + g4);
-          ld_r[g4] = __ldg(reinterpret_cast<const float4*>(p.saved + o) + g4);
-          ld_z[g4] = __ldg(reinterpret_cast<const float4*>(p.saved + p.saved_qstride + o) + g4);
-          ld_n[g4] = __ldg(reinterpret_cast<const float4*>(p.saved + 2 * p.saved_qstride + o) + g4);
-          ld_hn[g4] = __ldg(reinterpret_cast<const float4*>(p.saved + 3 * p.saved_qstride + o) + g4);
-          if (tp_ok) ld_hp[g4] = __ldg(reinterpret_cast<const float4*>(p.out + op) + g4);
+          ld_do[g4] = ldv_nc4(p.dout + o + g4 * 4);
+          ld_r[g4] = ldv_nc4(p.saved + o + g4 * 4);
+          ld_z[g4] = ldv_nc4(p.saved + p.saved_qstride + o + g4 * 4);
+          ld_n[g4] = ldv_nc4(p.saved + 2 * p.saved_qstride + o + g4 * 4);
+          ld_hn[g4] = ldv_nc4(p.saved + 3 * p.saved_qstride + o + g4 * 4);
+          if (tp_ok) ld_hp[g4] = ldv_nc4(p.out + op + g4 * 4);
         }
       }
       if (b_ok && nu > 0 && s + 1 < T) {
@@ -354,15 +407,21 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
         prefetch_l2(p.dout + on); prefetch_l2(p.saved + on); prefetch_l2(p.saved + p.saved_qstride + on);
         prefetch_l2(p.saved + 2 * p.saved_qstride + on); prefetch_l2(p.saved + 3 * p.saved_qstride + on);
       }
+      if (etid == 0) stamp(p.trace, s, 0);
       if (s > 0) {
         if (etid == 0) spin_until(counter, p.UC * s);
         epi_bar256();
       }
+      if (etid == 0) stamp(p.trace, s, 1);
       float carry[HU];
 #pragma unroll
       for (int j = 0; j < HU; ++j) carry[j] = dhc[j];
       if (s > 0 && b_ok) {
-        const float* Pin = p.partial + (long long)((s - 1) & 1) * pstride_parity + ((long long)dir * p.B + b) * p.UC * HP + uu0;
+        // partial layout [parity][dir][chunk cc][k4 = unit/4][clip b][4]: producers and consumers both touch it with
+        // consecutive lanes = consecutive clips, i.e. fully coalesced 16-byte accesses
+        const long long k4n = HP / 4;
+        const float* Pin = p.partial + (long long)((s - 1) & 1) * pstride_parity + (long long)dir * p.UC * k4n * p.B * 4 +
+                           ((long long)(uu0 / 4) * p.B + b) * 4;
         // four rounds (one float4 of units each); within a round all UC partial loads are issued before the first add
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
@@ -371,7 +430,7 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
 #pragma unroll
             for (int cc = 0; cc < MAXUC; ++cc) {
               tv[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (cc < p.UC) tv[cc] = __ldcg(reinterpret_cast<const float4*>(Pin + (long long)cc * HP) + g4);
+              if (cc < p.UC) tv[cc] = ldv_cg4(Pin + ((long long)cc * k4n + g4) * p.B * 4);
             }
 #pragma unroll
             for (int cc = 0; cc < MAXUC; ++cc) {
@@ -380,6 +439,7 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
           }
         }
       }
+      if (etid == 0) { stamp(carry[0] == 12345.678f ? nullptr : p.trace, s, 2); }
       float* gp = p.dgi + row * 6 * H + dir * 3 * H + uu0;
       float* hp = p.dgh + row * 6 * H + dir * 3 * H + uu0;
 #pragma unroll
@@ -414,14 +474,18 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
         *reinterpret_cast<float4*>(At + 2 * A_CHUNK + off) = make_float4(dnr4[0], dnr4[1], dnr4[2], dnr4[3]);
       }
       if (s + 1 < T) {
+        if (etid == 0) stamp(p.trace, s, 3);
         fence_proxy_async_smem();
         tc_fence_before();
         epi_bar256();
         if (etid == 0) mbar_arrive(a_ready);
+        if (etid == 0) stamp(p.trace, s, 4);
         // partial dh_{prev}[b, 0..H) of this chunk -> L2 (each of the two threads of a row stores half of the columns)
         mbar_wait(tmem_full, (uint32_t)(s & 1));
+        if (etid == 0) stamp(p.trace, s, 5);
         tc_fence_after();
-        float* Pout = p.partial + (long long)(s & 1) * pstride_parity + (((long long)dir * p.B + b) * p.UC + c) * HP;
+        const long long k4n = HP / 4;
+        float* Pout = p.partial + (long long)(s & 1) * pstride_parity + ((long long)dir * p.UC + c) * k4n * p.B * 4 + (long long)b * 4;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
           float v[32];
@@ -430,14 +494,17 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
           if (b_ok) {
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4)
-              if (ch * 32 + j4 < HP) __stcg(reinterpret_cast<float4*>(Pout + ch * 32 + j4), make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]));
+              if (ch * 32 + j4 < HP)
+                __stcg(reinterpret_cast<float4*>(Pout + (long long)(ch * 8 + (j4 >> 2)) * p.B * 4), make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]));
           }
           __syncwarp();
         }
+        if (etid == 0) stamp(p.trace, s, 6);
         tc_fence_before();
         __threadfence();
+        if (etid == 0) stamp(p.trace, s, 7);
         epi_bar256();
-        if (etid == 0) atomicAdd(counter, 1);
+        if (etid == 0) { atomicAdd(counter, 1); stamp(p.trace, s, 8); }
       }
     }
   }
@@ -486,6 +553,8 @@ int map_h3d(CUtensorMap* m, const float* base, int B, int T, int H, int box_b, c
   return 0;
 }
 
+long long* g_trace = nullptr;
+
 struct FwdPlan { int u, UC, BT, ntiles, NB, nkc; };
 int fwd_plan(int B, int H, FwdPlan* pl) {
   if (H < 32 || H > 384 || (H & 3)) return -1;
@@ -521,6 +590,11 @@ int launch_fwd(const CUtensorMap* maps, const FwdP& p, const FwdPlan& pl, cudaSt
 
 }  // namespace
 
+extern "C" int tg_debug_gru_trace(long long* device_buf) {
+  g_trace = device_buf;
+  return 0;
+}
+
 extern "C" int tg_gru_tf32_sync_ints(int B, int H) {
   FwdPlan pl;
   if (fwd_plan(B, H, &pl)) return -1;
@@ -545,6 +619,7 @@ extern "C" int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const 
   FwdP p;
   p.gi = gi; p.bhh[0] = bhh_f; p.bhh[1] = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.sync = sync;
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.UC = pl.UC; p.NB = pl.NB; p.ntiles = pl.ntiles; p.nkc = pl.nkc;
+  p.trace = g_trace;
   if (pl.BT == 16) return launch_fwd<16>(maps, p, pl, s);
   if (pl.BT == 32) return launch_fwd<32>(maps, p, pl, s);
   return launch_fwd<48>(maps, p, pl, s);
@@ -575,7 +650,7 @@ extern "C" int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const 
   if ((rc = map_2d(&maps[0], whhT_f, H, 3ll * H, 3ll * H, p.Nh, "tg_gru_layer_bwd_tf32(W^T)"))) return rc;
   if ((rc = map_2d(&maps[1], whhT_r, H, 3ll * H, 3ll * H, p.Nh, "tg_gru_layer_bwd_tf32(W^T)"))) return rc;
   p.dout = dout; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.dgi = dgi; p.dgh = dgh; p.partial = partial; p.sync = sync;
-  p.B = B; p.T = T; p.H = H;
+  p.B = B; p.T = T; p.H = H; p.trace = g_trace;
   const size_t smem = (size_t)3 * p.nh * p.Nh * 128 + 3 * 128 * 128 + 8 * 8 + 16 + 1024;
   TG_REQUIRE(smem <= (size_t)tg_max_smem_optin(), "tg_gru_layer_bwd_tf32");
   e = cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -111,6 +111,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;          // layout_type = SWIZZLE_128B
   return d;
 }
+// MN-major 32-bit operands (tf32 read "transposed"): canonical atom = 4 K-rows x 128 B with Swizzle<2,5,2>
+// (cute Layout_MN_SW128_32B_Atom; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), layout_type = SWIZZLE_128B_BASE32B.
+// lbo = bytes between 32-element groups along MN, sbo = bytes between 4-row groups along K.
+__device__ __forceinline__ uint64_t smem_desc_mn_tf32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // version = 1
+  d |= (uint64_t)1 << 61;          // layout_type = SWIZZLE_128B_BASE32B
+  return d;
+}
 // instruction descriptor: tf32 x tf32 -> f32, dense; a_major/b_major: 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |

@@ -59,6 +59,13 @@ class GemmTf32(ctypes.Structure):
                 ('act2', ctypes.c_int), ('accumulate', ctypes.c_int)]
 
 
+class WgradTf32(ctypes.Structure):
+    """tg_wgrad_tf32_t (include/tg_b200.h)."""
+    _fields_ = [('G', ctypes.c_void_p), ('ldg', ctypes.c_int), ('X', ctypes.c_void_p), ('ldx', ctypes.c_int),
+                ('dW', ctypes.c_void_p), ('ldw', ctypes.c_int), ('dbias', ctypes.c_void_p),
+                ('B', ctypes.c_int), ('T', ctypes.c_int), ('N', ctypes.c_int), ('Cin', ctypes.c_int), ('shift', ctypes.c_int)]
+
+
 def _ctype(decl: str):
     d = decl.strip()
     if '*' in d:

@@ -62,6 +62,19 @@ def mm_nn(dY, W, Wt, dX, *, M, N, K, **epi):
         ops.linear_dgrad(dY, W, dX, M=M, K=K, N=N, **epi)
 
 
+def wgrad(X, G, dW, *, B, T, N, Cin, shift=0, ldx=None, ldg=None, ldw=None, dbias=None):
+    """dW[N,Cin] += sum_{b,t} G[(b,t), :]^T X[(b,t+shift), :] (rows outside the clip are zero): tcgen05 TF32 kernel in fast mode
+    when TMA can describe the operands, fp32 FFMA split-K kernel otherwise."""
+    ldx = Cin if ldx is None else ldx
+    ldg = N if ldg is None else ldg
+    if (config.fast() and Cin >= 32 and N >= 16 and ldx % 4 == 0 and ldg % 4 == 0 and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0
+            and (shift == 0 or T <= 40)):
+        ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=ldx, ldw=ldw, dbias=dbias)
+    else:
+        ops.conv_wgrad(X, G, dW, B=B, Tin=T, Tout=T, N=N, Cin=Cin, taps=1, pad=-shift, lda=ldx, ldg=ldg, ldw=Cin if ldw is None else ldw,
+                       dbias=dbias)
+
+
 def _conv_out(tin, k, stride, pad=0, dil=1):
     return (tin + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
@@ -169,11 +182,11 @@ class GruPlan:
                 inp = ws[f'{tag}.drop{l - 1}'][r0:r1]
             else:
                 inp = ws[f'{tag}.out{l - 1}'][r0:r1]
-            ops.conv_wgrad(inp, dgi, self._g('weight_ih', l), B=1, Tin=Mb, Tout=Mb, N=6 * H, Cin=K, ldw=K, dbias=self._g('bias_ih', l))
+            wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
             for d in (0, 1):
                 # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
-                ops.conv_wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, Tin=T, Tout=T, N=3 * H, Cin=H,
-                               taps=1, pad=(1 if d == 0 else -1), lda=2 * H, ldg=6 * H, ldw=H, dbias=self._g('bias_hh', l, bool(d)))
+                wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
+                      shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
             if l > 0 or need_dx:
                 dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
                 m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
@@ -379,6 +392,12 @@ class GeneratorEngine:
                           bias=bias, **epi)
 
     @staticmethod
+    def _tcn_wgrad(x, dy, dw_tap, dbias, B, T, cin, cout, k, d):
+        """dw_tap[j][n][c] += sum dy[(b,t), n] x[(b, t - (k-1-j)*d), c] for every tap j (tap-major gradient buffer)."""
+        for j in range(k):
+            wgrad(x, dy, dw_tap[j * cout * cin:], B=B, T=T, N=cout, Cin=cin, shift=-(k - 1 - j) * d, dbias=dbias if j == 0 else None)
+
+    @staticmethod
     def _tcn_dgrad(dy, w_tap, wT_tap, dx, B, T, cin, cout, k, d, **epi):
         """Data gradient of _tcn_conv: dx[t] = sum_j dy[t + (k-1-j)*d] W_j (anti-causal)."""
         if k == 2 and wT_tap is not None and _tf32_ok(dy, cout, wT_tap, cout, cout):
@@ -395,7 +414,7 @@ class GeneratorEngine:
         k = self.tcn_k
         sl = lambda t: t[r0:r1] if t is not None else None
         xl = ws[f'txt.x{self.n_tcn - 1}'][r0:r1]
-        ops.linear_wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), self.G('text_encoder.decoder.bias'), M=Mb, K=H, N=32)
+        wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), B=Bb, T=T, N=32, Cin=H, dbias=self.G('text_encoder.decoder.bias'))
         dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dc = ws.get('txt.dC', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
         mm_nn(d_feat, self.P('text_encoder.decoder.weight'), ws.t.get('T.text_encoder.decoder.weight') if config.fast() else None, dx,
               M=Mb, N=32, K=H)
@@ -411,15 +430,13 @@ class GeneratorEngine:
             ops.relu_mask_bwd(dpre, y2, m2, dc, Mb * H)                        # dropout2 + relu2
             dw = ws.get('tcn.dw', (k * H * max(cin, H),)); dw.zero_()                 # tap-major [k][H][cin]
             wT = lambda j: ws.t.get(f'tcn.wT{i}_{j}') if config.fast() else None
-            ops.conv_wgrad(y1, dc, dw, B=Bb, Tin=T, Tout=T, N=H, Cin=H, taps=k, dil=d, pad=(k - 1) * d, ldw=H, wsj=H * H, wsc=1,
-                           dbias=self.G(q + '.conv2.bias'))
+            self._tcn_wgrad(y1, dc, dw, self.G(q + '.conv2.bias'), Bb, T, H, H, k, d)
             ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
                                 self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H, k)
             self._tcn_dgrad(dc, ws[f'tcn.w{i}_2'], wT(2), dy1, Bb, T, H, H, k, d)
             ops.relu_mask_bwd(dy1, y1, m1, dc, Mb * H)                         # dropout1 + relu1
             dw.zero_()
-            ops.conv_wgrad(xin, dc, dw, B=Bb, Tin=T, Tout=T, N=H, Cin=cin, taps=k, dil=d, pad=(k - 1) * d, ldw=cin, wsj=H * cin, wsc=1,
-                           dbias=self.G(q + '.conv1.bias'))
+            self._tcn_wgrad(xin, dc, dw, self.G(q + '.conv1.bias'), Bb, T, cin, H, k, d)
             ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
                                 self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin, k)
             # d x_in = conv1^T(dc) + residual branch (dpre)
@@ -483,7 +500,7 @@ class GeneratorEngine:
         dy1 = ws.get('g.dy1', (Mb, H // 2)); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
         ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
         ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)          # K = 27 reduction: fp32 kernel
-        ops.linear_wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), self.G('out.0.bias'), M=Mb, K=H, N=H // 2)
+        wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=H // 2, Cin=H, dbias=self.G('out.0.bias'))
         mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=H // 2, K=H)
         ops.dup_halves(dhs, dout, Mb, H)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None

@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ConvGemm, ConvWgrad, GemmTf32, check
+from ._lib import ConvGemm, ConvWgrad, GemmTf32, WgradTf32, check
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 
@@ -100,6 +100,18 @@ def gemm_tf32(A, Bw, C, *, M, N, K, lda=None, ldb=None, ldc=None, a_rows=None, t
     g.act2 = act2; g.accumulate = 1 if accumulate else 0
     check(_L().tg_gemm_tf32(ctypes.byref(g), _s()), 'tg_gemm_tf32')
     _count()
+
+
+def wgrad_tf32(G, X, dW, *, B, T, N, Cin, shift=0, ldg=None, ldx=None, ldw=None, dbias=None):
+    """dW[N,Cin] += G^T X over B clips x T rows on the tensor cores (TF32); see tg_wgrad_tf32_t."""
+    g = WgradTf32()
+    g.G = _p(_f32(G)); g.ldg = N if ldg is None else ldg
+    g.X = _p(_f32(X)); g.ldx = Cin if ldx is None else ldx
+    g.dW = _p(_f32(dW)); g.ldw = Cin if ldw is None else ldw
+    g.dbias = _p(dbias)
+    g.B, g.T, g.N, g.Cin, g.shift = B, T, N, Cin, shift
+    check(_L().tg_wgrad_tf32(ctypes.byref(g), _s()), 'tg_wgrad_tf32')
+    _count(2 if dbias is not None else 1)
 
 
 def linear(x, W, bias, out, *, M, K, N, **kw):

@@ -90,6 +90,20 @@ typedef struct {
 } tg_gemm_tf32_t;
 int tg_gemm_tf32(const tg_gemm_tf32_t* p, tg_stream stream);
 
+/* Fast-mode weight gradient on the tensor cores:  dW[n*ldw + c] += sum_{b,t} G[(b*T+t)*ldg + n] * X[(b*T+t+shift)*ldx + c]
+ * with rows t+shift outside [0,T) of clip b contributing zero (shift != 0 needs T <= 40: the TCN taps, tcn.py:19-31,
+ * and the recurrent weight_hh gradient whose operand is the layer output one step earlier / later).
+ * dbias (optional): dbias[n] += sum G[., n].  TF32 operands, fp32 accumulate, atomic accumulation into dW. */
+typedef struct {
+  const float* G; int ldg;
+  const float* X; int ldx;
+  float* dW;      int ldw;
+  float* dbias;
+  int B, T, N, Cin, shift;
+} tg_wgrad_tf32_t;
+int tg_wgrad_tf32(const tg_wgrad_tf32_t* p, tg_stream stream);
+int tg_col_sum_f32(const float* g, int ld, long long M, int N, float* out, tg_stream stream);
+
 /* Direct strided convolution for a single input channel (WavEncoder conv1: Conv1d(1,16,15,stride 5,pad 1600),
  * multimodal_context_net.py:13).  HBM-bound: x [B,Tin] -> y [B,Tout,N] channels-last, N <= 32, taps <= 32. */
 int tg_conv1_direct_f32(const float* x, const float* w, const float* bias, float* y,
@@ -193,6 +207,9 @@ int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream
  * to the fp32 kernels: forward takes weight_hh as stored [3H,H], backward takes its transpose [H,3H].
  * H % 4 == 0, 32 <= H <= 384.  sync: int[tg_gru_tf32_sync_ints(B,H)], partial: tg_gru_bwd_tf32_scratch_floats(B,H). */
 int tg_gru_tf32_sync_ints(int B, int H);
+/* development aid: when a device buffer of >= 16*T int64 is set, CTA (0,0,0) of the tensor-core GRU kernels stamps
+ * %globaltimer at its per-step phases (NULL switches it off) */
+int tg_debug_gru_trace(long long* device_buf);
 size_t tg_gru_bwd_tf32_scratch_floats(int B, int H);
 int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
                           float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream);

@@ -110,3 +110,30 @@ def test_gru_layer_tensor_core_fwd_bwd(dev, B, T, I, H):
         e = rel_l2(dwhh, pd['whh'][d].grad)
         assert e < 3 * TF32_TOL, (d, e)
         assert rel_l2(dbhh, pd['bhh'][d].grad) < 3 * TF32_TOL
+
+
+@pytest.mark.parametrize('B,T,N,Cin,shift', [(128, 34, 1800, 600, 0), (128, 34, 300, 300, -4), (128, 34, 900, 300, 1), (3, 34, 900, 300, -1),
+                                              (128, 34, 150, 300, 0), (5, 34, 32, 300, 0), (128, 34, 300, 300, 8)])
+def test_wgrad_tf32(dev, B, T, N, Cin, shift):
+    """MN-major tcgen05 weight gradient: dW += G^T X with clip-local shifted rows of X (zero outside the clip)."""
+    from tgb200 import ops
+    M = B * T
+    ldg = (N + 8 + 3) // 4 * 4                          # pitched views (16-byte aligned rows), like dgh[:, d*3H:] / out[:, d*H:]
+    G = _rand(M, ldg, dev=dev)[:, :N]
+    X = _rand(M, Cin + 4, dev=dev, seed=1)[:, :Cin]
+    dW = torch.ones(N, Cin, device=dev)
+    db = torch.zeros(N, device=dev)
+    ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=Cin + 4, dbias=db)
+    torch.cuda.synchronize()
+    Xs = torch.zeros(B, T, Cin, device=dev, dtype=torch.float64)
+    X3 = X.double().reshape(B, T, Cin)
+    if shift == 0:
+        Xs = X3
+    elif shift > 0:
+        Xs[:, :T - shift] = X3[:, shift:]
+    else:
+        Xs[:, -shift:] = X3[:, :T + shift]
+    ref = G.double().t() @ Xs.reshape(M, Cin) + 1.0
+    e = rel_l2(dW, ref)
+    assert e < TF32_TOL, e
+    assert rel_l2(db, G.double().sum(0)) < 1e-5
