@@ -295,8 +295,11 @@ constexpr int MAXUC = 12;                // H <= 384
 __device__ __forceinline__ void epi_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// 320 threads: warp 0 = TMA (weights, once), warp 1 = TMEM + MMA issuer, warps 2-9 = 256 epilogue threads; two epilogue
-// threads share one batch row (TMEM lane): each owns 16 of the CTA's 32 hidden units and half of the accumulator columns.
+// 320 threads: warp 0 = TMA (weights, once), warp 1 = TMEM + MMA issuer, warps 2-9 = 256 epilogue threads.
+// RB = clips owned by one CTA (rows 0..RB-1 of the 128-row MMA; the rest stay zero).  Small RB spreads the L2 exchange of
+// the partial dh and the operand streams over more SMs (the MMA itself is far from being the bottleneck): with B = 128,
+// RB = 32 gives 80 CTAs and each epilogue thread handles one float4 of units - one round of loads per step.
+template <int RB>
 __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1,
                                                             const BwdP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
   const size_t B_CHUNK = (size_t)nrows * 128;
   constexpr int A_CHUNK = 128 * 128;
   uint8_t* Bt = smem;                                   // [3 gates][nrows][128 B]   W_hh^T slice, resident
-  uint8_t* At = smem + 3 * B_CHUNK;                     // [3 gates][128 batch rows][128 B] dgh tile (swizzled)
+  uint8_t* At = smem + 3 * B_CHUNK;                     // [3 gates][128 rows][128 B] dgh tile (swizzled)
   uint64_t* w_full = reinterpret_cast<uint64_t*>(At + 3 * A_CHUNK);
   uint64_t* a_ready = w_full + 1;
   uint64_t* tmem_full = a_ready + 1;
@@ -363,20 +366,26 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
     }
   } else {
     const int etid = threadIdx.x - 64;                  // 0..255
-    const int q = warp & 3;                             // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;                   // which 16 units / which half of the accumulator columns
-    const int rl = q * 32 + lane;                       // local batch row
-    const int b = by * 128 + rl;
+    constexpr int TPR = 256 / RB;                       // threads per clip row
+    constexpr int HU = BU / TPR;                        // hidden units per thread (4, 8 or 16)
+    constexpr int NG = HU / 4;                          // float4 groups per thread
+    const int rl = etid / TPR, sub = etid - rl * TPR;   // clip row of the tile, unit sub-range
+    const int b = by * RB + rl;
     const bool b_ok = b < p.B;
     const long long row2H = 2ll * H;
     const long long pstride_parity = 2ll * p.B * p.UC * HP;
-    constexpr int HU = BU / 2;                          // 16 units per thread
-    const int uu0 = u0 + half * HU;
+    const long long k4n = HP / 4;
+    const int uu0 = u0 + sub * HU;
     float dhc[HU];
 #pragma unroll
     for (int j = 0; j < HU; ++j) dhc[j] = 0.f;
     int nu = H - uu0;                                   // valid units of this thread (multiple of 4)
     nu = nu < 0 ? 0 : (nu > HU ? HU : nu);
+    // accumulator read-out: TMEM lanes 32q..32q+31 are only visible to warps with (warp & 3) == q
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const bool t_warp = q * 32 < RB;
+    const int tb = by * RB + q * 32 + lane;             // clip whose accumulator row this thread reads
+    const bool tb_ok = t_warp && (q * 32 + lane) < RB && tb < p.B;
     const int nchunk = (nrows + 31) / 32;
     const int ch_lo = half == 0 ? 0 : (nchunk + 1) / 2, ch_hi = half == 0 ? (nchunk + 1) / 2 : nchunk;
     for (int s = 0; s < T; ++s) {
@@ -386,10 +395,10 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
       const long long row = (long long)b * T + t;
       const long long o = row * row2H + dir * H + uu0;
       const long long op = ((long long)b * T + tp) * row2H + dir * H + uu0;
-      // recurrence-independent operands of this step, one batch of loads, issued BEFORE waiting for the other CTAs
-      float4 ld_do[4], ld_r[4], ld_z[4], ld_n[4], ld_hn[4], ld_hp[4];
+      // recurrence-independent operands of this step: one batch of loads issued BEFORE waiting for the other CTAs
+      float4 ld_do[NG], ld_r[NG], ld_z[NG], ld_n[NG], ld_hn[NG], ld_hp[NG];
 #pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
+      for (int g4 = 0; g4 < NG; ++g4) {
         ld_do[g4] = ld_r[g4] = ld_z[g4] = ld_n[g4] = ld_hn[g4] = ld_hp[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b_ok && g4 * 4 < nu) {
           ld_do[g4] = ldv_nc4(p.dout + o + g4 * 4);
@@ -399,13 +408,6 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
           ld_hn[g4] = ldv_nc4(p.saved + 3 * p.saved_qstride + o + g4 * 4);
           if (tp_ok) ld_hp[g4] = ldv_nc4(p.out + op + g4 * 4);
         }
-      }
-      if (b_ok && nu > 0 && s + 1 < T) {
-        // pull the next step's operand rows towards L2 while this step runs
-        const int tn = dir == 0 ? t - 1 : t + 1;
-        const long long on = ((long long)b * T + tn) * row2H + dir * H + uu0;
-        prefetch_l2(p.dout + on); prefetch_l2(p.saved + on); prefetch_l2(p.saved + p.saved_qstride + on);
-        prefetch_l2(p.saved + 2 * p.saved_qstride + on); prefetch_l2(p.saved + 3 * p.saved_qstride + on);
       }
       if (etid == 0) stamp(p.trace, s, 0);
       if (s > 0) {
@@ -417,14 +419,11 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < HU; ++j) carry[j] = dhc[j];
       if (s > 0 && b_ok) {
-        // partial layout [parity][dir][chunk cc][k4 = unit/4][clip b][4]: producers and consumers both touch it with
-        // consecutive lanes = consecutive clips, i.e. fully coalesced 16-byte accesses
-        const long long k4n = HP / 4;
+        // partial layout [parity][dir][chunk cc][k4 = unit/4][clip b][4]: consecutive lanes touch consecutive clips
         const float* Pin = p.partial + (long long)((s - 1) & 1) * pstride_parity + (long long)dir * p.UC * k4n * p.B * 4 +
                            ((long long)(uu0 / 4) * p.B + b) * 4;
-        // four rounds (one float4 of units each); within a round all UC partial loads are issued before the first add
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
+        for (int g4 = 0; g4 < NG; ++g4) {
           if (g4 * 4 < nu) {
             float4 tv[MAXUC];
 #pragma unroll
@@ -439,11 +438,11 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
           }
         }
       }
-      if (etid == 0) { stamp(carry[0] == 12345.678f ? nullptr : p.trace, s, 2); }
+      if (etid == 0) stamp(carry[0] == 12345.678f ? nullptr : p.trace, s, 2);
       float* gp = p.dgi + row * 6 * H + dir * 3 * H + uu0;
       float* hp = p.dgh + row * 6 * H + dir * 3 * H + uu0;
 #pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
+      for (int g4 = 0; g4 < NG; ++g4) {
         float dr4[4] = {0.f, 0.f, 0.f, 0.f}, dz4[4] = {0.f, 0.f, 0.f, 0.f}, dn4[4] = {0.f, 0.f, 0.f, 0.f}, dnr4[4] = {0.f, 0.f, 0.f, 0.f};
         if (b_ok && g4 * 4 < nu) {
           const float dov[4] = {ld_do[g4].x, ld_do[g4].y, ld_do[g4].z, ld_do[g4].w}, rv[4] = {ld_r[g4].x, ld_r[g4].y, ld_r[g4].z, ld_r[g4].w};
@@ -467,7 +466,7 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
           *reinterpret_cast<float4*>(hp + 2 * H + g4 * 4) = make_float4(dnr4[0], dnr4[1], dnr4[2], dnr4[3]);
         }
         // A operand: K-major, 128B swizzle: 16-byte unit index XOR (row & 7)
-        const uint32_t unit16 = (uint32_t)(half * 4 + g4) ^ (uint32_t)(rl & 7);
+        const uint32_t unit16 = (uint32_t)(sub * NG + g4) ^ (uint32_t)(rl & 7);
         const size_t off = (size_t)(rl >> 3) * 1024 + (size_t)(rl & 7) * 128 + (size_t)unit16 * 16;
         *reinterpret_cast<float4*>(At + 0 * A_CHUNK + off) = make_float4(dr4[0], dr4[1], dr4[2], dr4[3]);
         *reinterpret_cast<float4*>(At + 1 * A_CHUNK + off) = make_float4(dz4[0], dz4[1], dz4[2], dz4[3]);
@@ -480,27 +479,28 @@ __global__ void __launch_bounds__(320, 1) gru_bwd_tc_kernel(const __grid_constan
         epi_bar256();
         if (etid == 0) mbar_arrive(a_ready);
         if (etid == 0) stamp(p.trace, s, 4);
-        // partial dh_{prev}[b, 0..H) of this chunk -> L2 (each of the two threads of a row stores half of the columns)
-        mbar_wait(tmem_full, (uint32_t)(s & 1));
-        if (etid == 0) stamp(p.trace, s, 5);
-        tc_fence_after();
-        const long long k4n = HP / 4;
-        float* Pout = p.partial + (long long)(s & 1) * pstride_parity + ((long long)dir * p.UC + c) * k4n * p.B * 4 + (long long)b * 4;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int ch = ch_lo; ch < ch_hi; ++ch) {
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-          tmem_ld_wait();
-          if (b_ok) {
+        if (t_warp) {
+          // partial dh_{prev}[clip, 0..H) of this chunk -> L2 (the two warps of a lane quarter split the columns)
+          mbar_wait(tmem_full, (uint32_t)(s & 1));
+          if (etid == 0) stamp(p.trace, s, 5);
+          tc_fence_after();
+          float* Pout = p.partial + (long long)(s & 1) * pstride_parity + ((long long)dir * p.UC + c) * k4n * p.B * 4 + (long long)tb * 4;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+          for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+            tmem_ld_wait();
+            if (tb_ok) {
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4)
-              if (ch * 32 + j4 < HP)
-                __stcg(reinterpret_cast<float4*>(Pout + (long long)(ch * 8 + (j4 >> 2)) * p.B * 4), make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]));
+              for (int j4 = 0; j4 < 32; j4 += 4)
+                if (ch * 32 + j4 < HP)
+                  __stcg(reinterpret_cast<float4*>(Pout + (long long)(ch * 8 + (j4 >> 2)) * p.B * 4), make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]));
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          tc_fence_before();
         }
         if (etid == 0) stamp(p.trace, s, 6);
-        tc_fence_before();
         __threadfence();
         if (etid == 0) stamp(p.trace, s, 7);
         epi_bar256();
@@ -598,7 +598,7 @@ extern "C" int tg_debug_gru_trace(long long* device_buf) {
 extern "C" int tg_gru_tf32_sync_ints(int B, int H) {
   FwdPlan pl;
   if (fwd_plan(B, H, &pl)) return -1;
-  int nb_bwd = tg_ceil_div(B, 128);
+  int nb_bwd = tg_ceil_div(B, 32);
   return 2 * (pl.NB > nb_bwd ? pl.NB : nb_bwd);
 }
 
@@ -630,6 +630,25 @@ extern "C" size_t tg_gru_bwd_tf32_scratch_floats(int B, int H) {
   return (size_t)2 * 2 * B * UC * HP;
 }
 
+static int bwd_rows_per_cta(int B, int H) {
+  const int UC = tg_ceil_div(H, BU);
+  const int cands[3] = {32, 64, 128};
+  for (int i = 0; i < 3; ++i)
+    if (2 * UC * tg_ceil_div(B, cands[i]) <= tg_num_sms()) return cands[i];
+  return 0;
+}
+
+template <int RB>
+static int launch_bwd(const CUtensorMap* maps, const BwdP& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(gru_bwd_tc_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
+  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&p};
+  dim3 grid(p.UC, p.NB, 2);
+  e = cudaLaunchCooperativeKernel((const void*)gru_bwd_tc_kernel<RB>, grid, dim3(320), args, smem, s);
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: cooperative launch (%u,%u,2): %s", grid.x, grid.y, cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
 extern "C" int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const float* saved, long long saved_qstride,
                                      const float* whhT_f, const float* whhT_r, float* dgi, float* dgh, float* partial, int* sync,
                                      int B, int T, int H, tg_stream stream) {
@@ -637,8 +656,9 @@ extern "C" int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const 
   TG_REQUIRE(H >= 32 && H <= 384 && (H & 3) == 0, "tg_gru_layer_bwd_tf32");
   BwdP p;
   p.UC = tg_ceil_div(H, BU);
-  p.NB = tg_ceil_div(B, 128);
-  TG_REQUIRE(2 * p.UC * p.NB <= tg_num_sms(), "tg_gru_layer_bwd_tf32");
+  const int RB = bwd_rows_per_cta(B, H);
+  TG_REQUIRE(RB > 0, "tg_gru_layer_bwd_tf32");
+  p.NB = tg_ceil_div(B, RB);
   p.nh = H > 256 ? 2 : 1;
   p.Nh = ((tg_ceil_div(H, p.nh) + 15) / 16) * 16;
   p.HP = (H + 3) & ~3;
@@ -653,11 +673,7 @@ extern "C" int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const 
   p.B = B; p.T = T; p.H = H; p.trace = g_trace;
   const size_t smem = (size_t)3 * p.nh * p.Nh * 128 + 3 * 128 * 128 + 8 * 8 + 16 + 1024;
   TG_REQUIRE(smem <= (size_t)tg_max_smem_optin(), "tg_gru_layer_bwd_tf32");
-  e = cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
-  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&p};
-  dim3 grid(p.UC, p.NB, 2);
-  e = cudaLaunchCooperativeKernel((const void*)gru_bwd_tc_kernel, grid, dim3(320), args, smem, s);
-  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: cooperative launch: %s", cudaGetErrorString(e)); return -2; }
-  return 0;
+  if (RB == 32) return launch_bwd<32>(maps, p, smem, s);
+  if (RB == 64) return launch_bwd<64>(maps, p, smem, s);
+  return launch_bwd<128>(maps, p, smem, s);
 }
