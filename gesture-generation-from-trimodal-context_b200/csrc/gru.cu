@@ -475,7 +475,13 @@ static int coop_launch(K kernel, const P& params, dim3 grid, size_t smem, cudaSt
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { tg_set_error("%s: smem attr (%zu B): %s", name, smem, cudaGetErrorString(e)); return -3; }
   void* args[] = {(void*)&params};
-  e = cudaLaunchCooperativeKernel((const void*)kernel, grid, dim3(256), args, smem, s);
+  // Cooperative launch = the runtime checks that all CTAs can be co-resident (they step together through L2 counters).
+  // Stream capture does not accept cooperative launches: inside a CUDA graph the same kernel is launched normally - the
+  // grid is sized to at most one CTA per SM, and no two of these stepping kernels ever run concurrently in our schedule.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap != cudaStreamCaptureStatusNone) e = cudaLaunchKernel((const void*)kernel, grid, dim3(256), args, smem, s);
+  else e = cudaLaunchCooperativeKernel((const void*)kernel, grid, dim3(256), args, smem, s);
   if (e != cudaSuccess) { tg_set_error("%s: cooperative launch grid (%u,%u,%u) smem %zu: %s", name, grid.x, grid.y, grid.z, smem,
                                        cudaGetErrorString(e)); return -2; }
   return 0;

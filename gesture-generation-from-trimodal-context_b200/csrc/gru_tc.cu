@@ -583,7 +583,10 @@ int launch_fwd(const CUtensorMap* maps, const FwdP& p, const FwdPlan& pl, cudaSt
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
   void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
   dim3 grid(pl.UC, pl.NB, 2);
-  e = cudaLaunchCooperativeKernel((const void*)gru_fwd_tc_kernel<BT>, grid, dim3(576), args, smem, s);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);       // see gru.cu: cooperative launches cannot be captured into a CUDA graph
+  if (cap != cudaStreamCaptureStatusNone) e = cudaLaunchKernel((const void*)gru_fwd_tc_kernel<BT>, grid, dim3(576), args, smem, s);
+  else e = cudaLaunchCooperativeKernel((const void*)gru_fwd_tc_kernel<BT>, grid, dim3(576), args, smem, s);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: cooperative launch (%u,%u,2) smem %zu: %s", grid.x, grid.y, smem, cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -644,7 +647,10 @@ static int launch_bwd(const CUtensorMap* maps, const BwdP& p, size_t smem, cudaS
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
   void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&p};
   dim3 grid(p.UC, p.NB, 2);
-  e = cudaLaunchCooperativeKernel((const void*)gru_bwd_tc_kernel<RB>, grid, dim3(320), args, smem, s);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap != cudaStreamCaptureStatusNone) e = cudaLaunchKernel((const void*)gru_bwd_tc_kernel<RB>, grid, dim3(320), args, smem, s);
+  else e = cudaLaunchCooperativeKernel((const void*)gru_bwd_tc_kernel<RB>, grid, dim3(320), args, smem, s);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: cooperative launch (%u,%u,2): %s", grid.x, grid.y, cudaGetErrorString(e)); return -2; }
   return 0;
 }

@@ -143,7 +143,7 @@ class ParamArena:
         if host_step:
             self.step += 1
             self._step_tensor.fill_(float(self.step))
-            ops.increment_i64(self.step_dev, 1)
+        ops.increment_i64(self.step_dev, 1)
         b1, b2 = g['betas']
         ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.numel, float(g['lr']), float(b1), float(b2),
                       float(g['eps']), float(grad_scale), self.step_dev)

@@ -26,3 +26,33 @@ def set_mode(m: str) -> str:
 
 def fast() -> bool:
     return _MODE == 'tf32'
+
+
+_OVERLAP = os.environ.get('TGB200_OVERLAP', '1') == '1'
+
+
+def overlap() -> bool:
+    """Run off-critical-path launch sequences (weight gradients, the audio encoder, the discriminator's real-clip pass) on
+    auxiliary CUDA streams so that they fill the SMs the latency-bound persistent kernels leave idle."""
+    return _OVERLAP
+
+
+def set_overlap(v: bool) -> bool:
+    global _OVERLAP
+    old, _OVERLAP = _OVERLAP, bool(v)
+    return old
+
+
+_GRAPHS = os.environ.get('TGB200_GRAPHS', '1') == '1'
+
+
+def graphs() -> bool:
+    """Capture the whole train_iter_gan launch sequence (~400 launches over 4 streams) into one CUDA graph after two eager
+    iterations and replay it afterwards: removes the host-side launch cost, which otherwise exceeds the GPU time."""
+    return _GRAPHS
+
+
+def set_graphs(v: bool) -> bool:
+    global _GRAPHS
+    old, _GRAPHS = _GRAPHS, bool(v)
+    return old

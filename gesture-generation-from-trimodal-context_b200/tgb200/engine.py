@@ -9,12 +9,62 @@ Reference anchors: scripts/model/multimodal_context_net.py:9-28 (WavEncoder), :3
 (TextEncoderTCN), :110-160 (PoseGenerator.forward), :207-252 (ConvDiscriminator)."""
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional
 
 import torch
 
-from . import config, ops
+from . import _lib, config, ops
 from .arena import ParamArena
+
+
+class _Overlap:
+    """Fork / join helper over a few auxiliary CUDA streams (per device).  `with side.on(i):` makes stream i wait for
+    everything queued so far on the current stream and runs the body there; `side.join(i)` makes the current stream wait
+    for stream i.  Disabled (body runs inline) without CUDA, in trace mode, or with TGB200_OVERLAP=0."""
+
+    def __init__(self):
+        self._streams = {}
+        self._active = set()          # side streams with work forked since their last join
+
+    def enabled(self):
+        return config.overlap() and not _lib.TRACE_ONLY and torch.cuda.is_available()
+
+    def _stream(self, device, i):
+        key = (device.index, i)
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
+
+    @contextlib.contextmanager
+    def on(self, i):
+        if not self.enabled():
+            yield
+            return
+        cur = torch.cuda.current_stream()
+        s = self._stream(cur.device, i)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        s.wait_event(ev)
+        self._active.add((cur.device.index, i))
+        with torch.cuda.stream(s):
+            yield
+
+    def join(self, i):
+        if not self.enabled():
+            return
+        cur = torch.cuda.current_stream()
+        key = (cur.device.index, i)
+        if key not in self._active or self._streams[key] == cur:
+            return                        # nothing outstanding (also keeps un-forked streams out of a CUDA-graph capture)
+        self._active.discard(key)
+        ev = torch.cuda.Event()
+        ev.record(self._streams[key])
+        cur.wait_event(ev)
+
+
+side = _Overlap()
+S_WGRAD, S_WAV, S_DREAL = 1, 2, 3
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -121,7 +171,7 @@ class GruPlan:
                 wt = self.ws.get(f'{self.tag}.whhT{l}_{d}', (H, 3 * H))
                 ops.transpose(self._w('weight_hh', l, bool(d)), wt, 3 * H, H)
             K = self.I if l == 0 else 2 * H
-            if config.fast() and l > 0:
+            if config.fast() and K % 4 == 0 and K >= 32:
                 # [6H, K] (both directions, adjacent in the arena) -> [K, 6H]: operand of the data-gradient GEMM
                 ops.transpose(self._w('weight_ih', l), self.ws.get(f'{self.tag}.wihT{l}', (K, 6 * H)), 6 * H, K)
 
@@ -160,13 +210,14 @@ class GruPlan:
         Bb = hi - lo
         Mb, M_all = Bb * T, B_all * T
         r0, r1 = lo * T, hi * T
-        dgi = ws.get(f'{tag}.dgi', (Mb, 6 * H))
-        dgh = ws.get(f'{tag}.dgh', (Mb, 6 * H))
         tc = self.tc()
+        side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading dgi / dgh
         partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_tf32_scratch_floats(Bb, H) if tc else ops.gru_bwd_scratch_floats(Bb, H), 1),))
         sync = ws.get(f'{tag}.bsync', (max(ops.gru_tf32_sync_ints(Bb, H) if tc else ops.gru_sync_ints(Bb, H), 1),), torch.int32)
         dx = None
         for l in range(self.L - 1, -1, -1):
+            dgi = ws.get(f'{tag}.dgi{l}', (Mb, 6 * H))      # per layer: the weight gradients consume them on a side stream
+            dgh = ws.get(f'{tag}.dgh{l}', (Mb, 6 * H))
             out = ws[f'{tag}.out{l}'][r0:r1]
             saved = ws[f'{tag}.saved{l}'][:, r0:r1]          # plane stride stays M_all*2H
             if tc:
@@ -182,11 +233,12 @@ class GruPlan:
                 inp = ws[f'{tag}.drop{l - 1}'][r0:r1]
             else:
                 inp = ws[f'{tag}.out{l - 1}'][r0:r1]
-            wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
-            for d in (0, 1):
-                # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
-                wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
-                      shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
+            with side.on(S_WGRAD):
+                wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
+                for d in (0, 1):
+                    # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
+                    wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
+                          shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
             if l > 0 or need_dx:
                 dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
                 m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
@@ -415,7 +467,8 @@ class GeneratorEngine:
         sl = lambda t: t[r0:r1] if t is not None else None
         xl = ws[f'txt.x{self.n_tcn - 1}'][r0:r1]
         wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), B=Bb, T=T, N=32, Cin=H, dbias=self.G('text_encoder.decoder.bias'))
-        dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dc = ws.get('txt.dC', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
+        dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
+        side.join(S_WGRAD)
         mm_nn(d_feat, self.P('text_encoder.decoder.weight'), ws.t.get('T.text_encoder.decoder.weight') if config.fast() else None, dx,
               M=Mb, N=32, K=H)
         for i in range(self.n_tcn - 1, -1, -1):
@@ -426,21 +479,24 @@ class GeneratorEngine:
             y1, y2, xo = ws[f'txt.y1_{i}'][r0:r1], ws[f'txt.y2_{i}'][r0:r1], ws[f'txt.x{i}'][r0:r1]
             m1 = sl(masks.get(f'tcn{i}_1')) if masks else None
             m2 = sl(masks.get(f'tcn{i}_2')) if masks else None
+            dc2 = ws.get(f'txt.dc2_{i}', (Mb, H)); dc1 = ws.get(f'txt.dc1_{i}', (Mb, H))   # per conv: read by the side stream
             ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                      # through the block's final ReLU
-            ops.relu_mask_bwd(dpre, y2, m2, dc, Mb * H)                        # dropout2 + relu2
-            dw = ws.get('tcn.dw', (k * H * max(cin, H),)); dw.zero_()                 # tap-major [k][H][cin]
+            ops.relu_mask_bwd(dpre, y2, m2, dc2, Mb * H)                       # dropout2 + relu2
             wT = lambda j: ws.t.get(f'tcn.wT{i}_{j}') if config.fast() else None
-            self._tcn_wgrad(y1, dc, dw, self.G(q + '.conv2.bias'), Bb, T, H, H, k, d)
-            ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
-                                self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H, k)
-            self._tcn_dgrad(dc, ws[f'tcn.w{i}_2'], wT(2), dy1, Bb, T, H, H, k, d)
-            ops.relu_mask_bwd(dy1, y1, m1, dc, Mb * H)                         # dropout1 + relu1
-            dw.zero_()
-            self._tcn_wgrad(xin, dc, dw, self.G(q + '.conv1.bias'), Bb, T, cin, H, k, d)
-            ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
-                                self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin, k)
+            with side.on(S_WGRAD):
+                dw = ws.get(f'tcn.dw{i}_2', (k * H * H,)); dw.zero_()                 # tap-major [k][H][cin]
+                self._tcn_wgrad(y1, dc2, dw, self.G(q + '.conv2.bias'), Bb, T, H, H, k, d)
+                ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
+                                    self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H, k)
+            self._tcn_dgrad(dc2, ws[f'tcn.w{i}_2'], wT(2), dy1, Bb, T, H, H, k, d)
+            ops.relu_mask_bwd(dy1, y1, m1, dc1, Mb * H)                        # dropout1 + relu1
+            with side.on(S_WGRAD):
+                dw = ws.get(f'tcn.dw{i}_1', (k * H * cin,)); dw.zero_()
+                self._tcn_wgrad(xin, dc1, dw, self.G(q + '.conv1.bias'), Bb, T, cin, H, k, d)
+                ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
+                                    self.G(q + '.conv1.weight_v'), self.G(q + '.conv1.weight_g'), H, cin, k)
             # d x_in = conv1^T(dc) + residual branch (dpre)
-            self._tcn_dgrad(dc, ws[f'tcn.w{i}_1'], wT(1), dx, Bb, T, cin, H, k, d, residual=dpre)
+            self._tcn_dgrad(dc1, ws[f'tcn.w{i}_1'], wT(1), dx, Bb, T, cin, H, k, d, residual=dpre)
         emb_p = self.arena.params['text_encoder.embedding.weight']
         if emb_p.requires_grad:
             Ba = in_text.shape[0]
@@ -457,7 +513,10 @@ class GeneratorEngine:
         Dp = pre_seq.shape[2]
         M = Bt * T
         self.ctx = dict(Bt=Bt, Ba=Ba, T=T, masks=masks, pre_seq=pre_seq, in_text=in_text, in_audio=in_audio, vid=vid, eps=eps)
-        audio_feat = self.wav_forward(in_audio, training, n_bn_updates) if self.use_audio else None
+        audio_feat = None
+        if self.use_audio:
+            with side.on(S_WAV):            # the audio encoder is independent of the text / speaker branches
+                audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
         text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
         z = mu = logvar = None
         Z = 0
@@ -473,6 +532,7 @@ class GeneratorEngine:
         elif self.z_mode == 'random':
             Z = 16
             z = eps
+        side.join(S_WAV)
         in_data = ws.get('g.in', (M, self.I))
         Da = 32 if self.use_audio else 0
         Dt = 32 if self.use_text else 0
@@ -507,6 +567,7 @@ class GeneratorEngine:
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'
         d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx)
         if not need_dx:
+            side.join(S_WGRAD)
             return
         Dp = c['pre_seq'].shape[2]
         Da = 32 if self.use_audio else 0
@@ -532,11 +593,14 @@ class GeneratorEngine:
             ops.linear_wgrad(e0, de1, self.G('speaker_embedding.1.weight'), self.G('speaker_embedding.1.bias'), M=Bb, K=Zs, N=Zs)
             ops.linear_dgrad(de1, self.P('speaker_embedding.1.weight'), de0, M=Bb, K=Zs, N=Zs)
             ops.embedding_scatter_add(de0, c['vid'][lo:hi], None, self.G('speaker_embedding.0.weight'), Bb, Zs)
-        if self.use_text:
-            self.text_backward(d_text, c['in_text'], lo, hi, T, masks)
         if self.use_audio:
             assert Bb == Ba and lo % Ba == 0
-            self.wav_backward(d_audio, c['in_audio'])
+            with side.on(S_WAV):
+                self.wav_backward(d_audio, c['in_audio'])
+        if self.use_text:
+            self.text_backward(d_text, c['in_text'], lo, hi, T, masks)
+        side.join(S_WAV)
+        side.join(S_WGRAD)
 
 
 # =====================================================================================================================
@@ -667,6 +731,7 @@ class DiscriminatorEngine:
             ops.bn_bwd_apply(da, x, da, B * tin, cin, mean, rstd, sc, sh, 1.0, self.P(bn + '.weight'), sums, self.G(bn + '.weight'),
                              self.G(bn + '.bias'))
             dy = da
+        side.join(S_WGRAD)
         return dposes
 
 

@@ -17,7 +17,8 @@ from typing import Dict, Optional
 
 import torch
 
-from tgb200 import _lib, ops
+from tgb200 import _lib, config, ops
+from tgb200.engine import S_DREAL, side
 
 
 def add_noise(data):
@@ -63,6 +64,29 @@ def _allreduce_grads(arena, bucket_floats=4 << 20):
         w.wait()
 
 
+class _GraphSlot:
+    """One captured CUDA graph of the whole iteration for a fixed (modules, batch shape, schedule, hyper-parameters)."""
+
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.failed = False
+        self.static = None
+
+
+_graph_slots = {}
+_GRAPH_WARMUP = 2          # eager iterations (allocate every workspace) before the iteration is captured
+
+
+def _flags(args, epoch):
+    after = epoch > args.loss_warmup
+    do_d = after and args.loss_gan_weight > 0.0
+    z_type = getattr(args, 'z_type', 'speaker')
+    do_div = z_type in ('speaker', 'random') and args.loss_reg_weight > 0.0
+    do_kld = do_div and z_type == 'speaker'
+    return after, do_d, do_div, do_kld
+
+
 def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, pose_decoder, discriminator, pose_dec_optim, dis_optim):
     _lib.require_cuda()
     global _injected_noise
@@ -72,19 +96,98 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
     if not target_poses.is_cuda and not _lib.TRACE_ONLY:
         raise _lib.TgError('train_iter_gan runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
     B, T, Dm = target_poses.shape
-    after = epoch > args.loss_warmup
-    do_d = after and args.loss_gan_weight > 0.0
-    z_type = getattr(args, 'z_type', 'speaker')
-    do_div = z_type in ('speaker', 'random') and args.loss_reg_weight > 0.0
-    do_kld = do_div and z_type == 'speaker'
+    after, do_d, do_div, do_kld = _flags(args, epoch)
     world = _dist_world()
-
-    ge = G.engine().ensure(dev, 'train_%d' % B)
-    de = D.engine().ensure(dev, 'train_%d' % B)
-    ws = ge.ws
     target = target_poses.contiguous().float()
     in_text = in_text.contiguous()
     in_audio = in_audio.contiguous().float()
+    vid = vid_indices.contiguous() if vid_indices is not None else None
+
+    use_graph = (config.graphs() and noise is None and world == 1 and not _lib.TRACE_ONLY and torch.cuda.is_available())
+    sc = None
+    if use_graph:
+        gg, dg = pose_dec_optim.param_groups[0], dis_optim.param_groups[0]
+        key = (id(G), id(D), id(pose_dec_optim), id(dis_optim), dev.index, B, T, Dm, tuple(in_audio.shape), after, do_d, do_div, do_kld,
+               G.training, D.training, config.mode(), config.overlap(), float(gg['lr']), float(dg['lr']), tuple(gg['betas']), tuple(dg['betas']),
+               float(args.loss_regression_weight), float(args.loss_gan_weight), float(args.loss_kld_weight), float(args.loss_reg_weight),
+               int(args.n_pre_poses))
+        slot = _graph_slots.setdefault(key, _GraphSlot())
+        slot.calls += 1
+        if not slot.failed and slot.calls > _GRAPH_WARMUP and G.engine().arena.is_current() and D.engine().arena.is_current():
+            sc = _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim)
+    if sc is None:
+        sc = _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step=True)
+
+    # ---- one device->host copy for the logged scalars (train_gan.py:94-102)
+    s = sc.cpu().tolist()
+    huber = s[0] / (B * T * Dm)
+    ret: Dict[str, float] = {'loss': args.loss_regression_weight * huber}
+    if do_kld:
+        kld = -0.5 * s[2] / (B * 16)
+        if kld:
+            ret['KLD'] = args.loss_kld_weight * kld
+    if do_div:
+        div = s[1] / B
+        if div:
+            ret['DIV_REG'] = args.loss_reg_weight * div
+    if do_d:
+        ret['gen'] = args.loss_gan_weight * s[3]
+        ret['dis'] = s[4] + s[5]
+    return ret
+
+
+def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt, d_opt):
+    """Replays (capturing on first use) the CUDA graph of one iteration on static input buffers.  Everything random is
+    drawn inside the graph from device-resident Philox offsets and the Adam step counters live on the device, so every
+    replay is a fresh iteration.  Returns the scalars buffer, or None if capture is not possible (falls back to eager)."""
+    ge, de = G.engine(), D.engine()
+    B = target.shape[0]
+    ge.ensure(target.device, 'train_%d' % B)
+    ws = ge.ws
+    if slot.static is None:
+        slot.static = dict(in_text=ws.get('ti.s_text', tuple(in_text.shape), torch.int64), in_audio=ws.get('ti.s_audio', tuple(in_audio.shape)),
+                           target=ws.get('ti.s_target', tuple(target.shape)),
+                           vid=ws.get('ti.s_vid', tuple(vid.shape), torch.int64) if vid is not None else None)
+    st = slot.static
+    st['in_text'].copy_(in_text); st['in_audio'].copy_(in_audio); st['target'].copy_(target)
+    if vid is not None:
+        st['vid'].copy_(vid)
+    if slot.graph is None:
+        try:
+            ge.arena.bind_optimizer(g_opt); de.arena.bind_optimizer(d_opt)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                slot.sc = _enqueue_step(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None, 1,
+                                        host_step=False)
+            slot.graph = graph
+        except Exception as exc:            # capture unsupported for some launch: stay on the eager path
+            slot.failed = True
+            import traceback
+            import warnings
+            root = exc
+            while root.__context__ is not None:
+                root = root.__context__
+            warnings.warn('tgb200: CUDA-graph capture of train_iter_gan failed (%s | root cause: %s %s); continuing with eager launches'
+                          % (str(exc).splitlines()[0], type(root).__name__, str(root).splitlines()[0] if str(root) else ''))
+            torch.cuda.synchronize()
+            return None
+    slot.graph.replay()
+    _, do_d, _, _ = _flags(args, epoch)
+    ge.arena.note_steps(1)
+    if do_d:
+        de.arena.note_steps(1)
+    return slot.sc
+
+
+def _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step):
+    """Enqueues every kernel of one iteration (no host synchronisation); returns the fp64 scalars buffer."""
+    dev = target.device
+    B, T, Dm = target.shape
+    after, do_d, do_div, do_kld = _flags(args, epoch)
+    ge = G.engine().ensure(dev, 'train_%d' % B)
+    de = D.engine().ensure(dev, 'train_%d' % B)
+    ws = ge.ws
 
     # ---- pass list: [D-step forward] + G-step forward + [permuted-speaker forward]
     passes = (['d'] if do_d else []) + ['g'] + (['r'] if do_div else [])
@@ -105,7 +208,6 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
         else:
             ops.philox_normal(eps_all, Bt * 16, seed, off, 1000)
     if ge.z_mode == 'speaker':
-        vid = vid_indices.contiguous()
         vid_all = ws.get('ti.vid', (Bt,), torch.int64)
         for i, p in enumerate(passes):
             if p == 'r':
@@ -133,26 +235,32 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
         m = de.make_masks(B, T - 6, D._noise.seed, D._noise.offset_dev(dev), sid0=16 * i)
         return m
 
-    # ---- all generator passes in one sweep
-    ge.prep_weights()
-    poses, z, mu, logvar = ge.forward(pre_seq, in_text, in_audio, vid_all, eps_all, Bt, G.training, g_masks, n_bn_updates=n_pass)
     sc = ws.get('ti.scalars', (8,), torch.float64)
     sc.zero_()
     dlogit = ws.get('ti.dlogit', (B, 1))
-
-    # ---- train D (train_gan.py:24-43)
     de.prep_weights()
     if do_d:
+        # D(real) forward + backward does not depend on the generator: it runs on an auxiliary stream underneath the
+        # generator passes (train_gan.py:38,41-42; BatchNorm statistics still see real before fake)
         de.arena.zero_grad()
-        p_real = de.forward(target, D.training, d_masks_for(0))
-        ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
-        de.backward(dlogit, need_dposes=False)
+        with side.on(S_DREAL):
+            p_real = de.forward(target, D.training, d_masks_for(0))
+            ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
+            de.backward(dlogit, need_dposes=False)
+
+    # ---- all generator passes in one sweep
+    ge.prep_weights()
+    poses, z, mu, logvar = ge.forward(pre_seq, in_text, in_audio, vid_all, eps_all, Bt, G.training, g_masks, n_bn_updates=n_pass)
+
+    # ---- train D (train_gan.py:24-43)
+    if do_d:
+        side.join(S_DREAL)
         p_fake = de.forward(poses[0:B], D.training, d_masks_for(1))          # generator output of the D-step pass (detached)
         ops.bce_sigmoid(p_fake, B, -1.0, 1.0, 1.0, sc[5:], dlogit)
         de.backward(dlogit, need_dposes=False)
         if world > 1:
             _allreduce_grads(de.arena)
-        de.arena.adam_step(dis_optim, grad_scale=1.0 / world)
+        de.arena.adam_step(dis_optim, grad_scale=1.0 / world, host_step=host_step)
         de.prep_weights()
 
     # ---- train G (train_gan.py:45-92)
@@ -176,24 +284,8 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
     ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
     if world > 1:
         _allreduce_grads(ge.arena)
-    ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world)
-
-    # ---- one device->host copy for the logged scalars (train_gan.py:94-102)
-    s = sc.cpu().tolist()
-    huber = s[0] / (B * T * Dm)
-    ret: Dict[str, float] = {'loss': args.loss_regression_weight * huber}
-    if do_kld:
-        kld = -0.5 * s[2] / (B * 16)
-        if kld:
-            ret['KLD'] = args.loss_kld_weight * kld
-    if do_div:
-        div = s[1] / B
-        if div:
-            ret['DIV_REG'] = args.loss_reg_weight * div
-    if do_d:
-        ret['gen'] = args.loss_gan_weight * s[3]
-        ret['dis'] = s[4] + s[5]
-    return ret
+    ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world, host_step=host_step)
+    return sc
 
 
 def _stack_masks(ws, per_pass, rows_per_pass):

@@ -297,3 +297,39 @@ def test_fast_mode_train_iter_full_size_vs_oracle(dev, B, epoch):
         worst = max(worst, (k, rel_l2(p.grad, r)), key=lambda t: t[1])
     print('fast-mode pose rel-L2 %.2e, worst gradient rel-L2 %s %.2e' % (e, worst[0], worst[1]))
     assert worst[1] < 5e-2, worst
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    """The captured iteration (4 streams, ~400 launches, cooperative persistent kernels) replays to the same numbers
+    as eager launches: both paths draw their randomness from the same device-resident Philox offsets."""
+    from tgb200 import config
+    from train_eval import train_gan as TG
+    config.set_mode('tf32')
+    cfg = O.HotPathConfig(n_words=300, n_speakers=12)
+    inp = to_dev(synth.make_inputs(cfg, 8, seed=11), dev)
+    hist = {}
+    for use_graph in (False, True):
+        old = config.set_graphs(use_graph)
+        torch.manual_seed(123)
+        args, G, D, _, _ = build_ours(cfg, dev)
+        G.train(); D.train()
+        g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+        d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+        rets = [TG.train_iter_gan(args, 11, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt) for _ in range(6)]
+        hist[use_graph] = (rets, {k: v.detach().clone() for k, v in G.state_dict().items()}, int(g_opt.state_dict()['state'][0]['step']))
+        config.set_graphs(old)
+    if use_graph:
+        slots = [s for s in TG._graph_slots.values() if s.graph is not None]
+        assert slots, 'the iteration was never captured into a CUDA graph'
+    # atomically-accumulated gradients are not bit-reproducible and a GAN amplifies round-off from step to step:
+    # the first replayed steps must agree tightly, later ones loosely
+    for i, (a, b) in enumerate(zip(hist[False][0], hist[True][0])):
+        assert set(a) == set(b)
+        worst = max(abs(a[k] - b[k]) / (abs(a[k]) + 1e-6) for k in a)
+        print('step %d eager-vs-graph worst relative loss difference %.2e' % (i, worst))
+        assert worst <= (1e-3 if i <= 2 else 3e-2), (i, a, b)
+    assert hist[False][2] == hist[True][2] == 6
+    for k, v in hist[False][1].items():
+        # (biases whose gradient is analytically zero random-walk by +-lr under Adam: excluded)
+        if v.is_floating_point() and v.numel() >= 256 and k not in ZERO_GRAD_KEYS:
+            assert rel_l2(hist[True][1][k], v) < 5e-2, k
