@@ -175,6 +175,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')            # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     from model import vocab

@@ -103,12 +103,12 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
     in_audio = in_audio.contiguous().float()
     vid = vid_indices.contiguous() if vid_indices is not None else None
 
-    use_graph = (config.graphs() and noise is None and world == 1 and not _lib.TRACE_ONLY and torch.cuda.is_available())
+    use_graph = (config.graphs() and noise is None and not _lib.TRACE_ONLY and torch.cuda.is_available())
     sc = None
     if use_graph:
         gg, dg = pose_dec_optim.param_groups[0], dis_optim.param_groups[0]
         key = (id(G), id(D), id(pose_dec_optim), id(dis_optim), dev.index, B, T, Dm, tuple(in_audio.shape), after, do_d, do_div, do_kld,
-               G.training, D.training, config.mode(), config.overlap(), float(gg['lr']), float(dg['lr']), tuple(gg['betas']), tuple(dg['betas']),
+               G.training, D.training, config.mode(), config.overlap(), world, float(gg['lr']), float(dg['lr']), tuple(gg['betas']), tuple(dg['betas']),
                float(args.loss_regression_weight), float(args.loss_gan_weight), float(args.loss_kld_weight), float(args.loss_reg_weight),
                int(args.n_pre_poses))
         slot = _graph_slots.setdefault(key, _GraphSlot())
@@ -156,14 +156,22 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
         try:
             ge.arena.bind_optimizer(g_opt); de.arena.bind_optimizer(d_opt)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                slot.sc = _enqueue_step(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None, 1,
-                                        host_step=False)
-            slot.graph = graph
+            out = {}
+            gen = _step_segments(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None,
+                                 _dist_world(), False, out)
+            graphs, arenas = [], []
+            done = False
+            while not done:                       # one CUDA graph per collective-free stretch of the iteration
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    try:
+                        arenas.append(next(gen))
+                    except StopIteration:
+                        done = True
+                graphs.append(graph)
+            slot.graph, slot.arenas, slot.sc = graphs, arenas, out['sc']
         except Exception as exc:            # capture unsupported for some launch: stay on the eager path
             slot.failed = True
-            import traceback
             import warnings
             root = exc
             while root.__context__ is not None:
@@ -172,7 +180,10 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
                           % (str(exc).splitlines()[0], type(root).__name__, str(root).splitlines()[0] if str(root) else ''))
             torch.cuda.synchronize()
             return None
-    slot.graph.replay()
+    for i, graph in enumerate(slot.graph):
+        graph.replay()
+        if i < len(slot.arenas):
+            _allreduce_grads(slot.arenas[i])      # eager NCCL call between two graph segments
     _, do_d, _, _ = _flags(args, epoch)
     ge.arena.note_steps(1)
     if do_d:
@@ -181,7 +192,19 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
 
 
 def _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step):
-    """Enqueues every kernel of one iteration (no host synchronisation); returns the fp64 scalars buffer."""
+    """Eager iteration: enqueues every kernel (no host synchronisation) and runs the gradient all-reduces in line;
+    returns the fp64 scalars buffer."""
+    out = {}
+    for arena in _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, out):
+        _allreduce_grads(arena)
+    return out['sc']
+
+
+def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, result):
+    """Generator over the launch sequence of one iteration.  With world > 1 it yields the flat gradient arena at the two
+    points where gradients must be summed across ranks (after D's backward, after G's backward): the caller performs
+    the collective (NCCL) and resumes.  Each stretch between yields touches no collective, has all auxiliary streams
+    joined at its ends and can therefore be captured as its own CUDA graph.  result['sc'] = fp64 scalars buffer."""
     dev = target.device
     B, T, Dm = target.shape
     after, do_d, do_div, do_kld = _flags(args, epoch)
@@ -259,7 +282,7 @@ def _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_op
         ops.bce_sigmoid(p_fake, B, -1.0, 1.0, 1.0, sc[5:], dlogit)
         de.backward(dlogit, need_dposes=False)
         if world > 1:
-            _allreduce_grads(de.arena)
+            yield de.arena
         de.arena.adam_step(dis_optim, grad_scale=1.0 / world, host_step=host_step)
         de.prep_weights()
 
@@ -283,9 +306,9 @@ def _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_op
         ops.add(d_out, dposes, d_out, B * T * Dm)
     ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
     if world > 1:
-        _allreduce_grads(ge.arena)
+        yield ge.arena
     ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world, host_step=host_step)
-    return sc
+    result['sc'] = sc
 
 
 def _stack_masks(ws, per_pass, rows_per_pass):
