@@ -27,7 +27,9 @@ __device__ __forceinline__ void spin_until(const int* counter, int target) {
   while (ld_acquire_gpu(counter) < target) { __nanosleep(20); }
 }
 __device__ __forceinline__ void epi_bar512() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// fast-mode gate non-linearities (absolute error ~1e-6, far below the TF32 rounding of the products they follow)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 // optional per-step phase stamps of CTA (0,0,0) (tg_debug_gru_trace): trace[step*16 + slot] = %globaltimer
 __device__ __forceinline__ void stamp(long long* trace, int step, int slot) {
   if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
           if (s > 0) { ghr += ghs[jj * GS + bb]; ghz += ghs[(u + jj) * GS + bb]; ghn += ghs[(2 * u + jj) * GS + bb]; }
           const float r = sigmoidf_(gir[e] + ghr);
           const float z = sigmoidf_(giz[e] + ghz);
-          const float n = tanhf(gin[e] + r * ghn);
+          const float n = tanhf_(gin[e] + r * ghn);
           const float h = (1.f - z) * n + z * hpv[e];
           const long long o = ((long long)b * T + t) * row2H + dir * H + unit;
           p.out[o] = h;

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from model import vocab
 from model.tcn import TemporalConvNet
-from tgb200 import _lib, ops
+from tgb200 import _lib, config, ops
 from tgb200.engine import DiscriminatorEngine, GeneratorEngine
 
 _RING = 4          # live training forwards whose activations are kept for a later backward (reference pattern needs 3)
@@ -153,6 +153,7 @@ class PoseGenerator(nn.Module):
         self._slot_gen = {}
         self._gen_counter = itertools.count(1)
         self._ring = itertools.cycle(range(_RING))
+        self._graphs = {}
 
     # ---- engine plumbing (not part of the reference API) ------------------------------------------------------------
     def engine(self) -> GeneratorEngine:
@@ -179,6 +180,10 @@ class PoseGenerator(nn.Module):
             assert vid_indices is not None
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         slot = ('ring%d_%d' % (next(self._ring), B)) if grad else ('nograd_%d' % B)
+        if not grad and self._injected is None and config.graphs() and not _lib.TRACE_ONLY:
+            out = self._forward_graphed(pre_seq, in_text, in_audio, vid_indices, slot)
+            if out is not None:
+                return out
         eng.ensure(dev, slot)
         eps, masks = (None, None)
         if self._injected is not None:
@@ -204,6 +209,63 @@ class PoseGenerator(nn.Module):
         if in_text_c is not None and self.input_context != 'none':
             assert poses.shape[1] == in_text.shape[1]
         return poses, z, mu, logvar
+
+
+def _pg_forward_graphed(self, pre_seq, in_text, in_audio, vid_indices, slot):
+    """Inference fast path (no autograd): after two eager calls with a given shape the ~70 launches of the forward are
+    captured into a CUDA graph on static input buffers and replayed; the speaker-style noise is drawn inside the graph
+    from the device-resident Philox offset, so every call still samples a fresh z (embedding_net.py:10-13)."""
+    dev = pre_seq.device
+    eng = self.engine().ensure(dev, slot)
+    B, T = pre_seq.shape[0], pre_seq.shape[1]
+    key = (slot, dev.index, tuple(pre_seq.shape), tuple(in_text.shape) if in_text is not None else None,
+           tuple(in_audio.shape) if in_audio is not None else None, self.training, config.mode(), config.overlap())
+    st = self._graphs.setdefault(key, {'calls': 0, 'graph': None, 'failed': False})
+    st['calls'] += 1
+    if st['failed'] or st['calls'] <= 2:
+        return None
+    ws = eng.ws
+    if 'pre' not in st:
+        st['pre'] = ws.get('gi.pre', tuple(pre_seq.shape))
+        st['text'] = ws.get('gi.text', tuple(in_text.shape), torch.int64) if in_text is not None else None
+        st['audio'] = ws.get('gi.audio', tuple(in_audio.shape)) if in_audio is not None else None
+        st['vid'] = ws.get('gi.vid', tuple(vid_indices.shape), torch.int64) if vid_indices is not None else None
+    st['pre'].copy_(pre_seq)
+    if st['text'] is not None:
+        st['text'].copy_(in_text)
+    if st['audio'] is not None:
+        st['audio'].copy_(in_audio)
+    if st['vid'] is not None:
+        st['vid'].copy_(vid_indices)
+    if st['graph'] is None:
+        try:
+            off = self._noise.offset_dev(dev)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                eps = None
+                if self.z_mode is not None:
+                    eps = ws.get('noise.eps', (B, 16))
+                    ops.philox_normal(eps, B * 16, self._noise.seed, off, 1000)
+                masks = eng.make_masks(B, T, self._noise.seed, off) if self.training else None
+                self._noise.advance()
+                eng.prep_weights()
+                st['outs'] = eng.forward(st['pre'], st['text'], st['audio'], st['vid'], eps, B, self.training, masks, n_bn_updates=1,
+                                         save=False)
+            st['graph'] = graph
+        except Exception as exc:
+            st['failed'] = True
+            import warnings
+            warnings.warn('tgb200: CUDA-graph capture of PoseGenerator.forward failed (%s); using eager launches' % (str(exc).splitlines()[0],))
+            torch.cuda.synchronize()
+            return None
+    st['graph'].replay()
+    poses, z, mu, logvar = st['outs']
+    return (poses.clone(), z.clone() if z is not None else None, mu.clone() if mu is not None else None,
+            logvar.clone() if logvar is not None else None)
+
+
+PoseGenerator._forward_graphed = _pg_forward_graphed
 
 
 class _DiscriminatorFn(torch.autograd.Function):

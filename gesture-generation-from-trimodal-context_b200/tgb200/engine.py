@@ -310,13 +310,14 @@ class GeneratorEngine:
                     wT = ws.get(f'tcn.wT{i}_{j}', (k, Cin, N)) if config.fast() else None
                     ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (k, N, Cin)), wT, ws.get(f'tcn.inv{i}_{j}', (N,)),
                                         N, Cin, k)
-        if config.fast():
-            for name in ('text_encoder.decoder.weight', 'out.0.weight', 'out.2.weight'):
-                if name.startswith('text') and not self.use_text:
-                    continue
-                w = self.P(name)
-                ops.transpose(w, ws.get('T.' + name, (w.shape[1], w.shape[0])), w.shape[0], w.shape[1])
-        self.gru.prep()
+        with side.on(S_WAV):        # not needed before the GRU / the backward pass: off the critical path (joined before the GRU input)
+            if config.fast():
+                for name in ('text_encoder.decoder.weight', 'out.0.weight', 'out.2.weight'):
+                    if name.startswith('text') and not self.use_text:
+                        continue
+                    w = self.P(name)
+                    ops.transpose(w, ws.get('T.' + name, (w.shape[1], w.shape[0])), w.shape[0], w.shape[1])
+            self.gru.prep()
 
     def make_masks(self, Bt, T, seed, offset_dev, sid0=0):
         """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel."""
