@@ -23,6 +23,7 @@ constexpr int A_STAGE_BYTES = BM * 128;
 struct GemmP {
   float* C; int ldc;
   int M, N, K, taps, shift0, T;
+  int clip_rows, tiles_per_clip;     // clip mode (clip_rows > 0): tile = 128 rows of one clip; C row = clip*clip_rows + t
   const float* escale; const float* bias; int act1; float slope1;
   const float* mask; int ldmask; const float* residual; int ldres; int act2; int accumulate;
 };
@@ -40,7 +41,13 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // flat mode: tile rows m0.. of the [M,K] matrix (A map = {K, a_rows, 1}); clip mode: rows t0.. of clip `clip`
+  // (A map = {K, clip_rows, clips} with its own row / clip pitches, e.g. overlapping convolution windows)
+  const int clip = p.clip_rows > 0 ? blockIdx.x / p.tiles_per_clip : 0;
+  const int t0 = p.clip_rows > 0 ? (blockIdx.x - clip * p.tiles_per_clip) * BM : blockIdx.x * BM;
+  const int m0 = clip * p.clip_rows + t0;                    // first output row of the tile
+  const int m_end = p.clip_rows > 0 ? clip * p.clip_rows + p.clip_rows : p.M;
+  const int n0 = blockIdx.y * BN;
   const int nkb = (p.K + BKF - 1) / BKF;
   const int iters = nkb * p.taps;
   constexpr uint32_t TMEM_COLS_1 = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(sa, &tmA, &full_bar[s], kb * BKF, m0 + shift);
+        tma_load_3d(sa, &tmA, &full_bar[s], kb * BKF, t0 + shift, clip);
         tma_load_2d(sb, &tmB, &full_bar[s], kb * BKF, tap * p.N + n0);
       }
     }
@@ -104,7 +111,6 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
     bool tap0_ok = true;
     if (p.taps == 2) {
       const int t = m % p.T;
@@ -115,8 +121,17 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
     const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                         (!p.mask || ((p.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) &&
                         (!p.residual || ((p.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
+    // All TMA loads have landed and every MMA has retired once tmem_full_bar fires, so the pipeline stages are free:
+    // each epilogue warp transposes its 32x32 chunk through a padded staging tile there (row pitch 36 floats: the
+    // float4 writes of 8 consecutive rows and the float4 reads of one row are both bank-conflict free), after which a
+    // warp instruction touches 4 rows x 128 contiguous bytes of C / mask / residual instead of 32 rows x 16 bytes.
+    constexpr int SP = 36;
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * SP);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int nb = n0 + c0;
+      if (nb >= p.N) break;
       float v[32];
       if (p.taps == 2) {
         float v0[32];
@@ -131,52 +146,60 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
         tmem_ld32(lane_addr + (uint32_t)c0, v);
         tmem_ld_wait();
       }
-      const int nb = n0 + c0;
-      if (row_ok && nb < p.N) {
-      float* crow = p.C + (long long)m * p.ldc + nb;
-      const float* mrow = p.mask ? p.mask + (long long)m * p.ldmask + nb : nullptr;
-      const float* rrow = p.residual ? p.residual + (long long)m * p.ldres + nb : nullptr;
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        if (nb + j4 >= p.N) break;
-        const bool full4 = vec_ok && (nb + j4 + 3 < p.N);
-        float o[4];
+      for (int j4 = 0; j4 < 32; j4 += 4) *reinterpret_cast<float4*>(stg + lane * SP + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+      __syncwarp();
+      const int n = nb + c4;                      // this lane's 4 columns
+      float es[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n + e < p.N) {
+          if (p.escale) es[e] = __ldg(p.escale + n + e);
+          if (p.bias) bs[e] = __ldg(p.bias + n + e);
+        }
+      }
+      const bool full4 = vec_ok && (n + 3 < p.N);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        const int mr = m0 + q * 32 + r;
+        if (mr >= m_end || n >= p.N) continue;
+        const float4 x4 = *reinterpret_cast<const float4*>(stg + r * SP + c4);
+        float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        float* crow = p.C + (long long)mr * p.ldc + n;
+        const float* mrow = p.mask ? p.mask + (long long)mr * p.ldmask + n : nullptr;
+        const float* rrow = p.residual ? p.residual + (long long)mr * p.ldres + n : nullptr;
         float mk[4] = {1.f, 1.f, 1.f, 1.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
         if (full4) {
-          if (mrow) { const float4 t4 = *reinterpret_cast<const float4*>(mrow + j4); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
-          if (rrow) { const float4 t4 = *reinterpret_cast<const float4*>(rrow + j4); rs[0] = t4.x; rs[1] = t4.y; rs[2] = t4.z; rs[3] = t4.w; }
-          if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(crow + j4); old[0] = t4.x; old[1] = t4.y; old[2] = t4.z; old[3] = t4.w; }
+          if (mrow) { const float4 t4 = *reinterpret_cast<const float4*>(mrow); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
+          if (rrow) { const float4 t4 = *reinterpret_cast<const float4*>(rrow); rs[0] = t4.x; rs[1] = t4.y; rs[2] = t4.z; rs[3] = t4.w; }
+          if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(crow); old[0] = t4.x; old[1] = t4.y; old[2] = t4.z; old[3] = t4.w; }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (nb + j4 + e < p.N) {
-              if (mrow) mk[e] = mrow[j4 + e];
-              if (rrow) rs[e] = rrow[j4 + e];
-              if (p.accumulate) old[e] = crow[j4 + e];
+            if (n + e < p.N) {
+              if (mrow) mk[e] = mrow[e];
+              if (rrow) rs[e] = rrow[e];
+              if (p.accumulate) old[e] = crow[e];
             }
           }
         }
+        float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int n = nb + j4 + e;
-          float x = v[j4 + e];
-          if (n < p.N) {
-            if (p.escale) x *= __ldg(p.escale + n);
-            if (p.bias) x += __ldg(p.bias + n);
-          }
-          x = tg_act(x, p.act1, p.slope1);
-          x = x * mk[e] + rs[e];
-          x = tg_act(x, p.act2, 0.f);
-          o[e] = x + old[e];
+          float y = x[e] * es[e] + bs[e];
+          y = tg_act(y, p.act1, p.slope1);
+          y = y * mk[e] + rs[e];
+          y = tg_act(y, p.act2, 0.f);
+          o[e] = y + old[e];
         }
         if (full4) {
-          *reinterpret_cast<float4*>(crow + j4) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (nb + j4 + e < p.N) crow[j4 + e] = o[e];
+            if (n + e < p.N) crow[e] = o[e];
         }
-      }
       }
       __syncwarp();
     }
@@ -212,10 +235,34 @@ int make_map_2d(CUtensorMap* m, const float* base, long long rows, long long col
   return 0;
 }
 
+// A operand: [clips][rows][cols] with row pitch ld and clip pitch cp (floats); box = 32 floats x 128 rows x 1 clip
+int make_map_a(CUtensorMap* m, const float* base, long long clips, long long rows, long long cols, long long ld, long long cp, const char* name) {
+  auto enc = get_encode();
+  if (!enc) { tg_set_error("%s: cuTensorMapEncodeTiled unavailable", name); return -4; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 4) & 15) || ((cp * 4) & 15)) {
+    tg_set_error("%s: TMA needs 16-byte aligned base and pitches (ld=%lld clip pitch=%lld)", name, ld, cp); return -1;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)clips};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)cp * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tg_set_error("%s: cuTensorMapEncodeTiled(3d) failed (%d) clips=%lld rows=%lld cols=%lld ld=%lld cp=%lld", name, (int)r, clips, rows, cols, ld, cp);
+    return -4;
+  }
+  return 0;
+}
+
 template <int BN, int NSTAGE>
 int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   CUtensorMap ta, tb;
-  int rc = make_map_2d(&ta, g.A, g.a_rows, g.K, g.lda, BM, "tg_gemm_tf32(A)");
+  const bool clipm = g.clip_rows > 0;
+  const long long clips = clipm ? g.M / g.clip_rows : 1;
+  const long long arows = clipm ? g.clip_rows : g.a_rows;
+  const long long cp = clipm ? g.a_clip_pitch : arows * (long long)g.lda;
+  int rc = make_map_a(&ta, g.A, clips, arows, g.K, g.lda, cp > 0 ? cp : 4, "tg_gemm_tf32(A)");
   if (rc) return rc;
   rc = make_map_2d(&tb, g.Bw, (long long)g.taps * g.N, g.K, g.ldb, BN, "tg_gemm_tf32(B)");
   if (rc) return rc;
@@ -223,6 +270,8 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   p.C = g.C; p.ldc = g.ldc; p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.shift0 = g.shift0; p.T = g.T > 0 ? g.T : 1;
   p.escale = g.escale; p.bias = g.bias; p.act1 = g.act1; p.slope1 = g.slope1; p.mask = g.mask; p.ldmask = g.ldmask;
   p.residual = g.residual; p.ldres = g.ldres; p.act2 = g.act2; p.accumulate = g.accumulate;
+  p.clip_rows = clipm ? g.clip_rows : 0;
+  p.tiles_per_clip = clipm ? tg_ceil_div(g.clip_rows, BM) : 0;
   constexpr size_t smem = (size_t)NSTAGE * (A_STAGE_BYTES + BN * 128) + (2 * NSTAGE + 1) * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -230,7 +279,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
     if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
     attr_done = true;
   }
-  dim3 grid(tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN));
+  dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN));
   gemm_tf32_kernel<BN, NSTAGE><<<grid, 192, smem, s>>>(ta, tb, p);
   TG_CHECK_LAUNCH("tg_gemm_tf32");
   return 0;
@@ -242,6 +291,7 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   const tg_gemm_tf32_t& g = *gp;
   TG_REQUIRE(g.A && g.Bw && g.C && g.M > 0 && g.N > 0 && g.K > 0, "tg_gemm_tf32");
   TG_REQUIRE(g.taps == 1 || g.taps == 2, "tg_gemm_tf32");
+  TG_REQUIRE(g.clip_rows == 0 || (g.clip_rows > 0 && g.taps == 1 && g.M % g.clip_rows == 0 && g.a_clip_pitch > 0), "tg_gemm_tf32(clip mode)");
   cudaStream_t s = (cudaStream_t)stream;
   // tile width: minimise padded N, prefer wider tiles on ties (fewer A re-reads)
   int bn;

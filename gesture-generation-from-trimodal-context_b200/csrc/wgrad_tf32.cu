@@ -13,7 +13,6 @@ namespace {
 
 using namespace umma;
 
-constexpr int NSTAGE = 4;
 
 struct WgP {
   float* dW; int ldw; int N, Cin;
@@ -24,8 +23,8 @@ struct WgP {
 
 // MN-major operand descriptor: 8 x (8 rows x 128 B) atoms; LBO = bytes between 32-element groups along MN, SBO = bytes
 // between 8-row groups along K
-template <int TK>
-__global__ void __launch_bounds__(192, 1) wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+template <int TK, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(192, MINB) wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                                                             const WgP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,18 +97,39 @@ __global__ void __launch_bounds__(192, 1) wgrad_tf32_kernel(const __grid_constan
       const int q = warp & 3;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
-      const int n = n0 + q * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      // every stage is free once tmem_full fires: transpose each 32x32 chunk through a padded staging tile so that one
+      // warp-wide reduction covers 4 rows x 128 contiguous bytes of dW (vector red.global.add.v4.f32 where aligned)
+      constexpr int SP = 36;
+      float* stg = reinterpret_cast<float*>(smem) + q * (32 * SP);
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+      const bool vec_ok = (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
 #pragma unroll 1
       for (int cc = 0; cc < 128; cc += 32) {
+        if (c0 + cc >= p.Cin) break;
         float v[32];
         tmem_ld32(lane_addr + (uint32_t)cc, v);
         tmem_ld_wait();
-        if (n < p.N && c0 + cc < p.Cin) {
-          float* dst = p.dW + (long long)n * p.ldw + c0 + cc;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + cc + j < p.Cin) atomicAdd(dst + j, v[j]);
+        for (int j4 = 0; j4 < 32; j4 += 4) *reinterpret_cast<float4*>(stg + lane * SP + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+        __syncwarp();
+        const int c = c0 + cc + c4;
+        const bool full4 = vec_ok && (c + 3 < p.Cin);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rsub;
+          const int n = n0 + q * 32 + r;
+          if (n >= p.N || c >= p.Cin) continue;
+          const float4 x = *reinterpret_cast<const float4*>(stg + r * SP + c4);
+          float* dst = p.dW + (long long)n * p.ldw + c;
+          if (full4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+          } else {
+            atomicAdd(dst, x.x);
+            if (c + 1 < p.Cin) atomicAdd(dst + 1, x.y);
+            if (c + 2 < p.Cin) atomicAdd(dst + 2, x.z);
+            if (c + 3 < p.Cin) atomicAdd(dst + 3, x.w);
+          }
         }
         __syncwarp();
       }
@@ -151,12 +171,14 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // [B clips][T rows][cols] row-major, pitch ld floats, clip stride Tfull*ld: box = 32 cols x TK rows x 1 clip
-int map_3d(CUtensorMap* m, const float* base, int B, long long T, long long Tfull, long long cols, long long ld, int TK, const char* name) {
+int map_3d(CUtensorMap* m, const float* base, int B, long long T, long long clip_pitch, long long cols, long long ld, int TK, const char* name) {
   auto enc = get_encode();
   if (!enc) { tg_set_error("%s: cuTensorMapEncodeTiled unavailable", name); return -4; }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 4) & 15)) { tg_set_error("%s: TMA alignment (ld=%lld)", name, ld); return -1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 4) & 15) || ((clip_pitch * 4) & 15)) {
+    tg_set_error("%s: TMA alignment (ld=%lld clip pitch=%lld)", name, ld, clip_pitch); return -1;
+  }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)Tfull * ld * 4};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)clip_pitch * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)TK, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -165,30 +187,34 @@ int map_3d(CUtensorMap* m, const float* base, int B, long long T, long long Tful
   return 0;
 }
 
-template <int TK>
+template <int TK, int NSTAGE, int MINB>
 int launch(const tg_wgrad_tf32_t& g, int B, int T, cudaStream_t s) {
   CUtensorMap tg_, tx_;
   int rc;
-  if ((rc = map_3d(&tg_, g.G, B, T, T, g.N, g.ldg, TK, "tg_wgrad_tf32(G)"))) return rc;
-  if ((rc = map_3d(&tx_, g.X, B, T, T, g.Cin, g.ldx, TK, "tg_wgrad_tf32(X)"))) return rc;
+  const long long xcp = (g.x_clip_pitch > 0 && B > 1) ? g.x_clip_pitch : (long long)T * g.ldx;
+  if ((rc = map_3d(&tg_, g.G, B, T, (long long)T * g.ldg, g.N, g.ldg, TK, "tg_wgrad_tf32(G)"))) return rc;
+  if ((rc = map_3d(&tx_, g.X, B, T, xcp, g.Cin, g.ldx, TK, "tg_wgrad_tf32(X)"))) return rc;
   WgP p;
   p.dW = g.dW; p.ldw = g.ldw; p.N = g.N; p.Cin = g.Cin; p.B = B; p.T = T; p.TKrows = TK; p.nt = tg_ceil_div(T, TK); p.shift = g.shift;
   const int tiles = tg_ceil_div(g.Cin, 128) * tg_ceil_div(g.N, 128);
   const int total_chunks = B * p.nt;
-  int splits = (2 * tg_num_sms()) / tiles;
+  // one wave of resident CTAs (MINB per SM); at least 4 chunks per CTA so that the fixed per-CTA cost (TMEM allocation,
+  // pipeline fill, 128x128 atomic epilogue) and the number of atomics per gradient element stay bounded for small matrices
+  int splits = (MINB * tg_num_sms()) / tiles;
   if (splits < 1) splits = 1;
   if (splits > total_chunks) splits = total_chunks;
   p.chunks_per_split = tg_ceil_div(total_chunks, splits);
+  if (p.chunks_per_split < 4) p.chunks_per_split = total_chunks < 4 ? total_chunks : 4;
   splits = tg_ceil_div(total_chunks, p.chunks_per_split);
   constexpr size_t smem = (size_t)NSTAGE * 2 * 4 * TK * 128 + (2 * NSTAGE + 1) * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel<TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel<TK, NSTAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { tg_set_error("tg_wgrad_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
     attr_done = true;
   }
   dim3 grid(tg_ceil_div(g.Cin, 128), tg_ceil_div(g.N, 128), splits);
-  wgrad_tf32_kernel<TK><<<grid, 192, smem, s>>>(tg_, tx_, p);
+  wgrad_tf32_kernel<TK, NSTAGE, MINB><<<grid, 192, smem, s>>>(tg_, tx_, p);
   TG_CHECK_LAUNCH("tg_wgrad_tf32");
   return 0;
 }
@@ -214,10 +240,14 @@ extern "C" int tg_wgrad_tf32(const tg_wgrad_tf32_t* gp, tg_stream stream) {
     int rc = tg_col_sum_f32(g.G, g.ldg, (long long)g.B * g.T, g.N, g.dbias, stream);
     if (rc) return rc;
   }
+  if (g.x_clip_pitch > 0) {
+    // X rows are per-clip windows (row pitch ldx < Cin allowed: strided-convolution windows read in place): 32-row chunks per clip
+    return launch<32, 3, 2>(g, g.B, g.T, s);
+  }
   if (g.shift == 0 || g.B == 1) {
     // no clip boundaries to respect: one flat sequence of rows, 32-row chunks
-    return launch<32>(g, 1, g.B * g.T, s);
+    return launch<32, 3, 2>(g, 1, g.B * g.T, s);      // 3 stages x 32 KB: two CTAs per SM
   }
   TG_REQUIRE(g.T <= 40, "tg_wgrad_tf32");       // shifted taps: one zero-padded chunk per clip
-  return launch<40>(g, g.B, g.T, s);
+  return launch<40, 4, 1>(g, g.B, g.T, s);
 }

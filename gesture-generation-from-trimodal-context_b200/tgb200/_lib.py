@@ -56,14 +56,16 @@ class GemmTf32(ctypes.Structure):
                 ('act1', ctypes.c_int), ('slope1', ctypes.c_float),
                 ('mask', ctypes.c_void_p), ('ldmask', ctypes.c_int),
                 ('residual', ctypes.c_void_p), ('ldres', ctypes.c_int),
-                ('act2', ctypes.c_int), ('accumulate', ctypes.c_int)]
+                ('act2', ctypes.c_int), ('accumulate', ctypes.c_int),
+                ('clip_rows', ctypes.c_int), ('a_clip_pitch', ctypes.c_longlong)]
 
 
 class WgradTf32(ctypes.Structure):
     """tg_wgrad_tf32_t (include/tg_b200.h)."""
     _fields_ = [('G', ctypes.c_void_p), ('ldg', ctypes.c_int), ('X', ctypes.c_void_p), ('ldx', ctypes.c_int),
                 ('dW', ctypes.c_void_p), ('ldw', ctypes.c_int), ('dbias', ctypes.c_void_p),
-                ('B', ctypes.c_int), ('T', ctypes.c_int), ('N', ctypes.c_int), ('Cin', ctypes.c_int), ('shift', ctypes.c_int)]
+                ('B', ctypes.c_int), ('T', ctypes.c_int), ('N', ctypes.c_int), ('Cin', ctypes.c_int), ('shift', ctypes.c_int),
+                ('x_clip_pitch', ctypes.c_longlong)]
 
 
 def _ctype(decl: str):

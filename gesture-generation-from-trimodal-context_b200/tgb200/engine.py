@@ -64,7 +64,7 @@ class _Overlap:
 
 
 side = _Overlap()
-S_WGRAD, S_WAV, S_DREAL = 1, 2, 3
+S_WGRAD, S_WAV, S_DREAL, S_WAVW = 1, 2, 3, 4
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -319,31 +319,52 @@ class GeneratorEngine:
                     ops.transpose(w, ws.get('T.' + name, (w.shape[1], w.shape[0])), w.shape[0], w.shape[1])
             self.gru.prep()
 
-    def make_masks(self, Bt, T, seed, offset_dev, sid0=0):
-        """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel."""
+    def make_masks(self, Bt, T, seed, offset_dev, sid0=0, split=False):
+        """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel.
+        split=True: only the masks the first TCN block needs are drawn on the current stream; the others are drawn on
+        the weight-gradient stream (idle during the forward pass) and joined in text_forward before block 1."""
         ws, M = self.ws, Bt * T
         masks = {}
+        jobs = []                                   # (early, buffer, numel, p, stream id)
         sid = sid0
         if self.use_text:
             if self.p_emb > 0:
-                masks['emb'] = ws.get('mask.emb', (M, self.E)); ops.philox_dropout_mask(masks['emb'], M * self.E, self.p_emb, seed, offset_dev, sid)
+                masks['emb'] = ws.get('mask.emb', (M, self.E)); jobs.append((True, masks['emb'], M * self.E, self.p_emb, sid))
             sid += 1
             for i in range(self.n_tcn):
                 for j in (1, 2):
                     if self.p_tcn > 0:
                         mk = ws.get(f'mask.tcn{i}_{j}', (M, self.H))
-                        ops.philox_dropout_mask(mk, M * self.H, self.p_tcn, seed, offset_dev, sid)
+                        jobs.append((i == 0, mk, M * self.H, self.p_tcn, sid))
                         masks[f'tcn{i}_{j}'] = mk
                     sid += 1
         for l in range(self.L - 1):
             if self.p_gru > 0:
                 mk = ws.get(f'mask.gru{l}', (M, 2 * self.H))
-                ops.philox_dropout_mask(mk, M * 2 * self.H, self.p_gru, seed, offset_dev, sid)
+                jobs.append((False, mk, M * 2 * self.H, self.p_gru, sid))
                 masks[f'gru{l}'] = mk
             sid += 1
+        for early, mk, n, p, sd in jobs:
+            if early or not split:
+                ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
+        if split:
+            with side.on(S_WGRAD):
+                for early, mk, n, p, sd in jobs:
+                    if not early:
+                        ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
         return masks
 
+    def start_wav(self, in_audio, training, n_bn_updates=1):
+        """Queues the WavEncoder forward on its side stream ahead of everything else of the iteration (it is the longest
+        chain in front of the GRU); forward() picks the result up instead of launching it again."""
+        with side.on(S_WAV):
+            self._wav_feat = self.wav_forward(in_audio, training, n_bn_updates)
+
     # -------------------------------------------------------------------------------------------- WavEncoder
+    def wav_fast(self):
+        """conv2-4 on the tensor cores (fast mode): every pad is 0 and every pitch is a multiple of 4 floats."""
+        return config.fast() and all(p == 0 and c % 4 == 0 for (c, _, _, _, p) in self.WAV[1:])
+
     def wav_forward(self, audio, training: bool, n_updates: int = 1):
         """multimodal_context_net.py:9-28.  audio [Ba, L] -> [Ba*T, 32].  BatchNorm+LeakyReLU(0.3) are never materialised:
         they are applied as the next convolution's operand prologue."""
@@ -353,6 +374,7 @@ class GeneratorEngine:
         self.wav_T = [L]
         x = audio
         scale = shift = None
+        fast = self.wav_fast()
         for li, (cin, cout, k, s, pad) in enumerate(self.WAV):
             conv = pre + str(3 * li)
             tin = self.wav_T[-1]
@@ -361,6 +383,15 @@ class GeneratorEngine:
             y = ws.get(f'wav.y{li}', (Ba * tout, cout))
             if li == 0:
                 ops.conv1_direct(x, self.P(conv + '.weight'), self.P(conv + '.bias'), y, B=Ba, Tin=tin, Tout=tout, N=cout, taps=k, stride=s, pad=pad)
+            elif fast:
+                # tensor cores: materialise lrelu(bn(y_prev)) once, then a TF32 GEMM whose A rows are the overlapping
+                # windows [k*cin] of that channels-last activation (row pitch s*cin floats), read in place by TMA
+                a = ws.get(f'wav.a{li - 1}', (Ba * tin, cin))
+                ops.affine_lrelu(x, a, Ba * tin, cin, scale, shift, 0.3)
+                w2 = ws.get(f'wav.w2_{li}', (cout, k * cin)); w2t = ws.get(f'wav.w2t_{li}', (k * cin, cout))
+                ops.window_weights(self.P(conv + '.weight'), w2, w2t, cout, cin, k)
+                ops.gemm_tf32(a, w2, y, M=Ba * tout, N=cout, K=k * cin, lda=s * cin, clip_rows=tout, a_clip_pitch=tin * cin,
+                              bias=self.P(conv + '.bias'))
             else:
                 ops.conv1d(x, self.P(conv + '.weight'), self.P(conv + '.bias'), y, B=Ba, Tin=tin, Cin=cin, N=cout, k=k, stride=s, pad=pad,
                            pscale=scale, pshift=shift, pslope=0.3)
@@ -387,6 +418,7 @@ class GeneratorEngine:
         Ba = audio.shape[0]
         pre = 'audio_encoder.feat_extractor.'
         dy = d_feat
+        fast = self.wav_fast()
         for li in (3, 2, 1, 0):
             cin, cout, k, s, pad = self.WAV[li]
             conv = pre + str(3 * li)
@@ -394,12 +426,28 @@ class GeneratorEngine:
             x = audio if li == 0 else ws[f'wav.y{li - 1}']
             sc = ws[f'wav.scale{li - 1}'] if li > 0 else None
             sh = ws[f'wav.shift{li - 1}'] if li > 0 else None
-            ops.conv1d_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k,
-                             stride=s, pad=pad, pscale=sc, pshift=sh, pslope=0.3)
-            if li == 0:
+            if fast and li > 0:
+                a = ws[f'wav.a{li - 1}']
+                with side.on(S_WAVW):               # weight gradient off the data-gradient chain
+                    dw2 = ws.get(f'wav.dw2_{li}', (cout, k * cin)); dw2.zero_()
+                    ops.wgrad_tf32(dy, a, dw2, B=Ba, T=tout, N=cout, Cin=k * cin, ldx=s * cin, x_clip_pitch=tin * cin,
+                                   dbias=self.G(conv + '.bias'))
+                    ops.window_wgrad_add(dw2, self.G(conv + '.weight'), cout, cin, k)
+                col = ws.get('wav.col', (Ba * self.wav_T[2] * self.WAV[1][2] * self.WAV[1][0],))[:Ba * tout * k * cin].view(Ba * tout, k * cin)
+                ops.gemm_tf32(dy, ws[f'wav.w2t_{li}'], col, M=Ba * tout, N=k * cin, K=cout)
+                da = ws.get(f'wav.da{li - 1}', (Ba * tin, cin))
+                ops.col2im(col, da, B=Ba, Tin=tin, Tout=tout, Cin=cin, k=k, stride=s)
+            elif fast and cin == 1 and cout == 16 and k <= 15:
+                ops.conv1_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=Ba, Tin=tin, Tout=tout, N=cout, taps=k, stride=s,
+                                pad=pad)
                 break
-            da = ws.get(f'wav.da{li - 1}', (Ba * tin, cin))
-            ops.conv1d_dgrad(dy, self.P(conv + '.weight'), da, B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s, pad=pad)
+            else:
+                ops.conv1d_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k,
+                                 stride=s, pad=pad, pscale=sc, pshift=sh, pslope=0.3)
+                if li == 0:
+                    break
+                da = ws.get(f'wav.da{li - 1}', (Ba * tin, cin))
+                ops.conv1d_dgrad(dy, self.P(conv + '.weight'), da, B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s, pad=pad)
             bn = pre + str(3 * (li - 1) + 1)
             sums = ws.get(f'wav.bsums{li - 1}', (2 * cin,), torch.float64)
             sums.zero_()
@@ -408,6 +456,7 @@ class GeneratorEngine:
             ops.bn_bwd_apply(da, x, da, Ba * tin, cin, mean, rstd, sc, sh, 0.3, self.P(bn + '.weight'), sums, self.G(bn + '.weight'),
                              self.G(bn + '.bias'))
             dy = da
+        side.join(S_WAVW)
 
     # -------------------------------------------------------------------------------------------- TextEncoderTCN
     def text_forward(self, in_text, Bt, T, masks):
@@ -421,6 +470,8 @@ class GeneratorEngine:
         x, cin = emb, E
         k = self.tcn_k
         for i in range(self.n_tcn):
+            if i == 1:
+                side.join(S_WGRAD)                 # masks of the later blocks / the GRU drawn on the side stream (make_masks split=True)
             d = 2 ** i
             q = f'text_encoder.tcn.network.{i}'
             assert cin == H, 'TemporalBlock.downsample (n_inputs != n_outputs) is not on the configured path (tcn.py:33)'
@@ -516,8 +567,11 @@ class GeneratorEngine:
         self.ctx = dict(Bt=Bt, Ba=Ba, T=T, masks=masks, pre_seq=pre_seq, in_text=in_text, in_audio=in_audio, vid=vid, eps=eps)
         audio_feat = None
         if self.use_audio:
-            with side.on(S_WAV):            # the audio encoder is independent of the text / speaker branches
-                audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
+            audio_feat = getattr(self, '_wav_feat', None)
+            self._wav_feat = None
+            if audio_feat is None:
+                with side.on(S_WAV):        # the audio encoder is independent of the text / speaker branches
+                    audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
         text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
         z = mu = logvar = None
         Z = 0
@@ -534,6 +588,7 @@ class GeneratorEngine:
             Z = 16
             z = eps
         side.join(S_WAV)
+        side.join(S_WGRAD)                          # side-stream mask draws, if text_forward did not already join them
         in_data = ws.get('g.in', (M, self.I))
         Da = 32 if self.use_audio else 0
         Dt = 32 if self.use_text else 0

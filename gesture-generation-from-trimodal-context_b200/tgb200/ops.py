@@ -87,7 +87,7 @@ def conv_wgrad(A, G, dW, *, B, Tin, Tout, N, Cin, taps=1, stride=1, dil=1, pad=0
 
 
 def gemm_tf32(A, Bw, C, *, M, N, K, lda=None, ldb=None, ldc=None, a_rows=None, taps=1, shift0=0, T=1, escale=None, bias=None, act1=0,
-              slope1=0.0, mask=None, ldmask=None, residual=None, ldres=None, act2=0, accumulate=False):
+              slope1=0.0, mask=None, ldmask=None, residual=None, ldres=None, act2=0, accumulate=False, clip_rows=0, a_clip_pitch=0):
     """C[M,N] = epi(A[M,K] @ Bw[N,K]^T) on the tcgen05 tensor cores (TF32 operands, fp32 accumulate); see tg_gemm_tf32_t."""
     g = GemmTf32()
     g.A = _p(_f32(A)); g.lda = K if lda is None else lda; g.a_rows = M if a_rows is None else a_rows
@@ -98,11 +98,12 @@ def gemm_tf32(A, Bw, C, *, M, N, K, lda=None, ldb=None, ldc=None, a_rows=None, t
     g.mask = _p(mask); g.ldmask = N if ldmask is None else ldmask
     g.residual = _p(residual); g.ldres = N if ldres is None else ldres
     g.act2 = act2; g.accumulate = 1 if accumulate else 0
+    g.clip_rows = clip_rows; g.a_clip_pitch = a_clip_pitch
     check(_L().tg_gemm_tf32(ctypes.byref(g), _s()), 'tg_gemm_tf32')
     _count()
 
 
-def wgrad_tf32(G, X, dW, *, B, T, N, Cin, shift=0, ldg=None, ldx=None, ldw=None, dbias=None):
+def wgrad_tf32(G, X, dW, *, B, T, N, Cin, shift=0, ldg=None, ldx=None, ldw=None, dbias=None, x_clip_pitch=0):
     """dW[N,Cin] += G^T X over B clips x T rows on the tensor cores (TF32); see tg_wgrad_tf32_t."""
     g = WgradTf32()
     g.G = _p(_f32(G)); g.ldg = N if ldg is None else ldg
@@ -110,6 +111,7 @@ def wgrad_tf32(G, X, dW, *, B, T, N, Cin, shift=0, ldg=None, ldx=None, ldw=None,
     g.dW = _p(_f32(dW)); g.ldw = Cin if ldw is None else ldw
     g.dbias = _p(dbias)
     g.B, g.T, g.N, g.Cin, g.shift = B, T, N, Cin, shift
+    g.x_clip_pitch = x_clip_pitch
     check(_L().tg_wgrad_tf32(ctypes.byref(g), _s()), 'tg_wgrad_tf32')
     _count(2 if dbias is not None else 1)
 
@@ -163,6 +165,24 @@ def conv1d_dgrad(dy, W, dx, *, B, Tin, Tout, Cin, N, k, stride=1, dil=1, pad=0, 
 
 def conv1_direct(x, w, bias, y, *, B, Tin, Tout, N, taps, stride, pad):
     check(_L().tg_conv1_direct_f32(_p(x), _p(w), _p(bias), _p(y), B, Tin, Tout, N, taps, stride, pad, _s()), 'tg_conv1_direct_f32')
+    _count()
+
+
+# ------------------------------------------------------------------------------------------ tensor-core WavEncoder helpers
+def window_weights(w, w2, w2t, N, Cin, k):
+    check(_L().tg_window_weights(_p(_f32(w)), _p(_f32(w2)), _p(w2t), N, Cin, k, _s()), 'tg_window_weights'); _count()
+
+
+def window_wgrad_add(dw2, dw, N, Cin, k):
+    check(_L().tg_window_wgrad_add(_p(_f32(dw2)), _p(_f32(dw)), N, Cin, k, _s()), 'tg_window_wgrad_add'); _count()
+
+
+def col2im(col, da, *, B, Tin, Tout, Cin, k, stride):
+    check(_L().tg_col2im(_p(_f32(col)), _p(_f32(da)), B, Tin, Tout, Cin, k, stride, _s()), 'tg_col2im'); _count()
+
+
+def conv1_wgrad(x, dy, dW, dbias, *, B, Tin, Tout, N, taps, stride, pad):
+    check(_L().tg_conv1_wgrad(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dW)), _p(dbias), B, Tin, Tout, N, taps, stride, pad, _s()), 'tg_conv1_wgrad')
     _count()
 
 

@@ -217,6 +217,8 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     n_pass = len(passes)
     Bt = n_pass * B
     ig = passes.index('g')
+    if ge.use_audio:
+        ge.start_wav(in_audio, G.training, n_pass)          # longest chain in front of the GRU: queue it first (side stream)
     pre_seq = ws.get('ti.pre', (B, T, Dm + 1))
     ops.make_pre_seq(target, pre_seq, B, T, Dm, args.n_pre_poses)
 
@@ -247,8 +249,7 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         if noise is not None and noise.g_masks is not None:
             g_masks = _stack_masks(ws, noise.g_masks[-n_pass:] if len(noise.g_masks) > n_pass else noise.g_masks, B * T)
         else:
-            g_masks = ge.make_masks(Bt, T, seed, off)
-    G._noise.advance()
+            g_masks = ge.make_masks(Bt, T, seed, off, split=True)
 
     def d_masks_for(i):
         if not D.training:
@@ -274,6 +275,7 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     # ---- all generator passes in one sweep
     ge.prep_weights()
     poses, z, mu, logvar = ge.forward(pre_seq, in_text, in_audio, vid_all, eps_all, Bt, G.training, g_masks, n_bn_updates=n_pass)
+    G._noise.advance()          # after the forward has joined the side-stream mask draws that still read this iteration's offset
 
     # ---- train D (train_gan.py:24-43)
     if do_d:

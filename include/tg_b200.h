@@ -75,6 +75,10 @@ int tg_conv_wgrad_f32(const tg_conv_wgrad_t* p, tg_stream stream);
  * as TF32 (10-bit mantissa), accumulation is fp32.  taps == 2 is the TCN causal dilated convolution (tcn.py:19-31)
  * and its data gradient: the shifted tap only contributes to rows whose clip-local time t = m % T satisfies
  * 0 <= t + shift0 < T.  Epilogue as tg_conv_gemm_f32.  Same reference call sites as tg_conv_gemm_f32.
+ * Clip mode (clip_rows > 0, taps == 1): the M = clips*clip_rows logical rows of A are addressed as
+ * A + clip*a_clip_pitch + t*lda (+ k), where lda may be SMALLER than K - row t is then the window of a strided
+ * convolution over a channels-last signal (lda = stride*Cin, K = k*Cin: WavEncoder conv2-4,
+ * multimodal_context_net.py:16-22) read in place by the TMA unit: no im2col copy.  C / mask / residual stay flat [M, .].
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* A;  int lda; long long a_rows;
@@ -87,6 +91,7 @@ typedef struct {
   const float* residual; int ldres;
   int act2;
   int accumulate;
+  int clip_rows; long long a_clip_pitch;    /* clip mode, see above (0 = flat) */
 } tg_gemm_tf32_t;
 int tg_gemm_tf32(const tg_gemm_tf32_t* p, tg_stream stream);
 
@@ -100,6 +105,9 @@ typedef struct {
   float* dW;      int ldw;
   float* dbias;
   int B, T, N, Cin, shift;
+  long long x_clip_pitch;   /* > 0: clip b of X starts at X + b*x_clip_pitch and its row t at + t*ldx, where ldx may be smaller
+                               than Cin (row t = the window of a strided convolution, Cin = k*channels: WavEncoder conv2-4
+                               weight gradients, multimodal_context_net.py:16-22); 0: X is the flat [B*T, Cin] matrix */
 } tg_wgrad_tf32_t;
 int tg_wgrad_tf32(const tg_wgrad_tf32_t* p, tg_stream stream);
 int tg_col_sum_f32(const float* g, int ld, long long M, int N, float* out, tg_stream stream);
@@ -108,6 +116,24 @@ int tg_col_sum_f32(const float* g, int ld, long long M, int N, float* out, tg_st
  * multimodal_context_net.py:13).  HBM-bound: x [B,Tin] -> y [B,Tout,N] channels-last, N <= 32, taps <= 32. */
 int tg_conv1_direct_f32(const float* x, const float* w, const float* bias, float* y,
                         int B, int Tin, int Tout, int N, int taps, int stride, int pad, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core WavEncoder path (fast mode; multimodal_context_net.py:12-23 forward and autograd).  conv2-4 run as
+ * tg_gemm_tf32 (clip mode) / tg_wgrad_tf32 (x_clip_pitch) over the overlapping-window view of the channels-last
+ * activation (BatchNorm + LeakyReLU(0.3) materialised by tg_affine_lrelu); these are the CUDA-core pieces around them.
+ * --------------------------------------------------------------------------------------------------------- */
+/* nn.Conv1d filter w [N,Cin,k] -> w2 [N, k*Cin] (tap-major: the element order of a window row) and, if non-NULL,
+ * w2t [k*Cin, N] (operand of the data-gradient GEMM) */
+int tg_window_weights(const float* w, float* w2, float* w2t, int N, int Cin, int k, tg_stream stream);
+/* dw [N,Cin,k] += dw2 [N, k*Cin] */
+int tg_window_wgrad_add(const float* dw2, float* dw, int N, int Cin, int k, tg_stream stream);
+/* data gradient of a strided, unpadded Conv1d from the "column" matrix col [B*Tout, k*Cin] = dY @ w2:
+ * da[b, s, c] = sum over (t, j) with t*stride + j == s of col[(b*Tout+t), j*Cin + c]; gather, no atomics; Cin % 4 == 0 */
+int tg_col2im(const float* col, float* da, int B, int Tin, int Tout, int Cin, int k, int stride, tg_stream stream);
+/* conv1 (Cin = 1, N = 16, taps <= 15) weight and bias gradient: dW[n,j] += sum dy[(b,t),n] * x[b, t*stride + j - pad];
+ * dbias[n] += sum dy[(b,t),n] (dbias may be NULL) */
+int tg_conv1_wgrad(const float* x, const float* dy, float* dW, float* dbias, int B, int Tin, int Tout, int N, int taps, int stride,
+                   int pad, tg_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * BatchNorm1d, train mode (multimodal_context_net.py:14,17,20,214,217) over a [M,C] channels-last matrix.

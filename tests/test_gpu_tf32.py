@@ -137,3 +137,54 @@ def test_wgrad_tf32(dev, B, T, N, Cin, shift):
     e = rel_l2(dW, ref)
     assert e < TF32_TOL, e
     assert rel_l2(db, G.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('B,Tin,cin,cout,k,s', [(3, 200, 16, 32, 15, 6), (128, 1313, 32, 64, 15, 6), (128, 217, 64, 32, 15, 6),
+                                                (4, 7891, 16, 32, 15, 6)])
+def test_strided_conv_window_gemm_fwd_bwd(dev, B, Tin, cin, cout, k, s):
+    """WavEncoder conv2-4 (multimodal_context_net.py:16-22) on the tensor cores: forward = TF32 GEMM over the overlapping-window
+    view (tg_gemm_tf32 clip mode), weight gradient = tg_wgrad_tf32 over the same view, data gradient = column GEMM + tg_col2im."""
+    from tgb200 import ops
+    Tout = (Tin - k) // s + 1
+    x = _rand(B, Tin, cin, dev=dev); w = _rand(cout, cin, k, dev=dev, seed=1, scale=(cin * k) ** -0.5); b = _rand(cout, dev=dev, seed=2)
+    w2 = torch.empty(cout, k * cin, device=dev); w2t = torch.empty(k * cin, cout, device=dev)
+    ops.window_weights(w, w2, w2t, cout, cin, k)
+    assert torch.equal(w2, w.permute(0, 2, 1).reshape(cout, k * cin)) and torch.equal(w2t, w2.t())
+    y = torch.full((B * Tout, cout), float('nan'), device=dev)
+    ops.gemm_tf32(x.view(B * Tin, cin), w2, y, M=B * Tout, N=cout, K=k * cin, lda=s * cin, clip_rows=Tout, a_clip_pitch=Tin * cin, bias=b)
+    xr = x.double().transpose(1, 2).requires_grad_(True)
+    wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    ref = F.conv1d(xr, wr, br, stride=s)
+    assert rel_l2(y.view(B, Tout, cout), ref.transpose(1, 2)) < TF32_TOL
+    dy = _rand(B, Tout, cout, dev=dev, seed=3)
+    ref.backward(dy.double().transpose(1, 2))
+    # weight gradient (accumulates)
+    dw2 = torch.zeros(cout, k * cin, device=dev); db = torch.ones(cout, device=dev); dw = torch.ones(cout, cin, k, device=dev)
+    ops.wgrad_tf32(dy.view(B * Tout, cout), x.view(B * Tin, cin), dw2, B=B, T=Tout, N=cout, Cin=k * cin, ldx=s * cin, x_clip_pitch=Tin * cin,
+                   dbias=db)
+    ops.window_wgrad_add(dw2, dw, cout, cin, k)
+    assert rel_l2(dw - 1.0, wr.grad) < TF32_TOL, rel_l2(dw - 1.0, wr.grad)
+    assert rel_l2(db - 1.0, br.grad) < 1e-5
+    # data gradient
+    col = torch.empty(B * Tout, k * cin, device=dev); da = torch.full((B * Tin, cin), float('nan'), device=dev)
+    ops.gemm_tf32(dy.view(B * Tout, cout), w2t, col, M=B * Tout, N=k * cin, K=cout)
+    ops.col2im(col, da, B=B, Tin=Tin, Tout=Tout, Cin=cin, k=k, stride=s)
+    torch.cuda.synchronize()
+    assert rel_l2(da.view(B, Tin, cin), xr.grad.transpose(1, 2)) < TF32_TOL
+
+
+@pytest.mark.parametrize('B,Tin', [(2, 1000), (128, 36267), (5, 36266)])
+def test_conv1_wgrad(dev, B, Tin):
+    """Weight / bias gradient of WavEncoder conv1 (Conv1d(1,16,15,stride 5,pad 1600), multimodal_context_net.py:13), fp32."""
+    from tgb200 import ops
+    k, s, pad, N = 15, 5, 1600, 16
+    Tout = (Tin + 2 * pad - k) // s + 1
+    x = _rand(B, Tin, dev=dev); dy = _rand(B, Tout, N, dev=dev, seed=1)
+    w = torch.zeros(N, 1, k, dtype=torch.float64, device=dev, requires_grad=True); bb = torch.zeros(N, dtype=torch.float64, device=dev, requires_grad=True)
+    ref = F.conv1d(x.double().unsqueeze(1), w, bb, stride=s, padding=pad)
+    ref.backward(dy.double().transpose(1, 2))
+    dw = torch.ones(N, k, device=dev); db = torch.ones(N, device=dev)
+    ops.conv1_wgrad(x, dy.view(B * Tout, N), dw, db, B=B, Tin=Tin, Tout=Tout, N=N, taps=k, stride=s, pad=pad)
+    torch.cuda.synchronize()
+    assert rel_l2(dw - 1.0, w.grad.view(N, k)) < 1e-4, rel_l2(dw - 1.0, w.grad.view(N, k))
+    assert rel_l2(db - 1.0, bb.grad) < 1e-4
