@@ -20,7 +20,18 @@ using namespace umma;
 constexpr int BM = 128, BKF = 32;            // BKF floats = 128 bytes
 constexpr int A_STAGE_BYTES = BM * 128;
 
+// optional phase stamps of CTA (0,0) (tg_debug_gemm_trace): trace[slot] = %globaltimer
+long long* g_trace = nullptr;
+__device__ __forceinline__ void stamp(long long* trace, int slot) {
+  if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+    trace[slot] = (long long)t;
+  }
+}
+
 struct GemmP {
+  long long* trace;
   float* C; int ldc;
   int M, N, K, taps, shift0, T;
   int clip_rows, tiles_per_clip;     // clip mode (clip_rows > 0): tile = 128 rows of one clip; C row = clip*clip_rows + t
@@ -54,6 +65,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
   constexpr uint32_t TMEM_COLS_2 = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   const uint32_t tmem_cols = p.taps == 2 ? TMEM_COLS_2 : TMEM_COLS_1;
 
+  if (threadIdx.x == 0) stamp(p.trace, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -67,6 +79,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p.trace, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -91,6 +104,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
         const uint32_t ph = (it / NSTAGE) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (it == 0) stamp(p.trace, 2);
         const int tap = it / nkb, kb = it - tap * nkb;
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + A_STAGE_BYTES;
@@ -104,12 +118,14 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
         tc_commit(&empty_bar[s]);
       }
       tc_commit(tmem_full_bar);
+      stamp(p.trace, 3);
     }
   } else {
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) stamp(p.trace, 4);
     const int m = m0 + q * 32 + lane;
     bool tap0_ok = true;
     if (p.taps == 2) {
@@ -204,9 +220,11 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
       __syncwarp();
     }
   }
+  if (threadIdx.x == 64) stamp(p.trace, 5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (threadIdx.x == 32) stamp(p.trace, 6);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -267,6 +285,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   rc = make_map_2d(&tb, g.Bw, (long long)g.taps * g.N, g.K, g.ldb, BN, "tg_gemm_tf32(B)");
   if (rc) return rc;
   GemmP p;
+  p.trace = g_trace;
   p.C = g.C; p.ldc = g.ldc; p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.shift0 = g.shift0; p.T = g.T > 0 ? g.T : 1;
   p.escale = g.escale; p.bias = g.bias; p.act1 = g.act1; p.slope1 = g.slope1; p.mask = g.mask; p.ldmask = g.ldmask;
   p.residual = g.residual; p.ldres = g.ldres; p.act2 = g.act2; p.accumulate = g.accumulate;
@@ -286,6 +305,11 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
 }
 
 }  // namespace
+
+extern "C" int tg_debug_gemm_trace(long long* device_buf) {
+  g_trace = device_buf;
+  return 0;
+}
 
 extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   const tg_gemm_tf32_t& g = *gp;

@@ -64,7 +64,7 @@ class _Overlap:
 
 
 side = _Overlap()
-S_WGRAD, S_WAV, S_DREAL, S_WAVW = 1, 2, 3, 4
+S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK = 1, 2, 3, 4, 5
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -91,8 +91,9 @@ class Workspace:
 
 
 def _tf32_ok(A, lda, W, ldw, K):
-    """Operands a TMA descriptor can describe: 16-byte aligned base and pitch, K at least one 32-float swizzle atom."""
-    return (config.fast() and K >= 32 and lda % 4 == 0 and ldw % 4 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
+    """Operands a TMA descriptor can describe: 16-byte aligned base and pitch (K < 32 is zero-filled up to one 32-float swizzle atom
+    by the TMA unit: a latency-bound small GEMM still beats the FFMA kernel's 128-row CTAs)."""
+    return (config.fast() and K >= 8 and K % 4 == 0 and lda % 4 == 0 and ldw % 4 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
 
 
 def mm_nt(A, W, C, *, M, N, K, lda=None, **epi):
@@ -117,7 +118,7 @@ def wgrad(X, G, dW, *, B, T, N, Cin, shift=0, ldx=None, ldg=None, ldw=None, dbia
     when TMA can describe the operands, fp32 FFMA split-K kernel otherwise."""
     ldx = Cin if ldx is None else ldx
     ldg = N if ldg is None else ldg
-    if (config.fast() and Cin >= 32 and N >= 16 and ldx % 4 == 0 and ldg % 4 == 0 and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0
+    if (config.fast() and Cin >= 8 and Cin % 4 == 0 and N >= 16 and ldx % 4 == 0 and ldg % 4 == 0 and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0
             and (shift == 0 or T <= 40)):
         ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=ldx, ldw=ldw, dbias=dbias)
     else:
@@ -171,7 +172,7 @@ class GruPlan:
                 wt = self.ws.get(f'{self.tag}.whhT{l}_{d}', (H, 3 * H))
                 ops.transpose(self._w('weight_hh', l, bool(d)), wt, 3 * H, H)
             K = self.I if l == 0 else 2 * H
-            if config.fast() and K % 4 == 0 and K >= 32:
+            if config.fast() and K % 4 == 0 and K >= 8:
                 # [6H, K] (both directions, adjacent in the arena) -> [K, 6H]: operand of the data-gradient GEMM
                 ops.transpose(self._w('weight_ih', l), self.ws.get(f'{self.tag}.wihT{l}', (K, 6 * H)), 6 * H, K)
 
@@ -302,7 +303,7 @@ class GeneratorEngine:
         """Per-optimiser-step derived weights: weight-norm'ed TCN filters and transposed recurrent matrices."""
         ws = self.ws
         if self.use_text:
-            for i in range(self.n_tcn):
+            def norm_block(i):
                 for j in (1, 2):
                     q = f'text_encoder.tcn.network.{i}.conv{j}'
                     v = self.P(q + '.weight_v')
@@ -310,6 +311,10 @@ class GeneratorEngine:
                     wT = ws.get(f'tcn.wT{i}_{j}', (k, Cin, N)) if config.fast() else None
                     ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (k, N, Cin)), wT, ws.get(f'tcn.inv{i}_{j}', (N,)),
                                         N, Cin, k)
+            norm_block(0)
+            with side.on(S_WAVW):       # filters of the later blocks: joined in text_forward before block 1
+                for i in range(1, self.n_tcn):
+                    norm_block(i)
         with side.on(S_WAV):        # not needed before the GRU / the backward pass: off the critical path (joined before the GRU input)
             if config.fast():
                 for name in ('text_encoder.decoder.weight', 'out.0.weight', 'out.2.weight'):
@@ -472,6 +477,7 @@ class GeneratorEngine:
         for i in range(self.n_tcn):
             if i == 1:
                 side.join(S_WGRAD)                 # masks of the later blocks / the GRU drawn on the side stream (make_masks split=True)
+                side.join(S_WAVW)                  # weight-normed filters of the later blocks (prep_weights)
             d = 2 ** i
             q = f'text_encoder.tcn.network.{i}'
             assert cin == H, 'TemporalBlock.downsample (n_inputs != n_outputs) is not on the configured path (tcn.py:33)'
@@ -572,23 +578,26 @@ class GeneratorEngine:
             if audio_feat is None:
                 with side.on(S_WAV):        # the audio encoder is independent of the text / speaker branches
                     audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
-        text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
         z = mu = logvar = None
         Z = 0
         if self.z_mode == 'speaker':
             Z = 16
             e0, e1 = ws.get('spk.e0', (Bt, Z)), ws.get('spk.e1', (Bt, Z))
             mu, logvar, z = ws.get('spk.mu', (Bt, Z)), ws.get('spk.logvar', (Bt, Z)), ws.get('spk.z', (Bt, Z))
-            ops.embedding_gather(self.P('speaker_embedding.0.weight'), vid, 0, None, e0, Bt, Z)
-            ops.linear(e0, self.P('speaker_embedding.1.weight'), self.P('speaker_embedding.1.bias'), e1, M=Bt, K=Z, N=Z)
-            ops.linear(e1, self.P('speaker_mu.weight'), self.P('speaker_mu.bias'), mu, M=Bt, K=Z, N=Z)
-            ops.linear(e1, self.P('speaker_logvar.weight'), self.P('speaker_logvar.bias'), logvar, M=Bt, K=Z, N=Z)
-            ops.reparam_fwd(mu, logvar, eps, z, Bt * Z)
+            with side.on(S_SPK):            # a chain of tiny launches: off the text-encoder chain
+                ops.embedding_gather(self.P('speaker_embedding.0.weight'), vid, 0, None, e0, Bt, Z)
+                ops.linear(e0, self.P('speaker_embedding.1.weight'), self.P('speaker_embedding.1.bias'), e1, M=Bt, K=Z, N=Z)
+                ops.linear(e1, self.P('speaker_mu.weight'), self.P('speaker_mu.bias'), mu, M=Bt, K=Z, N=Z)
+                ops.linear(e1, self.P('speaker_logvar.weight'), self.P('speaker_logvar.bias'), logvar, M=Bt, K=Z, N=Z)
+                ops.reparam_fwd(mu, logvar, eps, z, Bt * Z)
         elif self.z_mode == 'random':
             Z = 16
             z = eps
+        text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
+        side.join(S_SPK)
         side.join(S_WAV)
         side.join(S_WGRAD)                          # side-stream mask draws, if text_forward did not already join them
+        side.join(S_WAVW)
         in_data = ws.get('g.in', (M, self.I))
         Da = 32 if self.use_audio else 0
         Dt = 32 if self.use_text else 0

@@ -18,7 +18,7 @@ from typing import Dict, Optional
 import torch
 
 from tgb200 import _lib, config, ops
-from tgb200.engine import S_DREAL, side
+from tgb200.engine import S_DREAL, S_SPK, side
 
 
 def add_noise(data):
@@ -225,25 +225,26 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     off = G._noise.offset_dev(dev)
     seed = G._noise.seed
     vid_all = eps_all = None
-    if ge.z_mode is not None:
-        eps_all = ws.get('ti.eps', (Bt, 16))
-        if noise is not None and noise.eps is not None:
-            for i, e in enumerate(noise.eps[-n_pass:] if len(noise.eps) > n_pass else noise.eps):
-                eps_all[i * B:(i + 1) * B].copy_(e)
-        else:
-            ops.philox_normal(eps_all, Bt * 16, seed, off, 1000)
-    if ge.z_mode == 'speaker':
-        vid_all = ws.get('ti.vid', (Bt,), torch.int64)
-        for i, p in enumerate(passes):
-            if p == 'r':
-                perm = ws.get('ti.perm', (B,), torch.int64)
-                if noise is not None and noise.perm is not None:
-                    perm.copy_(noise.perm)
-                else:
-                    ops.philox_randperm(perm, B, seed, off, 1001)
-                ops.gather_i64(vid, perm, vid_all[i * B:(i + 1) * B], B)
+    with side.on(S_SPK):        # noise / speaker ids feed the speaker branch that ge.forward queues on the same stream
+        if ge.z_mode is not None:
+            eps_all = ws.get('ti.eps', (Bt, 16))
+            if noise is not None and noise.eps is not None:
+                for i, e in enumerate(noise.eps[-n_pass:] if len(noise.eps) > n_pass else noise.eps):
+                    eps_all[i * B:(i + 1) * B].copy_(e)
             else:
-                vid_all[i * B:(i + 1) * B].copy_(vid)
+                ops.philox_normal(eps_all, Bt * 16, seed, off, 1000)
+        if ge.z_mode == 'speaker':
+            vid_all = ws.get('ti.vid', (Bt,), torch.int64)
+            for i, p in enumerate(passes):
+                if p == 'r':
+                    perm = ws.get('ti.perm', (B,), torch.int64)
+                    if noise is not None and noise.perm is not None:
+                        perm.copy_(noise.perm)
+                    else:
+                        ops.philox_randperm(perm, B, seed, off, 1001)
+                    ops.gather_i64(vid, perm, vid_all[i * B:(i + 1) * B], B)
+                else:
+                    vid_all[i * B:(i + 1) * B].copy_(vid)
     g_masks = None
     if G.training:
         if noise is not None and noise.g_masks is not None:
@@ -262,12 +263,14 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     sc = ws.get('ti.scalars', (8,), torch.float64)
     sc.zero_()
     dlogit = ws.get('ti.dlogit', (B, 1))
-    de.prep_weights()
+    if not do_d:
+        de.prep_weights()
     if do_d:
         # D(real) forward + backward does not depend on the generator: it runs on an auxiliary stream underneath the
         # generator passes (train_gan.py:38,41-42; BatchNorm statistics still see real before fake)
         de.arena.zero_grad()
         with side.on(S_DREAL):
+            de.prep_weights()
             p_real = de.forward(target, D.training, d_masks_for(0))
             ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
             de.backward(dlogit, need_dposes=False)

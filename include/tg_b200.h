@@ -236,6 +236,8 @@ int tg_gru_tf32_sync_ints(int B, int H);
 /* development aid: when a device buffer of >= 16*T int64 is set, CTA (0,0,0) of the tensor-core GRU kernels stamps
  * %globaltimer at its per-step phases (NULL switches it off) */
 int tg_debug_gru_trace(long long* device_buf);
+/* development aid: %globaltimer stamps of CTA (0,0) of the next tg_gemm_tf32 launches (7 slots; NULL disables) */
+int tg_debug_gemm_trace(long long* device_buf);
 size_t tg_gru_bwd_tf32_scratch_floats(int B, int H);
 int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
                           float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream);
