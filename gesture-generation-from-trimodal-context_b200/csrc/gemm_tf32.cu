@@ -4,7 +4,7 @@
 //   C[m, n] = epi( sum_tap sum_k A[m + shift_tap, k] * B[tap*N + n, k] )        A, B row-major (K contiguous)
 //
 // 128 x BN tile per CTA, BK = 32 floats (one 128-byte swizzle atom), NSTAGE-deep TMA->MMA mbarrier pipeline,
-// warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
+// warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-9 = epilogue
 // (tcgen05.ld 32x32b, one TMEM lane = one output row per thread).
 // Two-tap mode (the TCN's causal dilated convolution, tcn.py:19-31, and its anti-causal data gradient): the shifted
 // tap accumulates in a second TMEM accumulator and is masked per row in the epilogue (t + shift outside the clip),
@@ -40,7 +40,7 @@ struct GemmP {
 };
 
 template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                            const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
       stamp(p.trace, 3);
     }
   } else {
-    // ---- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31
-    const int q = warp & 3;
+    // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4) .. +31, so warps w and w+4 share a lane quarter and
+    // split its 32-column chunks (even / odd).  One epilogue warp per scheduler cannot hide its own instruction latency, so
+    // the per-element work is kept branch-free: act(v) = max(v, v*s) (s = 1 none, 0 relu, slope leaky), every option folded
+    // into per-chunk constants, row addresses advanced by pointer increments.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) stamp(p.trace, 4);
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
       tap0_ok = ts >= 0 && ts < p.T;
     }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+    const bool vec_ok = (p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                         (!p.mask || ((p.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) &&
                         (!p.residual || ((p.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
     // All TMA loads have landed and every MMA has retired once tmem_full_bar fires, so the pipeline stages are free:
@@ -142,10 +145,14 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
     // float4 writes of 8 consecutive rows and the float4 reads of one row are both bank-conflict free), after which a
     // warp instruction touches 4 rows x 128 contiguous bytes of C / mask / residual instead of 32 rows x 16 bytes.
     constexpr int SP = 36;
-    float* stg = reinterpret_cast<float*>(smem) + q * (32 * SP);
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * SP);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const float s1 = p.act1 == 0 ? 1.f : (p.act1 == 1 ? 0.f : p.slope1);
+    const float s2 = p.act2 == 0 ? 1.f : 0.f;
+    const int row0 = m0 + q * 32 + rsub;             // this lane's first row; it handles rows row0 + 4*i
+    const int rows_left = m_end - row0;              // row i is valid iff 4*i < rows_left
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
       const int nb = n0 + c0;
       if (nb >= p.N) break;
       float v[32];
@@ -166,55 +173,59 @@ __global__ void __launch_bounds__(192, 2) gemm_tf32_kernel(const __grid_constant
       for (int j4 = 0; j4 < 32; j4 += 4) *reinterpret_cast<float4*>(stg + lane * SP + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
       __syncwarp();
       const int n = nb + c4;                      // this lane's 4 columns
-      float es[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec_ok) {
+        if (n < p.N) {                            // N % 4 == 0: the lane's four columns are all valid or all invalid
+          float4 es = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.escale) es = __ldg(reinterpret_cast<const float4*>(p.escale + n));
+          if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          float* crow = p.C + (long long)row0 * p.ldc + n;
+          const float* mrow = p.mask ? p.mask + (long long)row0 * p.ldmask + n : nullptr;
+          const float* rrow = p.residual ? p.residual + (long long)row0 * p.ldres + n : nullptr;
+          const float* srow = stg + rsub * SP + c4;
+          const long long cstep = 4ll * p.ldc, mstep = 4ll * p.ldmask, rstep = 4ll * p.ldres;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (n + e < p.N) {
-          if (p.escale) es[e] = __ldg(p.escale + n + e);
-          if (p.bias) bs[e] = __ldg(p.bias + n + e);
-        }
-      }
-      const bool full4 = vec_ok && (n + 3 < p.N);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rsub;
-        const int mr = m0 + q * 32 + r;
-        if (mr >= m_end || n >= p.N) continue;
-        const float4 x4 = *reinterpret_cast<const float4*>(stg + r * SP + c4);
-        float x[4] = {x4.x, x4.y, x4.z, x4.w};
-        float* crow = p.C + (long long)mr * p.ldc + n;
-        const float* mrow = p.mask ? p.mask + (long long)mr * p.ldmask + n : nullptr;
-        const float* rrow = p.residual ? p.residual + (long long)mr * p.ldres + n : nullptr;
-        float mk[4] = {1.f, 1.f, 1.f, 1.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full4) {
-          if (mrow) { const float4 t4 = *reinterpret_cast<const float4*>(mrow); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
-          if (rrow) { const float4 t4 = *reinterpret_cast<const float4*>(rrow); rs[0] = t4.x; rs[1] = t4.y; rs[2] = t4.z; rs[3] = t4.w; }
-          if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(crow); old[0] = t4.x; old[1] = t4.y; old[2] = t4.z; old[3] = t4.w; }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (n + e < p.N) {
-              if (mrow) mk[e] = mrow[e];
-              if (rrow) rs[e] = rrow[e];
-              if (p.accumulate) old[e] = crow[e];
+          for (int i = 0; i < 8; ++i) {
+            if (4 * i < rows_left) {
+              float4 x = *reinterpret_cast<const float4*>(srow + i * 4 * SP);
+              x.x = fmaf(x.x, es.x, bs.x); x.y = fmaf(x.y, es.y, bs.y); x.z = fmaf(x.z, es.z, bs.z); x.w = fmaf(x.w, es.w, bs.w);
+              x.x = fmaxf(x.x, x.x * s1); x.y = fmaxf(x.y, x.y * s1); x.z = fmaxf(x.z, x.z * s1); x.w = fmaxf(x.w, x.w * s1);
+              if (mrow) {
+                const float4 t4 = *reinterpret_cast<const float4*>(mrow + i * mstep);
+                x.x *= t4.x; x.y *= t4.y; x.z *= t4.z; x.w *= t4.w;
+              }
+              if (rrow) {
+                const float4 t4 = *reinterpret_cast<const float4*>(rrow + i * rstep);
+                x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+              }
+              x.x = fmaxf(x.x, x.x * s2); x.y = fmaxf(x.y, x.y * s2); x.z = fmaxf(x.z, x.z * s2); x.w = fmaxf(x.w, x.w * s2);
+              if (p.accumulate) {
+                const float4 t4 = *reinterpret_cast<const float4*>(crow + i * cstep);
+                x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+              }
+              *reinterpret_cast<float4*>(crow + i * cstep) = x;
             }
           }
         }
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float y = x[e] * es[e] + bs[e];
-          y = tg_act(y, p.act1, p.slope1);
-          y = y * mk[e] + rs[e];
-          y = tg_act(y, p.act2, 0.f);
-          o[e] = y + old[e];
-        }
-        if (full4) {
-          *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < p.N) crow[e] = o[e];
+      } else {
+        // unaligned / N % 4 != 0 (e.g. the 150-wide head): scalar path, not unrolled
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          if (4 * i >= rows_left) break;
+          const int mr = row0 + 4 * i;
+#pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            if (n + e >= p.N) break;
+            float y = stg[(rsub + 4 * i) * SP + c4 + e];
+            if (p.escale) y *= __ldg(p.escale + n + e);
+            if (p.bias) y += __ldg(p.bias + n + e);
+            y = fmaxf(y, y * s1);
+            if (p.mask) y *= p.mask[(long long)mr * p.ldmask + n + e];
+            if (p.residual) y += p.residual[(long long)mr * p.ldres + n + e];
+            y = fmaxf(y, y * s2);
+            float* dst = p.C + (long long)mr * p.ldc + n + e;
+            if (p.accumulate) y += *dst;
+            *dst = y;
+          }
         }
       }
       __syncwarp();
@@ -299,7 +310,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
     attr_done = true;
   }
   dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN));
-  gemm_tf32_kernel<BN, NSTAGE><<<grid, 192, smem, s>>>(ta, tb, p);
+  gemm_tf32_kernel<BN, NSTAGE><<<grid, 320, smem, s>>>(ta, tb, p);
   TG_CHECK_LAUNCH("tg_gemm_tf32");
   return 0;
 }
@@ -315,6 +326,8 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   const tg_gemm_tf32_t& g = *gp;
   TG_REQUIRE(g.A && g.Bw && g.C && g.M > 0 && g.N > 0 && g.K > 0, "tg_gemm_tf32");
   TG_REQUIRE(g.taps == 1 || g.taps == 2, "tg_gemm_tf32");
+  // epilogue activations are evaluated as max(v, v*s): none, relu, leaky-relu with 0 <= slope <= 1 (no sigmoid on this path)
+  TG_REQUIRE(g.act1 >= 0 && g.act1 <= 2 && (g.act1 != 2 || (g.slope1 >= 0.f && g.slope1 <= 1.f)) && (g.act2 == 0 || g.act2 == 1), "tg_gemm_tf32(activation)");
   TG_REQUIRE(g.clip_rows == 0 || (g.clip_rows > 0 && g.taps == 1 && g.M % g.clip_rows == 0 && g.a_clip_pitch > 0), "tg_gemm_tf32(clip mode)");
   cudaStream_t s = (cudaStream_t)stream;
   // tile width: minimise padded N, prefer wider tiles on ties (fewer A re-reads)

@@ -24,7 +24,7 @@ struct WgP {
 // MN-major operand descriptor: 8 x (8 rows x 128 B) atoms; LBO = bytes between 32-element groups along MN, SBO = bytes
 // between 8-row groups along K
 template <int TK, int NSTAGE, int MINB>
-__global__ void __launch_bounds__(192, MINB) wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(320, MINB) wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                                                             const WgP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -94,18 +94,21 @@ __global__ void __launch_bounds__(192, MINB) wgrad_tf32_kernel(const __grid_cons
         tc_commit(tmem_full);
       }
     } else {
-      const int q = warp & 3;
+      // 8 epilogue warps: warps w and w+4 share TMEM lane quarter w%4 and split its four 32-column chunks (even / odd)
+      const int q = warp & 3, half = (warp - 2) >> 2;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       // every stage is free once tmem_full fires: transpose each 32x32 chunk through a padded staging tile so that one
       // warp-wide reduction covers 4 rows x 128 contiguous bytes of dW (vector red.global.add.v4.f32 where aligned)
       constexpr int SP = 36;
-      float* stg = reinterpret_cast<float*>(smem) + q * (32 * SP);
+      float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * SP);
       const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-      const bool vec_ok = (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
+      const bool vec_ok = (p.ldw & 3) == 0 && (p.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
+      const int row0 = n0 + q * 32 + rsub;
+      const int rows_left = p.N - row0;
 #pragma unroll 1
-      for (int cc = 0; cc < 128; cc += 32) {
+      for (int cc = half * 32; cc < 128; cc += 64) {
         if (c0 + cc >= p.Cin) break;
         float v[32];
         tmem_ld32(lane_addr + (uint32_t)cc, v);
@@ -114,21 +117,24 @@ __global__ void __launch_bounds__(192, MINB) wgrad_tf32_kernel(const __grid_cons
         for (int j4 = 0; j4 < 32; j4 += 4) *reinterpret_cast<float4*>(stg + lane * SP + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
         __syncwarp();
         const int c = c0 + cc + c4;
-        const bool full4 = vec_ok && (c + 3 < p.Cin);
+        if (c < p.Cin) {
+          float* dst = p.dW + (long long)row0 * p.ldw + c;
+          const float* srow = stg + rsub * SP + c4;
+          const long long dstep = 4ll * p.ldw;
+          if (vec_ok) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rsub;
-          const int n = n0 + q * 32 + r;
-          if (n >= p.N || c >= p.Cin) continue;
-          const float4 x = *reinterpret_cast<const float4*>(stg + r * SP + c4);
-          float* dst = p.dW + (long long)n * p.ldw + c;
-          if (full4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+            for (int i = 0; i < 8; ++i) {
+              if (4 * i < rows_left) {
+                const float4 x = *reinterpret_cast<const float4*>(srow + i * 4 * SP);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i * dstep), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+              }
+            }
           } else {
-            atomicAdd(dst, x.x);
-            if (c + 1 < p.Cin) atomicAdd(dst + 1, x.y);
-            if (c + 2 < p.Cin) atomicAdd(dst + 2, x.z);
-            if (c + 3 < p.Cin) atomicAdd(dst + 3, x.w);
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              if (4 * i >= rows_left) break;
+              for (int e = 0; e < 4 && c + e < p.Cin; ++e) atomicAdd(dst + i * dstep + e, srow[i * 4 * SP + e]);
+            }
           }
         }
         __syncwarp();
@@ -214,7 +220,7 @@ int launch(const tg_wgrad_tf32_t& g, int B, int T, cudaStream_t s) {
     attr_done = true;
   }
   dim3 grid(tg_ceil_div(g.Cin, 128), tg_ceil_div(g.N, 128), splits);
-  wgrad_tf32_kernel<TK, NSTAGE, MINB><<<grid, 192, smem, s>>>(tg_, tx_, p);
+  wgrad_tf32_kernel<TK, NSTAGE, MINB><<<grid, 320, smem, s>>>(tg_, tx_, p);
   TG_CHECK_LAUNCH("tg_wgrad_tf32");
   return 0;
 }
