@@ -208,3 +208,50 @@ def with_tcn_aliases(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if '.tcn.network.' in k and '.conv2.' in k:
             out[k.replace('.conv2.', '.net.4.')] = v
     return out
+
+
+# --------------------------------------------------------------------------------------
+# seq2seq baseline (config/seq2seq.yml)
+# --------------------------------------------------------------------------------------
+def _gru_uni(sd, rng, prefix, in_size, hidden, layers):
+    s = 1.0 / np.sqrt(hidden)
+    for l in range(layers):
+        isz = in_size if l == 0 else hidden
+        sd[f'{prefix}.weight_ih_l{l}'] = torch.from_numpy((s * rng.standard_normal((3 * hidden, isz))).astype(np.float32))
+        sd[f'{prefix}.weight_hh_l{l}'] = torch.from_numpy((s * rng.standard_normal((3 * hidden, hidden))).astype(np.float32))
+        sd[f'{prefix}.bias_ih_l{l}'] = torch.from_numpy((s * rng.standard_normal(3 * hidden)).astype(np.float32))
+        sd[f'{prefix}.bias_hh_l{l}'] = torch.from_numpy((s * rng.standard_normal(3 * hidden)).astype(np.float32))
+
+
+def seq2seq_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of Seq2SeqNet (seq2seq_net.py:217-227) in reference key order; cfg = seq2seq_oracle.Seq2SeqConfig."""
+    rng = _rng(7000 + seed)
+    H, D = cfg.hidden_size, cfg.pose_dim
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    sd['encoder.embedding.weight'] = torch.from_numpy((0.5 * rng.standard_normal((cfg.n_words, cfg.wordembed_dim))).astype(np.float32))
+    _gru(sd, rng, 'encoder.gru', cfg.wordembed_dim, H, cfg.n_layers)
+    p = 'decoder.decoder.'
+    _lin(sd, rng, p + 'pre_linear.0', (H, D + H), D + H)
+    _bn(sd, rng, p + 'pre_linear.1', H)
+    _lin(sd, rng, p + 'attn.attn', (H, 2 * H), 2 * H)
+    sd[p + 'attn.v'] = torch.from_numpy((rng.standard_normal(H) / np.sqrt(H)).astype(np.float32))
+    _gru_uni(sd, rng, p + 'gru', H, H, cfg.n_layers)
+    _lin(sd, rng, p + 'out', (D, H), H)
+    return sd
+
+
+def seq2seq_inputs(cfg, batch: int, seed: int = 0, max_len: int = 12, min_len: int = 4) -> Dict[str, torch.Tensor]:
+    """in_text [B, L_max] = [SOS=1, words.., EOS=2] padded with 0 and sorted by decreasing length (what the reference's
+    collate function produces, lmdb_data_loader.py:22-41,142-149), lengths [B], target poses [B,n_poses,D]."""
+    rng = _rng(8000 + seed)
+    lengths = np.sort(rng.integers(min_len, max_len + 1, size=batch))[::-1].copy()
+    lengths[0] = max_len
+    text = np.zeros((batch, max_len), dtype=np.int64)
+    for b in range(batch):
+        n = int(lengths[b])
+        text[b, 0] = 1
+        text[b, 1:n - 1] = rng.integers(4, cfg.n_words, size=n - 2)
+        text[b, n - 1] = 2
+    walk = np.cumsum(0.02 * rng.standard_normal((batch, cfg.n_poses, cfg.pose_dim)), axis=1)
+    target = (walk + 0.1 * rng.standard_normal((batch, 1, cfg.pose_dim))).astype(np.float32)
+    return {'in_text': torch.from_numpy(text), 'lengths': torch.from_numpy(lengths.astype(np.int64)), 'target': torch.from_numpy(target)}

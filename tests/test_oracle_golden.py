@@ -98,3 +98,33 @@ def test_embedding_net_and_fgd_match_reference():
     fgd, fdist = O.fgd_scores(ff.numpy(), rf.numpy())
     assert abs(fgd - float(g['fgd'])) <= 1e-3 * abs(float(g['fgd']))
     assert abs(fdist - float(g['feat_dist'])) <= 1e-4 * abs(float(g['feat_dist']))
+
+
+def test_seq2seq_oracle_matches_reference():
+    """oracle/seq2seq_oracle.py vs. the reference Seq2SeqNet + train_iter_seq2seq (two consecutive steps, dropout 0):
+    eval-mode outputs, loss, every clipped gradient, post-Adam weights and BatchNorm running statistics."""
+    from oracle import seq2seq_oracle as S
+    from oracle.make_golden_seq2seq import golden_cfg as s2s_cfg
+    cfg = s2s_cfg()
+    g = np.load(os.path.join(GOLDEN, 'seq2seq_step.npz'))
+    sd = synth.seq2seq_state_dict(cfg)
+    inp = synth.seq2seq_inputs(cfg, 6, seed=3, max_len=9)
+    with torch.no_grad():
+        out_eval = S.seq2seq_forward(sd, cfg, inp['in_text'], inp['lengths'], inp['target'], False)
+    assert rel_l2(out_eval, g['out_eval']) < TOL
+    opt = None
+    for it in range(2):
+        ret = S.train_iter_seq2seq_oracle(cfg, sd, inp['in_text'], inp['lengths'], inp['target'], opt, step=it + 1)
+        ref = float(g[f'loss{it}'])
+        assert abs(float(ret['loss']) - ref) <= 1e-4 * abs(ref), (it, float(ret['loss']), ref)
+        for k, gr in ret['grads'].items():
+            _digest_close(digest(gr), g[f'grad{it}/' + k], 5e-4)
+        for k, v in ret['new_sd'].items():
+            if k.endswith('num_batches_tracked'):
+                assert int(v) == int(g[f'post{it}/' + k][1])
+            elif S.is_param(k):
+                # the Linear bias in front of the train-mode BatchNorm has an analytically zero gradient (round-off only)
+                _post_close(digest(v), g[f'post{it}/' + k], cfg.learning_rate, noisy=(it > 0 or k == 'decoder.decoder.pre_linear.0.bias'))
+            else:
+                _digest_close(digest(v), g[f'post{it}/' + k], 1e-4)
+        sd, opt = ret['new_sd'], ret['opt']
