@@ -1,0 +1,296 @@
+// Kernels of the seq2seq baseline (scripts/model/seq2seq_net.py, scripts/train_eval/train_seq2seq.py) that are not plain
+// GEMMs: the GRU gate non-linearities of one time step (forward / backward, with the length mask that restates
+// pack_padded_sequence), Bahdanau attention of one decoder step (forward / backward), custom_loss value + gradient,
+// the decoder-input gather, and global-norm gradient clipping.  All fp32, one launch per call, no host sync.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+// one GRU step for B rows: gi = W_ih x + b_ih, gh = W_hh h + b_hh already computed (gate order r,z,n)
+__global__ void __launch_bounds__(256) gru_gates_fwd_kernel(const float* __restrict__ gi, long long ldgi, const float* __restrict__ gh,
+                                                            const float* __restrict__ hprev, const long long* __restrict__ lengths, int t,
+                                                            float* __restrict__ hnew, float* __restrict__ out, long long ldout,
+                                                            float* __restrict__ saved, long long plane, int B, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i - b * H;
+  const float hp = hprev ? hprev[i] : 0.f;
+  const bool valid = lengths == nullptr || (long long)t < lengths[b];
+  const float* gib = gi + (long long)b * ldgi;
+  const float* ghb = gh + (long long)b * 3 * H;
+  const float r = sigm(gib[j] + ghb[j]);
+  const float z = sigm(gib[H + j] + ghb[H + j]);
+  const float hn = ghb[2 * H + j];
+  const float n = tanhf(gib[2 * H + j] + r * hn);
+  const float h = (1.f - z) * n + z * hp;
+  hnew[i] = valid ? h : hp;
+  if (out) out[(long long)b * ldout + j] = valid ? h : 0.f;
+  if (saved) { saved[i] = r; saved[plane + i] = z; saved[2 * plane + i] = n; saved[3 * plane + i] = hn; }
+}
+
+// backward of the step above.  dh = gradient carried from later steps, dadd = gradient of this step's output (optional).
+// dgi / dgh = gradients of the two pre-activation projections; dhprev = elementwise part of d h_{t-1} (the caller adds
+// dgh @ W_hh).  Rows past their length pass the carry through untouched.  dhprev may alias dh.
+__global__ void __launch_bounds__(256) gru_gates_bwd_kernel(const float* dh, const float* __restrict__ dadd, long long ldadd,
+                                                            const float* __restrict__ saved, long long plane, const float* __restrict__ hprev,
+                                                            const long long* __restrict__ lengths, int t, float* __restrict__ dgi,
+                                                            long long lddgi, float* __restrict__ dgh, float* dhprev, int B, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i - b * H;
+  const bool valid = lengths == nullptr || (long long)t < lengths[b];
+  const float carry = dh ? dh[i] : 0.f;
+  float* dgib = dgi + (long long)b * lddgi;
+  float* dghb = dgh + (long long)b * 3 * H;
+  if (!valid) {
+    dgib[j] = dgib[H + j] = dgib[2 * H + j] = 0.f;
+    dghb[j] = dghb[H + j] = dghb[2 * H + j] = 0.f;
+    dhprev[i] = carry;
+    return;
+  }
+  const float g = carry + (dadd ? dadd[(long long)b * ldadd + j] : 0.f);
+  const float r = saved[i], z = saved[plane + i], n = saved[2 * plane + i], hn = saved[3 * plane + i];
+  const float hp = hprev ? hprev[i] : 0.f;
+  const float dn = g * (1.f - z);
+  const float dz = g * (hp - n);
+  const float dpn = dn * (1.f - n * n);
+  const float dpz = dz * z * (1.f - z);
+  const float dpr = dpn * hn * r * (1.f - r);
+  dgib[j] = dpr; dgib[H + j] = dpz; dgib[2 * H + j] = dpn;
+  dghb[j] = dpr; dghb[H + j] = dpz; dghb[2 * H + j] = dpn * r;
+  dhprev[i] = g * z;
+}
+
+// Bahdanau attention of one decoder step (seq2seq_net.py:72-94,172-174).  One block per sample.
+//   energy[tau, j] = tanh(hq[b, j] + eproj[b, tau, j]);  score[tau] = sum_j v[j] energy[tau, j];  w = softmax_tau(score)
+//   ctx[b, j] = sum_tau w[tau] enc[b, tau, j]            (the softmax runs over padded positions too, as in the reference)
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ hq, const float* __restrict__ eproj, const float* __restrict__ enc,
+                                                       const float* __restrict__ v, float* __restrict__ w, float* __restrict__ ctx, int Tm, int H) {
+  extern __shared__ float sm[];
+  float* score = sm;                 // [Tm]
+  const int b = blockIdx.x;
+  for (int tau = threadIdx.x; tau < Tm; tau += blockDim.x) score[tau] = 0.f;
+  __syncthreads();
+  const float* ep = eproj + (long long)b * Tm * H;
+  for (int tau = 0; tau < Tm; ++tau) {
+    float part = 0.f;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) part += v[j] * tanhf(hq[(long long)b * H + j] + ep[(long long)tau * H + j]);
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&score[tau], part);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int tau = 0; tau < Tm; ++tau) mx = fmaxf(mx, score[tau]);
+    float s = 0.f;
+    for (int tau = 0; tau < Tm; ++tau) { score[tau] = expf(score[tau] - mx); s += score[tau]; }
+    const float inv = 1.f / s;
+    for (int tau = 0; tau < Tm; ++tau) score[tau] *= inv;
+  }
+  __syncthreads();
+  for (int tau = threadIdx.x; tau < Tm; tau += blockDim.x) w[(long long)b * Tm + tau] = score[tau];
+  const float* en = enc + (long long)b * Tm * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float c = 0.f;
+    for (int tau = 0; tau < Tm; ++tau) c = fmaf(score[tau], en[(long long)tau * H + j], c);
+    ctx[(long long)b * H + j] = c;
+  }
+}
+
+// backward: dctx [B,H] -> denc += w dctx, deproj += dpre, dhq = sum_tau dpre, dv += sum dscore * energy
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ dctx, const float* __restrict__ w, const float* __restrict__ hq,
+                                                       const float* __restrict__ eproj, const float* __restrict__ enc, const float* __restrict__ v,
+                                                       float* __restrict__ denc, float* __restrict__ deproj, float* __restrict__ dv,
+                                                       float* __restrict__ dhq, int Tm, int H) {
+  extern __shared__ float sm[];
+  float* dw = sm;                    // [Tm] -> dscore
+  __shared__ float dot;
+  const int b = blockIdx.x;
+  for (int tau = threadIdx.x; tau < Tm; tau += blockDim.x) dw[tau] = 0.f;
+  __syncthreads();
+  const float* en = enc + (long long)b * Tm * H;
+  const float* ep = eproj + (long long)b * Tm * H;
+  const float* wb = w + (long long)b * Tm;
+  for (int tau = 0; tau < Tm; ++tau) {
+    float part = 0.f;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) part += dctx[(long long)b * H + j] * en[(long long)tau * H + j];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&dw[tau], part);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int tau = 0; tau < Tm; ++tau) s += wb[tau] * dw[tau];
+    dot = s;
+  }
+  __syncthreads();
+  const float d0 = dot;
+  __syncthreads();
+  for (int tau = threadIdx.x; tau < Tm; tau += blockDim.x) dw[tau] = wb[tau] * (dw[tau] - d0);   // dscore
+  __syncthreads();
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const float hqj = hq[(long long)b * H + j], vj = v[j], dc = dctx[(long long)b * H + j];
+    float dh = 0.f, dvj = 0.f;
+    for (int tau = 0; tau < Tm; ++tau) {
+      const long long o = ((long long)b * Tm + tau) * H + j;
+      const float e = tanhf(hqj + ep[(long long)tau * H + j]);
+      const float dpre = dw[tau] * vj * (1.f - e * e);
+      dh += dpre;
+      dvj = fmaf(dw[tau], e, dvj);
+      deproj[o] += dpre;
+      denc[o] = fmaf(wb[tau], dc, denc[o]);
+    }
+    dhq[(long long)b * H + j] = dh;
+    atomicAdd(dv + j, dvj);
+  }
+}
+
+// custom_loss (train_seq2seq.py:6-36) value and gradient.  out / target [B,T,D]; dy is written TIME-major [T,B,D] (the
+// decoder's backward sweep walks time), dy[0] = 0 (frame 0 is a copy of the input pose).  One thread per (b, d).
+__global__ void __launch_bounds__(128) s2s_loss_kernel(const float* __restrict__ out, const float* __restrict__ target, double* __restrict__ loss,
+                                                       float* __restrict__ dy, int B, int T, int D, float w_mse, float w_cont, float w_var) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double local = 0.0;
+  if (i < B * D) {
+    const int b = i / D, d = i - b * D;
+    const float inv_n = 1.f / ((float)B * T * D);
+    const float* o = out + (long long)b * T * D + d;
+    const float* tg = target + (long long)b * T * D + d;
+    float ss = 0.f;
+    for (int t = 0; t < T; ++t) ss = fmaf(o[(long long)t * D], o[(long long)t * D], ss);
+    const float nrm = sqrtf(ss);
+    float mse = 0.f, cont = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float ot = o[(long long)t * D];
+      const float df = ot - tg[(long long)t * D];
+      mse = fmaf(df, df, mse);
+      float g = 2.f * df * w_mse * inv_n - (nrm > 0.f ? ot / nrm : 0.f) * w_var * inv_n;
+      if (t > 0) {
+        const float dd = ot - o[(long long)(t - 1) * D];
+        cont += fabsf(dd);
+        g += (dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f)) * w_cont * inv_n;
+      }
+      if (t + 1 < T) {
+        const float dd = o[(long long)(t + 1) * D] - ot;
+        g -= (dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f)) * w_cont * inv_n;
+      }
+      dy[((long long)t * B + b) * D + d] = t == 0 ? 0.f : g;
+    }
+    local = ((double)mse * w_mse + (double)cont * w_cont - (double)nrm * w_var) * inv_n;
+  }
+  local = warp_sum_d(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, local);
+}
+
+// xin[t, b, :] = input of decoder step t (t >= 1): the target pose t-1 while t-1 < n_pre, the previous output afterwards
+__global__ void s2s_gather_inputs_kernel(const float* __restrict__ poses, const float* __restrict__ outputs, float* __restrict__ xin, int B, int T,
+                                         int D, int n_pre) {
+  const long long total = (long long)T * B * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long tb = i / D;
+    const int b = (int)(tb % B), t = (int)(tb / B);
+    float v = 0.f;
+    if (t >= 1) v = ((t - 1 < n_pre) ? poses : outputs)[((long long)b * T + (t - 1)) * D + d];
+    xin[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    s += (double)v * v;
+  }
+  s = warp_sum_d(s);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(out, t);
+  }
+}
+
+// torch.nn.utils.clip_grad_norm_: x *= min(1, max_norm / (sqrt(sumsq) + 1e-6))
+__global__ void __launch_bounds__(256) clip_scale_kernel(float* __restrict__ x, long long n, const double* __restrict__ sumsq, float max_norm) {
+  const float coef = fminf(1.f, max_norm / ((float)sqrt(*sumsq) + 1e-6f));
+  if (coef >= 1.f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= coef;
+}
+
+inline int grid_for(long long n, int per_block = 256) {
+  long long b = (n + per_block - 1) / per_block;
+  const long long cap = (long long)tg_num_sms() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int tg_gru_gates_fwd(const float* gi, long long ldgi, const float* gh, const float* hprev, const long long* lengths, int t,
+                                float* hnew, float* out, long long ldout, float* saved, long long saved_plane, int B, int H,
+                                tg_stream stream) {
+  TG_REQUIRE(gi && gh && hnew && B > 0 && H > 0, "tg_gru_gates_fwd");
+  gru_gates_fwd_kernel<<<tg_ceil_div((long long)B * H, 256), 256, 0, (cudaStream_t)stream>>>(gi, ldgi, gh, hprev, lengths, t, hnew, out, ldout,
+                                                                                            saved, saved_plane, B, H);
+  TG_CHECK_LAUNCH("tg_gru_gates_fwd");
+  return 0;
+}
+
+extern "C" int tg_gru_gates_bwd(const float* dh, const float* dadd, long long ldadd, const float* saved, long long saved_plane,
+                                const float* hprev, const long long* lengths, int t, float* dgi, long long lddgi, float* dgh,
+                                float* dhprev, int B, int H, tg_stream stream) {
+  TG_REQUIRE(saved && dgi && dgh && dhprev && B > 0 && H > 0, "tg_gru_gates_bwd");
+  gru_gates_bwd_kernel<<<tg_ceil_div((long long)B * H, 256), 256, 0, (cudaStream_t)stream>>>(dh, dadd, ldadd, saved, saved_plane, hprev, lengths,
+                                                                                            t, dgi, lddgi, dgh, dhprev, B, H);
+  TG_CHECK_LAUNCH("tg_gru_gates_bwd");
+  return 0;
+}
+
+extern "C" int tg_attn_fwd(const float* hq, const float* eproj, const float* enc, const float* v, float* w, float* ctx, int B, int Tm, int H,
+                           tg_stream stream) {
+  TG_REQUIRE(hq && eproj && enc && v && w && ctx && B > 0 && Tm > 0 && Tm <= 4096 && H > 0, "tg_attn_fwd");
+  attn_fwd_kernel<<<B, 256, Tm * sizeof(float), (cudaStream_t)stream>>>(hq, eproj, enc, v, w, ctx, Tm, H);
+  TG_CHECK_LAUNCH("tg_attn_fwd");
+  return 0;
+}
+
+extern "C" int tg_attn_bwd(const float* dctx, const float* w, const float* hq, const float* eproj, const float* enc, const float* v,
+                           float* denc, float* deproj, float* dv, float* dhq, int B, int Tm, int H, tg_stream stream) {
+  TG_REQUIRE(dctx && w && hq && eproj && enc && v && denc && deproj && dv && dhq && B > 0 && Tm > 0 && Tm <= 4096 && H > 0, "tg_attn_bwd");
+  attn_bwd_kernel<<<B, 256, Tm * sizeof(float), (cudaStream_t)stream>>>(dctx, w, hq, eproj, enc, v, denc, deproj, dv, dhq, Tm, H);
+  TG_CHECK_LAUNCH("tg_attn_bwd");
+  return 0;
+}
+
+extern "C" int tg_s2s_loss(const float* out, const float* target, double* loss, float* dy_tmajor, int B, int T, int D, float w_mse,
+                           float w_cont, float w_var, tg_stream stream) {
+  TG_REQUIRE(out && target && loss && dy_tmajor && B > 0 && T > 0 && D > 0, "tg_s2s_loss");
+  s2s_loss_kernel<<<tg_ceil_div((long long)B * D, 128), 128, 0, (cudaStream_t)stream>>>(out, target, loss, dy_tmajor, B, T, D, w_mse, w_cont, w_var);
+  TG_CHECK_LAUNCH("tg_s2s_loss");
+  return 0;
+}
+
+extern "C" int tg_s2s_gather_inputs(const float* poses, const float* outputs, float* xin, int B, int T, int D, int n_pre, tg_stream stream) {
+  TG_REQUIRE(poses && outputs && xin && B > 0 && T > 0 && D > 0, "tg_s2s_gather_inputs");
+  s2s_gather_inputs_kernel<<<grid_for((long long)T * B * D), 256, 0, (cudaStream_t)stream>>>(poses, outputs, xin, B, T, D, n_pre);
+  TG_CHECK_LAUNCH("tg_s2s_gather_inputs");
+  return 0;
+}
+
+extern "C" int tg_sumsq_f64(const float* x, long long n, double* out, tg_stream stream) {
+  TG_REQUIRE(x && out && n > 0, "tg_sumsq_f64");
+  sumsq_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  TG_CHECK_LAUNCH("tg_sumsq_f64");
+  return 0;
+}
+
+extern "C" int tg_clip_scale(float* x, long long n, const double* sumsq, float max_norm, tg_stream stream) {
+  TG_REQUIRE(x && sumsq && n > 0 && max_norm > 0.f, "tg_clip_scale");
+  clip_scale_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, n, sumsq, max_norm);
+  TG_CHECK_LAUNCH("tg_clip_scale");
+  return 0;
+}

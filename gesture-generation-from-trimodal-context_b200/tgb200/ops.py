@@ -357,3 +357,40 @@ def feature_stats(feat, n, F, acc):
 
 def l1_dist(a, b, n, acc):
     check(_L().tg_l1_dist_f64(_p(a), _p(b), n, _p(acc), _s()), 'tg_l1_dist_f64'); _count()
+
+
+# ------------------------------------------------------------------------------------------ seq2seq baseline
+def gru_gates_fwd(gi, ldgi, gh, hprev, lengths, t, hnew, out, ldout, saved, saved_plane, B, H):
+    check(_L().tg_gru_gates_fwd(_p(gi), ldgi, _p(gh), _p(hprev), _p(lengths), t, _p(hnew), _p(out), ldout, _p(saved), saved_plane, B, H, _s()),
+          'tg_gru_gates_fwd'); _count()
+
+
+def gru_gates_bwd(dh, dadd, ldadd, saved, saved_plane, hprev, lengths, t, dgi, lddgi, dgh, dhprev, B, H):
+    check(_L().tg_gru_gates_bwd(_p(dh), _p(dadd), ldadd, _p(saved), saved_plane, _p(hprev), _p(lengths), t, _p(dgi), lddgi, _p(dgh),
+                                _p(dhprev), B, H, _s()), 'tg_gru_gates_bwd'); _count()
+
+
+def attn_fwd(hq, eproj, enc, v, w, ctx, B, Tm, H):
+    check(_L().tg_attn_fwd(_p(hq), _p(eproj), _p(enc), _p(v), _p(w), _p(ctx), B, Tm, H, _s()), 'tg_attn_fwd'); _count()
+
+
+def attn_bwd(dctx, w, hq, eproj, enc, v, denc, deproj, dv, dhq, B, Tm, H):
+    check(_L().tg_attn_bwd(_p(dctx), _p(w), _p(hq), _p(eproj), _p(enc), _p(v), _p(denc), _p(deproj), _p(dv), _p(dhq), B, Tm, H, _s()),
+          'tg_attn_bwd'); _count()
+
+
+def s2s_loss(out, target, loss, dy_tmajor, B, T, D, w_mse, w_cont, w_var):
+    check(_L().tg_s2s_loss(_p(out), _p(target), _p(loss), _p(dy_tmajor), B, T, D, float(w_mse), float(w_cont), float(w_var), _s()),
+          'tg_s2s_loss'); _count()
+
+
+def s2s_gather_inputs(poses, outputs, xin, B, T, D, n_pre):
+    check(_L().tg_s2s_gather_inputs(_p(poses), _p(outputs), _p(xin), B, T, D, n_pre, _s()), 'tg_s2s_gather_inputs'); _count()
+
+
+def sumsq(x, n, out):
+    check(_L().tg_sumsq_f64(_p(x), n, _p(out), _s()), 'tg_sumsq_f64'); _count()
+
+
+def clip_scale(x, n, sumsq_dev, max_norm):
+    check(_L().tg_clip_scale(_p(x), n, _p(sumsq_dev), float(max_norm), _s()), 'tg_clip_scale'); _count()

@@ -235,6 +235,36 @@ int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream
 int tg_gru_tf32_sync_ints(int B, int H);
 /* development aid: when a device buffer of >= 16*T int64 is set, CTA (0,0,0) of the tensor-core GRU kernels stamps
  * %globaltimer at its per-step phases (NULL switches it off) */
+/* ---------------------------------------------------------------------------------------------------------
+ * seq2seq baseline (scripts/model/seq2seq_net.py, scripts/train_eval/train_seq2seq.py; config/seq2seq.yml).
+ * The projections are GEMMs (tg_conv_gemm_f32 / tg_gemm_tf32); these are the per-step non-GEMM pieces.
+ * --------------------------------------------------------------------------------------------------------- */
+/* One GRU time step for B rows from gi = W_ih x + b_ih (row pitch ldgi) and gh = W_hh h + b_hh ([B,3H]); gate order r,z,n.
+ * lengths (optional, device int64 [B]) restates pack_padded_sequence (seq2seq_net.py:52-56): rows with t >= length keep
+ * hprev and emit 0.  out (optional, row pitch ldout) receives the step output; saved (optional) = planes r,z,n,hn. */
+int tg_gru_gates_fwd(const float* gi, long long ldgi, const float* gh, const float* hprev, const long long* lengths, int t,
+                     float* hnew, float* out, long long ldout, float* saved, long long saved_plane, int B, int H, tg_stream stream);
+/* Backward of tg_gru_gates_fwd: g = dh (carry, optional) + dadd (this step's output gradient, optional, row pitch ldadd);
+ * writes dgi (row pitch lddgi), dgh [B,3H] and dhprev = g*z (the caller adds dgh @ W_hh); masked rows: zeros / carry. */
+int tg_gru_gates_bwd(const float* dh, const float* dadd, long long ldadd, const float* saved, long long saved_plane,
+                     const float* hprev, const long long* lengths, int t, float* dgi, long long lddgi, float* dgh,
+                     float* dhprev, int B, int H, tg_stream stream);
+/* Attn.forward (seq2seq_net.py:72-94) + context (:172-174) of one decoder step: hq = W_a[:, :H] h + b_a [B,H],
+ * eproj = W_a[:, H:] enc [B,Tm,H] (computed once per forward), enc [B,Tm,H], v [H] -> w [B,Tm], ctx [B,H]. */
+int tg_attn_fwd(const float* hq, const float* eproj, const float* enc, const float* v, float* w, float* ctx, int B, int Tm, int H,
+                tg_stream stream);
+int tg_attn_bwd(const float* dctx, const float* w, const float* hq, const float* eproj, const float* enc, const float* v,
+                float* denc, float* deproj, float* dv, float* dhq, int B, int Tm, int H, tg_stream stream);
+/* custom_loss (train_seq2seq.py:6-36): *loss += w_mse*mse + w_cont*continuity + w_var*variance term; dy_tmajor [T,B,D] =
+ * gradient w.r.t. out [B,T,D] (row t = 0 is zero: frame 0 is a copy of the input, seq2seq_net.py:244-245). */
+int tg_s2s_loss(const float* out, const float* target, double* loss, float* dy_tmajor, int B, int T, int D, float w_mse,
+                float w_cont, float w_var, tg_stream stream);
+/* xin[t,b,:] = decoder input of step t >= 1 (seq2seq_net.py:244-252): poses[b,t-1] while t-1 < n_pre, else outputs[b,t-1] */
+int tg_s2s_gather_inputs(const float* poses, const float* outputs, float* xin, int B, int T, int D, int n_pre, tg_stream stream);
+/* torch.nn.utils.clip_grad_norm_ (train_seq2seq.py:48) over a flat gradient arena: *out += sum x^2; x *= min(1, max/(norm+1e-6)) */
+int tg_sumsq_f64(const float* x, long long n, double* out, tg_stream stream);
+int tg_clip_scale(float* x, long long n, const double* sumsq, float max_norm, tg_stream stream);
+
 int tg_debug_gru_trace(long long* device_buf);
 /* development aid: %globaltimer stamps of CTA (0,0) of the next tg_gemm_tf32 launches (7 slots; NULL disables) */
 int tg_debug_gemm_trace(long long* device_buf);
