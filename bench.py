@@ -152,6 +152,55 @@ def workload_config(a, world):
             'l2': 'per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; inputs rotate over 8 distinct batches'}
 
 
+def aux_workloads(dev, timed):
+    """Side measurements of the other BASELINE.json configs on one GPU (reported next to the headline, not part of it):
+    configs[3] seq2seq training step at batch 128, configs[4] FGD over 10k synthetic clip pairs."""
+    out = {}
+    from model.seq2seq_net import Seq2SeqNet
+    from train_eval.train_seq2seq import train_iter_seq2seq
+    s_args = argparse.Namespace(hidden_size=200, n_layers=2, dropout_prob=0.1, n_pre_poses=4, GAN_noise_size=0, loss_regression_weight=250.0,
+                                loss_kld_weight=0.1, loss_reg_weight=25.0)                     # config/seq2seq.yml:17-19,26-28
+    net = Seq2SeqNet(s_args, POSE_DIM, T, N_WORDS, 300, None).to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    rng = np.random.Generator(np.random.PCG64(7))
+    lengths = np.sort(rng.integers(4, 13, size=128))[::-1].copy(); lengths[0] = 12
+    text_np = np.zeros((128, 12), dtype=np.int64)
+    for b in range(128):                                            # [SOS=1, words.., EOS=2], PAD 0, sorted by decreasing length
+        n = int(lengths[b]); text_np[b, 0] = 1; text_np[b, 1:n - 1] = rng.integers(4, N_WORDS, size=n - 2); text_np[b, n - 1] = 2
+    inp = {'lengths': torch.from_numpy(lengths.astype(np.int64))}
+    text, target = torch.from_numpy(text_np).to(dev), synth_batch(128, 77)['target'].to(dev)
+    f = lambda i: train_iter_seq2seq(s_args, 0, text, inp['lengths'], target, net, opt)
+    for i in range(5):
+        f(i)
+    ms, _, _, _ = timed(f, 20)
+    out['seq2seq_train_samples_per_s'] = 128 * 20 / (ms / 1e3)
+    out['seq2seq_config'] = 'config/seq2seq.yml: hidden 200, 2 layers, batch 128, text length 4..12, 34 frames; fp32 kernels, CUDA-graph replay'
+    # FGD: EmbeddingNet('pose') features of 10k real + 10k generated clips -> fp64 moments on the device -> host sqrtm
+    from model.embedding_net import EmbeddingNet
+    from model.embedding_space_evaluator import EmbeddingSpaceEvaluator
+    e_args = argparse.Namespace(hidden_size=300, n_layers=4, dropout_prob=0.3, freeze_wordembed=False)
+    enet = EmbeddingNet(e_args, POSE_DIM, T, N_WORDS, 300, None, 'pose').to(dev)
+    ev = EmbeddingSpaceEvaluator.from_net(enet, 4, dev)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    real = (0.5 * torch.randn(10000, T, POSE_DIM, generator=g)).to(dev)
+    fake = (torch.randn(10000, T, POSE_DIM, generator=g) + 0.3).to(dev)
+
+    def fgd(i):
+        ev.reset()
+        for o in range(0, 10000, 500):
+            ev.push_samples(None, None, fake[o:o + 500], real[o:o + 500])
+        return ev.get_scores()
+    fgd(0)
+    t0 = time.perf_counter()
+    score = fgd(1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['fgd_10k_pairs_seconds'] = dt
+    out['fgd_clips_per_s'] = 20000 / dt
+    out['fgd_value'] = score[0]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -162,6 +211,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
+    ap.add_argument('--no-aux', action='store_true', help='skip the seq2seq / FGD side measurements (BASELINE.json configs[3], configs[4])')
     a = ap.parse_args()
     if a.impl == 'reference':
         return run_reference(a)
@@ -265,6 +315,9 @@ def main():
             ims, _, _, _ = timed(f, n_it)
             infer['b%d' % bs] = world * bs * n_it / (ims / 1e3)
     G.train()
+    aux = {}
+    if world == 1 and not a.no_aux:
+        aux = aux_workloads(dev, timed)
 
     line = None
     if rank == 0:
@@ -273,10 +326,15 @@ def main():
         if not a.no_kernel_profile:
             # per-launch CUDA-event timing of two more steps -> dominant kernel family and its achieved rate
             old_graphs = tg_config.set_graphs(False)      # per-launch events need eager launches
+            old_overlap = tg_config.set_overlap(False)    # one stream: an event pair must not include waiting for SMs held by another stream
             with KernelTimer() as kt:
                 for i in range(2):
+                    # park the GPU behind ~25 ms of spin so the host (slower than the GPU in eager mode) queues the whole step
+                    # ahead of it: every event pair then brackets exactly one kernel's device time, not the host's launch gap
+                    torch.cuda._sleep(int(0.025 * 1.9e9))
                     step_resident(i)
             tg_config.set_graphs(old_graphs)
+            tg_config.set_overlap(old_overlap)
             agg = kt.summary()
             try:
                 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
@@ -290,12 +348,25 @@ def main():
             top = max(agg.items(), key=lambda kv: kv[1]['ms'])
             name, v = top
             tflops = v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] > 0 else 0.0
+            traffic = None
+            try:                                            # dram__bytes_read+write per launch from the committed ncu --set full capture
+                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')))
+                traffic = tr.get(name, {}).get('dram_bytes_per_launch')
+            except (OSError, ValueError):
+                pass
+            kinds = {'tg_gemm_tf32': 'tcgen05 kind::tf32 GEMM family (all shapes of a step, fp32 accumulate in TMEM)',
+                     'tg_wgrad_tf32': 'tcgen05 kind::tf32 weight-gradient GEMM family',
+                     'tg_gru_layer_fwd_tf32': 'persistent tensor-core GRU forward (latency-bound recurrence, 34 sequential steps per launch)',
+                     'tg_gru_layer_bwd_tf32': 'persistent tensor-core GRU backward (latency-bound recurrence)'}
             roof = {'bound': 'tensor', 'kernel': name, 'achieved': tflops, 'peak': peaks['tf_sust'], 'unit': 'TFLOP/s',
-                    'frac': tflops / peaks['tf_sust'], 'traffic': None, 'peak_source': peaks['src'] + ' bf16 dense sustained',
+                    'frac': tflops / peaks['tf_sust'], 'traffic': traffic, 'peak_source': peaks['src'] + ' bf16 dense sustained',
                     'share_of_step': v['ms'] / total_ms, 'launches_per_step': v['calls'] / 2,
-                    'note': 'fp32 CUDA-core kernel measured against the bf16 tensor-pipe peak (strict-fp32 mode); whole-step fraction = '
-                            '%.4f' % (value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12)),
-                    'by_kernel_ms_per_step': {k: round(x['ms'] / 2, 4) for k, x in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:8]}}
+                    'note': '%s; algorithmic FLOPs of its launches / their summed CUDA-event durations, measured against the bf16 tensor-pipe '
+                            'peak (TF32 peak is half of it); whole-step fraction = %.4f'
+                            % (kinds.get(name, 'fp32 CUDA-core kernel'), value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12)),
+                    'by_kernel_ms_per_step': {k: round(x['ms'] / 2, 4) for k, x in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:8]},
+                    'by_kernel_tflops': {k: round(x['flops'] / (x['ms'] / 1e3) / 1e12, 1) for k, x in
+                                         sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:8] if x['ms'] > 0 and x['flops'] > 0}}
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             r = cpu_reference_run(2, 1, a.batch, budget_s=45.0)
@@ -310,7 +381,7 @@ def main():
                 'gpu_launches': launches_per_step * a.steps, 'launches_per_step': launches_per_step,
                 'cuda_graph': tg_config.graphs(), 'clocks': clock_info, 'roofline': roof, 'cpu_baseline': cpu,
                 'step_roofline_frac': value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12),
-                'infer_clips_per_s': infer, 'last_losses': ret}
+                'infer_clips_per_s': infer, 'aux': aux, 'last_losses': ret}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
