@@ -345,22 +345,23 @@ def main():
             except OSError:
                 pass
             total_ms = sum(v['ms'] for v in agg.values())
-            top = max(agg.items(), key=lambda kv: kv[1]['ms'])
-            name, v = top
+            # dominant kernel = the single (entry point, shape) with the most device time per step
+            (name, tag), v = max(kt.by_shape().items(), key=lambda kv: kv[1]['ms'])
             tflops = v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] > 0 else 0.0
             traffic = None
             try:                                            # dram__bytes_read+write per launch from the committed ncu --set full capture
                 tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')))
-                traffic = tr.get(name, {}).get('dram_bytes_per_launch')
+                traffic = tr.get('%s|%s' % (name, tag), {}).get('dram_bytes_per_launch')
             except (OSError, ValueError):
                 pass
             kinds = {'tg_gemm_tf32': 'tcgen05 kind::tf32 GEMM family (all shapes of a step, fp32 accumulate in TMEM)',
                      'tg_wgrad_tf32': 'tcgen05 kind::tf32 weight-gradient GEMM family',
                      'tg_gru_layer_fwd_tf32': 'persistent tensor-core GRU forward (latency-bound recurrence, 34 sequential steps per launch)',
                      'tg_gru_layer_bwd_tf32': 'persistent tensor-core GRU backward (latency-bound recurrence)'}
-            roof = {'bound': 'tensor', 'kernel': name, 'achieved': tflops, 'peak': peaks['tf_sust'], 'unit': 'TFLOP/s',
+            roof = {'bound': 'tensor', 'kernel': name, 'shape': tag, 'achieved': tflops, 'peak': peaks['tf_sust'], 'unit': 'TFLOP/s',
                     'frac': tflops / peaks['tf_sust'], 'traffic': traffic, 'peak_source': peaks['src'] + ' bf16 dense sustained',
                     'share_of_step': v['ms'] / total_ms, 'launches_per_step': v['calls'] / 2,
+                    'avg_launch_us': 1e3 * v['ms'] / v['calls'], 'flops_per_launch': v['flops'] / v['calls'],
                     'note': '%s; algorithmic FLOPs of its launches / their summed CUDA-event durations, measured against the bf16 tensor-pipe '
                             'peak (TF32 peak is half of it); whole-step fraction = %.4f'
                             % (kinds.get(name, 'fp32 CUDA-core kernel'), value / world * FLOP_PER_SAMPLE_STEP / (peaks['tf_sust'] * 1e12)),

@@ -295,7 +295,11 @@ extern "C" int tg_conv_gemm_f32(const tg_conv_gemm_t* pp, tg_stream stream) {
     int pad64 = tg_ceil_div(p.N, 64) * 64, pad128 = tg_ceil_div(p.N, 128) * 128;
     bn = (pad128 <= pad64) ? 128 : 64;
   }
-  dim3 grid(tg_ceil_div(M, BM), tg_ceil_div(p.N, bn));
+  // few row tiles (the per-step GEMMs of the seq2seq decoder, M = batch): a wide tile would leave all but 2-5 SMs idle while each of
+  // those grinds through a 128x128 FFMA tile - narrow the tile until the grid covers a good part of the chip
+  const int mt = tg_ceil_div(M, BM);
+  while (bn > 32 && (long long)mt * tg_ceil_div(p.N, bn) < tg_num_sms() / 2) bn >>= 1;
+  dim3 grid(mt, tg_ceil_div(p.N, bn));
   TG_REQUIRE(grid.y < 65536, "tg_conv_gemm_f32");
   if (bn == 128) conv_gemm_kernel<128, 8><<<grid, 256, 0, s>>>(p);
   else if (bn == 64) conv_gemm_kernel<64, 4><<<grid, 256, 0, s>>>(p);

@@ -13,26 +13,47 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import config, ops
 from .arena import ParamArena
 from .engine import BN_EPS, BN_MOM, F32, Workspace
 
+_WT = {}          # id(weight tensor storage) -> transposed copy [K_total, N] of the current iteration (fast mode, see prep_weights)
+
+
+def _al16(t):
+    return t.data_ptr() % 16 == 0
+
 
 def _lin(x, W, b, out, *, M, K, N, ldw=None, w_off=0, lda=None, ldc=None, accumulate=False):
-    """out[M,N] (+)= x[M,K] @ W[:, w_off:w_off+K]^T + b   (W rows have pitch ldw)"""
-    ops.conv_gemm(x, W, out, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=K if ldw is None else ldw, wsc=1, w_off=w_off, lda=lda, ldc=ldc,
-                  bias=b, accumulate=accumulate)
+    """out[M,N] (+)= x[M,K] @ W[:, w_off:w_off+K]^T + b   (W rows have pitch ldw).  Fast mode: tcgen05 TF32 GEMM when TMA can
+    describe the operands (16-byte aligned bases and pitches), fp32 FFMA GEMM otherwise."""
+    ldw_ = K if ldw is None else ldw
+    lda_ = K if lda is None else lda
+    if (config.fast() and K >= 8 and K % 4 == 0 and lda_ % 4 == 0 and ldw_ % 4 == 0 and w_off % 4 == 0 and _al16(x) and _al16(W)):
+        ops.gemm_tf32(x, W.reshape(-1)[w_off:], out, M=M, N=N, K=K, lda=lda_, ldb=ldw_, ldc=ldc, bias=b, accumulate=accumulate)
+    else:
+        ops.conv_gemm(x, W, out, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=ldw_, wsc=1, w_off=w_off, lda=lda, ldc=ldc, bias=b,
+                      accumulate=accumulate)
 
 
 def _dlin(dy, W, dx, *, M, K, N, ldw=None, w_off=0, ldc=None, accumulate=False):
-    """dx[M,K] (+)= dy[M,N] @ W[:, w_off:w_off+K]"""
-    ops.conv_gemm(dy, W, dx, B=1, Tin=M, Tout=M, N=K, Cin=N, taps=1, ldw=1, wsc=K if ldw is None else ldw, w_off=w_off, ldc=ldc,
-                  accumulate=accumulate)
+    """dx[M,K] (+)= dy[M,N] @ W[:, w_off:w_off+K].  Fast mode reads the transposed copy W^T prepared by prep_weights()."""
+    ldw_ = K if ldw is None else ldw
+    wt = _WT.get(W.data_ptr()) if config.fast() else None
+    if (wt is not None and N >= 8 and N % 4 == 0 and (w_off * N) % 4 == 0 and _al16(dy)):
+        ops.gemm_tf32(dy, wt.reshape(-1)[w_off * N:], dx, M=M, N=K, K=N, ldc=ldc, accumulate=accumulate)
+    else:
+        ops.conv_gemm(dy, W, dx, B=1, Tin=M, Tout=M, N=K, Cin=N, taps=1, ldw=1, wsc=ldw_, w_off=w_off, ldc=ldc, accumulate=accumulate)
 
 
 def _wg(x, dy, dW, dbias, *, M, K, N, ldw=None, dw_off=0):
     """dW[:, dw_off:dw_off+K] += dy[M,N]^T x[M,K];  dbias += colsum(dy)"""
-    ops.conv_wgrad(x, dy, dW, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=K if ldw is None else ldw, wsc=1, dbias=dbias, dw_off=dw_off)
+    ldw_ = K if ldw is None else ldw
+    if (config.fast() and K >= 8 and K % 4 == 0 and N >= 16 and N % 4 == 0 and ldw_ % 4 == 0 and dw_off % 4 == 0 and _al16(x) and _al16(dy)
+            and _al16(dW)):
+        ops.wgrad_tf32(dy, x, dW.reshape(-1)[dw_off:], B=1, T=M, N=N, Cin=K, ldw=ldw_, dbias=dbias)
+    else:
+        ops.conv_wgrad(x, dy, dW, B=1, Tin=M, Tout=M, N=N, Cin=K, taps=1, ldw=ldw_, wsc=1, dbias=dbias, dw_off=dw_off)
 
 
 class Seq2SeqEngine:
@@ -70,6 +91,20 @@ class Seq2SeqEngine:
     def G(self, name):
         return self.arena.gview(name)
 
+    def prep_weights(self):
+        """Fast mode: transposed copies of every matrix the backward data path multiplies by (weights change every optimiser step)."""
+        if not config.fast():
+            return
+        ws = self.ws
+        names = [n for n in self.arena.names if '.gru.weight_' in n or n.endswith(('attn.attn.weight', 'pre_linear.0.weight'))]
+        for n in dict.fromkeys(names):
+            W = self.P(n)
+            if W.dim() != 2 or W.shape[0] % 4 != 0:
+                continue
+            wt = ws.get('T.' + n, (W.shape[1], W.shape[0]))
+            ops.transpose(W, wt, W.shape[0], W.shape[1])
+            _WT[W.data_ptr()] = wt
+
     # ------------------------------------------------------------------------------------------------ masks
     def make_masks(self, B, Tm, seed, offset_dev):
         """Inter-layer dropout keep-masks (train mode): encoder layer l < L-1 outputs [B*Tm, 2H], decoder layer l < L-1 outputs of
@@ -98,6 +133,8 @@ class Seq2SeqEngine:
         ws, H, L, E, D, T = self.ws, self.H, self.L, self.E, self.D, self.T
         B = poses.shape[0]
         self.ctx = dict(B=B, Tm=Tm, masks=masks, poses=poses, training=training, lengths=lengths_dev)
+        if save:
+            self.prep_weights()
         idx = ws.get('enc.idx', (B, Tm), torch.int64)
         idx.copy_(in_text[:, :Tm])
         emb = ws.get('enc.emb', (B * Tm, E))
