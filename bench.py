@@ -319,22 +319,27 @@ def main():
     if world == 1 and not a.no_aux:
         aux = aux_workloads(dev, timed)
 
+    kt = None
+    if not a.no_kernel_profile:
+        # per-launch CUDA-event timing of two more steps -> dominant kernel and its achieved rate.  EVERY rank runs them (the steps
+        # contain the gradient all-reduces: a rank-0-only pass would wait for its peers forever); only rank 0 reports.
+        old_graphs = tg_config.set_graphs(False)      # per-launch events need eager launches
+        old_overlap = tg_config.set_overlap(False)    # one stream: an event pair must not include waiting for SMs held by another stream
+        with KernelTimer() as kt:
+            for i in range(2):
+                # park the GPU behind ~25 ms of spin so the host (slower than the GPU in eager mode) queues the whole step
+                # ahead of it: every event pair then brackets exactly one kernel's device time, not the host's launch gap
+                torch.cuda._sleep(int(0.025 * 1.9e9))
+                step_resident(i)
+        tg_config.set_graphs(old_graphs)
+        tg_config.set_overlap(old_overlap)
+        barrier()
+
     line = None
     if rank == 0:
         peaks = load_peaks()
         roof = None
-        if not a.no_kernel_profile:
-            # per-launch CUDA-event timing of two more steps -> dominant kernel family and its achieved rate
-            old_graphs = tg_config.set_graphs(False)      # per-launch events need eager launches
-            old_overlap = tg_config.set_overlap(False)    # one stream: an event pair must not include waiting for SMs held by another stream
-            with KernelTimer() as kt:
-                for i in range(2):
-                    # park the GPU behind ~25 ms of spin so the host (slower than the GPU in eager mode) queues the whole step
-                    # ahead of it: every event pair then brackets exactly one kernel's device time, not the host's launch gap
-                    torch.cuda._sleep(int(0.025 * 1.9e9))
-                    step_resident(i)
-            tg_config.set_graphs(old_graphs)
-            tg_config.set_overlap(old_overlap)
+        if kt is not None:
             agg = kt.summary()
             try:
                 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
