@@ -294,3 +294,56 @@ extern "C" int tg_clip_scale(float* x, long long n, const double* sumsq, float m
   TG_CHECK_LAUNCH("tg_clip_scale");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Validation metrics of evaluate_testset (scripts/train.py:283,293-310) on the device: L1 of the direction vectors, MAE of the
+// joint coordinates (convert_dir_vec_to_pose, scripts/utils/data_utils.py:14-15,77-98) over frames >= n_pre and the "accel"
+// mismatch of second time differences.  Everything is linear in (out - target), so the mean direction vector the reference adds to
+// both operands cancels; sums are accumulated in fp64.  One thread per (clip, frame).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__constant__ int c_bone_parent[9] = {0, 1, 2, 1, 4, 5, 1, 7, 8};
+__constant__ int c_bone_child[9] = {1, 2, 3, 4, 5, 6, 7, 8, 9};
+__constant__ double c_bone_len[9] = {0.26, 0.18, 0.14, 0.22, 0.36, 0.33, 0.22, 0.36, 0.33};
+
+__device__ __forceinline__ void joint_err(const float* __restrict__ o, const float* __restrict__ t, double e[30]) {
+  e[0] = e[1] = e[2] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int a = c_bone_parent[j], b = c_bone_child[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e[b * 3 + k] = e[a * 3 + k] + c_bone_len[j] * ((double)o[j * 3 + k] - (double)t[j * 3 + k]);
+  }
+}
+
+__global__ void __launch_bounds__(128) pose_eval_metrics_kernel(const float* __restrict__ out, const float* __restrict__ target, int B, int T,
+                                                                int n_pre, double* __restrict__ acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double l1 = 0.0, mae = 0.0, ac = 0.0;
+  if (i < B * T) {
+    const int t = i % T;
+    const float* o = out + (long long)i * 27;
+    const float* g = target + (long long)i * 27;
+    for (int k = 0; k < 27; ++k) l1 += (double)fabsf(o[k] - g[k]);
+    double e0[30];
+    joint_err(o, g, e0);
+    if (t >= n_pre)
+      for (int k = 0; k < 30; ++k) mae += fabs(e0[k]);
+    if (t >= 2) {
+      double e1[30], e2[30];
+      joint_err(o - 27, g - 27, e1);
+      joint_err(o - 54, g - 54, e2);
+      for (int k = 0; k < 30; ++k) ac += fabs(e0[k] - 2.0 * e1[k] + e2[k]);
+    }
+  }
+  l1 = warp_sum_d(l1); mae = warp_sum_d(mae); ac = warp_sum_d(ac);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(acc, l1); atomicAdd(acc + 1, mae); atomicAdd(acc + 2, ac); }
+}
+}  // namespace
+
+extern "C" int tg_pose_eval_metrics(const float* out, const float* target, int B, int T, int D, int n_pre, double* acc, tg_stream stream) {
+  TG_REQUIRE(out && target && acc && B > 0 && T > 0 && D == 27 && n_pre >= 0, "tg_pose_eval_metrics");
+  pose_eval_metrics_kernel<<<tg_ceil_div((long long)B * T, 128), 128, 0, (cudaStream_t)stream>>>(out, target, B, T, n_pre, acc);
+  TG_CHECK_LAUNCH("tg_pose_eval_metrics");
+  return 0;
+}

@@ -394,3 +394,7 @@ def sumsq(x, n, out):
 
 def clip_scale(x, n, sumsq_dev, max_norm):
     check(_L().tg_clip_scale(_p(x), n, _p(sumsq_dev), float(max_norm), _s()), 'tg_clip_scale'); _count()
+
+
+def pose_eval_metrics(out, target, B, T, D, n_pre, acc):
+    check(_L().tg_pose_eval_metrics(_p(_f32(out)), _p(_f32(target)), B, T, D, n_pre, _p(acc), _s()), 'tg_pose_eval_metrics'); _count()

@@ -265,6 +265,11 @@ int tg_s2s_gather_inputs(const float* poses, const float* outputs, float* xin, i
 int tg_sumsq_f64(const float* x, long long n, double* out, tg_stream stream);
 int tg_clip_scale(float* x, long long n, const double* sumsq, float max_norm, tg_stream stream);
 
+/* Validation metrics of evaluate_testset (scripts/train.py:283,293-310; convert_dir_vec_to_pose, scripts/utils/data_utils.py:77-98)
+ * for out / target [B,T,27] direction vectors: acc[0] += sum |out - target|, acc[1] += sum over frames >= n_pre of |joint position
+ * error| (10 joints x 3), acc[2] += sum over frames >= 2 of |second time difference of the joint position error| (fp64 accumulators). */
+int tg_pose_eval_metrics(const float* out, const float* target, int B, int T, int D, int n_pre, double* acc, tg_stream stream);
+
 int tg_debug_gru_trace(long long* device_buf);
 /* development aid: %globaltimer stamps of CTA (0,0) of the next tg_gemm_tf32 launches (7 slots; NULL disables) */
 int tg_debug_gemm_trace(long long* device_buf);

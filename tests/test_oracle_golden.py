@@ -128,3 +128,13 @@ def test_seq2seq_oracle_matches_reference():
             else:
                 _digest_close(digest(v), g[f'post{it}/' + k], 1e-4)
         sd, opt = ret['new_sd'], ret['opt']
+
+
+def test_eval_metrics_oracle_matches_reference_function():
+    """oracle/eval_oracle.py vs. the reference's own convert_dir_vec_to_pose + the metric lines of evaluate_testset (train.py:293-310)."""
+    from oracle import eval_oracle as E
+    g = np.load(os.path.join(GOLDEN, 'eval_metrics.npz'))
+    l1, mae, acc = E.batch_metrics(g['out'], g['target'], g['mean_dir_vec'], int(g['n_pre']))
+    assert abs(l1 - float(g['l1'])) < 1e-12 and abs(mae - float(g['mae'])) < 1e-12 and abs(acc - float(g['accel'])) < 1e-12
+    pos = E.convert_dir_vec_to_pose(g['out'].astype(np.float64) + g['mean_dir_vec'])
+    assert np.abs(pos - g['joint_poses']).max() < 1e-12
