@@ -50,7 +50,12 @@ def test_evaluate_testset_seq2seq_matches_oracle_metrics(dev):
             out = S.seq2seq_forward({k: v for k, v in synth.seq2seq_state_dict(cfg).items()}, cfg, inp['in_text'], inp['lengths'], inp['target'], False)
         l1, mae, acc = E.batch_metrics(out.numpy(), inp['target'].numpy(), mean_dir_vec, cfg.n_pre_poses)
         l1s.append(l1); maes.append(mae); accs.append(acc); ns.append(B)
-    ret = evaluate_testset(batches, net, None, None, args)
+    from tgb200 import config
+    old = config.set_mode('fp32')              # strict mode: this test pins the metric plumbing, not the TF32 tolerance
+    try:
+        ret = evaluate_testset(batches, net, None, None, args)
+    finally:
+        config.set_mode(old)
     w = np.array(ns, dtype=np.float64) / sum(ns)                     # AverageMeter: batch means weighted by batch size (train.py:289,306)
     assert net.training, 'evaluate_testset must restore the training flag (train.py:313)'
     assert abs(ret['loss'] - float((w * l1s).sum())) <= 2e-4 * float((w * l1s).sum())
