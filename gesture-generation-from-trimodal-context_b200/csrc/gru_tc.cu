@@ -184,6 +184,15 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
     const int lr = q * 32 + lane;
     const float* bhh = p.bhh[dir];
     const long long row2H = 2ll * H;
+    // (clip, unit) pair owned by this thread in slot e: loop invariant (the integer divisions were a quarter of all executed
+    // instructions when they sat inside the step loop - ncu source view, profiles/README.md)
+    int ppk[NP];                                   // (clip << 16) | unit, or -1
+#pragma unroll
+    for (int e = 0; e < NP; ++e) {
+      const int i = etid + 512 * e;
+      const int bb = i / u;
+      ppk[e] = (i < BT * u) ? ((bb << 16) | (i - bb * u)) : -1;
+    }
     int it = 0;
     for (int s = 0; s < T; ++s) {
       const int t = dir == 0 ? s : T - 1 - s;
@@ -194,10 +203,9 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
         float gir[NP], giz[NP], gin[NP], hpv[NP], bhh_r_[NP], bhh_z_[NP], bhh_n_[NP];
 #pragma unroll
         for (int e = 0; e < NP; ++e) {
-          const int i = etid + 512 * e;
           gir[e] = giz[e] = gin[e] = hpv[e] = bhh_r_[e] = bhh_z_[e] = bhh_n_[e] = 0.f;
-          if (i < BT * u) {
-            const int bb = i / u, jj = i - bb * u;
+          if (ppk[e] >= 0) {
+            const int bb = ppk[e] >> 16, jj = ppk[e] & 0xffff;
             const int b = b0 + bb, unit = u0 + jj;
             if (b < p.B && unit < H) {
               const float* gip = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + unit;
@@ -229,9 +237,8 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
         // here depends on a fresh memory round trip.
 #pragma unroll
         for (int e = 0; e < NP; ++e) {
-          const int i = etid + 512 * e;
-          if (i >= BT * u) continue;
-          const int bb = i / u, jj = i - bb * u;
+          if (ppk[e] < 0) continue;
+          const int bb = ppk[e] >> 16, jj = ppk[e] & 0xffff;
           const int b = b0 + bb, unit = u0 + jj;
           if (b >= p.B || unit >= H) continue;
           float ghr = bhh_r_[e], ghz = bhh_z_[e], ghn = bhh_n_[e];
@@ -264,9 +271,8 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
         if (p.saved) {
 #pragma unroll
           for (int e = 0; e < NP; ++e) {
-            const int i = etid + 512 * e;
-            if (i >= BT * u) continue;
-            const int bb = i / u, jj = i - bb * u;
+            if (ppk[e] < 0) continue;
+            const int bb = ppk[e] >> 16, jj = ppk[e] & 0xffff;
             const int b = b0 + bb, unit = u0 + jj;
             if (b >= p.B || unit >= H) continue;
             const long long o = ((long long)b * T + t) * row2H + dir * H + unit;
