@@ -295,17 +295,28 @@ def main():
     ms, launches, t0, t1 = timed(step_resident, a.steps)
     clock_info = clocks.stop(t0, t1) if rank == 0 else None
     value = world * a.batch * a.steps / (ms / 1e3)
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e, _, _, _ = timed(step_e2e, a.steps)
+    # end to end: every step's inputs come from pinned host memory inside the timed region; train_eval.staging.DevicePrefetcher issues the
+    # copy of batch i+1 on its own stream while step i runs (the reference does a blocking .to(device) per batch, train.py:171-176)
+    from train_eval.staging import DevicePrefetcher
+
+    def e2e_run(steps):
+        feed = DevicePrefetcher((pinned[i % n_pool] for i in range(steps)), dev)
+        it = iter(feed)
+
+        def f(i):
+            b = next(it)
+            return train_iter_gan(args, 11, b['in_text'], b['in_audio'], b['target'], b['vid'], G, D, g_opt, d_opt)   # returns python floats (D2H)
+        return timed(f, steps)
+    e2e_run(2)
+    ms_e2e, _, _, _ = e2e_run(a.steps)
     e2e_value = world * a.batch * a.steps / (ms_e2e / 1e3)
 
     # ---- PoseGenerator inference (the metric's "clips/s"): eval forward, batch 128 and batch 1, device-resident inputs
     G.eval()
     infer = {}
     with torch.no_grad():
-        for bs in (a.batch, 1):
-            b = {k: v[:bs].contiguous() for k, v in resident[0].items()}
+        for bs in (512, a.batch, 1):
+            b = {k: torch.cat([r[k] for r in resident[:(bs + a.batch - 1) // a.batch]])[:bs].contiguous() for k in resident[0]}
             pre = torch.zeros(bs, T, POSE_DIM + 1, device=dev)
             pre[:, :4, :-1] = b['target'][:, :4]; pre[:, :4, -1] = 1
             f = lambda i: G(pre, b['in_text'], b['in_audio'], b['vid'])

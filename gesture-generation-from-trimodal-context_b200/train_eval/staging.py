@@ -1,0 +1,71 @@
+"""Input staging around the hot path: what `for data in train_data_loader: x = x.to(device)` does in the reference
+(scripts/train.py:166-183), restructured so that the host->device copy of batch i+1 overlaps the training step of batch i.
+
+DevicePrefetcher wraps any iterable of batches (tuples / lists / dicts of CPU tensors, e.g. a torch DataLoader with pin_memory=True) and
+yields the same structure with every tensor resident on the device.  Copies are issued on a dedicated CUDA stream from pinned memory
+(non-pinned tensors are pinned through a reusable staging buffer first); the consumer's stream waits on the copy's event, and a batch's
+device buffers are only recycled after the consumer has moved on (record_stream), so the only sizeable host->device stream of the path -
+18.6 MB of raw audio per 128-clip batch - never sits on the critical path."""
+import torch
+
+
+def _map(obj, fn):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map(v, fn) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_map(v, fn) for v in obj)
+    return obj
+
+
+class DevicePrefetcher:
+    def __init__(self, loader, device, depth=2):
+        assert depth >= 1
+        self.loader, self.device, self.depth = loader, torch.device(device), depth
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pin = {}
+
+    def _to_device(self, t):
+        if not t.is_pinned():
+            key = (tuple(t.shape), t.dtype, self._slot)
+            buf = self._pin.get(key)
+            if buf is None:
+                buf = self._pin[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t)
+            t = buf
+        return t.to(self.device, non_blocking=True)
+
+    def _issue(self, batch, slot):
+        self._slot = slot
+        with torch.cuda.stream(self.stream):
+            dev_batch = _map(batch, self._to_device)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev_batch, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        queue = []
+        n = 0
+        try:
+            while len(queue) < self.depth:
+                queue.append(self._issue(next(it), n % (self.depth + 1)))
+                n += 1
+        except StopIteration:
+            it = None
+        while queue:
+            dev_batch, ev = queue.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            _map(dev_batch, lambda t: (t.record_stream(cur), t)[1])
+            if it is not None:
+                try:
+                    queue.append(self._issue(next(it), n % (self.depth + 1)))
+                    n += 1
+                except StopIteration:
+                    it = None
+            yield dev_batch
+
+    def __len__(self):
+        return len(self.loader)

@@ -84,3 +84,22 @@ def test_evaluate_testset_multimodal_with_fgd(dev):
     assert set(ret) == {'loss', 'joint_mae', 'frechet', 'feat_dist'}
     assert all(np.isfinite(v) for v in ret.values()) and ret['loss'] > 0 and ret['joint_mae'] > 0
     assert G.training and ev.get_no_of_samples() == 3
+
+
+def test_device_prefetcher_yields_identical_batches(dev):
+    """Input staging: pinned and pageable host batches arrive on the device unchanged and in order."""
+    from train_eval.staging import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    host = []
+    for i in range(7):
+        a = torch.randn(16, 1000, generator=g)
+        t = torch.randint(0, 50, (16, 34), generator=g)
+        host.append({'audio': a.pin_memory() if i % 2 == 0 else a, 'text': t, 'meta': ('clip%d' % i, [a[:2].clone()])})
+    n = 0
+    for i, b in enumerate(DevicePrefetcher(host, dev, depth=2)):
+        assert b['audio'].is_cuda and b['text'].is_cuda and b['meta'][0] == 'clip%d' % i
+        y = b['audio'] * 2.0                                  # consume on the current stream
+        assert torch.equal(b['audio'].cpu(), host[i]['audio']) and torch.equal(b['text'].cpu(), host[i]['text'])
+        assert torch.equal(b['meta'][1][0].cpu(), host[i]['meta'][1][0]) and torch.equal(y.cpu(), host[i]['audio'] * 2.0)
+        n += 1
+    assert n == 7
