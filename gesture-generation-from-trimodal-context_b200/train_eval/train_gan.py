@@ -136,6 +136,15 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
     return ret
 
 
+def _stage(dst, src):
+    """Copy into a graph's static input buffer.  Device sources go through an elementwise KERNEL, not cudaMemcpyAsync: a copy-engine
+    D2D copy queues behind whatever host->device transfer a prefetcher has in flight (train_eval/staging.py) and would stall the step."""
+    if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
+        torch.add(src, 0, out=dst)
+    else:
+        dst.copy_(src)
+
+
 def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt, d_opt):
     """Replays (capturing on first use) the CUDA graph of one iteration on static input buffers.  Everything random is
     drawn inside the graph from device-resident Philox offsets and the Adam step counters live on the device, so every
@@ -149,9 +158,9 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
                            target=ws.get('ti.s_target', tuple(target.shape)),
                            vid=ws.get('ti.s_vid', tuple(vid.shape), torch.int64) if vid is not None else None)
     st = slot.static
-    st['in_text'].copy_(in_text); st['in_audio'].copy_(in_audio); st['target'].copy_(target)
+    _stage(st['in_text'], in_text); _stage(st['in_audio'], in_audio); _stage(st['target'], target)
     if vid is not None:
-        st['vid'].copy_(vid)
+        _stage(st['vid'], vid)
     if slot.graph is None:
         try:
             ge.arena.bind_optimizer(g_opt); de.arena.bind_optimizer(d_opt)
