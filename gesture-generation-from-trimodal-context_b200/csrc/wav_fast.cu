@@ -145,3 +145,33 @@ extern "C" int tg_conv1_wgrad(const float* x, const float* dy, float* dW, float*
   TG_CHECK_LAUNCH("tg_conv1_wgrad");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Input staging (train_eval/staging.py): host->device copy of a pinned batch done by a KERNEL that reads the mapped pinned memory
+// directly over PCIe.  A cudaMemcpyAsync would occupy a copy engine for ~0.35 ms per 18.6 MB audio batch, and every copy-engine
+// operation of the concurrently running training step (graph memset / memcpy nodes) queues behind it; a handful of otherwise idle
+// CTAs do the same transfer without touching the copy engines.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) copy_bytes_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long long n16,
+                                                         unsigned char* __restrict__ dst_tail, const unsigned char* __restrict__ src_tail, int ntail) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+}  // namespace
+
+extern "C" int tg_copy_bytes(void* dst, const void* src, long long nbytes, int max_ctas, tg_stream stream) {
+  TG_REQUIRE(dst && src && nbytes > 0, "tg_copy_bytes");
+  TG_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0, "tg_copy_bytes(alignment)");
+  const long long n16 = nbytes / 16;
+  const int ntail = (int)(nbytes - n16 * 16);
+  long long blocks = (n16 + 255) / 256;
+  if (max_ctas < 1) max_ctas = 64;
+  if (blocks > max_ctas) blocks = max_ctas;
+  if (blocks < 1) blocks = 1;
+  copy_bytes_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n16,
+                                                                    reinterpret_cast<unsigned char*>(dst) + n16 * 16,
+                                                                    reinterpret_cast<const unsigned char*>(src) + n16 * 16, ntail);
+  TG_CHECK_LAUNCH("tg_copy_bytes");
+  return 0;
+}

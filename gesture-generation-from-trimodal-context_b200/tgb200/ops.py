@@ -398,3 +398,11 @@ def clip_scale(x, n, sumsq_dev, max_norm):
 
 def pose_eval_metrics(out, target, B, T, D, n_pre, acc):
     check(_L().tg_pose_eval_metrics(_p(_f32(out)), _p(_f32(target)), B, T, D, n_pre, _p(acc), _s()), 'tg_pose_eval_metrics'); _count()
+
+
+def copy_bytes(dst, src, max_ctas=64):
+    """dst (device tensor) <- src (device or PINNED host tensor, same byte size), by a kernel (no copy engine); see tg_copy_bytes."""
+    assert dst.is_cuda and dst.is_contiguous() and src.is_contiguous() and (src.is_cuda or src.is_pinned())
+    nbytes = dst.numel() * dst.element_size()
+    assert nbytes == src.numel() * src.element_size()
+    check(_L().tg_copy_bytes(dst.data_ptr(), src.data_ptr(), nbytes, max_ctas, _s()), 'tg_copy_bytes'); _count()

@@ -270,6 +270,11 @@ int tg_clip_scale(float* x, long long n, const double* sumsq, float max_norm, tg
  * error| (10 joints x 3), acc[2] += sum over frames >= 2 of |second time difference of the joint position error| (fp64 accumulators). */
 int tg_pose_eval_metrics(const float* out, const float* target, int B, int T, int D, int n_pre, double* acc, tg_stream stream);
 
+/* Input staging (scripts/train.py:171-176 `.to(device)` of a collated batch): copies nbytes from src to dst with at most max_ctas CTAs.
+ * src may be PINNED HOST memory (read over PCIe through its mapped address): unlike cudaMemcpyAsync this uses no copy engine, so
+ * copy-engine operations of a concurrently running step never queue behind the transfer.  16-byte aligned pointers. */
+int tg_copy_bytes(void* dst, const void* src, long long nbytes, int max_ctas, tg_stream stream);
+
 int tg_debug_gru_trace(long long* device_buf);
 /* development aid: %globaltimer stamps of CTA (0,0) of the next tg_gemm_tf32 launches (7 slots; NULL disables) */
 int tg_debug_gemm_trace(long long* device_buf);
