@@ -300,17 +300,13 @@ def main():
     from train_eval.staging import DevicePrefetcher
 
     def e2e_run(steps):
-        from train_eval import train_gan as TG
-        TG.clear_post_launch_hooks()
-        feed = DevicePrefetcher((pinned[i % n_pool] for i in range(steps)), dev).attach(TG.add_post_launch_hook)
+        feed = DevicePrefetcher((pinned[i % n_pool] for i in range(steps)), dev)
         it = iter(feed)
 
         def f(i):
             b = next(it)
             return train_iter_gan(args, 11, b['in_text'], b['in_audio'], b['target'], b['vid'], G, D, g_opt, d_opt)   # returns python floats (D2H)
-        r = timed(f, steps)
-        TG.clear_post_launch_hooks()
-        return r
+        return timed(f, steps)
     e2e_run(2)
     ms_e2e, _, _, _ = e2e_run(a.steps)
     e2e_value = world * a.batch * a.steps / (ms_e2e / 1e3)

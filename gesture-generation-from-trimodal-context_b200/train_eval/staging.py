@@ -62,41 +62,31 @@ class DevicePrefetcher:
             ev.record(self.stream)
         return dev_batch, ev, slot
 
-    # -- iteration -----------------------------------------------------------------------------------------------------------
-    def _top_up(self):
-        """Issues copies until `depth` batches are in flight.  Host-side work (tensor-tree walk, launches): ~0.2 ms per batch."""
-        while self._it is not None and len(self._queue) < self.depth:
-            try:
-                batch = next(self._it)
-            except StopIteration:
-                self._it = None
-                break
-            self._queue.append(self._issue(batch, self._n % (self.depth + 1)))
-            self._n += 1
-
-    def attach(self, register_hook):
-        """register_hook(fn): fn is called by the step function right after it has queued a step's launches and BEFORE it blocks on the
-        step's scalars (train_eval.train_gan.add_post_launch_hook).  The prefetcher then does its host work while the GPU runs the
-        step instead of in the idle gap between two steps.  Returns self."""
-        register_hook(self._top_up)
-        self._hooked = True
-        return self
-
     def __iter__(self):
-        self._it = iter(self.loader)
-        self._queue, self._n = [], 0
-        self._top_up()
+        it = iter(self.loader)
+        queue = []
+        n = 0
+        try:
+            while len(queue) < self.depth:
+                queue.append(self._issue(next(it), n % (self.depth + 1)))
+                n += 1
+        except StopIteration:
+            it = None
         prev_slot = None
-        while self._queue:
-            dev_batch, ev, slot = self._queue.pop(0)
+        while queue:
+            dev_batch, ev, slot = queue.pop(0)
             cur = torch.cuda.current_stream(self.device)
             if prev_slot is not None:                  # everything the consumer queued on the previous batch is in front of this event
                 done = torch.cuda.Event()
                 done.record(cur)
                 self._free[prev_slot] = done
             cur.wait_event(ev)
-            if not getattr(self, '_hooked', False) or not self._queue:
-                self._top_up()
+            if it is not None:
+                try:
+                    queue.append(self._issue(next(it), n % (self.depth + 1)))
+                    n += 1
+                except StopIteration:
+                    it = None
             prev_slot = slot
             yield dev_batch
 

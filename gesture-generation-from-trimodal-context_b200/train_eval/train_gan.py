@@ -75,18 +75,6 @@ class _GraphSlot:
 
 
 _graph_slots = {}
-_post_launch_hooks = []
-
-
-def add_post_launch_hook(fn):
-    """fn() runs after every iteration's launches are queued and before the blocking read-back of its scalars."""
-    _post_launch_hooks.append(fn)
-
-
-def clear_post_launch_hooks():
-    del _post_launch_hooks[:]
-
-
 _GRAPH_WARMUP = 2          # eager iterations (allocate every workspace) before the iteration is captured
 
 
@@ -130,8 +118,6 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
     if sc is None:
         sc = _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step=True)
 
-    for hook in _post_launch_hooks:          # e.g. the input prefetcher: host work while the GPU runs the step queued above
-        hook()
     # ---- one device->host copy for the logged scalars (train_gan.py:94-102)
     s = sc.cpu().tolist()
     huber = s[0] / (B * T * Dm)
