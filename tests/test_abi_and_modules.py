@@ -81,3 +81,59 @@ def test_no_cpu_fallback_without_cuda():
     from train_eval.train_gan import train_iter_gan
     with pytest.raises(_lib.TgError):
         train_iter_gan(None, 0, None, None, torch.zeros(1, 34, 27), None, None, None, None, None)
+
+
+def test_seq2seq_module_keys_and_no_cpu_fallback():
+    """Seq2SeqNet carries the reference's state_dict keys (strict load of the synthetic reference-keyed weights) and refuses CPU tensors."""
+    import argparse
+    from oracle.make_golden_seq2seq import golden_cfg as s2s_cfg
+    from model.seq2seq_net import Seq2SeqNet
+    from tgb200 import _lib
+    from train_eval.train_seq2seq import train_iter_seq2seq
+    cfg = s2s_cfg()
+    args = argparse.Namespace(hidden_size=cfg.hidden_size, n_layers=cfg.n_layers, dropout_prob=0.1, n_pre_poses=cfg.n_pre_poses, GAN_noise_size=0,
+                              loss_regression_weight=250.0, loss_kld_weight=0.1, loss_reg_weight=25.0)
+    net = Seq2SeqNet(args, cfg.pose_dim, cfg.n_poses, cfg.n_words, cfg.wordembed_dim, None)
+    sd = synth.seq2seq_state_dict(cfg)
+    net.load_state_dict(sd, strict=True)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    if not torch.cuda.is_available():
+        inp = synth.seq2seq_inputs(cfg, 4, seed=1, max_len=6)
+        with pytest.raises(_lib.TgError):
+            net(inp['in_text'], inp['lengths'], inp['target'], None)
+        with pytest.raises(_lib.TgError):
+            train_iter_seq2seq(args, 0, inp['in_text'], inp['lengths'], inp['target'], net.train(), torch.optim.Adam(net.parameters()))
+
+
+def test_seq2seq_launch_plan_trace():
+    """Host logic of the seq2seq plan without a GPU: TGB200_TRACE_ONLY records which C-ABI entry points one training iteration would call."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, argparse, collections
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import torch
+from oracle import synth
+from oracle.make_golden_seq2seq import golden_cfg
+from model.seq2seq_net import Seq2SeqNet
+from train_eval.train_seq2seq import train_iter_seq2seq
+from tgb200 import _lib
+cfg = golden_cfg()
+args = argparse.Namespace(hidden_size=cfg.hidden_size, n_layers=cfg.n_layers, dropout_prob=0.1, n_pre_poses=cfg.n_pre_poses, GAN_noise_size=0,
+                          loss_regression_weight=250.0, loss_kld_weight=0.1, loss_reg_weight=25.0)
+net = Seq2SeqNet(args, cfg.pose_dim, cfg.n_poses, cfg.n_words, cfg.wordembed_dim, None).train()
+inp = synth.seq2seq_inputs(cfg, 6, seed=3, max_len=9)
+train_iter_seq2seq(args, 0, inp['in_text'], inp['lengths'], inp['target'], net, torch.optim.Adam(net.parameters(), lr=1e-4))
+c = collections.Counter(_lib.trace)
+T, Tm, L = cfg.n_poses, 9, cfg.n_layers
+assert c['tg_attn_fwd'] == T - 1 and c['tg_attn_bwd'] == T - 1, c
+assert c['tg_gru_gates_fwd'] == (T - 1) * L + Tm * 2 * L and c['tg_gru_gates_bwd'] == c['tg_gru_gates_fwd'], c
+assert c['tg_s2s_loss'] == 1 and c['tg_sumsq_f64'] == 1 and c['tg_clip_scale'] == 1 and c['tg_adam_flat'] == 1, c
+assert c['tg_bn_finalize'] == T - 1 and c['tg_bn_bwd_apply'] == T - 1, c
+print('ok', sum(c.values()))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TGB200_TRACE_ONLY='1')
+    r = subprocess.run([sys.executable, '-c', code % (root, os.path.join(root, 'gesture-generation-from-trimodal-context_b200'))], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
