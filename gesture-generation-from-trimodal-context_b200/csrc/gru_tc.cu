@@ -154,7 +154,12 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
         if (lane == 0 && it > 0) mbar_wait(epi_done, (uint32_t)((it - 1) & 1));
         __syncwarp();
         if (lane < nkc) {
-          fence_proxy_async_all();       // h_{t-1} was written through the generic proxy (by other CTAs); the TMA reads through the async proxy
+          // h_{t-1} was written through the generic proxy by other CTAs: each writer ran fence.proxy.async after its stores and before
+          // its release (below), lane 0 acquired the counter and __syncwarp ordered this lane behind it - no reader-side proxy fence
+          // (it cost ~1 us per step: TGB200_GRU_READER_FENCE=1 at build time restores it)
+#ifdef TGB200_GRU_READER_FENCE
+          fence_proxy_async_all();
+#endif
           mbar_expect_tx(&h_full[lane], (uint32_t)H_CHUNK);
           tma_load_3d(Ht + (size_t)lane * H_CHUNK, tmH, &h_full[lane], lane * 32, tp, tile * BT);
         }
