@@ -3,7 +3,6 @@ dominant kernel of a step and its achieved FLOP/s or GB/s; never enabled inside 
 from __future__ import annotations
 
 import collections
-import ctypes
 
 import torch
 

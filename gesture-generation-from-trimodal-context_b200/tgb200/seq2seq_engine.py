@@ -15,7 +15,7 @@ import torch
 
 from . import config, ops
 from .arena import ParamArena
-from .engine import BN_EPS, BN_MOM, F32, Workspace
+from .engine import BN_EPS, BN_MOM, Workspace
 
 _WT = {}          # id(weight tensor storage) -> transposed copy [K_total, N] of the current iteration (fast mode, see prep_weights)
 

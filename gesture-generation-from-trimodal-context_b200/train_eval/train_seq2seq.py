@@ -4,7 +4,7 @@ Same signature and returned dict ({'loss': float}).  The whole iteration (forwar
 33-step attention decoder and the packed encoder, clip_grad_norm_(5), Adam) is a fixed sequence of C-ABI kernel launches
 with no host synchronisation until the single loss read-back; after two eager iterations the sequence is captured into
 a CUDA graph per (batch shape, max text length) and replayed."""
-from typing import Dict, Optional
+from typing import Optional
 
 import torch
 
