@@ -22,13 +22,16 @@ def _map(obj, fn):
 
 
 class DevicePrefetcher:
-    """depth batches in flight; depth + 1 ring slots of pre-allocated device buffers (no allocation in steady state: a fresh 18.6 MB
+    """copy_ctas: CTAs of the copy kernel.  8 CTAs already move 18.6 MB in well under a step, and every additional CTA measurably slows the
+    concurrently running step (resident inputs 6.16 ms/step; 4-8 CTAs 6.29-6.30; 16: 6.35; 32: 6.44; 64: 6.50 - tests/sweep_e2e_copy.py).
+
+    depth batches in flight; depth + 1 ring slots of pre-allocated device buffers (no allocation in steady state: a fresh 18.6 MB
     device tensor per batch made the caching allocator fall back to cudaMalloc while the previous blocks were still held by
     record_stream events, which cost more than the copy itself)."""
 
-    def __init__(self, loader, device, depth=2):
+    def __init__(self, loader, device, depth=2, copy_ctas=8):
         assert depth >= 1
-        self.loader, self.device, self.depth = loader, torch.device(device), depth
+        self.loader, self.device, self.depth, self.copy_ctas = loader, torch.device(device), depth, copy_ctas
         self.stream = torch.cuda.Stream(device=self.device)
         self._pin = {}
         self._dev = {}
@@ -47,7 +50,7 @@ class DevicePrefetcher:
         if d is None:
             d = self._dev[key] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
         if t.numel() * t.element_size() >= (1 << 20) and t.is_contiguous() and t.data_ptr() % 16 == 0:
-            ops.copy_bytes(d, t)           # kernel reading the pinned buffer over PCIe: keeps the copy engines free (see tg_copy_bytes)
+            ops.copy_bytes(d, t, self.copy_ctas)           # kernel reading the pinned buffer over PCIe: keeps the copy engines free (see tg_copy_bytes)
         else:
             d.copy_(t, non_blocking=True)
         return d
