@@ -255,3 +255,26 @@ def seq2seq_inputs(cfg, batch: int, seed: int = 0, max_len: int = 12, min_len: i
     walk = np.cumsum(0.02 * rng.standard_normal((batch, cfg.n_poses, cfg.pose_dim)), axis=1)
     target = (walk + 0.1 * rng.standard_normal((batch, 1, cfg.pose_dim))).astype(np.float32)
     return {'in_text': torch.from_numpy(text), 'lengths': torch.from_numpy(lengths.astype(np.int64)), 'target': torch.from_numpy(target)}
+
+
+def generator_state_dict_variant(cfg, input_context: str, z_mode, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of PoseGenerator built with args.input_context / z_obj variants (multimodal_context_net.py:72-93): the first GRU
+    layer keeps only the input columns that exist ([pre_seq 28 | audio 32 | text 32 | z 16] for 'both' + z), and the speaker layers
+    exist only for a Vocab z_obj.  Derived from generator_state_dict so no extra fixture is needed."""
+    sd = generator_state_dict(cfg, seed)
+    D1 = cfg.pose_dim + 1
+    cols = list(range(0, D1))
+    if input_context in ('both', 'audio'):
+        cols += list(range(D1, D1 + 32))
+    if input_context in ('both', 'text'):
+        cols += list(range(D1 + 32, D1 + 64))
+    if z_mode is not None:
+        cols += list(range(D1 + 64, D1 + 64 + cfg.z_size))
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.startswith('speaker_') and z_mode != 'speaker':
+            continue
+        if k in ('gru.weight_ih_l0', 'gru.weight_ih_l0_reverse'):
+            v = v[:, cols].contiguous()
+        out[k] = v
+    return out

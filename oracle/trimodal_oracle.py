@@ -224,15 +224,25 @@ def speaker_style(sd: SD, vid: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Ten
 def pose_generator_forward(sd: SD, cfg: HotPathConfig, pre_seq: Tensor, in_text: Tensor,
                            in_audio: Tensor, vid: Tensor, eps: Tensor, training: bool = False,
                            masks: Optional[Dict[str, Tensor]] = None,
-                           stats_out: Optional[Dict[str, Tensor]] = None):
-    """PoseGenerator.forward (multimodal_context_net.py:110-160), input_context='both',
-    z_obj = speaker Vocab.  Returns (poses [B,T,D], z, mu, logvar).
+                           stats_out: Optional[Dict[str, Tensor]] = None,
+                           input_context: str = 'both', z_mode: Optional[str] = 'speaker'):
+    """PoseGenerator.forward (multimodal_context_net.py:110-160).  Returns (poses [B,T,D], z, mu, logvar).
+    input_context in {'both','audio','text','none'} (:139-148); z_mode 'speaker' (z_obj is a Vocab: embedding -> mu/logvar ->
+    reparameterize with eps, :125-131), 'random' (any other truthy z_obj: z = eps ~ N(0,1), :132-134) or None (:135-137).
     masks keys: 'emb', 'tcn{i}_{1|2}', 'gru{l}' (l < n_layers-1)."""
-    audio = wav_encoder(sd, 'audio_encoder', in_audio, training, stats_out)
-    text = text_encoder_tcn(sd, 'text_encoder', in_text, cfg.n_layers, masks)
-    assert audio.shape[1] == text.shape[1]
-    z, mu, logvar = speaker_style(sd, vid, eps)
-    in_data = torch.cat((pre_seq, audio, text, z.unsqueeze(1).expand(-1, pre_seq.shape[1], -1)), dim=2)
+    parts = [pre_seq]
+    if input_context in ('both', 'audio'):
+        parts.append(wav_encoder(sd, 'audio_encoder', in_audio, training, stats_out))
+    if input_context in ('both', 'text'):
+        parts.append(text_encoder_tcn(sd, 'text_encoder', in_text, cfg.n_layers, masks))
+    z = mu = logvar = None
+    if z_mode == 'speaker':
+        z, mu, logvar = speaker_style(sd, vid, eps)
+    elif z_mode == 'random':
+        z = eps
+    if z is not None:
+        parts.append(z.unsqueeze(1).expand(-1, pre_seq.shape[1], -1))
+    in_data = torch.cat(parts, dim=2)
     gmasks = None
     if masks is not None:
         gmasks = [masks.get(f'gru{l}') for l in range(cfg.n_layers)]

@@ -333,3 +333,45 @@ def test_cuda_graph_replay_matches_eager(dev):
         # (biases whose gradient is analytically zero random-walk by +-lr under Adam: excluded)
         if v.is_floating_point() and v.numel() >= 256 and k not in ZERO_GRAD_KEYS:
             assert rel_l2(hist[True][1][k], v) < 5e-2, k
+
+
+@pytest.mark.parametrize('ctx,zm', [('audio', 'speaker'), ('text', 'random'), ('none', None), ('both', 'random'), ('none', 'speaker')])
+def test_constructor_variants_vs_reference_golden(dev, ctx, zm):
+    """The other constructor variants of the drop-in boundary (args.input_context, z_obj a Vocab / truthy / None;
+    multimodal_context_net.py:65-93,139-153): strict state_dict load, eval forward vs. the reference module's output (fp32 mode)."""
+    import numpy as np
+    from gpu_util import make_args
+    from model import vocab
+    from model.multimodal_context_net import PoseGenerator
+    from tgb200 import config
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_variants.npz'))
+    args = make_args(cfg)
+    args.input_context = ctx
+    z_obj = None
+    if zm == 'speaker':
+        z_obj = vocab.Vocab('vid', insert_default_tokens=False)
+        while z_obj.n_words < cfg.n_speakers:
+            z_obj.index_word('spk%d' % z_obj.n_words)
+    elif zm == 'random':
+        z_obj = 1
+    G = PoseGenerator(args, cfg.pose_dim, cfg.n_words, cfg.wordembed_dim, None, z_obj=z_obj)
+    G.load_state_dict(synth.with_tcn_aliases(synth.generator_state_dict_variant(cfg, ctx, zm)), strict=True)
+    G = G.to(dev).eval()
+    inp = to_dev(synth.make_inputs(cfg, 3, seed=1), dev)
+    pre = O.make_pre_seq(inp['target'].cpu(), cfg.n_pre_poses).to(dev)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0].to(dev)
+    old = config.set_mode('fp32')
+    try:
+        with torch.no_grad():
+            G.set_noise(eps=eps if zm is not None else None)
+            poses, z, mu, logvar = G(pre, inp['in_text'], inp['in_audio'], inp['vid'] if zm == 'speaker' else None)
+        torch.cuda.synchronize()
+    finally:
+        config.set_mode(old)
+    assert rel_l2(poses, g[f'{ctx}_{zm}/poses']) < 1e-4, rel_l2(poses, g[f'{ctx}_{zm}/poses'])
+    if zm is None:
+        assert z is None and mu is None and logvar is None
+    else:
+        assert rel_l2(z, g[f'{ctx}_{zm}/z']) < 1e-4
+        assert (mu is None) == (zm == 'random')

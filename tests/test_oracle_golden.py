@@ -138,3 +138,20 @@ def test_eval_metrics_oracle_matches_reference_function():
     assert abs(l1 - float(g['l1'])) < 1e-12 and abs(mae - float(g['mae'])) < 1e-12 and abs(acc - float(g['accel'])) < 1e-12
     pos = E.convert_dir_vec_to_pose(g['out'].astype(np.float64) + g['mean_dir_vec'])
     assert np.abs(pos - g['joint_poses']).max() < 1e-12
+
+
+def test_forward_variants_oracle_matches_reference():
+    """input_context / z_obj constructor variants (multimodal_context_net.py:72-93,139-153) vs. the reference module."""
+    from oracle.make_golden_variants import VARIANTS
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_variants.npz'))
+    inp = synth.make_inputs(cfg, 3, seed=1)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0]
+    for ctx, zm in VARIANTS:
+        sd = synth.generator_state_dict_variant(cfg, ctx, zm)
+        with torch.no_grad():
+            poses, z, _, _ = O.pose_generator_forward(sd, cfg, pre, inp['in_text'], inp['in_audio'], inp['vid'], eps, input_context=ctx, z_mode=zm)
+        assert rel_l2(poses, g[f'{ctx}_{zm}/poses']) < TOL, (ctx, zm)
+        if zm is not None:
+            assert rel_l2(z, g[f'{ctx}_{zm}/z']) < TOL
