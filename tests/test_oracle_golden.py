@@ -155,3 +155,43 @@ def test_forward_variants_oracle_matches_reference():
         assert rel_l2(poses, g[f'{ctx}_{zm}/poses']) < TOL, (ctx, zm)
         if zm is not None:
             assert rel_l2(z, g[f'{ctx}_{zm}/z']) < TOL
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_seq2seq_encoder_length_masks_equal_packed_sequence(seed):
+    """The oracle restates pack_padded_sequence / pad_packed_sequence (seq2seq_net.py:52-56) with length masks; here it is checked
+    directly against torch's own packed nn.GRU on random ragged batches (incl. length-1 rows and a full-length row)."""
+    from oracle import seq2seq_oracle as S
+    g = torch.Generator().manual_seed(seed)
+    cfg = S.Seq2SeqConfig(n_words=50, wordembed_dim=12, hidden_size=10, n_layers=2)
+    B, Tmax = 7, 9
+    lengths = torch.sort(torch.randint(1, Tmax + 1, (B,), generator=g), descending=True).values
+    lengths[0] = Tmax
+    text = torch.zeros(B, Tmax, dtype=torch.int64)
+    for b in range(B):
+        text[b, :lengths[b]] = torch.randint(1, cfg.n_words, (int(lengths[b]),), generator=g)
+    emb = torch.nn.Embedding(cfg.n_words, cfg.wordembed_dim)
+    gru = torch.nn.GRU(cfg.wordembed_dim, cfg.hidden_size, cfg.n_layers, bidirectional=True)
+    sd = {'encoder.embedding.weight': emb.weight.detach()}
+    sd.update({'encoder.gru.' + k: v.detach() for k, v in gru.state_dict().items()})
+    with torch.no_grad():
+        packed = torch.nn.utils.rnn.pack_padded_sequence(emb(text.t()), lengths)
+        out, hid = gru(packed, None)
+        out, _ = torch.nn.utils.rnn.pad_packed_sequence(out)
+        ref_out = (out[:, :, :cfg.hidden_size] + out[:, :, cfg.hidden_size:]).transpose(0, 1)
+        enc, hidden = S.encoder_forward(sd, cfg, text, lengths)
+    assert rel_l2(enc, ref_out) < 1e-6 and rel_l2(hidden, hid) < 1e-6
+
+
+def test_eval_metrics_are_shift_invariant_and_linear():
+    """Properties the device kernel relies on (tg_pose_eval_metrics drops the mean direction vector): the joint MAE and accel terms of
+    train.py:293-310 do not depend on the vector added to both operands, and scale linearly with the error."""
+    from oracle import eval_oracle as E
+    rng = np.random.Generator(np.random.PCG64(5))
+    tgt = rng.standard_normal((4, 34, 27)).astype(np.float32)
+    err = (0.1 * rng.standard_normal((4, 34, 27))).astype(np.float32)
+    m0 = E.batch_metrics(tgt + err, tgt, np.zeros(27), 4)
+    m1 = E.batch_metrics(tgt + err, tgt, rng.standard_normal(27), 4)
+    m2 = E.batch_metrics(tgt + 2 * err, tgt, np.zeros(27), 4)
+    assert abs(m0[1] - m1[1]) < 1e-12 and abs(m0[2] - m1[2]) < 1e-12
+    assert abs(m2[1] - 2 * m0[1]) < 1e-6 * m0[1] and abs(m2[2] - 2 * m0[2]) < 1e-6 * m0[2]
