@@ -1,14 +1,18 @@
 """EmbeddingNet(mode='pose') - the pose auto-encoder whose 32-d latent is the feature space of the Frechet Gesture
 Distance (reference: scripts/model/embedding_net.py:10-13, 16-39, 42-82, 165-217, 262-314).
 
-Parameter containers with the reference's names; the forward runs as 14 fused sm_100a GEMM launches with eval-mode
-BatchNorm folded into their epilogues (tgb200.engine.EmbeddingEngine).  Only what FGD needs is built: mode='pose',
-eval mode.  The joint-embedding baseline (ContextEncoder / PoseDecoderGRU / PoseDecoderFC, embedding_net.py:85-162,
-220-259) and training of the auto-encoder (train_feature_extractor.py) are outside the hot path."""
+Parameter containers with the reference's names.  Eval mode (what FGD uses): 14 fused sm_100a GEMM launches with the
+running-statistics BatchNorm folded into their epilogues (tgb200.engine.EmbeddingEngine).  Train mode (batch statistics,
+running-statistics update): tgb200.embed_engine.AutoEncoderTrainEngine, which also holds the hand-derived backward used by the
+auto-encoder step functions (train_feature_extractor.train_iter, train_eval.train_joint_embed.train_iter_embed).
+The module-level forward returns detached tensors: training goes through those step functions, not through autograd.
+The joint-embedding baseline (mode != 'pose': ContextEncoder / PoseDecoderGRU / PoseDecoderFC, embedding_net.py:85-162,220-259) is
+not built."""
 import torch
 import torch.nn as nn
 
 from tgb200 import _lib, ops
+from tgb200.embed_engine import AutoEncoderTrainEngine
 from tgb200.engine import EmbeddingEngine
 
 
@@ -77,11 +81,17 @@ class EmbeddingNet(nn.Module):
         self.decoder = PoseDecoderConv(n_frames, pose_dim)
         self.mode = mode
         self._engine = None
+        self._train_engine = None
 
     def engine(self) -> EmbeddingEngine:
         if self._engine is None:
             self._engine = EmbeddingEngine(self)
         return self._engine
+
+    def train_engine(self) -> AutoEncoderTrainEngine:
+        if self._train_engine is None:
+            self._train_engine = AutoEncoderTrainEngine(self)
+        return self._train_engine
 
     def forward(self, in_text, in_audio, pre_poses, poses, input_mode=None, variational_encoding=False):
         _lib.require_cuda()
@@ -89,11 +99,14 @@ class EmbeddingNet(nn.Module):
             assert self.mode is not None
             input_mode = self.mode
         assert input_mode == 'pose', "EmbeddingNet(mode='pose') has no context encoder (embedding_net.py:270-273,282)"
-        if self.training:
-            raise RuntimeError('EmbeddingNet kernels implement the eval-mode (running-statistics) forward used by FGD; '
-                               'training the auto-encoder is outside the hot path')
         if not poses.is_cuda and not _lib.TRACE_ONLY:
             raise _lib.TgError('EmbeddingNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+        if self.training:
+            # batch-statistics forward (updates the BatchNorm running statistics like the reference's train-mode forward)
+            assert not variational_encoding, 'the reference trains the auto-encoder with variational_encoding=False (train_feature_extractor.py:58)'
+            teng = self.train_engine().ensure(poses.device)
+            mu, logvar, recon = teng.forward(poses.detach().contiguous().float(), training=True)
+            return None, None, None, mu.clone(), mu.clone(), logvar.clone(), recon.clone()
         eng = self.engine().ensure(poses.device)
         poses_c = poses.detach().contiguous().float()
         eps = None

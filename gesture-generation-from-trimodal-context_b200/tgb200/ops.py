@@ -400,6 +400,16 @@ def pose_eval_metrics(out, target, B, T, D, n_pre, acc):
     check(_L().tg_pose_eval_metrics(_p(_f32(out)), _p(_f32(target)), B, T, D, n_pre, _p(acc), _s()), 'tg_pose_eval_metrics'); _count()
 
 
+def ae_recon_loss(recon, target, B, T, D, use_diff, weight, acc, d_recon):
+    check(_L().tg_ae_recon_loss(_p(_f32(recon)), _p(_f32(target)), B, T, D, 1 if use_diff else 0, float(weight), _p(acc), _p(d_recon), _s()),
+          'tg_ae_recon_loss'); _count()
+
+
+def transpose_batched(x, out, B, R, C):
+    """out[b][c][r] = x[b][r][c]"""
+    check(_L().tg_transpose_batched_f32(_p(_f32(x)), _p(_f32(out)), B, R, C, _s()), 'tg_transpose_batched_f32'); _count()
+
+
 def copy_bytes(dst, src, max_ctas=64):
     """dst (device tensor) <- src (device or PINNED host tensor, same byte size), by a kernel (no copy engine); see tg_copy_bytes."""
     assert dst.is_cuda and dst.is_contiguous() and src.is_contiguous() and (src.is_cuda or src.is_pinned())

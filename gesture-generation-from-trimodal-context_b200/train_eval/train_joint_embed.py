@@ -1,0 +1,107 @@
+"""train_iter_embed / eval_embed - drop-in for scripts/train_eval/train_joint_embed.py:5-65, for the pose auto-encoder
+(EmbeddingNet(mode='pose'), the FGD feature extractor).  Same signatures, same returned values.
+
+One optimiser step = the train-mode forward, the L1 reconstruction loss (value + gradient in one kernel), the hand-derived
+backward and one flat Adam launch (tgb200.embed_engine.AutoEncoderTrainEngine): ~75 launches of a few microseconds each, no host
+synchronisation until the single loss read-back.  After two eager steps the sequence is captured into a CUDA graph per
+(net, optimiser, batch shape) and replayed - the step is launch-latency bound, so this is where the time goes.
+train_feature_extractor.train_iter (which adds the frame-difference term) shares `ae_step`."""
+import torch
+
+from tgb200 import _lib, config
+
+_GRAPH_WARMUP = 2          # eager steps (allocate every workspace) before the step is captured
+
+
+class _Slot:
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.failed = False
+        self.static = None
+
+
+def _unwrap(m):
+    return m.module if isinstance(m, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel)) else m
+
+
+def _enqueue(eng, optim, target, use_diff, weight, acc, host_step):
+    eng.arena.zero_grad()                                   # optim.zero_grad(), train_joint_embed.py:9
+    _, _, recon = eng.forward(target, training=True)        # :17-19
+    acc.zero_()
+    d_rec = eng.loss(recon, target, use_diff, weight, acc)  # :21-29,46
+    eng.backward(d_rec)                                     # :48
+    eng.arena.adam_step(optim, 1.0, host_step=host_step)    # :49
+
+
+def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> float:
+    """One auto-encoder step on target_data [B,34,27]; returns recon_loss (python float, the step's only host read-back)."""
+    _lib.require_cuda()
+    net_ = _unwrap(net)
+    if getattr(net_, 'mode', None) != 'pose':
+        raise NotImplementedError("only the pose auto-encoder (EmbeddingNet(mode='pose')) is built; the joint-embedding model is not")
+    if not target_data.is_cuda and not _lib.TRACE_ONLY:
+        raise _lib.TgError('the auto-encoder step runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+    assert net_.training, 'the auto-encoder step expects net.train() (BatchNorm batch statistics)'
+    dev = target_data.device
+    target = target_data.detach().contiguous().float()
+    eng = net_.train_engine().ensure(dev)
+    acc = eng.ws.get('ae.acc', (2,), torch.float64)
+    use_graph = config.graphs() and not _lib.TRACE_ONLY and torch.cuda.is_available()
+    done = False
+    if use_graph:
+        g = optim.param_groups[0]
+        key = (id(optim), dev.index, tuple(target.shape), bool(use_diff), float(weight), float(g['lr']), tuple(g['betas']))
+        slot = eng.graph_slots.setdefault(key, _Slot())          # slots live on the engine: they die with the net they captured
+        slot.calls += 1
+        if not slot.failed and slot.calls > _GRAPH_WARMUP and eng.arena.is_current():
+            if slot.static is None:
+                slot.static = eng.ws.get('ae.s_target', tuple(target.shape))
+            slot.static.copy_(target)
+            if slot.graph is None:
+                try:
+                    eng.arena.bind_optimizer(optim)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        _enqueue(eng, optim, slot.static, use_diff, weight, acc, host_step=False)
+                    slot.graph = graph
+                except Exception as exc:                    # capture unsupported for some launch: stay on the eager path
+                    slot.failed = True
+                    import warnings
+                    warnings.warn('tgb200: CUDA-graph capture of the auto-encoder step failed (%s); continuing with eager launches'
+                                  % str(exc).splitlines()[0])
+                    torch.cuda.synchronize()
+            if slot.graph is not None:
+                slot.graph.replay()
+                eng.arena.note_steps(1)
+                done = True
+    if not done:
+        _enqueue(eng, optim, target, use_diff, weight, acc, host_step=True)
+    return float(acc.cpu()[0])
+
+
+def train_iter_embed(args, epoch, in_text, in_audio, target_data, net, optim, mode=None):
+    """train_joint_embed.py:5-51 with variational_encoding=False (:12-15): loss = sum over the batch of the per-sample mean L1
+    (the frame-difference term is switched off there, :24).  in_text / in_audio are ignored by a mode='pose' net
+    (context_encoder is None, embedding_net.py:282); mode must resolve to 'pose'."""
+    assert mode in (None, 'pose'), "EmbeddingNet(mode='pose') has no context encoder: input_mode must be 'pose' (embedding_net.py:295-303)"
+    return {'loss': ae_step(net, optim, target_data, use_diff=False)}
+
+
+def eval_embed(in_text, in_audio, pre_poses, target_poses, net, mode=None):
+    """train_joint_embed.py:54-65 -> (loss, recon_poses): batch mean of the per-sample mean L1, whatever mode (train / eval) the
+    net is in - like the reference, a train-mode net normalises with batch statistics and updates its running statistics."""
+    _lib.require_cuda()
+    assert mode in (None, 'pose')
+    net_ = _unwrap(net)
+    if not target_poses.is_cuda and not _lib.TRACE_ONLY:
+        raise _lib.TgError('eval_embed runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+    target = target_poses.detach().contiguous().float()
+    eng = net_.train_engine().ensure(target.device)
+    _, _, recon = eng.forward(target, training=net_.training)
+    acc = eng.ws.get('ae.acc_eval', (2,), torch.float64)
+    acc.zero_()
+    eng.loss(recon, target, False, 1.0, acc, want_grad=False)
+    loss = (acc[1] / target.shape[0]).float()
+    return loss, recon.clone()

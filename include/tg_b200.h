@@ -319,6 +319,19 @@ int tg_feature_stats_f64(const float* feat, long long n, int F, double* acc, tg_
 /* sum_i sum_f |a-b| accumulated in fp64 (feat_dist, embedding_space_evaluator.py:95-99) */
 int tg_l1_dist_f64(const float* a, const float* b, long long n, double* acc, tg_stream stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * FGD auto-encoder trainer (train_feature_extractor.py:54-97 train_iter, train_joint_embed.py:5-65 train_iter_embed /
+ * eval_embed on EmbeddingNet(mode='pose')).  The networks themselves run on the conv / BatchNorm / Adam entries above.
+ * --------------------------------------------------------------------------------------------------------- */
+/* L1 reconstruction loss, one CTA per clip (train_feature_extractor.py:64-72, train_joint_embed.py:21-29,59-61):
+ *   l0_b = mean_{t,d} |recon - target|,  l1_b = mean_{t<T-1,d} |(recon[t+1]-recon[t]) - (target[t+1]-target[t])|
+ *   acc[0] += sum_b (l0_b + use_diff*l1_b)  (the trainer's recon_loss),  acc[1] += sum_b l0_b  (eval_embed's numerator), fp64;
+ *   d_recon (may be NULL) = weight * d acc[0] / d recon, with d|x|/dx = sign(x) (0 at 0) like torch. */
+int tg_ae_recon_loss(const float* recon, const float* target, int B, int T, int D, int use_diff, float weight, double* acc,
+                     float* d_recon, tg_stream stream);
+/* out[b][c][r] = in[b][r][c]: channels-last [B,T,C] <-> the reference's channel-major flatten / view (embedding_net.py:71,213) */
+int tg_transpose_batched_f32(const float* in, float* out, int B, int R, int C, tg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
