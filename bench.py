@@ -198,6 +198,20 @@ def aux_workloads(dev, timed):
     out['fgd_10k_pairs_seconds'] = dt
     out['fgd_clips_per_s'] = 20000 / dt
     out['fgd_value'] = score[0]
+    # training step of that auto-encoder (train_feature_extractor.train_iter), batch 128, CUDA-graph replay
+    try:
+        import train_feature_extractor as tfx
+        anet = EmbeddingNet(e_args, POSE_DIM, T, None, None, None, 'pose').to(dev).train()
+        aopt = torch.optim.Adam(anet.parameters(), lr=5e-4, betas=(0.5, 0.999))
+        tg = [synth_batch(128, 90 + i)['target'].to(dev) for i in range(4)]
+        fa = lambda i: tfx.train_iter(None, 0, tg[i % 4], anet, aopt)
+        for i in range(5):
+            fa(i)
+        ms, _, _, _ = timed(fa, 50)
+        out['autoencoder_train_samples_per_s'] = 128 * 50 / (ms / 1e3)
+        out['autoencoder_train_ms_per_step'] = ms / 50
+    except Exception as exc:                                          # a side measurement must never take the headline line down
+        out['autoencoder_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
     return out
 
 

