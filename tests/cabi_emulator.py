@@ -7,7 +7,8 @@ tensors and its RESULT can be compared with the oracle in the `-m "not gpu"` sui
 themselves are checked on the GPU (tests/test_gpu_*.py).  It is not a fallback: the product never imports tests/, and without this
 fixture a CPU tensor raises TgError (tests/test_abi_and_modules.py::test_no_cpu_fallback_without_cuda).
 
-Only the entry points the auto-encoder trainer and the eval-mode EmbeddingNet forward use are restated; anything else raises."""
+Restated: every entry point the strict-fp32 (`TGB200_MODE=fp32`) plans of train_iter_gan, the auto-encoder trainer and the eval-mode
+EmbeddingNet forward call; anything else (the tcgen05 / tensor-core entries) raises NotImplementedError."""
 import ctypes
 import math
 
@@ -226,6 +227,428 @@ class EmuLib:
     def tg_transpose_batched_f32(self, x, out, B, R, C, stream):
         self.calls.append('tg_transpose_batched_f32')
         _arr(out, B * R * C)[:] = _arr(x, B * R * C).reshape(B, R, C).transpose(0, 2, 1).reshape(-1)
+        return 0
+
+    # ---------------------------------------------------------------------------------------- small elementwise (csrc/elementwise.cu)
+    def tg_transpose_f32(self, x, out, R, C, stream):
+        self.calls.append('tg_transpose_f32')
+        _arr(out, R * C)[:] = _arr(x, R * C).reshape(R, C).T.reshape(-1)
+        return 0
+
+    def tg_mul(self, a, b, out, n, stream):
+        self.calls.append('tg_mul')
+        _arr(out, n)[:] = _arr(a, n) * _arr(b, n)
+        return 0
+
+    def tg_add(self, a, b, out, n, relu, stream):
+        self.calls.append('tg_add')
+        v = _arr(a, n) + _arr(b, n)
+        _arr(out, n)[:] = np.maximum(v, 0) if relu else v
+        return 0
+
+    def tg_relu_mask_bwd(self, dy, y, mask, dx, n, stream):
+        self.calls.append('tg_relu_mask_bwd')
+        v = np.where(_arr(y, n) > 0, _arr(dy, n), np.float32(0))
+        if mask:
+            v = v * _arr(mask, n)
+        _arr(dx, n)[:] = v
+        return 0
+
+    def tg_sum_halves(self, x, out, M, H, stream):
+        self.calls.append('tg_sum_halves')
+        X = _arr(x, M * 2 * H).reshape(M, 2 * H)
+        _arr(out, M * H)[:] = (X[:, :H] + X[:, H:]).reshape(-1)
+        return 0
+
+    def tg_dup_halves(self, d, dx, M, H, stream):
+        self.calls.append('tg_dup_halves')
+        D = _arr(d, M * H).reshape(M, H)
+        _arr(dx, M * 2 * H)[:] = np.concatenate([D, D], axis=1).reshape(-1)
+        return 0
+
+    def tg_reparam_fwd(self, mu, lv, eps, z, n, stream):
+        self.calls.append('tg_reparam_fwd')
+        _arr(z, n)[:] = _arr(mu, n) + _arr(eps, n) * np.exp(np.float32(0.5) * _arr(lv, n))
+        return 0
+
+    def tg_reparam_bwd(self, dz, lv, eps, dmu, dlv, n, stream):
+        self.calls.append('tg_reparam_bwd')
+        _arr(dmu, n)[:] += _arr(dz, n)
+        _arr(dlv, n)[:] += _arr(dz, n) * _arr(eps, n) * np.float32(0.5) * np.exp(np.float32(0.5) * _arr(lv, n))
+        return 0
+
+    def tg_make_pre_seq(self, target, pre, B, T, D, n_pre, stream):
+        self.calls.append('tg_make_pre_seq')
+        P = np.zeros((B, T, D + 1), np.float32)
+        P[:, :n_pre, :D] = _arr(target, B * T * D).reshape(B, T, D)[:, :n_pre]
+        P[:, :n_pre, D] = 1
+        _arr(pre, B * T * (D + 1))[:] = P.reshape(-1)
+        return 0
+
+    def tg_gru_input_concat(self, pre, audio, text, z, out, B, Ba, T, Dp, Da, Dt, Dz, stream):
+        self.calls.append('tg_gru_input_concat')
+        bi = np.arange(B) % Ba
+        parts = []
+        if Dp:
+            parts.append(_arr(pre, Ba * T * Dp).reshape(Ba, T, Dp)[bi])
+        if Da:
+            parts.append(_arr(audio, Ba * T * Da).reshape(Ba, T, Da)[bi])
+        if Dt:
+            parts.append(_arr(text, B * T * Dt).reshape(B, T, Dt))
+        if Dz:
+            parts.append(np.repeat(_arr(z, B * Dz).reshape(B, 1, Dz), T, axis=1))
+        _arr(out, B * T * (Dp + Da + Dt + Dz))[:] = np.concatenate(parts, axis=2).reshape(-1)
+        return 0
+
+    def tg_gru_input_split_bwd(self, din, daudio, dtext, dz, B, T, Dp, Da, Dt, Dz, stream):
+        self.calls.append('tg_gru_input_split_bwd')
+        D = Dp + Da + Dt + Dz
+        X = _arr(din, B * T * D).reshape(B, T, D)
+        if Da:
+            _arr(daudio, B * T * Da)[:] = X[:, :, Dp:Dp + Da].reshape(-1)
+        if Dt:
+            _arr(dtext, B * T * Dt)[:] = X[:, :, Dp + Da:Dp + Da + Dt].reshape(-1)
+        if Dz:
+            _arr(dz, B * Dz)[:] = X[:, :, Dp + Da + Dt:].astype(np.float64).sum(1).astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_gather_i64(self, src, idx, out, n, stream):
+        self.calls.append('tg_gather_i64')
+        ix = _arr(idx, n, ctypes.c_longlong)
+        _arr(out, n, ctypes.c_longlong)[:] = _arr(src, int(ix.max()) + 1, ctypes.c_longlong)[ix]
+        return 0
+
+    # ---------------------------------------------------------------------------------------- embedding / weight norm
+    def tg_embedding_gather(self, table, idx, idx_mod, mask, out, M, E, stream):
+        self.calls.append('tg_embedding_gather')
+        n_idx = idx_mod if idx_mod > 0 else M
+        ix = _arr(idx, n_idx, ctypes.c_longlong)[np.arange(M) % n_idx]
+        v = _arr(table, (int(ix.max()) + 1) * E).reshape(-1, E)[ix]
+        if mask:
+            v = v * _arr(mask, M * E).reshape(M, E)
+        _arr(out, M * E)[:] = v.reshape(-1)
+        return 0
+
+    def tg_embedding_scatter_add(self, dout, idx, mask, dtable, M, E, stream):
+        self.calls.append('tg_embedding_scatter_add')
+        ix = _arr(idx, M, ctypes.c_longlong)
+        v = _arr(dout, M * E).reshape(M, E)
+        if mask:
+            v = v * _arr(mask, M * E).reshape(M, E)
+        T = _arr(dtable, (int(ix.max()) + 1) * E).reshape(-1, E)
+        np.add.at(T, ix, v)
+        return 0
+
+    def tg_weight_norm_fwd(self, v, g, w, wT, inv_norm, N, Cin, taps, stream):
+        self.calls.append('tg_weight_norm_fwd')
+        V = _arr(v, N * Cin * taps).reshape(N, Cin, taps)
+        inv = (1.0 / np.sqrt((V.astype(np.float64) ** 2).sum((1, 2)))).astype(np.float32)
+        W = V * (_arr(g, N) * inv)[:, None, None]                        # [N, Cin, taps]
+        _arr(w, N * Cin * taps)[:] = W.transpose(2, 0, 1).reshape(-1)    # tap-major [taps][N][Cin]
+        if wT:
+            _arr(wT, N * Cin * taps)[:] = W.transpose(2, 1, 0).reshape(-1)   # [taps][Cin][N]
+        _arr(inv_norm, N)[:] = inv
+        return 0
+
+    def tg_weight_norm_bwd(self, dw, v, g, inv_norm, dv, dg, N, Cin, taps, stream):
+        self.calls.append('tg_weight_norm_bwd')
+        V = _arr(v, N * Cin * taps).reshape(N, Cin, taps).astype(np.float64)
+        DW = _arr(dw, N * Cin * taps).reshape(taps, N, Cin).transpose(1, 2, 0).astype(np.float64)      # -> [N, Cin, taps]
+        inv = _arr(inv_norm, N).astype(np.float64); gg = _arr(g, N).astype(np.float64)
+        dot = (DW * V).sum((1, 2))
+        _arr(dv, N * Cin * taps)[:] += ((gg * inv)[:, None, None] * (DW - V * (dot * inv * inv)[:, None, None])).astype(np.float32).reshape(-1)
+        _arr(dg, N)[:] += (dot * inv).astype(np.float32)
+        return 0
+
+    def tg_conv1_direct_f32(self, x, w, bias, y, B, Tin, Tout, N, taps, stride, pad, stream):
+        self.calls.append('tg_conv1_direct_f32')
+        X = _arr(x, B * Tin).reshape(B, Tin).astype(np.float64)
+        W = _arr(w, N * taps).reshape(N, taps).astype(np.float64)
+        ti = (np.arange(Tout) * stride - pad)[:, None] + np.arange(taps)[None, :]
+        ok = (ti >= 0) & (ti < Tin)
+        win = np.where(ok[None], X[:, np.where(ok, ti, 0)], 0.0)          # [B, Tout, taps]
+        v = win @ W.T
+        if bias:
+            v = v + _arr(bias, N)[None, None, :]
+        _arr(y, B * Tout * N)[:] = v.astype(np.float32).reshape(-1)
+        return 0
+
+    # ---------------------------------------------------------------------------------------- GRU recurrence (csrc/gru.cu)
+    def tg_gru_sync_ints(self, B, H):
+        return 64
+
+    def tg_gru_bwd_scratch_floats(self, B, H):
+        return 64
+
+    @staticmethod
+    def _sig(v):
+        return 1.0 / (1.0 + np.exp(-v))
+
+    def tg_gru_layer_fwd(self, gi, whhT_f, whhT_r, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream):
+        self.calls.append('tg_gru_layer_fwd')
+        GI = _arr(gi, B * T * 6 * H).reshape(B, T, 6 * H).astype(np.float64)
+        OUT = _arr(out, B * T * 2 * H).reshape(B, T, 2 * H)
+        S = _arr(saved, 3 * qstride + B * T * 2 * H) if saved else None
+        rows = np.arange(B) * T
+        for d, (wT, bh) in enumerate(((whhT_f, bhh_f), (whhT_r, bhh_r))):
+            WT = _arr(wT, H * 3 * H).reshape(H, 3 * H).astype(np.float64)
+            bhv = _arr(bh, 3 * H).astype(np.float64)
+            h = np.zeros((B, H))
+            for s in range(T):
+                t = s if d == 0 else T - 1 - s
+                gh = h @ WT + bhv
+                g = GI[:, t, d * 3 * H:(d + 1) * 3 * H]
+                r = self._sig(g[:, :H] + gh[:, :H]); z = self._sig(g[:, H:2 * H] + gh[:, H:2 * H])
+                n = np.tanh(g[:, 2 * H:] + r * gh[:, 2 * H:])
+                h = (1 - z) * n + z * h
+                OUT[:, t, d * H:(d + 1) * H] = h.astype(np.float32)
+                if S is not None:
+                    o = ((rows + t) * 2 * H + d * H)[:, None] + np.arange(H)[None, :]
+                    for q, val in enumerate((r, z, n, gh[:, 2 * H:])):
+                        S[q * qstride + o] = val.astype(np.float32)
+        return 0
+
+    def tg_gru_layer_bwd(self, dout, out, saved, qstride, whh_f, whh_r, dgi, dgh, partial, sync, B, T, H, stream):
+        self.calls.append('tg_gru_layer_bwd')
+        DOUT = _arr(dout, B * T * 2 * H).reshape(B, T, 2 * H).astype(np.float64)
+        OUT = _arr(out, B * T * 2 * H).reshape(B, T, 2 * H).astype(np.float64)
+        S = _arr(saved, 3 * qstride + B * T * 2 * H)
+        DGI = _arr(dgi, B * T * 6 * H).reshape(B, T, 6 * H); DGH = _arr(dgh, B * T * 6 * H).reshape(B, T, 6 * H)
+        rows = np.arange(B) * T
+        for d, wp in enumerate((whh_f, whh_r)):
+            W = _arr(wp, 3 * H * H).reshape(3 * H, H).astype(np.float64)
+            carry = np.zeros((B, H))
+            for s in range(T):
+                t = T - 1 - s if d == 0 else s
+                tp = t - 1 if d == 0 else t + 1
+                o = ((rows + t) * 2 * H + d * H)[:, None] + np.arange(H)[None, :]
+                r, z, n, hn = (S[q * qstride + o].astype(np.float64) for q in range(4))
+                hprev = OUT[:, tp, d * H:(d + 1) * H] if 0 <= tp < T else np.zeros((B, H))
+                dh = DOUT[:, t, d * H:(d + 1) * H] + carry
+                dn = dh * (1 - z) * (1 - n * n)
+                dzp = dh * (hprev - n) * z * (1 - z)
+                drp = dn * hn * r * (1 - r)
+                dnr = dn * r
+                DGI[:, t, d * 3 * H:(d + 1) * 3 * H] = np.concatenate([drp, dzp, dn], axis=1).astype(np.float32)
+                gh = np.concatenate([drp, dzp, dnr], axis=1)
+                DGH[:, t, d * 3 * H:(d + 1) * 3 * H] = gh.astype(np.float32)
+                carry = dh * z + gh @ W
+        return 0
+
+    # ---------------------------------------------------------------------------------------- losses (csrc/losses.cu)
+    @staticmethod
+    def _huber(x, y, beta):
+        uu = x / beta - y / beta
+        d = np.abs(uu)
+        return np.where(d < 1, 0.5 * d * d * beta, (d - 0.5) * beta), np.where(d < 1, uu, np.sign(uu))
+
+    def tg_gen_losses(self, out, target, out_rand, z, z_rand, mu, logvar, B, TD, Z, w_reg, w_div, w_kld, scalars, d_out, dmu, dlogvar, stream):
+        self.calls.append('tg_gen_losses')
+        o = _arr(out, B * TD).reshape(B, TD).astype(np.float64); tg = _arr(target, B * TD).reshape(B, TD).astype(np.float64)
+        sc = _arr(scalars, 3, ctypes.c_double)
+        hv, hg = self._huber(o, tg, 0.1)
+        sc[0] += hv.sum()
+        grad = (w_reg / (B * TD)) * hg
+        if out_rand:
+            orr = _arr(out_rand, B * TD).reshape(B, TD).astype(np.float64)
+            pv, pg = self._huber(o, orr, 0.05)
+            zl = np.abs(_arr(z, B * Z).reshape(B, Z).astype(np.float64) - _arr(z_rand, B * Z).reshape(B, Z)).sum(1) / Z
+            denom = zl + 1.0e-5
+            raw = -(pv.sum(1) / denom)
+            sc[1] += np.maximum(raw, -1000.0).sum()
+            coef = np.where(raw >= -1000.0, -1.0 / denom, 0.0)
+            grad = grad + (w_div * coef / B)[:, None] * pg
+        if mu:
+            m = _arr(mu, B * Z).astype(np.float64); lv = _arr(logvar, B * Z).astype(np.float64)
+            sc[2] += (1 + lv - m * m - np.exp(lv)).sum()
+            if dmu:
+                _arr(dmu, B * Z)[:] = (w_kld * m / (B * Z)).astype(np.float32)
+                _arr(dlogvar, B * Z)[:] = (-0.5 * w_kld * (1 - np.exp(lv)) / (B * Z)).astype(np.float32)
+        if d_out:
+            _arr(d_out, B * TD)[:] = grad.astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_bce_sigmoid(self, p, n, s, o, w, scalar, dlogit, stream):
+        self.calls.append('tg_bce_sigmoid')
+        pv = _arr(p, n).astype(np.float64)
+        a = (s * pv + o) + 1e-8
+        _arr(scalar, 1, ctypes.c_double)[0] += (-np.log(a)).sum() / n
+        if dlogit:
+            _arr(dlogit, n)[:] = (w * (-s / (n * a)) * pv * (1 - pv)).astype(np.float32)
+        return 0
+
+    # ---------------------------------------------------------------------------------------- FGD statistics (csrc/elementwise.cu)
+    def tg_feature_stats_f64(self, feat, n, F, acc, stream):
+        self.calls.append('tg_feature_stats_f64')
+        X = _arr(feat, n * F).reshape(n, F).astype(np.float64)
+        a = _arr(acc, 1 + F + F * F, ctypes.c_double)
+        a[0] += n; a[1:1 + F] += X.sum(0); a[1 + F:] += (X.T @ X).reshape(-1)
+        return 0
+
+    def tg_l1_dist_f64(self, a, b, n, acc, stream):
+        self.calls.append('tg_l1_dist_f64')
+        _arr(acc, 1, ctypes.c_double)[0] += np.abs(_arr(a, n) - _arr(b, n)).astype(np.float64).sum()
+        return 0
+
+    # ---------------------------------------------------------------------------------------- seq2seq baseline (csrc/seq2seq.cu)
+    def tg_gru_gates_fwd(self, gi, ldgi, gh, hprev, lengths, t, hnew, out, ldout, saved, plane, B, H, stream):
+        self.calls.append('tg_gru_gates_fwd')
+        bi = np.arange(B)[:, None]; j = np.arange(H)[None, :]
+        GI = _arr(gi, (B - 1) * ldgi + 3 * H)
+        g = [GI[bi * ldgi + q * H + j].astype(np.float64) for q in range(3)]
+        GH = _arr(gh, B * 3 * H).reshape(B, 3 * H).astype(np.float64)
+        hp = _arr(hprev, B * H).reshape(B, H).astype(np.float64) if hprev else np.zeros((B, H))
+        valid = np.ones((B, 1), bool) if not lengths else (t < _arr(lengths, B, ctypes.c_longlong))[:, None]
+        r = self._sig(g[0] + GH[:, :H]); z = self._sig(g[1] + GH[:, H:2 * H]); hn = GH[:, 2 * H:]
+        n = np.tanh(g[2] + r * hn)
+        h = (1 - z) * n + z * hp
+        _arr(hnew, B * H)[:] = np.where(valid, h, hp).astype(np.float32).reshape(-1)
+        if out:
+            _arr(out, (B - 1) * ldout + H)[bi * ldout + j] = np.where(valid, h, 0.0).astype(np.float32)
+        if saved:
+            S = _arr(saved, 3 * plane + B * H)
+            for q, val in enumerate((r, z, n, hn)):
+                S[q * plane:q * plane + B * H] = val.astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_gru_gates_bwd(self, dh, dadd, ldadd, saved, plane, hprev, lengths, t, dgi, lddgi, dgh, dhprev, B, H, stream):
+        self.calls.append('tg_gru_gates_bwd')
+        bi = np.arange(B)[:, None]; j = np.arange(H)[None, :]
+        valid = np.ones((B, 1), bool) if not lengths else (t < _arr(lengths, B, ctypes.c_longlong))[:, None]
+        carry = _arr(dh, B * H).reshape(B, H).astype(np.float64).copy() if dh else np.zeros((B, H))
+        g = carry + (_arr(dadd, (B - 1) * ldadd + H)[bi * ldadd + j].astype(np.float64) if dadd else 0.0)
+        S = _arr(saved, 3 * plane + B * H)
+        r, z, n, hn = (S[q * plane:q * plane + B * H].reshape(B, H).astype(np.float64) for q in range(4))
+        hp = _arr(hprev, B * H).reshape(B, H).astype(np.float64) if hprev else np.zeros((B, H))
+        dpn = g * (1 - z) * (1 - n * n)
+        dpz = g * (hp - n) * z * (1 - z)
+        dpr = dpn * hn * r * (1 - r)
+        DGI = _arr(dgi, (B - 1) * lddgi + 3 * H)
+        for q, val in enumerate((dpr, dpz, dpn)):
+            DGI[bi * lddgi + q * H + j] = np.where(valid, val, 0.0).astype(np.float32)
+        _arr(dgh, B * 3 * H)[:] = np.where(valid, np.concatenate([dpr, dpz, dpn * r], axis=1), 0.0).astype(np.float32).reshape(-1)
+        _arr(dhprev, B * H)[:] = np.where(valid, g * z, carry).astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_attn_fwd(self, hq, eproj, enc, v, w, ctx, B, Tm, H, stream):
+        self.calls.append('tg_attn_fwd')
+        HQ = _arr(hq, B * H).reshape(B, 1, H).astype(np.float64); EP = _arr(eproj, B * Tm * H).reshape(B, Tm, H).astype(np.float64)
+        EN = _arr(enc, B * Tm * H).reshape(B, Tm, H).astype(np.float64); V = _arr(v, H).astype(np.float64)
+        score = (np.tanh(HQ + EP) * V).sum(2)
+        e = np.exp(score - score.max(1, keepdims=True))
+        W = e / e.sum(1, keepdims=True)
+        _arr(w, B * Tm)[:] = W.astype(np.float32).reshape(-1)
+        _arr(ctx, B * H)[:] = (W[:, :, None] * EN).sum(1).astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_attn_bwd(self, dctx, w, hq, eproj, enc, v, denc, deproj, dv, dhq, B, Tm, H, stream):
+        self.calls.append('tg_attn_bwd')
+        DC = _arr(dctx, B * H).reshape(B, 1, H).astype(np.float64); W = _arr(w, B * Tm).reshape(B, Tm).astype(np.float64)
+        HQ = _arr(hq, B * H).reshape(B, 1, H).astype(np.float64); EP = _arr(eproj, B * Tm * H).reshape(B, Tm, H).astype(np.float64)
+        EN = _arr(enc, B * Tm * H).reshape(B, Tm, H).astype(np.float64); V = _arr(v, H).astype(np.float64)
+        dw = (DC * EN).sum(2)
+        dscore = W * (dw - (W * dw).sum(1, keepdims=True))
+        E = np.tanh(HQ + EP)
+        dpre = dscore[:, :, None] * V * (1 - E * E)
+        _arr(deproj, B * Tm * H)[:] += dpre.astype(np.float32).reshape(-1)
+        _arr(denc, B * Tm * H)[:] += (W[:, :, None] * DC).astype(np.float32).reshape(-1)
+        _arr(dhq, B * H)[:] = dpre.sum(1).astype(np.float32).reshape(-1)
+        _arr(dv, H)[:] += (dscore[:, :, None] * E).sum((0, 1)).astype(np.float32)
+        return 0
+
+    def tg_s2s_loss(self, out, target, loss, dy, B, T, D, w_mse, w_cont, w_var, stream):
+        self.calls.append('tg_s2s_loss')
+        O = _arr(out, B * T * D).reshape(B, T, D).astype(np.float64); Y = _arr(target, B * T * D).reshape(B, T, D).astype(np.float64)
+        inv_n = 1.0 / (B * T * D)
+        nrm = np.sqrt((O * O).sum(1))                                            # [B, D]: norm over TIME (train_seq2seq.py:17)
+        df = O - Y
+        dd = O[:, 1:] - O[:, :-1]
+        g = 2 * df * w_mse * inv_n - np.where(nrm[:, None, :] > 0, O / np.where(nrm > 0, nrm, 1.0)[:, None, :], 0.0) * w_var * inv_n
+        sg = np.sign(dd) * w_cont * inv_n
+        g[:, 1:] += sg
+        g[:, :-1] -= sg
+        g[:, 0] = 0.0
+        _arr(dy, T * B * D)[:] = g.transpose(1, 0, 2).astype(np.float32).reshape(-1)
+        _arr(loss, 1, ctypes.c_double)[0] += ((df * df).sum() * w_mse + np.abs(dd).sum() * w_cont - nrm.sum() * w_var) * inv_n
+        return 0
+
+    def tg_s2s_gather_inputs(self, poses, outputs, xin, B, T, D, n_pre, stream):
+        self.calls.append('tg_s2s_gather_inputs')
+        P = _arr(poses, B * T * D).reshape(B, T, D); O = _arr(outputs, B * T * D).reshape(B, T, D)
+        X = np.zeros((T, B, D), np.float32)
+        for t in range(1, T):
+            X[t] = (P if t - 1 < n_pre else O)[:, t - 1]
+        _arr(xin, T * B * D)[:] = X.reshape(-1)
+        return 0
+
+    def tg_sumsq_f64(self, x, n, out, stream):
+        self.calls.append('tg_sumsq_f64')
+        _arr(out, 1, ctypes.c_double)[0] += (_arr(x, n).astype(np.float64) ** 2).sum()
+        return 0
+
+    def tg_clip_scale(self, x, n, sumsq, max_norm, stream):
+        self.calls.append('tg_clip_scale')
+        coef = min(1.0, max_norm / (math.sqrt(_arr(sumsq, 1, ctypes.c_double)[0]) + 1e-6))
+        if coef < 1.0:
+            _arr(x, n)[:] *= np.float32(coef)
+        return 0
+
+    def tg_pose_eval_metrics(self, out, target, B, T, D, n_pre, acc, stream):
+        self.calls.append('tg_pose_eval_metrics')
+        assert D == 27
+        d = _arr(out, B * T * D).reshape(B, T, 9, 3).astype(np.float64) - _arr(target, B * T * D).reshape(B, T, 9, 3)
+        parent, child = (0, 1, 2, 1, 4, 5, 1, 7, 8), (1, 2, 3, 4, 5, 6, 7, 8, 9)
+        blen = (0.26, 0.18, 0.14, 0.22, 0.36, 0.33, 0.22, 0.36, 0.33)
+        e = np.zeros((B, T, 10, 3))
+        for j in range(9):
+            e[:, :, child[j]] = e[:, :, parent[j]] + blen[j] * d[:, :, j]
+        a = _arr(acc, 3, ctypes.c_double)
+        a[0] += np.abs(_arr(out, B * T * D) - _arr(target, B * T * D)).astype(np.float64).sum()
+        a[1] += np.abs(e[:, n_pre:]).sum()
+        a[2] += np.abs(e[:, 2:] - 2 * e[:, 1:-1] + e[:, :-2]).sum()
+        return 0
+
+    # ---------------------------------------------------------------------------------------- Philox-4x32-10 (csrc/common.cuh)
+    @staticmethod
+    def _philox(seed, stream_id, n4, offset_ptr):
+        """First 4x32-bit block of the counter stream of element group i (subsequence = (stream_id << 40) + i), as uint64 arrays."""
+        M = np.uint64(0xFFFFFFFF)
+        off = np.uint64(_arr(offset_ptr, 1, ctypes.c_longlong)[0]) if offset_ptr else np.uint64(0)
+        sub = (np.uint64(stream_id) << np.uint64(40)) + np.arange(n4, dtype=np.uint64)
+        k0, k1 = np.uint64(seed) & M, np.uint64(seed) >> np.uint64(32)
+        c0 = np.full(n4, off & M, np.uint64); c1 = np.full(n4, off >> np.uint64(32), np.uint64)
+        c2 = sub & M; c3 = sub >> np.uint64(32)
+        for _ in range(10):
+            p0 = np.uint64(0xD2511F53) * c0; p1 = np.uint64(0xCD9E8D57) * c2
+            c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & M, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & M
+            k0 = (k0 + np.uint64(0x9E3779B9)) & M; k1 = (k1 + np.uint64(0xBB67AE85)) & M
+        return c0, c1, c2, c3
+
+    @staticmethod
+    def _unit(x):
+        return ((x >> np.uint64(8)).astype(np.float64) * (1.0 / 16777216.0)).astype(np.float32)
+
+    def tg_philox_normal(self, out, n, seed, offset_dev, stream_id, stream):
+        self.calls.append('tg_philox_normal')
+        u = [self._unit(c) for c in self._philox(seed, stream_id, (n + 3) >> 2, offset_dev)]
+        two_pi = np.float32(6.2831853071795864)
+        r0 = np.sqrt(np.float32(-2) * np.log(np.float32(1) - u[0])); r1 = np.sqrt(np.float32(-2) * np.log(np.float32(1) - u[2]))
+        o = np.stack([r0 * np.cos(two_pi * u[1]), r0 * np.sin(two_pi * u[1]), r1 * np.cos(two_pi * u[3]), r1 * np.sin(two_pi * u[3])], axis=1)
+        _arr(out, n)[:] = o.reshape(-1)[:n].astype(np.float32)
+        return 0
+
+    def tg_philox_dropout_mask(self, out, n, p, seed, offset_dev, stream_id, stream):
+        self.calls.append('tg_philox_dropout_mask')
+        u = np.stack([self._unit(c) for c in self._philox(seed, stream_id, (n + 3) >> 2, offset_dev)], axis=1).reshape(-1)[:n]
+        pf = np.float32(p)
+        _arr(out, n)[:] = np.where(u >= pf, np.float32(1) / (np.float32(1) - pf), np.float32(0))
+        return 0
+
+    def tg_philox_randperm(self, out, n, seed, offset_dev, stream_id, stream):
+        self.calls.append('tg_philox_randperm')
+        c0, c1, _, _ = self._philox(seed, stream_id, n, offset_dev)
+        keys = (c0 << np.uint64(32)) | (c1 & np.uint64(0xFFFFF000)) | np.arange(n, dtype=np.uint64)
+        _arr(out, n, ctypes.c_longlong)[:] = (np.sort(keys) & np.uint64(0xFFF)).astype(np.int64)
         return 0
 
 

@@ -1,0 +1,53 @@
+"""CPU: the HEADLINE launch plan - train_iter_gan in strict-fp32 mode (tgb200/engine.py, train_eval/train_gan.py: the 3*B generator
+sweep, the discriminator passes, every hand-derived backward, both flat Adam steps) - executed on the NumPy restatement of the C-ABI
+entries it calls (tests/cabi_emulator.py) and held to the same reference-executed goldens as on the GPU: the assertions are the GPU
+tests' own (tests/test_gpu_parity.py), called here with CPU tensors.  This checks the HOST logic without a GPU; the kernels themselves
+are checked on the B200."""
+import pytest
+import torch
+
+import cabi_emulator
+import test_gpu_parity as GP
+
+CPU = torch.device('cpu')
+
+
+@pytest.fixture()
+def emu_fp32():
+    from tgb200 import config
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    try:
+        with cabi_emulator.installed() as e:
+            yield e
+    finally:
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+@pytest.mark.parametrize('tag,epoch,use_masks', [('train_e11', 11, True), ('train_e0', 0, False)])
+def test_train_iter_gan_plan_vs_reference_golden(emu_fp32, tag, epoch, use_masks):
+    GP.test_train_iter_vs_reference_golden(CPU, tag, epoch, use_masks)
+    assert emu_fp32.calls.count('tg_adam_flat') == (2 if epoch > 10 else 1)
+    assert 'tg_gru_layer_bwd' in emu_fp32.calls and 'tg_gen_losses' in emu_fp32.calls
+
+
+def test_forward_eval_plan_vs_reference_golden(emu_fp32):
+    GP.test_forward_eval_vs_reference_golden(CPU)
+
+
+def test_train_iter_gan_all_dropout_masks_vs_fp64_oracle(emu_fp32):
+    """Every dropout mask injected, incl. the GRU inter-layer masks the reference cannot take (hence the fp64 oracle); small batch."""
+    GP.test_train_iter_full_size_vs_oracle(CPU, 4, 11)
+
+
+def test_module_api_autograd_plan(emu_fp32):
+    """The torch.autograd glue of the nn.Module API (model/*.py): loss.backward() through our modules vs oracle autograd."""
+    GP.test_module_api_autograd_matches_oracle(CPU)
+
+
+@pytest.mark.parametrize('ctx,zm', [('audio', 'speaker'), ('text', 'random'), ('none', None)])
+def test_constructor_variant_plans(emu_fp32, ctx, zm):
+    GP.test_constructor_variants_vs_reference_golden(CPU, ctx, zm)
+
+
+def test_embedding_net_and_fgd_plan(emu_fp32):
+    GP.test_embedding_net_and_fgd_vs_reference_golden(CPU)

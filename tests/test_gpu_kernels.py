@@ -161,7 +161,8 @@ def test_gru_layer_fwd_bwd(dev, B, T, I, H):
     saved = torch.empty(4, M, 2 * H, device=dev)
     sync = torch.zeros(max(ops.gru_sync_ints(B, H), 1), dtype=torch.int32, device=dev)
     ops.gru_layer_fwd(gi, whhT[0], whhT[1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, sync, B, T, H)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     xd = x.double().requires_grad_(True)
     pd = {k: [t.double().requires_grad_(True) for t in v] for k, v in p.items()}
     ref = torch.cat([O.gru_cell_sequence(xd, pd['wih'][d], pd['whh'][d], pd['bih'][d], pd['bhh'][d], bool(d)) for d in (0, 1)], dim=2)
@@ -178,7 +179,8 @@ def test_gru_layer_fwd_bwd(dev, B, T, I, H):
     bsync = torch.zeros(max(ops.gru_sync_ints(Bb, H), 1), dtype=torch.int32, device=dev)
     ops.gru_layer_bwd(dout[lo:hi].contiguous().view(Mb, 2 * H), out[lo * T:hi * T], saved[0, lo * T:hi * T], M * 2 * H, p['whh'][0], p['whh'][1],
                       dgi, dgh, partial, bsync, Bb, T, H)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     # input grad and weight grads from dgi / dgh
     dx = torch.empty(Mb, I, device=dev)
     ops.linear_dgrad(dgi, wih, dx, M=Mb, K=I, N=6 * H)
