@@ -7,8 +7,10 @@ tensors and its RESULT can be compared with the oracle in the `-m "not gpu"` sui
 themselves are checked on the GPU (tests/test_gpu_*.py).  It is not a fallback: the product never imports tests/, and without this
 fixture a CPU tensor raises TgError (tests/test_abi_and_modules.py::test_no_cpu_fallback_without_cuda).
 
-Restated: every entry point the strict-fp32 (`TGB200_MODE=fp32`) plans of train_iter_gan, the auto-encoder trainer and the eval-mode
-EmbeddingNet forward call; anything else (the tcgen05 / tensor-core entries) raises NotImplementedError."""
+Restated: every entry point the launch plans call, in both arithmetic modes (the tensor-core entries tg_gemm_tf32 / tg_wgrad_tf32 /
+tg_gru_layer_*_tf32 are restated by their documented arithmetic in float64, i.e. without the TF32 operand rounding - the emulator checks
+which operands, strides and epilogues a plan passes, not the rounding); anything else (debug aids, tg_copy_bytes) raises
+NotImplementedError."""
 import ctypes
 import math
 
@@ -649,6 +651,136 @@ class EmuLib:
         c0, c1, _, _ = self._philox(seed, stream_id, n, offset_dev)
         keys = (c0 << np.uint64(32)) | (c1 & np.uint64(0xFFFFF000)) | np.arange(n, dtype=np.uint64)
         _arr(out, n, ctypes.c_longlong)[:] = (np.sort(keys) & np.uint64(0xFFF)).astype(np.int64)
+        return 0
+
+    # ---------------------------------------------------------------------------------------- tensor-core entries (documented arithmetic)
+    def _epilogue(self, p, v, rows, N):
+        n = np.arange(N)
+        if p.escale:
+            v = v * _arr(p.escale, N)[None, :]
+        if p.bias:
+            v = v + _arr(p.bias, N)[None, :]
+        v = _act(v, p.act1, p.slope1)
+        if p.mask:
+            mo = rows[:, None] * p.ldmask + n[None, :]
+            v = v * _arr(p.mask, mo.max() + 1)[mo]
+        if p.residual:
+            ro = rows[:, None] * p.ldres + n[None, :]
+            v = v + _arr(p.residual, ro.max() + 1)[ro]
+        return _act(v, p.act2, 0.0)
+
+    def tg_gemm_tf32(self, pref, stream):
+        p = pref._obj
+        self.calls.append('tg_gemm_tf32')
+        M, N, K = p.M, p.N, p.K
+        m = np.arange(M); k = np.arange(K)
+        Bw = _arr(p.Bw, (p.taps * N - 1) * p.ldb + K)
+        acc = np.zeros((M, N))
+        for tap in range(p.taps):
+            shift = p.shift0 if (p.taps == 2 and tap == 0) else 0
+            if p.clip_rows > 0:
+                assert p.taps == 1
+                off = ((m // p.clip_rows) * p.a_clip_pitch + (m % p.clip_rows) * p.lda)[:, None] + k[None, :]
+                ok = np.ones(M, bool)
+            else:
+                rows = m + shift
+                ok = (rows >= 0) & (rows < p.a_rows)
+                if shift != 0:
+                    t = m % p.T
+                    ok &= (t + shift >= 0) & (t + shift < p.T)
+                off = np.where(ok, rows, 0)[:, None] * p.lda + k[None, :]
+            A = np.where(ok[:, None], _arr(p.A, off.max() + 1)[off].astype(np.float64), 0.0)
+            wo = (tap * N + np.arange(N))[:, None] * p.ldb + k[None, :]
+            acc += A @ Bw[wo].astype(np.float64).T
+        v = self._epilogue(p, acc, m, N)
+        yo = m[:, None] * p.ldc + np.arange(N)[None, :]
+        Y = _arr(p.C, yo.max() + 1)
+        if p.accumulate:
+            v = v + Y[yo]
+        Y[yo] = v.astype(np.float32)
+        return 0
+
+    def tg_col_sum_f32(self, g, ld, M, N, out, stream):
+        self.calls.append('tg_col_sum_f32')
+        o = np.arange(M)[:, None] * ld + np.arange(N)[None, :]
+        _arr(out, N)[:] += _arr(g, o.max() + 1)[o].astype(np.float64).sum(0).astype(np.float32)
+        return 0
+
+    def tg_wgrad_tf32(self, pref, stream):
+        p = pref._obj
+        self.calls.append('tg_wgrad_tf32')
+        B, T, N, C = p.B, p.T, p.N, p.Cin
+        if p.dbias:
+            self.tg_col_sum_f32(p.G, p.ldg, B * T, N, p.dbias, stream)
+        b = np.repeat(np.arange(B), T); t = np.tile(np.arange(T), B)
+        go = (b * T + t)[:, None] * p.ldg + np.arange(N)[None, :]
+        G = _arr(p.G, go.max() + 1)[go].astype(np.float64)
+        ts = t + p.shift
+        ok = (ts >= 0) & (ts < T)
+        base = b * p.x_clip_pitch + np.where(ok, ts, 0) * p.ldx if p.x_clip_pitch > 0 else (b * T + np.where(ok, ts, 0)) * p.ldx
+        xo = base[:, None] + np.arange(C)[None, :]
+        X = np.where(ok[:, None], _arr(p.X, xo.max() + 1)[xo].astype(np.float64), 0.0)
+        wo = np.arange(N)[:, None] * p.ldw + np.arange(C)[None, :]
+        dW = _arr(p.dW, wo.max() + 1)
+        dW[wo] = (dW[wo] + G.T @ X).astype(np.float32)
+        return 0
+
+    def tg_gru_tf32_sync_ints(self, B, H):
+        return 64
+
+    def tg_gru_bwd_tf32_scratch_floats(self, B, H):
+        return 64
+
+    def tg_gru_layer_fwd_tf32(self, gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream):
+        """Weight layout swapped w.r.t. the fp32 entry: weight_hh as stored [3H,H]."""
+        tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(3 * H, H).T) for w in (whh_f, whh_r)]
+        rc = self.tg_gru_layer_fwd(gi, tr[0].ctypes.data, tr[1].ctypes.data, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream)
+        self.calls[-1] = 'tg_gru_layer_fwd_tf32'
+        return rc
+
+    def tg_gru_layer_bwd_tf32(self, dout, out, saved, qstride, whhT_f, whhT_r, dgi, dgh, partial, sync, B, T, H, stream):
+        """Takes the transposed recurrent weights [H,3H]."""
+        tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(H, 3 * H).T) for w in (whhT_f, whhT_r)]
+        rc = self.tg_gru_layer_bwd(dout, out, saved, qstride, tr[0].ctypes.data, tr[1].ctypes.data, dgi, dgh, partial, sync, B, T, H, stream)
+        self.calls[-1] = 'tg_gru_layer_bwd_tf32'
+        return rc
+
+    # ---------------------------------------------------------------------------------------- WavEncoder fast path (csrc/wav_fast.cu)
+    def tg_window_weights(self, w, w2, w2t, N, Cin, k, stream):
+        self.calls.append('tg_window_weights')
+        W2 = _arr(w, N * Cin * k).reshape(N, Cin, k).transpose(0, 2, 1).reshape(N, k * Cin)
+        _arr(w2, N * Cin * k)[:] = W2.reshape(-1)
+        if w2t:
+            _arr(w2t, N * Cin * k)[:] = W2.T.reshape(-1)
+        return 0
+
+    def tg_window_wgrad_add(self, dw2, dw, N, Cin, k, stream):
+        self.calls.append('tg_window_wgrad_add')
+        _arr(dw, N * Cin * k)[:] += _arr(dw2, N * Cin * k).reshape(N, k, Cin).transpose(0, 2, 1).reshape(-1)
+        return 0
+
+    def tg_col2im(self, col, da, B, Tin, Tout, Cin, k, stride, stream):
+        self.calls.append('tg_col2im')
+        COL = _arr(col, B * Tout * k * Cin).reshape(B, Tout, k, Cin).astype(np.float64)
+        DA = np.zeros((B, Tin, Cin))
+        for t in range(Tout):
+            for j in range(k):
+                s_ = t * stride + j
+                if s_ < Tin:
+                    DA[:, s_] += COL[:, t, j]
+        _arr(da, B * Tin * Cin)[:] = DA.astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_conv1_wgrad(self, x, dy, dW, dbias, B, Tin, Tout, N, taps, stride, pad, stream):
+        self.calls.append('tg_conv1_wgrad')
+        X = _arr(x, B * Tin).reshape(B, Tin).astype(np.float64)
+        DY = _arr(dy, B * Tout * N).reshape(B, Tout, N).astype(np.float64)
+        ti = (np.arange(Tout) * stride - pad)[:, None] + np.arange(taps)[None, :]
+        ok = (ti >= 0) & (ti < Tin)
+        win = np.where(ok[None], X[:, np.where(ok, ti, 0)], 0.0)          # [B, Tout, taps]
+        _arr(dW, N * taps)[:] += np.einsum('btn,btj->nj', DY, win).astype(np.float32).reshape(-1)
+        if dbias:
+            _arr(dbias, N)[:] += DY.sum((0, 1)).astype(np.float32)
         return 0
 
 

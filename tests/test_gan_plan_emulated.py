@@ -51,3 +51,23 @@ def test_constructor_variant_plans(emu_fp32, ctx, zm):
 
 def test_embedding_net_and_fgd_plan(emu_fp32):
     GP.test_embedding_net_and_fgd_vs_reference_golden(CPU)
+
+
+@pytest.fixture()
+def emu_fast():
+    from tgb200 import config
+    old_mode, old_graphs = config.set_mode('tf32'), config.set_graphs(False)
+    try:
+        with cabi_emulator.installed() as e:
+            yield e
+    finally:
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+def test_fast_mode_plans(emu_fast):
+    """The DEFAULT (tf32) mode routes the large GEMMs, weight gradients, the generator GRU and WavEncoder conv2-4 through the
+    tensor-core entries (window views, two-tap causal GEMM, col2im, MN-major weight gradients): same goldens / oracle, other plan."""
+    GP.test_fast_mode_forward_eval_vs_reference_golden(CPU)
+    GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11)
+    for sym in ('tg_gemm_tf32', 'tg_wgrad_tf32', 'tg_gru_layer_fwd_tf32', 'tg_gru_layer_bwd_tf32', 'tg_col2im', 'tg_conv1_wgrad'):
+        assert sym in emu_fast.calls, sym

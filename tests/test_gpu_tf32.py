@@ -28,7 +28,8 @@ def test_gemm_tf32_plain(dev, M, N, K):
     a = _rand(M, K, dev=dev); w = _rand(N, K, dev=dev, seed=1, scale=K ** -0.5); b = _rand(N, dev=dev, seed=2)
     c = torch.full((M, N), float('nan'), device=dev)
     ops.gemm_tf32(a, w, c, M=M, N=N, K=K, bias=b)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     ref = a.double() @ w.double().t() + b.double()
     assert rel_l2(c, ref) < TF32_TOL, rel_l2(c, ref)
     # epilogue: relu, mask, residual, second relu, accumulate
@@ -79,7 +80,8 @@ def test_gru_layer_tensor_core_fwd_bwd(dev, B, T, I, H):
     saved = torch.empty(4, M, 2 * H, device=dev)
     sync = torch.zeros(max(ops.gru_tf32_sync_ints(B, H), 1), dtype=torch.int32, device=dev)
     ops.gru_layer_fwd_tf32(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, sync, B, T, H)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     xd = x.double().requires_grad_(True)
     pd = {k: [t.double().requires_grad_(True) for t in v] for k, v in p.items()}
     ref = torch.cat([O.gru_cell_sequence(xd, pd['wih'][d], pd['whh'][d], pd['bih'][d], pd['bhh'][d], bool(d)) for d in (0, 1)], dim=2)
@@ -97,7 +99,8 @@ def test_gru_layer_tensor_core_fwd_bwd(dev, B, T, I, H):
     whhT = [p['whh'][d].t().contiguous() for d in (0, 1)]
     ops.gru_layer_bwd_tf32(dout[lo:hi].contiguous().view(Mb, 2 * H), out[lo * T:hi * T], saved[0, lo * T:hi * T], M * 2 * H, whhT[0], whhT[1],
                            dgi, dgh, partial, bsync, Bb, T, H)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     dx = torch.empty(Mb, I, device=dev)
     ops.linear_dgrad(dgi, wih, dx, M=Mb, K=I, N=6 * H)
     e = rel_l2(dx, xd.grad[lo:hi].reshape(Mb, I))
@@ -124,7 +127,8 @@ def test_wgrad_tf32(dev, B, T, N, Cin, shift):
     dW = torch.ones(N, Cin, device=dev)
     db = torch.zeros(N, device=dev)
     ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=Cin + 4, dbias=db)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     Xs = torch.zeros(B, T, Cin, device=dev, dtype=torch.float64)
     X3 = X.double().reshape(B, T, Cin)
     if shift == 0:
@@ -169,7 +173,8 @@ def test_strided_conv_window_gemm_fwd_bwd(dev, B, Tin, cin, cout, k, s):
     col = torch.empty(B * Tout, k * cin, device=dev); da = torch.full((B * Tin, cin), float('nan'), device=dev)
     ops.gemm_tf32(dy.view(B * Tout, cout), w2t, col, M=B * Tout, N=k * cin, K=cout)
     ops.col2im(col, da, B=B, Tin=Tin, Tout=Tout, Cin=cin, k=k, stride=s)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     assert rel_l2(da.view(B, Tin, cin), xr.grad.transpose(1, 2)) < TF32_TOL
 
 
@@ -185,6 +190,7 @@ def test_conv1_wgrad(dev, B, Tin):
     ref.backward(dy.double().transpose(1, 2))
     dw = torch.ones(N, k, device=dev); db = torch.ones(N, device=dev)
     ops.conv1_wgrad(x, dy.view(B * Tout, N), dw, db, B=B, Tin=Tin, Tout=Tout, N=N, taps=k, stride=s, pad=pad)
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     assert rel_l2(dw - 1.0, w.grad.view(N, k)) < 1e-4, rel_l2(dw - 1.0, w.grad.view(N, k))
     assert rel_l2(db - 1.0, bb.grad) < 1e-4

@@ -66,3 +66,15 @@ def test_noise_drawing_plans(emu_fp32):
         a = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])[0].clone()
         b = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])[0].clone()
     assert bool(torch.isfinite(a).all()) and not torch.equal(a, b)          # reparameterize draws noise in eval mode too
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+def test_seq2seq_batch128_plan_vs_fp64_oracle(mode):
+    """The benchmark shape (batch 128, text length 12) with injected inter-layer dropout masks, both arithmetic modes' plans."""
+    from tgb200 import config
+    old = config.set_graphs(False)
+    try:
+        with cabi_emulator.installed():
+            GS.test_seq2seq_step_batch128_vs_fp64_oracle(CPU, mode, 1e-4)      # the emulator does not round to TF32: fp32-class agreement in both
+    finally:
+        config.set_graphs(old)
