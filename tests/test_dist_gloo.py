@@ -75,3 +75,89 @@ def test_flat_gradient_allreduce_and_fgd_reduction_world2():
     fg = np.vstack([(torch.randn(64, 32, generator=torch.Generator().manual_seed(17 + r)) * 1.3 + 0.2).double().numpy() for r in range(2)])
     fgd, fdist = O.fgd_scores(fg, fr)
     assert abs(res[0][2] - fgd) <= 1e-6 * abs(fgd) and abs(res[0][3] - fdist) <= 1e-9 * abs(fdist)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Full data-parallel iteration, world 2: every rank runs train_iter_gan on ITS shard (the launch plan executes on the NumPy C-ABI
+# emulator, tests/cabi_emulator.py), the flat gradient arenas are summed over gloo where production uses NCCL, Adam averages.
+# ----------------------------------------------------------------------------------------------------------------------
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'gesture-generation-from-trimodal-context_b200'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(4)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import cabi_emulator
+        from gpu_util import build_ours, masks_to_ours
+        from oracle import synth
+        from oracle import trimodal_oracle as O
+        from oracle.make_golden import golden_cfg
+        from tgb200 import config
+        from train_eval import train_gan as TG
+        config.set_mode('fp32'); config.set_graphs(False)
+        cfg = golden_cfg()
+        Bl = 2
+        full = synth.make_inputs(cfg, Bl * world, seed=9)
+        inp = {k: v[rank * Bl:(rank + 1) * Bl].contiguous() for k, v in full.items()}
+        res = {}
+        with cabi_emulator.installed() as emu:
+            for epoch in (0, 11):
+                args, G, D, gsd, dsd = build_ours(cfg, None)
+                G.train(); D.train()
+                noise = synth.golden_noise(cfg, Bl, 20 + rank, True)          # every rank draws its own noise
+                g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+                d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+                TG.inject_noise(TG.StepNoise(eps=list(noise.eps), perm=noise.perm, g_masks=[masks_to_ours(m, None) if m else {} for m in noise.g_masks],
+                                             d_masks=[{}, {}, {}]))
+                ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+                ok = all(torch.isfinite(torch.tensor(v)) for v in ret.values())
+                # (1) replicas stay in lock-step: bit-identical parameters on every rank after the step
+                for net in (G, D):
+                    flat = net.engine().arena.flat.clone()
+                    ref = flat.clone()
+                    dist.broadcast(ref, src=0)
+                    ok = ok and torch.equal(flat, ref)
+                if epoch == 0:
+                    # (2) warm-up epoch (no D step): the update equals Adam on the MEAN over ranks of the rank-local oracle gradients
+                    from test_oracle_golden import ZERO_GRAD_KEYS
+                    n3 = O.StepNoise(eps=list(noise.eps), perm=noise.perm, g_masks=list(noise.g_masks), d_masks=[None, None, None])
+                    want = O.train_iter_gan_oracle(cfg, 0, gsd, dsd, synth.zeros_like_opt(gsd), synth.zeros_like_opt(dsd), 1,
+                                                   inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], n3)
+                    worst = 0.0
+                    sd = G.state_dict()
+                    for k, gr in want['g_grads'].items():
+                        g = gr.detach().clone()
+                        dist.all_reduce(g)
+                        g /= world
+                        p, _, _ = O.adam_step(gsd[k], g, torch.zeros_like(g), torch.zeros_like(g), 1, cfg.learning_rate)
+                        d = (sd[k] - p).abs()
+                        ok = ok and d.max().item() <= 2.2 * cfg.learning_rate + 1e-6          # round-off gradients may flip a +-lr step
+                        if k not in ZERO_GRAD_KEYS:                                            # analytically zero gradient: pure +-lr noise
+                            worst = max(worst, d.median().item())
+                    ok = ok and worst < 2e-6
+                    res['worst_median'] = worst
+                res['calls_%d' % epoch] = emu.calls.count('tg_adam_flat')
+                res['ok_%d' % epoch] = bool(ok)
+                emu.calls.clear()
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_train_iter_gan_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r['ok_0'] and r['ok_11'], (rank, r)
+        assert r['calls_0'] == 1 and r['calls_11'] == 2, r          # warm-up: generator Adam only; afterwards D and G
