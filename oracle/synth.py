@@ -278,3 +278,36 @@ def generator_state_dict_variant(cfg, input_context: str, z_mode, seed: int = 0)
             v = v[:, cols].contiguous()
         out[k] = v
     return out
+
+
+# --------------------------------------------------------------------------------------
+# joint-embedding model: EmbeddingNet(mode != 'pose') (embedding_net.py:130-162,220-273)
+# --------------------------------------------------------------------------------------
+def joint_embedding_state_dict(cfg: HotPathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of EmbeddingNet(mode='random'): ContextEncoder + PoseEncoderConv + PoseDecoderGRU, reference key order."""
+    rng = _rng(9000 + seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    g = generator_state_dict(cfg, seed + 5)
+    for k, v in g.items():                                    # ContextEncoder.text_encoder / .audio_encoder (:225-226)
+        if k.startswith('text_encoder.'):
+            sd['context_encoder.' + k] = v
+    for k, v in g.items():
+        if k.startswith('audio_encoder.'):
+            sd['context_encoder.' + k] = v
+    _gru_uni(sd, rng, 'context_encoder.gru', 64, 256, 2)       # :227-228
+    _lin(sd, rng, 'context_encoder.out.0', (128, 256), 256, scale=1.5)
+    _bn(sd, rng, 'context_encoder.out.1', 128)
+    _lin(sd, rng, 'context_encoder.out.3', (32, 128), 128, scale=1.5)
+    _lin(sd, rng, 'context_encoder.fc_mu', (32, 32), 32, scale=1.5)
+    _lin(sd, rng, 'context_encoder.fc_logvar', (32, 32), 32, scale=0.5)
+    pe = embedding_net_state_dict(cfg, seed + 3)
+    for k, v in pe.items():
+        if k.startswith('pose_encoder.'):
+            sd[k] = v
+    _lin(sd, rng, 'decoder.pre_pose_net.0', (32, cfg.pose_dim * 4), cfg.pose_dim * 4, scale=1.5)      # PoseDecoderGRU :138-143
+    _bn(sd, rng, 'decoder.pre_pose_net.1', 32)
+    _lin(sd, rng, 'decoder.pre_pose_net.3', (32, 32), 32, scale=1.5)
+    _gru(sd, rng, 'decoder.gru', 64, 300, 4)
+    _lin(sd, rng, 'decoder.out.0', (150, 300), 300)
+    _lin(sd, rng, 'decoder.out.2', (cfg.pose_dim, 150), 150)
+    return sd
