@@ -24,21 +24,10 @@ ENC_CONVS = ((3, 1), (3, 1), (4, 2))          # ConvNormRelu x3: (kernel, stride
 ENC_SLOPE = DEC_SLOPE = 0.2                   # nn.LeakyReLU(0.2) :31,208,211 ; nn.LeakyReLU(True) == slope 1.0 == identity :57,60,203
 
 
-class AutoEncoderTrainEngine:
-    def __init__(self, module):
-        self.m = module
-        self.arena = ParamArena(module)
-        self.ws: Optional[Workspace] = None
-        self.graph_slots = {}                 # captured CUDA graphs of the step (train_eval.train_joint_embed.ae_step)
-
-    def ensure(self, device):
-        if not self.arena.is_current():
-            self.graph_slots = {}             # parameters were moved / re-created: captured pointers are stale
-        self.arena.ensure(device)
-        if self.ws is None or self.ws.device != device:
-            self.ws = Workspace(device)
-        self.bufs = dict(self.m.named_buffers())
-        return self
+class _PlanBase:
+    """What every plan below needs: a workspace, the flat-arena accessors P (parameter) / G (gradient view) and the BatchNorm buffers."""
+    arena: ParamArena
+    ws: Optional[Workspace] = None
 
     def P(self, name):
         return self.arena.params[name].data
@@ -72,12 +61,17 @@ class AutoEncoderTrainEngine:
         ops.bn_bwd_apply(d, y, d, M, C, mean, rstd, scale, shift, slope, self.P(bn + '.weight'), sums, self.G(bn + '.weight'),
                          self.G(bn + '.bias'))
 
-    # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, poses, training=True):
-        """poses [B,34,27] -> (mu [B,32], logvar [B,32], recon [B,34,27]); feature = mu (variational_encoding=False)."""
+
+
+class PoseEncoderPlan(_PlanBase):
+    """PoseEncoderConv (embedding_net.py:42-82) forward / backward; ENC = parameter-name prefix inside self.arena."""
+    ENC = 'pose_encoder.'
+
+    def encode(self, poses, training=True):
+        """poses [B,34,27] -> (mu [B,32], logvar [B,32]); feature = mu (variational_encoding=False)."""
         ws = self.ws
         B, T, D = poses.shape
-        e, d = 'pose_encoder.', 'decoder.'
+        e = self.ENC
         self.ctx = dict(B=B, T=T, D=D, poses=poses, training=training)
         x, tin, cin, pro = poses, T, D, {}
         self.enc_T = [T]
@@ -116,7 +110,85 @@ class AutoEncoderTrainEngine:
         mu, logvar = ws.get('ae.mu', (B, 32)), ws.get('ae.logvar', (B, 32))
         ops.linear(h2, self.P(e + 'fc_mu.weight'), self.P(e + 'fc_mu.bias'), mu, M=B, K=n2, N=32)
         ops.linear(h2, self.P(e + 'fc_logvar.weight'), self.P(e + 'fc_logvar.bias'), logvar, M=B, K=n2, N=32)
-        # ---- decoder (PoseDecoderConv, length 34)
+        return mu, logvar
+
+    def encode_backward(self, dmu):
+        """dmu [B,32] = d loss / d mu.  fc_logvar never reaches the loss when variational_encoding is False: its gradient stays zero."""
+        ws, c = self.ws, self.ctx
+        assert c['training'], 'backward through eval-mode BatchNorm is not on this path'
+        B = c['B']
+        e = self.ENC
+        P, G = self.P, self.G
+        # ---- encoder head: fc_mu, out_net (fc_logvar never reaches the loss: its gradient stays zero, train_feature_extractor.py:58-86)
+        n2 = P(e + 'fc_mu.weight').shape[1]
+        ops.linear_wgrad(ws['ae.h2'], dmu, G(e + 'fc_mu.weight'), G(e + 'fc_mu.bias'), M=B, K=n2, N=32)
+        dh2 = ws.get('ae.d_h2', (B, n2))
+        ops.linear_dgrad(dmu, P(e + 'fc_mu.weight'), dh2, M=B, K=n2, N=32)
+        dprev = dh2
+        for name, src, bn in (('out_net.6', 'ae.h1', 'out_net.4'), ('out_net.3', 'ae.h0', 'out_net.1')):
+            w = P(e + name + '.weight'); n, kk = w.shape
+            ops.linear_wgrad(ws[src], dprev, G(e + name + '.weight'), G(e + name + '.bias'), M=B, K=kk, N=n,
+                             pscale=ws[src + '.scale'], pshift=ws[src + '.shift'], pslope=1.0)
+            dsrc = ws.get(src.replace('ae.', 'ae.d_'), (B, kk))
+            ops.linear_dgrad(dprev, w, dsrc, M=B, K=kk, N=n)
+            self._bn_bwd(src, dsrc, ws[src], B, kk, e + bn, 1.0)
+            dprev = dsrc
+        w0 = P(e + 'out_net.0.weight'); n0, nf = w0.shape
+        ops.linear_wgrad(ws['ae.f'], dprev, G(e + 'out_net.0.weight'), G(e + 'out_net.0.bias'), M=B, K=nf, N=n0)
+        df = ws.get('ae.d_f', (B, nf))
+        ops.linear_dgrad(dprev, w0, df, M=B, K=nf, N=n0)
+        eT = self.enc_T                                                           # [34, 32, 30, 14, 12]
+        c3 = P(e + 'net.3.weight').shape[0]
+        dy = ws.get('ae.d_y3', (B * eT[4], c3))
+        ops.transpose_batched(df, dy, B, c3, eT[4])                               # channel-major [B,32,12] -> channels-last [B,12,32]
+        # ---- encoder convs, last first
+        convs = [(f'{e}net.{i}.0', k, s) for i, (k, s) in enumerate(ENC_CONVS)] + [(e + 'net.3', 3, 1)]
+        for li in (3, 2, 1, 0):
+            name, k, s = convs[li]
+            w = P(name + '.weight'); cout, cin, _ = w.shape
+            tin, tout = eT[li], eT[li + 1]
+            if li > 0:
+                x = ws[f'ae.y{li - 1}']
+                pro = dict(pscale=ws[f'ae.y{li - 1}.scale'], pshift=ws[f'ae.y{li - 1}.shift'], pslope=ENC_SLOPE)
+            else:
+                x, pro = c['poses'], {}
+            ops.conv1d_wgrad(x, dy, G(name + '.weight'), G(name + '.bias'), B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s, **pro)
+            if li == 0:
+                break
+            dx = ws.get(f'ae.d_y{li - 1}', (B * tin, cin))
+            ops.conv1d_dgrad(dy, w, dx, B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s)
+            self._bn_bwd(f'ae.y{li - 1}', dx, x, B * tin, cin, f'{e}net.{li - 1}.1', ENC_SLOPE)
+            dy = dx
+
+
+class AutoEncoderTrainEngine(PoseEncoderPlan):
+    """EmbeddingNet(mode='pose'): PoseEncoderPlan + PoseDecoderConv (embedding_net.py:165-217) + loss."""
+
+    def __init__(self, module):
+        self.m = module
+        self.arena = ParamArena(module)
+        self.ws: Optional[Workspace] = None
+        self.graph_slots = {}                 # captured CUDA graphs of the step (train_eval.train_joint_embed.ae_step)
+
+    def ensure(self, device):
+        if not self.arena.is_current():
+            self.graph_slots = {}             # parameters were moved / re-created: captured pointers are stale
+        self.arena.ensure(device)
+        if self.ws is None or self.ws.device != device:
+            self.ws = Workspace(device)
+        self.bufs = dict(self.m.named_buffers())
+        return self
+
+    def forward(self, poses, training=True):
+        """poses [B,34,27] -> (mu [B,32], logvar [B,32], recon [B,34,27])."""
+        mu, logvar = self.encode(poses, training)
+        return mu, logvar, self.decode(mu, training)
+
+    def decode(self, mu, training=True):
+        """PoseDecoderConv, length 34: mu [B,32] -> recon [B,34,27]."""
+        ws = self.ws
+        B, T, D = self.ctx['B'], self.ctx['T'], self.ctx['D']
+        d = 'decoder.'
         wp = self.P(d + 'pre_net.0.weight'); c0 = wp.shape[0]
         g0 = ws.get('ae.g0', (B, c0))
         ops.linear(mu, wp, self.P(d + 'pre_net.0.bias'), g0, M=B, K=32, N=c0)
@@ -148,7 +220,7 @@ class AutoEncoderTrainEngine:
             x, tin, cin, pro = y, tout, cout, {}
             self.dec_T.append(tout)
         assert tin == T and cin == D, (tin, cin)
-        return mu, logvar, x.view(B, T, D)
+        return x.view(B, T, D)
 
     # ------------------------------------------------------------------------------------------------ loss
     def loss(self, recon, target, use_diff, weight, acc, want_grad=True):
@@ -165,7 +237,7 @@ class AutoEncoderTrainEngine:
         ws, c = self.ws, self.ctx
         assert c['training'], 'backward through eval-mode BatchNorm is not on this path'
         B = c['B']
-        e, d = 'pose_encoder.', 'decoder.'
+        d = 'decoder.'
         P, G = self.P, self.G
         # ---- decoder.net.7 / net.6 (Conv1d k=3)
         dT = self.dec_T                                                           # [34, 36, 38, 36, 34]
@@ -207,43 +279,4 @@ class AutoEncoderTrainEngine:
         ops.linear_wgrad(ws['ae.mu'], dg0, G(d + 'pre_net.0.weight'), G(d + 'pre_net.0.bias'), M=B, K=32, N=c0)
         dmu = ws.get('ae.d_mu', (B, 32))
         ops.linear_dgrad(dg0, P(d + 'pre_net.0.weight'), dmu, M=B, K=32, N=c0)
-        # ---- encoder head: fc_mu, out_net (fc_logvar never reaches the loss: its gradient stays zero, train_feature_extractor.py:58-86)
-        n2 = P(e + 'fc_mu.weight').shape[1]
-        ops.linear_wgrad(ws['ae.h2'], dmu, G(e + 'fc_mu.weight'), G(e + 'fc_mu.bias'), M=B, K=n2, N=32)
-        dh2 = ws.get('ae.d_h2', (B, n2))
-        ops.linear_dgrad(dmu, P(e + 'fc_mu.weight'), dh2, M=B, K=n2, N=32)
-        dprev = dh2
-        for name, src, bn in (('out_net.6', 'ae.h1', 'out_net.4'), ('out_net.3', 'ae.h0', 'out_net.1')):
-            w = P(e + name + '.weight'); n, kk = w.shape
-            ops.linear_wgrad(ws[src], dprev, G(e + name + '.weight'), G(e + name + '.bias'), M=B, K=kk, N=n,
-                             pscale=ws[src + '.scale'], pshift=ws[src + '.shift'], pslope=1.0)
-            dsrc = ws.get(src.replace('ae.', 'ae.d_'), (B, kk))
-            ops.linear_dgrad(dprev, w, dsrc, M=B, K=kk, N=n)
-            self._bn_bwd(src, dsrc, ws[src], B, kk, e + bn, 1.0)
-            dprev = dsrc
-        w0 = P(e + 'out_net.0.weight'); n0, nf = w0.shape
-        ops.linear_wgrad(ws['ae.f'], dprev, G(e + 'out_net.0.weight'), G(e + 'out_net.0.bias'), M=B, K=nf, N=n0)
-        df = ws.get('ae.d_f', (B, nf))
-        ops.linear_dgrad(dprev, w0, df, M=B, K=nf, N=n0)
-        eT = self.enc_T                                                           # [34, 32, 30, 14, 12]
-        c3 = P(e + 'net.3.weight').shape[0]
-        dy = ws.get('ae.d_y3', (B * eT[4], c3))
-        ops.transpose_batched(df, dy, B, c3, eT[4])                               # channel-major [B,32,12] -> channels-last [B,12,32]
-        # ---- encoder convs, last first
-        convs = [(f'{e}net.{i}.0', k, s) for i, (k, s) in enumerate(ENC_CONVS)] + [(e + 'net.3', 3, 1)]
-        for li in (3, 2, 1, 0):
-            name, k, s = convs[li]
-            w = P(name + '.weight'); cout, cin, _ = w.shape
-            tin, tout = eT[li], eT[li + 1]
-            if li > 0:
-                x = ws[f'ae.y{li - 1}']
-                pro = dict(pscale=ws[f'ae.y{li - 1}.scale'], pshift=ws[f'ae.y{li - 1}.shift'], pslope=ENC_SLOPE)
-            else:
-                x, pro = c['poses'], {}
-            ops.conv1d_wgrad(x, dy, G(name + '.weight'), G(name + '.bias'), B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s, **pro)
-            if li == 0:
-                break
-            dx = ws.get(f'ae.d_y{li - 1}', (B * tin, cin))
-            ops.conv1d_dgrad(dy, w, dx, B=B, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s)
-            self._bn_bwd(f'ae.y{li - 1}', dx, x, B * tin, cin, f'{e}net.{li - 1}.1', ENC_SLOPE)
-            dy = dx
+        self.encode_backward(dmu)
