@@ -6,13 +6,15 @@ running-statistics BatchNorm folded into their epilogues (tgb200.engine.Embeddin
 running-statistics update): tgb200.embed_engine.AutoEncoderTrainEngine, which also holds the hand-derived backward used by the
 auto-encoder step functions (train_feature_extractor.train_iter, train_eval.train_joint_embed.train_iter_embed).
 The module-level forward returns detached tensors: training goes through those step functions, not through autograd.
-The joint-embedding baseline (mode != 'pose': ContextEncoder / PoseDecoderGRU / PoseDecoderFC, embedding_net.py:85-162,220-259) is
-not built."""
+mode != 'pose' builds the joint-embedding model (ContextEncoder + PoseEncoderConv + PoseDecoderGRU, embedding_net.py:130-162,220-273;
+launch plan tgb200.embed_engine.JointEmbeddingEngine, step function train_eval.train_joint_embed.train_iter_embed)."""
+import random
+
 import torch
 import torch.nn as nn
 
 from tgb200 import _lib, ops
-from tgb200.embed_engine import AutoEncoderTrainEngine
+from tgb200.embed_engine import AutoEncoderTrainEngine, JointEmbeddingEngine
 from tgb200.engine import EmbeddingEngine
 
 
@@ -70,18 +72,77 @@ class PoseDecoderConv(nn.Module):
         raise RuntimeError('PoseDecoderConv holds parameters only; run EmbeddingNet.forward')
 
 
+class PoseDecoderGRU(nn.Module):
+    """embedding_net.py:130-162 (parameter container)."""
+
+    def __init__(self, gen_length, pose_dim):
+        super().__init__()
+        self.gen_length = gen_length
+        self.pose_dim = pose_dim
+        self.in_size = 32 + 32
+        self.hidden_size = 300
+        self.pre_pose_net = nn.Sequential(nn.Linear(pose_dim * 4, 32), nn.BatchNorm1d(32), nn.ReLU(), nn.Linear(32, 32))
+        self.gru = nn.GRU(self.in_size, hidden_size=self.hidden_size, num_layers=4, batch_first=True, bidirectional=True, dropout=0.3)
+        self.out = nn.Sequential(nn.Linear(self.hidden_size, self.hidden_size // 2), nn.LeakyReLU(True),
+                                 nn.Linear(self.hidden_size // 2, pose_dim))
+
+    def forward(self, latent_code, pre_poses):
+        raise RuntimeError('PoseDecoderGRU holds parameters only; run EmbeddingNet.forward')
+
+
+class ContextEncoder(nn.Module):
+    """embedding_net.py:220-259 (parameter container)."""
+
+    def __init__(self, args, n_frames, n_words, word_embed_size, word_embeddings):
+        super().__init__()
+        from model.multimodal_context_net import TextEncoderTCN, WavEncoder       # deferred: that module imports this one (as in the reference)
+        self.text_encoder = TextEncoderTCN(args, n_words, word_embed_size, pre_trained_embedding=word_embeddings)
+        self.audio_encoder = WavEncoder()
+        self.gru = nn.GRU(32 + 32, hidden_size=256, num_layers=2, bidirectional=False, batch_first=True)
+        self.out = nn.Sequential(nn.Linear(256, 128), nn.BatchNorm1d(128), nn.ReLU(inplace=True), nn.Linear(128, 32))
+        self.fc_mu = nn.Linear(32, 32)
+        self.fc_logvar = nn.Linear(32, 32)
+        self.do_flatten_parameters = False
+
+    def forward(self, in_text, in_spec):
+        raise RuntimeError('ContextEncoder holds parameters only; run EmbeddingNet.forward')
+
+
 class EmbeddingNet(nn.Module):
     def __init__(self, args, pose_dim, n_frames, n_words, word_embed_size, word_embeddings, mode):
         super().__init__()
         if mode != 'pose':
-            raise NotImplementedError("only EmbeddingNet(mode='pose') (the FGD feature extractor) is on the B200 hot path; the "
-                                      'joint-embedding baseline is out of scope (SURVEY.md 8 f4)')
-        self.context_encoder = None
-        self.pose_encoder = PoseEncoderConv(n_frames, pose_dim)
-        self.decoder = PoseDecoderConv(n_frames, pose_dim)
+            self.context_encoder = ContextEncoder(args, n_frames, n_words, word_embed_size, word_embeddings)
+            self.pose_encoder = PoseEncoderConv(n_frames, pose_dim)
+            self.decoder = PoseDecoderGRU(n_frames, pose_dim)
+        else:
+            self.context_encoder = None
+            self.pose_encoder = PoseEncoderConv(n_frames, pose_dim)
+            self.decoder = PoseDecoderConv(n_frames, pose_dim)
         self.mode = mode
         self._engine = None
         self._train_engine = None
+        self._joint_engine = None
+        self._noise_seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+
+    def joint_engine(self) -> JointEmbeddingEngine:
+        if self._joint_engine is None:
+            self._joint_engine = JointEmbeddingEngine(self)
+        return self._joint_engine
+
+    def _forward_joint(self, in_text, in_audio, pre_poses, poses, input_mode, variational_encoding):
+        """embedding_net.py:276-308 for the joint-embedding model; returns detached tensors (training goes through train_iter_embed)."""
+        assert not variational_encoding, 'the reference runs the joint-embedding model with variational_encoding=False (train_joint_embed.py:12-15,56)'
+        ref = poses if poses is not None else pre_poses
+        if not ref.is_cuda and not _lib.TRACE_ONLY:
+            raise _lib.TgError('EmbeddingNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+        if input_mode == 'random':
+            input_mode = 'speech' if random.random() > 0.5 else 'pose'                # embedding_net.py:295-296
+        assert input_mode in ('speech', 'pose')
+        eng = self.joint_engine().ensure(ref.device)
+        r = eng.forward(in_text, in_audio, pre_poses, poses, input_mode, self.training)
+        cl = lambda t: None if t is None else t.clone()
+        return cl(r['c_feat']), cl(r['c_mu']), cl(r['c_lv']), cl(r['p_mu']), cl(r['p_mu']), cl(r['p_lv']), cl(r['out'])
 
     def engine(self) -> EmbeddingEngine:
         if self._engine is None:
@@ -98,6 +159,8 @@ class EmbeddingNet(nn.Module):
         if input_mode is None:
             assert self.mode is not None
             input_mode = self.mode
+        if self.context_encoder is not None:
+            return self._forward_joint(in_text, in_audio, pre_poses, poses, input_mode, variational_encoding)
         assert input_mode == 'pose', "EmbeddingNet(mode='pose') has no context encoder (embedding_net.py:270-273,282)"
         if not poses.is_cuda and not _lib.TRACE_ONLY:
             raise _lib.TgError('EmbeddingNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')

@@ -19,8 +19,9 @@ def _ceil4(n: int) -> int:
 
 
 class ParamArena:
-    def __init__(self, module: nn.Module, order: Optional[List[str]] = None):
+    def __init__(self, module: nn.Module, order: Optional[List[str]] = None, partial: bool = False):
         self.module = module
+        self.partial = partial          # the bound optimiser may hold more parameters than this arena (one arena per sub-module)
         named = dict(module.named_parameters())
         names = list(order) if order is not None else list(named.keys())
         assert set(names) == set(named.keys()), (set(names) ^ set(named.keys()))
@@ -113,7 +114,7 @@ class ParamArena:
         assert g.get('weight_decay', 0) == 0 and not g.get('amsgrad', False) and not g.get('maximize', False)
         ours = {id(self.params[n]) for n in self.names}
         theirs = {id(p) for p in g['params'] if p.requires_grad}
-        assert ours == theirs, 'optimizer parameters differ from the module parameters'
+        assert (ours <= theirs) if self.partial else (ours == theirs), 'optimizer parameters differ from the module parameters'
         steps = set()
         for n in self.names:
             p = self.params[n]

@@ -1,11 +1,14 @@
-"""train_iter_embed / eval_embed - drop-in for scripts/train_eval/train_joint_embed.py:5-65, for the pose auto-encoder
-(EmbeddingNet(mode='pose'), the FGD feature extractor).  Same signatures, same returned values.
+"""train_iter_embed / eval_embed - drop-in for scripts/train_eval/train_joint_embed.py:5-65: the pose auto-encoder
+(EmbeddingNet(mode='pose'), the FGD feature extractor) and the joint-embedding model (EmbeddingNet(mode='random'): ContextEncoder +
+PoseEncoderConv + PoseDecoderGRU, `joint_step` below).  Same signatures, same returned values.
 
 One optimiser step = the train-mode forward, the L1 reconstruction loss (value + gradient in one kernel), the hand-derived
 backward and one flat Adam launch (tgb200.embed_engine.AutoEncoderTrainEngine): ~75 launches of a few microseconds each, no host
 synchronisation until the single loss read-back.  After two eager steps the sequence is captured into a CUDA graph per
 (net, optimiser, batch shape) and replayed - the step is launch-latency bound, so this is where the time goes.
 train_feature_extractor.train_iter (which adds the frame-difference term) shares `ae_step`."""
+import random
+
 import torch
 
 from tgb200 import _lib, config
@@ -81,10 +84,47 @@ def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> flo
     return float(acc.cpu()[0])
 
 
+def _resolve_mode(net_, mode):
+    """input_mode of EmbeddingNet.forward (embedding_net.py:277-296): None -> net.mode; 'random' flips a Python coin."""
+    if mode is None:
+        mode = net_.mode
+    if mode == 'random':
+        mode = 'speech' if random.random() > 0.5 else 'pose'
+    assert mode in ('speech', 'pose'), mode
+    return mode
+
+
+def joint_step(args, net, optim, in_text, in_audio, target_data, mode) -> float:
+    """One step of the joint-embedding model (train_joint_embed.py:5-51, variational_encoding=False): forward of both encoders, decode
+    the latent `mode` resolves to, loss = sum_b mean|recon - target|, backward through the decoder and THAT encoder, Adam on the
+    parameters that received a gradient (torch.optim.Adam skips the others).  Eager launches (no CUDA graph: the branch changes
+    from step to step)."""
+    _lib.require_cuda()
+    net_ = _unwrap(net)
+    if not target_data.is_cuda and not _lib.TRACE_ONLY:
+        raise _lib.TgError('the joint-embedding step runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+    assert net_.training, 'train_iter_embed expects net.train()'
+    branch = _resolve_mode(net_, mode)
+    target = target_data.detach().contiguous().float()
+    eng = net_.joint_engine().ensure(target.device)
+    for a in eng.arenas():
+        a.zero_grad()                                                           # optim.zero_grad(), :9
+    pre_seq = target[:, 0:args.n_pre_poses]                                     # :6
+    r = eng.forward(in_text, in_audio, pre_seq, target, branch, True)           # :17-19
+    acc = eng.ws.get('jd.acc', (2,), torch.float64)
+    acc.zero_()
+    eng.backward(eng.loss(r['out'], target, acc))                               # :21-29,46-48
+    for a in ((eng.a_ctx if branch == 'speech' else eng.a_pose), eng.a_dec):    # :49
+        a.adam_step(optim, 1.0, host_step=True)
+    return float(acc.cpu()[0])
+
+
 def train_iter_embed(args, epoch, in_text, in_audio, target_data, net, optim, mode=None):
     """train_joint_embed.py:5-51 with variational_encoding=False (:12-15): loss = sum over the batch of the per-sample mean L1
-    (the frame-difference term is switched off there, :24).  in_text / in_audio are ignored by a mode='pose' net
-    (context_encoder is None, embedding_net.py:282); mode must resolve to 'pose'."""
+    (the frame-difference term is switched off there, :24).  A mode='pose' net ignores in_text / in_audio (context_encoder is None,
+    embedding_net.py:282) and mode must resolve to 'pose'; a joint-embedding net decodes the branch `mode` resolves to."""
+    if getattr(_unwrap(net), 'context_encoder', None) is not None:
+        return {'loss': joint_step(args, net, optim, in_text, in_audio, target_data, mode)}
     assert mode in (None, 'pose'), "EmbeddingNet(mode='pose') has no context encoder: input_mode must be 'pose' (embedding_net.py:295-303)"
     return {'loss': ae_step(net, optim, target_data, use_diff=False)}
 
@@ -93,11 +133,18 @@ def eval_embed(in_text, in_audio, pre_poses, target_poses, net, mode=None):
     """train_joint_embed.py:54-65 -> (loss, recon_poses): batch mean of the per-sample mean L1, whatever mode (train / eval) the
     net is in - like the reference, a train-mode net normalises with batch statistics and updates its running statistics."""
     _lib.require_cuda()
-    assert mode in (None, 'pose')
     net_ = _unwrap(net)
     if not target_poses.is_cuda and not _lib.TRACE_ONLY:
         raise _lib.TgError('eval_embed runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
     target = target_poses.detach().contiguous().float()
+    if getattr(net_, 'context_encoder', None) is not None:
+        eng = net_.joint_engine().ensure(target.device)
+        r = eng.forward(in_text, in_audio, pre_poses, target, _resolve_mode(net_, mode), net_.training)
+        acc = eng.ws.get('jd.acc_eval', (2,), torch.float64)
+        acc.zero_()
+        eng.loss(r['out'], target, acc, want_grad=False)
+        return (acc[1] / target.shape[0]).float(), r['out'].clone()
+    assert mode in (None, 'pose')
     eng = net_.train_engine().ensure(target.device)
     _, _, recon = eng.forward(target, training=net_.training)
     acc = eng.ws.get('ae.acc_eval', (2,), torch.float64)
