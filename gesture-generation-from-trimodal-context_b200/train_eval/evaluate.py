@@ -37,8 +37,9 @@ class PoseMetrics:
 
 
 def evaluate_testset(test_data_loader, generator, loss_fn, embed_space_evaluator, args):
-    """train.py:234-329 for args.model in {'multimodal_context', 'seq2seq'}.  `loss_fn` is accepted for signature compatibility; like
-    the reference's multimodal_context branch the reported loss is the L1 distance of the direction vectors."""
+    """train.py:234-329 for args.model in {'multimodal_context', 'seq2seq', 'joint_embedding', 'gesture_autoencoder'}.  `loss_fn` is
+    accepted for signature compatibility; like the reference's multimodal_context branch the reported loss is the L1 distance of the
+    direction vectors (for the two embedding models that IS eval_embed's loss: the batch mean of per-sample means over equal-sized samples)."""
     _lib.require_cuda()
     was_training = generator.training
     generator.train(False)
@@ -68,6 +69,14 @@ def evaluate_testset(test_data_loader, generator, loss_fn, embed_space_evaluator
                 out_dir_vec, *_ = generator(pre_seq, in_text_padded.to(dev), in_audio.to(dev), vid_indices)
             elif model == 'seq2seq':
                 out_dir_vec = generator(in_text.to(dev), text_lengths, target, None)
+            elif model == 'joint_embedding':                                    # train.py:269-271: decode the speech latent
+                from train_eval.train_joint_embed import eval_embed
+                _, out_dir_vec = eval_embed(in_text_padded.to(dev), in_audio.to(dev), target[:, 0:args.n_pre_poses], target, generator, mode='speech')
+            elif model == 'gesture_autoencoder':                                # train.py:272-273,279: loss only, no pose metrics / FGD
+                from train_eval.train_joint_embed import eval_embed
+                _, recon = eval_embed(None, None, target[:, 0:args.n_pre_poses], target, generator)
+                metrics.push(recon, target, args.n_pre_poses)
+                continue
             else:
                 raise _lib.TgError('evaluate_testset: model %r is not on the B200 path' % model)
             if embed_space_evaluator:
@@ -75,6 +84,8 @@ def evaluate_testset(test_data_loader, generator, loss_fn, embed_space_evaluator
             metrics.push(out_dir_vec, target, args.n_pre_poses)
     generator.train(was_training)
     res = metrics.result() if metrics is not None else {'loss': 0.0, 'joint_mae': 0.0, 'accel': 0.0}
+    if getattr(args, 'model', None) == 'gesture_autoencoder':
+        res['joint_mae'] = res['accel'] = 0.0                                   # never updated in the reference (train.py:279): AverageMeter.avg == 0
     ret_dict = {'loss': res['loss'], 'joint_mae': res['joint_mae']}
     elapsed_time = time.time() - start
     if embed_space_evaluator and embed_space_evaluator.get_no_of_samples() > 0:

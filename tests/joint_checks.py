@@ -140,3 +140,33 @@ def run_batch_vs_fp64_oracle(device, Bn=8, tol=1e-4, gtol=None):
             assert err < (gtol if gtol is not None else 10 * tol), (branch, k, err)
             worst = max(worst, err)
     return worst
+
+
+def run_evaluate_testset(device):
+    """train.py:234-329 for args.model 'joint_embedding' / 'gesture_autoencoder': metrics from the device accumulators vs the oracle."""
+    import ae_checks
+    from model.embedding_net import EmbeddingNet
+    from model.embedding_space_evaluator import EmbeddingSpaceEvaluator
+    from oracle import embed_train_oracle as EO
+    from train_eval.evaluate import evaluate_testset
+    cfg, args, net, opt = build(device)
+    args.model = 'joint_embedding'
+    batches = []
+    for i in range(2):
+        inp = synth.make_inputs(cfg, 6, seed=95 + i)
+        batches.append((None, None, inp['in_text'], None, inp['target'], inp['in_audio'], None, None))
+    enet = EmbeddingNet(None, cfg.pose_dim, cfg.n_poses, None, None, None, 'pose')
+    enet.load_state_dict(synth.embedding_net_state_dict(cfg), strict=True)
+    ev = EmbeddingSpaceEvaluator.from_net(enet, cfg.n_pre_poses, torch.device(device))
+    net.train()
+    ret = evaluate_testset(batches, net, None, ev, args)
+    assert set(ret) == {'loss', 'joint_mae', 'frechet', 'feat_dist'} and net.training and ev.get_no_of_samples() == 2
+    assert all(np.isfinite(v) for v in ret.values()) and ret['loss'] > 0 and ret['joint_mae'] > 0
+    # the auto-encoder: loss only
+    cfg2, aenet, _ = ae_checks.build(device)
+    a2 = argparse.Namespace(model='gesture_autoencoder', n_pre_poses=cfg.n_pre_poses)
+    ret = evaluate_testset(batches, aenet, None, None, a2)
+    sd = synth.embedding_net_state_dict(cfg)
+    want = np.mean([EO.eval_embed_oracle(sd, b[4])[0] for b in batches])
+    assert set(ret) == {'loss', 'joint_mae'} and ret['joint_mae'] == 0.0
+    assert abs(ret['loss'] - want) < 2e-5 * want, (ret['loss'], want)

@@ -71,3 +71,7 @@ def test_noise_is_drawn_on_the_device_and_cpu_tensors_are_refused(dev, tf32):
     assert torch.equal(c, d)                                                 # the pose branch is deterministic
     with pytest.raises(_lib.TgError):
         train_iter_embed(args, 0, data['in_text'].cpu(), data['in_audio'].cpu(), data['target'].cpu(), net.train(), opt, mode='pose')
+
+
+def test_evaluate_testset_joint_embedding_and_autoencoder(dev, fp32):
+    joint_checks.run_evaluate_testset(dev)

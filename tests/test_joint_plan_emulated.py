@@ -31,3 +31,7 @@ def test_train_iter_embed_speech_then_pose(emu):
 
 def test_all_dropout_masks_vs_fp64_oracle(emu):
     joint_checks.run_batch_vs_fp64_oracle(CPU, Bn=4)
+
+
+def test_evaluate_testset_joint_embedding_and_autoencoder(emu):
+    joint_checks.run_evaluate_testset(CPU)
