@@ -28,13 +28,28 @@ def _unwrap(m):
     return m.module if isinstance(m, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel)) else m
 
 
-def _enqueue(eng, optim, target, use_diff, weight, acc, host_step):
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _allreduce(arena):
+    """Data parallel (one process per GPU, train.py:93-96 wraps every model family in nn.DataParallel): sum the flat gradient arena over
+    the ranks (NCCL; gloo in the CPU tests); the mean is taken inside Adam (grad_scale = 1/world).  BatchNorm statistics stay per rank,
+    like DataParallel's per-replica statistics."""
+    from train_eval.train_gan import _allreduce_grads
+    _allreduce_grads(arena)
+
+
+def _enqueue(eng, optim, target, use_diff, weight, acc, host_step, world=1):
     eng.arena.zero_grad()                                   # optim.zero_grad(), train_joint_embed.py:9
     _, _, recon = eng.forward(target, training=True)        # :17-19
     acc.zero_()
     d_rec = eng.loss(recon, target, use_diff, weight, acc)  # :21-29,46
     eng.backward(d_rec)                                     # :48
-    eng.arena.adam_step(optim, 1.0, host_step=host_step)    # :49
+    if world > 1:
+        _allreduce(eng.arena)
+    eng.arena.adam_step(optim, 1.0 / world, host_step=host_step)    # :49
 
 
 def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> float:
@@ -50,7 +65,8 @@ def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> flo
     target = target_data.detach().contiguous().float()
     eng = net_.train_engine().ensure(dev)
     acc = eng.ws.get('ae.acc', (2,), torch.float64)
-    use_graph = config.graphs() and not _lib.TRACE_ONLY and torch.cuda.is_available()
+    world = _world()
+    use_graph = config.graphs() and not _lib.TRACE_ONLY and torch.cuda.is_available() and world == 1    # the collective runs eagerly
     done = False
     if use_graph:
         g = optim.param_groups[0]
@@ -80,7 +96,7 @@ def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> flo
                 eng.arena.note_steps(1)
                 done = True
     if not done:
-        _enqueue(eng, optim, target, use_diff, weight, acc, host_step=True)
+        _enqueue(eng, optim, target, use_diff, weight, acc, host_step=True, world=world)
     return float(acc.cpu()[0])
 
 
@@ -90,6 +106,11 @@ def _resolve_mode(net_, mode):
         mode = net_.mode
     if mode == 'random':
         mode = 'speech' if random.random() > 0.5 else 'pose'
+        if _world() > 1:                                                        # every rank must decode (and all-reduce) the same branch
+            import torch.distributed as dist
+            pick = [mode]
+            dist.broadcast_object_list(pick, src=0)
+            mode = pick[0]
     assert mode in ('speech', 'pose'), mode
     return mode
 
@@ -114,8 +135,11 @@ def joint_step(args, net, optim, in_text, in_audio, target_data, mode) -> float:
     acc = eng.ws.get('jd.acc', (2,), torch.float64)
     acc.zero_()
     eng.backward(eng.loss(r['out'], target, acc))                               # :21-29,46-48
+    world = _world()
     for a in ((eng.a_ctx if branch == 'speech' else eng.a_pose), eng.a_dec):    # :49
-        a.adam_step(optim, 1.0, host_step=True)
+        if world > 1:
+            _allreduce(a)
+        a.adam_step(optim, 1.0 / world, host_step=True)
     return float(acc.cpu()[0])
 
 

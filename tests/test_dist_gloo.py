@@ -161,3 +161,88 @@ def test_data_parallel_train_iter_gan_world2():
     for rank, r in res:
         assert r['ok_0'] and r['ok_11'], (rank, r)
         assert r['calls_0'] == 1 and r['calls_11'] == 2, r          # warm-up: generator Adam only; afterwards D and G
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The embedding-model trainers under data parallelism, world 2 (plans on the emulator, gradients over gloo)
+# ----------------------------------------------------------------------------------------------------------------------
+def _embed_dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'gesture-generation-from-trimodal-context_b200'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(4)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import random
+        import ae_checks
+        import cabi_emulator
+        import joint_checks
+        import train_feature_extractor as tfx
+        from oracle import embed_train_oracle as EO
+        from oracle import synth
+        from oracle import trimodal_oracle as O
+        from tgb200 import config
+        from train_eval.train_joint_embed import train_iter_embed
+        config.set_mode('fp32'); config.set_graphs(False)
+        res = {}
+        with cabi_emulator.installed():
+            # ---- auto-encoder: update == Adam on the mean over ranks of the rank-local oracle gradients; replicas identical
+            cfg, net, opt = ae_checks.build(torch.device('cpu'))
+            net.train()
+            tgt = synth.make_inputs(cfg, 8, seed=33)['target'][rank * 4:(rank + 1) * 4].contiguous()
+            ret = tfx.train_iter(None, 0, tgt, net, opt)
+            sd0 = synth.embedding_net_state_dict(cfg)
+            want = EO.train_iter_ae_oracle(sd0, synth.zeros_like_opt(sd0), 1, tgt, 5e-4, True)
+            ok = abs(ret['loss'] - want['loss']) < 2e-5 * abs(want['loss'])          # the logged loss is rank-local
+            sd = net.state_dict()
+            worst = 0.0
+            for k, gr in want['grads'].items():
+                if k in EO.UNUSED_PARAMS:
+                    continue
+                g = gr.detach().clone()
+                dist.all_reduce(g)
+                g /= world
+                p, _, _ = O.adam_step(sd0[k], g, torch.zeros_like(g), torch.zeros_like(g), 1, 5e-4)
+                d = (sd[k] - p).abs()
+                ok = ok and d.max().item() <= 2.2 * 5e-4 + 1e-6
+                if k not in EO.ZERO_GRAD_PARAMS:
+                    worst = max(worst, d.median().item())
+            ok = ok and worst < 2e-6
+            flat = net.train_engine().arena.flat.clone(); ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            res['ae'] = bool(ok and torch.equal(flat, ref))
+            # ---- joint embedding, mode='random': ranks flip different coins, rank 0's choice is broadcast; replicas stay identical
+            random.seed(100 + rank)
+            cfg, args, jnet, jopt = joint_checks.build(torch.device('cpu'))
+            jnet.train()
+            same = True
+            for step in range(3):
+                data = synth.make_inputs(cfg, 4, seed=40 + step)
+                data = {k: v[rank * 2:(rank + 1) * 2].contiguous() for k, v in data.items()}
+                r = train_iter_embed(args, 0, data['in_text'], data['in_audio'], data['target'], jnet, jopt, mode='random')
+                same = same and r['loss'] == r['loss']
+                for a in jnet.joint_engine().arenas():
+                    flat = a.flat.clone(); ref = flat.clone()
+                    dist.broadcast(ref, src=0)
+                    same = same and torch.equal(flat, ref)
+            res['joint'] = bool(same)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_embedding_trainers_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_embed_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r['ae'] and r['joint'], (rank, r)
