@@ -16,9 +16,9 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import config, ops
 from .arena import ParamArena
-from .engine import BN_EPS, BN_MOM, Workspace, _conv_out
+from .engine import BN_EPS, BN_MOM, S_WAVW, S_WGRAD, GeneratorEngine, GruPlan, Workspace, _conv_out, gru_arena_order, side
 
 ENC_CONVS = ((3, 1), (3, 1), (4, 2))          # ConvNormRelu x3: (kernel, stride), embedding_net.py:20-26,46-48
 ENC_SLOPE = DEC_SLOPE = 0.2                   # nn.LeakyReLU(0.2) :31,208,211 ; nn.LeakyReLU(True) == slope 1.0 == identity :57,60,203
@@ -304,12 +304,12 @@ class _ContextHost(_Sub):
     """ContextEncoder.text_encoder / .audio_encoder are the generator's TextEncoderTCN / WavEncoder (embedding_net.py:225-226) and carry
     the same parameter names relative to their parent, so the generator's launch plans for them (tgb200.engine.GeneratorEngine: causal
     two-tap tensor-core GEMMs, window-view strided convolutions, BatchNorm prologues, their backward) run on this arena unchanged."""
-    from .engine import GeneratorEngine as _GE
-    WAV = _GE.WAV
-    wav_fast, wav_forward, wav_backward = _GE.wav_fast, _GE.wav_forward, _GE.wav_backward
-    text_forward, text_backward, make_masks = _GE.text_forward, _GE.text_backward, _GE.make_masks
-    _tcn_conv, _tcn_wgrad, _tcn_dgrad = staticmethod(_GE._tcn_conv), staticmethod(_GE._tcn_wgrad), staticmethod(_GE._tcn_dgrad)
-    del _GE
+    WAV = GeneratorEngine.WAV
+    wav_fast, wav_forward, wav_backward = GeneratorEngine.wav_fast, GeneratorEngine.wav_forward, GeneratorEngine.wav_backward
+    text_forward, text_backward, make_masks = GeneratorEngine.text_forward, GeneratorEngine.text_backward, GeneratorEngine.make_masks
+    _tcn_conv = staticmethod(GeneratorEngine._tcn_conv)
+    _tcn_wgrad = staticmethod(GeneratorEngine._tcn_wgrad)
+    _tcn_dgrad = staticmethod(GeneratorEngine._tcn_dgrad)
 
     def __init__(self, arena, ws, bufs, module):
         super().__init__(arena, ws, bufs)
@@ -324,7 +324,6 @@ class _ContextHost(_Sub):
 
     def prep(self):
         """Per-optimiser-step derived weights: weight-normed TCN filters (tap-major, + per-tap transposes in fast mode)."""
-        from . import config
         ws = self.ws
         for i in range(self.n_tcn):
             for j in (1, 2):
@@ -350,7 +349,6 @@ class JointEmbeddingEngine:
 
     def __init__(self, module):
         self.m = module
-        from .engine import gru_arena_order
         self.a_ctx = ParamArena(module.context_encoder, partial=True)
         self.a_pose = ParamArena(module.pose_encoder, partial=True)
         self.a_dec = ParamArena(module.decoder, gru_arena_order([n for n, _ in module.decoder.named_parameters()]), partial=True)
@@ -363,7 +361,6 @@ class JointEmbeddingEngine:
         return self.a_ctx, self.a_pose, self.a_dec
 
     def ensure(self, device):
-        from .engine import GruPlan
         rebuilt = not all(a.is_current() for a in self.arenas())
         for a in self.arenas():
             a.ensure(device)
@@ -381,7 +378,6 @@ class JointEmbeddingEngine:
         return self
 
     def _tc(self):
-        from . import config
         return config.fast()
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -497,7 +493,6 @@ class JointEmbeddingEngine:
 
     def backward(self, d_rec):
         """Accumulates the gradients of the decoder and of the branch that produced the latent into their (caller-zeroed) arenas."""
-        from .engine import S_WAVW, S_WGRAD, side
         ws, d, st, T, D = self.ws, self.dec, self.st, self.T, self.D
         assert st['training']
         B = st['B']
