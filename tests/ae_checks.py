@@ -120,6 +120,6 @@ def run_full_batch_vs_fp64_oracle(device, B=128, steps=3, tol=1e-4):
                 continue
             worst = max(worst, rel_l2(p.grad, want['grads'][k]))
         # from the second step on the two trajectories differ by the +-lr walk of the zero-gradient biases (absorbed by BatchNorm)
-        assert worst < (tol if step == 1 else 50 * tol), (step, worst)
+        assert worst < (tol if step == 1 else 100 * tol), (step, worst)
         sd, o_opt = {k: (v.float() if v.is_floating_point() else v) for k, v in want['sd'].items()}, want['opt']
     return worst

@@ -96,10 +96,11 @@ def test_train_forward_and_eval_embed_vs_reference_golden(dev):
 
 
 def test_batch128_steps_vs_fp64_oracle_with_graph_replay(dev):
-    """Five consecutive batch-128 steps: two eager, then the captured CUDA graph (capture + 2 replays), each vs the float64 oracle."""
+    """Four consecutive batch-128 steps: two eager, then the captured CUDA graph (capture + replay, then a second replay), each vs the
+    float64 oracle (step 1 at 1e-4; later steps only loosely: the trajectories separate by the +-lr walk of round-off gradients)."""
     from tgb200 import config
     assert config.graphs()
-    ae_checks.run_full_batch_vs_fp64_oracle(dev, B=128, steps=5)
+    ae_checks.run_full_batch_vs_fp64_oracle(dev, B=128, steps=4)
 
 
 def test_graph_replay_matches_eager(dev):
