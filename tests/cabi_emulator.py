@@ -118,6 +118,7 @@ class EmuLib:
     # ---------------------------------------------------------------------------------------- BatchNorm (csrc/elementwise.cu)
     def tg_col_stats_f64(self, x, ld, M, C, sums, stream):
         self.calls.append('tg_col_stats_f64')
+        assert 0 < C <= 256 and M > 0, 'TG_REQUIRE of tg_col_stats_f64'
         X = _arr(x, (M - 1) * ld + C)
         o = np.arange(M)[:, None] * ld + np.arange(C)[None, :]
         v = X[o].astype(np.float64)
@@ -168,6 +169,7 @@ class EmuLib:
 
     def tg_bn_bwd_reduce(self, dy, x, M, C, mean, rstd, scale, shift, slope, sums, stream):
         self.calls.append('tg_bn_bwd_reduce')
+        assert 0 < C <= 256, 'TG_REQUIRE of tg_bn_bwd_reduce'
         X, dz = self._dz(dy, x, M, C, scale, shift, slope)
         s = _arr(sums, 2 * C, ctypes.c_double)
         s[:C] += dz.sum(0)
@@ -196,6 +198,7 @@ class EmuLib:
 
     def tg_adam_flat(self, p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev, stream):
         self.calls.append('tg_adam_flat')
+        assert all(q % 16 == 0 for q in (p, g, m, v)), 'TG_REQUIRE of tg_adam_flat: 16-byte aligned arenas'
         step = float(_arr(step_dev, 1, ctypes.c_longlong)[0])
         f = np.float32
         bc1 = f(1.0 - math.pow(float(f(b1)), step)); bc2s = f(math.sqrt(1.0 - math.pow(float(f(b2)), step)))
@@ -364,6 +367,7 @@ class EmuLib:
 
     def tg_conv1_direct_f32(self, x, w, bias, y, B, Tin, Tout, N, taps, stride, pad, stream):
         self.calls.append('tg_conv1_direct_f32')
+        assert 0 < N <= 32 and taps <= 32, 'TG_REQUIRE of tg_conv1_direct_f32'
         X = _arr(x, B * Tin).reshape(B, Tin).astype(np.float64)
         W = _arr(w, N * taps).reshape(N, taps).astype(np.float64)
         ti = (np.arange(Tout) * stride - pad)[:, None] + np.arange(taps)[None, :]
@@ -388,6 +392,7 @@ class EmuLib:
 
     def tg_gru_layer_fwd(self, gi, whhT_f, whhT_r, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream):
         self.calls.append('tg_gru_layer_fwd')
+        assert 0 < H <= 384 and B > 0 and T > 0, 'TG_REQUIRE of tg_gru_layer_fwd'
         GI = _arr(gi, B * T * 6 * H).reshape(B, T, 6 * H).astype(np.float64)
         OUT = _arr(out, B * T * 2 * H).reshape(B, T, 2 * H)
         S = _arr(saved, 3 * qstride + B * T * 2 * H) if saved else None
@@ -482,6 +487,7 @@ class EmuLib:
     # ---------------------------------------------------------------------------------------- FGD statistics (csrc/elementwise.cu)
     def tg_feature_stats_f64(self, feat, n, F, acc, stream):
         self.calls.append('tg_feature_stats_f64')
+        assert 0 < F <= 64 and n > 0, 'TG_REQUIRE of tg_feature_stats_f64'
         X = _arr(feat, n * F).reshape(n, F).astype(np.float64)
         a = _arr(acc, 1 + F + F * F, ctypes.c_double)
         a[0] += n; a[1:1 + F] += X.sum(0); a[1 + F:] += (X.T @ X).reshape(-1)
@@ -648,6 +654,7 @@ class EmuLib:
 
     def tg_philox_randperm(self, out, n, seed, offset_dev, stream_id, stream):
         self.calls.append('tg_philox_randperm')
+        assert 0 < n <= 2048, 'TG_REQUIRE of tg_philox_randperm'
         c0, c1, _, _ = self._philox(seed, stream_id, n, offset_dev)
         keys = (c0 << np.uint64(32)) | (c1 & np.uint64(0xFFFFF000)) | np.arange(n, dtype=np.uint64)
         _arr(out, n, ctypes.c_longlong)[:] = (np.sort(keys) & np.uint64(0xFFF)).astype(np.int64)
@@ -672,6 +679,10 @@ class EmuLib:
     def tg_gemm_tf32(self, pref, stream):
         p = pref._obj
         self.calls.append('tg_gemm_tf32')
+        # TMA descriptors: 16-byte aligned bases and pitches; epilogue activations none / relu / leaky-relu(0..1); clip-mode contract
+        assert p.A % 16 == 0 and p.Bw % 16 == 0 and p.lda % 4 == 0 and p.ldb % 4 == 0, 'tg_gemm_tf32: TMA alignment'
+        assert p.taps in (1, 2) and 0 <= p.act1 <= 2 and p.act2 in (0, 1) and (p.act1 != 2 or 0.0 <= p.slope1 <= 1.0)
+        assert p.clip_rows == 0 or (p.taps == 1 and p.M % p.clip_rows == 0 and p.a_clip_pitch > 0)
         M, N, K = p.M, p.N, p.K
         m = np.arange(M); k = np.arange(K)
         Bw = _arr(p.Bw, (p.taps * N - 1) * p.ldb + K)
@@ -709,6 +720,8 @@ class EmuLib:
     def tg_wgrad_tf32(self, pref, stream):
         p = pref._obj
         self.calls.append('tg_wgrad_tf32')
+        assert p.G % 16 == 0 and p.X % 16 == 0 and p.ldg % 4 == 0 and p.ldx % 4 == 0, 'tg_wgrad_tf32: TMA alignment'
+        assert p.shift == 0 or p.B == 1 or p.x_clip_pitch > 0 or p.T <= 40, 'TG_REQUIRE of tg_wgrad_tf32: shifted taps need T <= 40'
         B, T, N, C = p.B, p.T, p.N, p.Cin
         if p.dbias:
             self.tg_col_sum_f32(p.G, p.ldg, B * T, N, p.dbias, stream)
@@ -733,6 +746,7 @@ class EmuLib:
 
     def tg_gru_layer_fwd_tf32(self, gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream):
         """Weight layout swapped w.r.t. the fp32 entry: weight_hh as stored [3H,H]."""
+        assert 32 <= H <= 384 and H % 4 == 0 and whh_f % 16 == 0 and whh_r % 16 == 0 and out % 16 == 0, 'tg_gru_layer_fwd_tf32: H range / TMA alignment'
         tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(3 * H, H).T) for w in (whh_f, whh_r)]
         rc = self.tg_gru_layer_fwd(gi, tr[0].ctypes.data, tr[1].ctypes.data, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream)
         self.calls[-1] = 'tg_gru_layer_fwd_tf32'
@@ -740,6 +754,7 @@ class EmuLib:
 
     def tg_gru_layer_bwd_tf32(self, dout, out, saved, qstride, whhT_f, whhT_r, dgi, dgh, partial, sync, B, T, H, stream):
         """Takes the transposed recurrent weights [H,3H]."""
+        assert 32 <= H <= 384 and H % 4 == 0 and whhT_f % 16 == 0 and whhT_r % 16 == 0, 'tg_gru_layer_bwd_tf32: H range / TMA alignment'
         tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(H, 3 * H).T) for w in (whhT_f, whhT_r)]
         rc = self.tg_gru_layer_bwd(dout, out, saved, qstride, tr[0].ctypes.data, tr[1].ctypes.data, dgi, dgh, partial, sync, B, T, H, stream)
         self.calls[-1] = 'tg_gru_layer_bwd_tf32'
@@ -761,6 +776,7 @@ class EmuLib:
 
     def tg_col2im(self, col, da, B, Tin, Tout, Cin, k, stride, stream):
         self.calls.append('tg_col2im')
+        assert Cin % 4 == 0 and col % 16 == 0 and da % 16 == 0, 'TG_REQUIRE of tg_col2im'
         COL = _arr(col, B * Tout * k * Cin).reshape(B, Tout, k, Cin).astype(np.float64)
         DA = np.zeros((B, Tin, Cin))
         for t in range(Tout):
@@ -773,6 +789,7 @@ class EmuLib:
 
     def tg_conv1_wgrad(self, x, dy, dW, dbias, B, Tin, Tout, N, taps, stride, pad, stream):
         self.calls.append('tg_conv1_wgrad')
+        assert N == 16 and 1 <= taps <= 15 and 1 <= stride <= 8 and dy % 16 == 0, 'TG_REQUIRE of tg_conv1_wgrad'
         X = _arr(x, B * Tin).reshape(B, Tin).astype(np.float64)
         DY = _arr(dy, B * Tout * N).reshape(B, Tout, N).astype(np.float64)
         ti = (np.arange(Tout) * stride - pad)[:, None] + np.arange(taps)[None, :]
