@@ -71,3 +71,10 @@ def test_fast_mode_plans(emu_fast):
     GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11)
     for sym in ('tg_gemm_tf32', 'tg_wgrad_tf32', 'tg_gru_layer_fwd_tf32', 'tg_gru_layer_bwd_tf32', 'tg_col2im', 'tg_conv1_wgrad'):
         assert sym in emu_fast.calls, sym
+
+
+@pytest.mark.parametrize('B', [1, 5])
+def test_small_and_odd_batches(emu_fast, B):
+    """Edge cases of the launch plan: a single clip (every 'batch' statistic is over one clip's frames) and a batch that is not a multiple
+    of any tile size, full G+D iteration with every dropout mask vs the fp64 oracle."""
+    GP.test_train_iter_full_size_vs_oracle(CPU, B, 11)
