@@ -72,6 +72,8 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+                # ... nor the test-only NumPy restatement of the C ABI (tests/cabi_emulator.py), nor anything else under tests/
+                assert 'cabi_emulator' not in src and 'import tests' not in src and 'from tests' not in src, f
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -81,6 +83,17 @@ def test_no_cpu_fallback_without_cuda():
     from train_eval.train_gan import train_iter_gan
     with pytest.raises(_lib.TgError):
         train_iter_gan(None, 0, None, None, torch.zeros(1, 34, 27), None, None, None, None, None)
+    # the embedding-model step functions and modules refuse CPU tensors as well
+    import train_feature_extractor as tfx
+    from model.embedding_net import EmbeddingNet
+    from train_eval.train_joint_embed import eval_embed, train_iter_embed
+    net = EmbeddingNet(None, 27, 34, None, None, None, 'pose').train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    x = torch.zeros(2, 34, 27)
+    for call in (lambda: tfx.train_iter(None, 0, x, net, opt), lambda: train_iter_embed(None, 0, None, None, x, net, opt),
+                 lambda: eval_embed(None, None, None, x, net), lambda: net(None, None, None, x, None)):
+        with pytest.raises(_lib.TgError):
+            call()
 
 
 def test_seq2seq_module_keys_and_no_cpu_fallback():
