@@ -150,3 +150,35 @@ print('ok', sum(c.values()))
     r = subprocess.run([sys.executable, '-c', code % (root, os.path.join(root, 'gesture-generation-from-trimodal-context_b200'))], env=env,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """the reference checkpoint {'args','epoch','lang_model','speaker_model','pose_dim','gen_dict','dis_dict'} (train.py:153-157)
+    written from our modules loads the way utils/train_utils.py:166-183 loads it: unpickle (model.vocab.Vocab resolves to our class),
+    train.init_model(...), load_state_dict(strict)."""
+    import argparse
+    import train
+    from model import vocab
+    cfg = golden_cfg()
+    lang = vocab.Vocab('words')
+    for i in range(cfg.n_words - lang.n_words):
+        lang.index_word('w%d' % i)
+    lang.word_embedding_weights = None
+    spk = vocab.Vocab('vid', insert_default_tokens=False)
+    for i in range(cfg.n_speakers - 1):
+        spk.index_word('spk%d' % i)
+    args = argparse.Namespace(model='multimodal_context', n_poses=cfg.n_poses, n_pre_poses=cfg.n_pre_poses, wordembed_dim=cfg.wordembed_dim,
+                              hidden_size=cfg.hidden_size, n_layers=cfg.n_layers, dropout_prob=cfg.dropout_prob, freeze_wordembed=False,
+                              z_type='speaker', input_context='both')
+    G, D, _ = train.init_model(args, lang, spk, cfg.pose_dim, torch.device('cpu'))
+    path = str(tmp_path / 'ckpt.bin')
+    torch.save({'args': args, 'epoch': 7, 'lang_model': lang, 'speaker_model': spk, 'pose_dim': cfg.pose_dim,
+                'gen_dict': G.state_dict(), 'dis_dict': D.state_dict()}, path)
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(ck) == {'args', 'epoch', 'lang_model', 'speaker_model', 'pose_dim', 'gen_dict', 'dis_dict'} and ck['epoch'] == 7
+    assert isinstance(ck['lang_model'], vocab.Vocab) and ck['speaker_model'].n_words == spk.n_words
+    G2, D2, _ = train.init_model(ck['args'], ck['lang_model'], ck['speaker_model'], ck['pose_dim'], torch.device('cpu'))
+    G2.load_state_dict(ck['gen_dict'])                       # strict=True by default, train_utils.py:178
+    D2.load_state_dict(ck['dis_dict'])
+    assert all(torch.equal(a, b) for a, b in zip(G.state_dict().values(), G2.state_dict().values()))
+    assert G2.z_obj is ck['speaker_model']                   # what utils.train_utils.get_speaker_model(generator) returns (:152-164)
