@@ -3,7 +3,7 @@
 PoseEncoderConv + PoseDecoderGRU, `joint_step` below).  Same signatures, same returned values.
 
 One optimiser step = the train-mode forward, the L1 reconstruction loss (value + gradient in one kernel), the hand-derived
-backward and one flat Adam launch (tgb200.embed_engine.AutoEncoderTrainEngine): ~75 launches of a few microseconds each, no host
+backward and one flat Adam launch (tgb200.embed_engine.AutoEncoderTrainEngine): 82 launches of a few microseconds each, no host
 synchronisation until the single loss read-back.  After two eager steps the sequence is captured into a CUDA graph per
 (net, optimiser, batch shape) and replayed - the step is launch-latency bound, so this is where the time goes.
 train_feature_extractor.train_iter (which adds the frame-difference term) shares `ae_step`."""
@@ -57,7 +57,7 @@ def ae_step(net, optim, target_data, use_diff: bool, weight: float = 1.0) -> flo
     _lib.require_cuda()
     net_ = _unwrap(net)
     if getattr(net_, 'mode', None) != 'pose':
-        raise NotImplementedError("only the pose auto-encoder (EmbeddingNet(mode='pose')) is built; the joint-embedding model is not")
+        raise ValueError("ae_step trains the pose auto-encoder (EmbeddingNet(mode='pose')); the joint-embedding model goes through joint_step")
     if not target_data.is_cuda and not _lib.TRACE_ONLY:
         raise _lib.TgError('the auto-encoder step runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
     assert net_.training, 'the auto-encoder step expects net.train() (BatchNorm batch statistics)'
