@@ -35,11 +35,24 @@ def _act(v, act, slope):
     return v
 
 
-class EmuLib:
-    """Stands in for the ctypes.CDLL object returned by tgb200._lib.load()."""
+def _tf32(a, mode):
+    """fp32 -> TF32 operand (10-bit mantissa) as float64: 'trunc' drops the low 13 mantissa bits (what a tensor core fed raw fp32 words
+    does), 'rna' rounds to nearest (ties away); None leaves the value alone."""
+    if mode is None:
+        return a.astype(np.float64)
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    if mode == 'rna':
+        u = u + np.uint32(0x1000)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
 
-    def __init__(self):
+
+class EmuLib:
+    """Stands in for the ctypes.CDLL object returned by tgb200._lib.load().  tf32_round: None (default: the tensor-core entries compute
+    on the exact fp32 operands) or 'trunc' / 'rna' (their operands are first cut to TF32, to PREDICT the fast mode's error on CPU)."""
+
+    def __init__(self, tf32_round=None):
         self.calls = []
+        self.tf32_round = tf32_round
 
     def __getattr__(self, name):
         if name.startswith('tg_'):
@@ -398,12 +411,13 @@ class EmuLib:
         S = _arr(saved, 3 * qstride + B * T * 2 * H) if saved else None
         rows = np.arange(B) * T
         for d, (wT, bh) in enumerate(((whhT_f, bhh_f), (whhT_r, bhh_r))):
-            WT = _arr(wT, H * 3 * H).reshape(H, 3 * H).astype(np.float64)
+            rnd = getattr(self, '_gru_round', None)
+            WT = _tf32(_arr(wT, H * 3 * H).reshape(H, 3 * H), rnd)
             bhv = _arr(bh, 3 * H).astype(np.float64)
             h = np.zeros((B, H))
             for s in range(T):
                 t = s if d == 0 else T - 1 - s
-                gh = h @ WT + bhv
+                gh = (_tf32(h.astype(np.float32), rnd) if rnd else h) @ WT + bhv
                 g = GI[:, t, d * 3 * H:(d + 1) * 3 * H]
                 r = self._sig(g[:, :H] + gh[:, :H]); z = self._sig(g[:, H:2 * H] + gh[:, H:2 * H])
                 n = np.tanh(g[:, 2 * H:] + r * gh[:, 2 * H:])
@@ -423,7 +437,8 @@ class EmuLib:
         DGI = _arr(dgi, B * T * 6 * H).reshape(B, T, 6 * H); DGH = _arr(dgh, B * T * 6 * H).reshape(B, T, 6 * H)
         rows = np.arange(B) * T
         for d, wp in enumerate((whh_f, whh_r)):
-            W = _arr(wp, 3 * H * H).reshape(3 * H, H).astype(np.float64)
+            rnd = getattr(self, '_gru_round', None)
+            W = _tf32(_arr(wp, 3 * H * H).reshape(3 * H, H), rnd)
             carry = np.zeros((B, H))
             for s in range(T):
                 t = T - 1 - s if d == 0 else s
@@ -439,7 +454,7 @@ class EmuLib:
                 DGI[:, t, d * 3 * H:(d + 1) * 3 * H] = np.concatenate([drp, dzp, dn], axis=1).astype(np.float32)
                 gh = np.concatenate([drp, dzp, dnr], axis=1)
                 DGH[:, t, d * 3 * H:(d + 1) * 3 * H] = gh.astype(np.float32)
-                carry = dh * z + gh @ W
+                carry = dh * z + (_tf32(gh.astype(np.float32), rnd) if rnd else gh) @ W
         return 0
 
     # ---------------------------------------------------------------------------------------- losses (csrc/losses.cu)
@@ -700,9 +715,9 @@ class EmuLib:
                     t = m % p.T
                     ok &= (t + shift >= 0) & (t + shift < p.T)
                 off = np.where(ok, rows, 0)[:, None] * p.lda + k[None, :]
-            A = np.where(ok[:, None], _arr(p.A, off.max() + 1)[off].astype(np.float64), 0.0)
+            A = np.where(ok[:, None], _tf32(_arr(p.A, off.max() + 1)[off], self.tf32_round), 0.0)
             wo = (tap * N + np.arange(N))[:, None] * p.ldb + k[None, :]
-            acc += A @ Bw[wo].astype(np.float64).T
+            acc += A @ _tf32(Bw[wo], self.tf32_round).T
         v = self._epilogue(p, acc, m, N)
         yo = m[:, None] * p.ldc + np.arange(N)[None, :]
         Y = _arr(p.C, yo.max() + 1)
@@ -727,12 +742,12 @@ class EmuLib:
             self.tg_col_sum_f32(p.G, p.ldg, B * T, N, p.dbias, stream)
         b = np.repeat(np.arange(B), T); t = np.tile(np.arange(T), B)
         go = (b * T + t)[:, None] * p.ldg + np.arange(N)[None, :]
-        G = _arr(p.G, go.max() + 1)[go].astype(np.float64)
+        G = _tf32(_arr(p.G, go.max() + 1)[go], self.tf32_round)
         ts = t + p.shift
         ok = (ts >= 0) & (ts < T)
         base = b * p.x_clip_pitch + np.where(ok, ts, 0) * p.ldx if p.x_clip_pitch > 0 else (b * T + np.where(ok, ts, 0)) * p.ldx
         xo = base[:, None] + np.arange(C)[None, :]
-        X = np.where(ok[:, None], _arr(p.X, xo.max() + 1)[xo].astype(np.float64), 0.0)
+        X = np.where(ok[:, None], _tf32(_arr(p.X, xo.max() + 1)[xo], self.tf32_round), 0.0)
         wo = np.arange(N)[:, None] * p.ldw + np.arange(C)[None, :]
         dW = _arr(p.dW, wo.max() + 1)
         dW[wo] = (dW[wo] + G.T @ X).astype(np.float32)
@@ -748,7 +763,11 @@ class EmuLib:
         """Weight layout swapped w.r.t. the fp32 entry: weight_hh as stored [3H,H]."""
         assert 32 <= H <= 384 and H % 4 == 0 and whh_f % 16 == 0 and whh_r % 16 == 0 and out % 16 == 0, 'tg_gru_layer_fwd_tf32: H range / TMA alignment'
         tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(3 * H, H).T) for w in (whh_f, whh_r)]
-        rc = self.tg_gru_layer_fwd(gi, tr[0].ctypes.data, tr[1].ctypes.data, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream)
+        self._gru_round = self.tf32_round
+        try:
+            rc = self.tg_gru_layer_fwd(gi, tr[0].ctypes.data, tr[1].ctypes.data, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream)
+        finally:
+            self._gru_round = None
         self.calls[-1] = 'tg_gru_layer_fwd_tf32'
         return rc
 
@@ -756,7 +775,11 @@ class EmuLib:
         """Takes the transposed recurrent weights [H,3H]."""
         assert 32 <= H <= 384 and H % 4 == 0 and whhT_f % 16 == 0 and whhT_r % 16 == 0, 'tg_gru_layer_bwd_tf32: H range / TMA alignment'
         tr = [np.ascontiguousarray(_arr(w, 3 * H * H).reshape(H, 3 * H).T) for w in (whhT_f, whhT_r)]
-        rc = self.tg_gru_layer_bwd(dout, out, saved, qstride, tr[0].ctypes.data, tr[1].ctypes.data, dgi, dgh, partial, sync, B, T, H, stream)
+        self._gru_round = self.tf32_round
+        try:
+            rc = self.tg_gru_layer_bwd(dout, out, saved, qstride, tr[0].ctypes.data, tr[1].ctypes.data, dgi, dgh, partial, sync, B, T, H, stream)
+        finally:
+            self._gru_round = None
         self.calls[-1] = 'tg_gru_layer_bwd_tf32'
         return rc
 
@@ -804,11 +827,14 @@ class EmuLib:
 class installed:
     """Context manager: routes tgb200's C-ABI calls to an EmuLib and lets CPU tensors through (trace-mode plumbing)."""
 
+    def __init__(self, tf32_round=None):
+        self.tf32_round = tf32_round
+
     def __enter__(self):
         from tgb200 import _lib
         self._lib = _lib
         self._saved = (_lib._lib, _lib.TRACE_ONLY)
-        self.emu = EmuLib()
+        self.emu = EmuLib(self.tf32_round)
         _lib._lib, _lib.TRACE_ONLY = self.emu, True
         return self.emu
 
