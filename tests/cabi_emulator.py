@@ -41,6 +41,8 @@ def _tf32(a, mode):
     if mode is None:
         return a.astype(np.float64)
     u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    if mode == 'bf16':                        # what-if: bf16 operands (8-bit mantissa), round to nearest
+        return ((u + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
     if mode == 'rna':
         u = u + np.uint32(0x1000)
     return (u & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
