@@ -91,3 +91,34 @@ def test_fast_mode_error_budget_under_tf32_operand_truncation():
             GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 8, 11)       # asserts losses / poses <= 1e-2, worst gradient <= 5e-2
     finally:
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+@pytest.mark.parametrize('kw', [dict(n_layers=2), dict(hidden_size=128, wordembed_dim=128), dict(n_layers=3, hidden_size=64, wordembed_dim=64),
+                                dict(n_pre_poses=2)], ids=lambda kw: ','.join('%s=%s' % it for it in kw.items()))
+def test_other_hyper_parameters(emu_fast, kw):
+    """The plan is not hard-wired to config/multimodal_context.yml: other layer counts, hidden / embedding widths (the generator GRU then
+    takes the single-CTA or the tensor-core kernel family depending on H) and seed-pose counts, full G+D iteration vs the fp64 oracle."""
+    from gpu_util import build_ours, masks_to_ours
+    from conftest import rel_l2
+    from oracle import synth
+    from oracle import trimodal_oracle as O
+    from train_eval import train_gan as TG
+    cfg = O.HotPathConfig(n_words=300, n_speakers=12, **kw)
+    B, epoch = 3, 11
+    args, G, D, gsd, dsd = build_ours(cfg, CPU)
+    G.train(); D.train()
+    inp = synth.make_inputs(cfg, B, seed=3)
+    noise = synth.make_noise(cfg, B, seed=4, dropout=True)
+    ref = GP._oracle_step(cfg, epoch, gsd, dsd, inp, noise, CPU)
+    g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=list(noise.eps), perm=noise.perm, g_masks=[masks_to_ours(m, CPU) for m in noise.g_masks],
+                                 d_masks=[masks_to_ours(m, CPU) for m in noise.d_masks]))
+    ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+    assert set(ret) == set(ref['losses'])
+    for k, v in ret.items():
+        assert abs(v - ref['losses'][k]) <= 1e-5 * abs(ref['losses'][k]) + 1e-7, (k, v, ref['losses'][k])
+    for k, p in G.named_parameters():
+        r = ref['g_grads'][k]
+        if r.norm() > 1e-6:
+            assert rel_l2(p.grad, r) < 1e-4, k
