@@ -334,11 +334,13 @@ class Seq2SeqEngine:
                 if emb_p.requires_grad:
                     ops.embedding_scatter_add(dinp, ws['enc.idx'], None, self.G('encoder.embedding.weight'), B * Tm, E)
 
-    def clip_and_step(self, optim, max_norm, host_step=True):
-        """torch.nn.utils.clip_grad_norm_(parameters, max_norm) + optimizer.step() (train_seq2seq.py:48-49)."""
+    def clip_and_step(self, optim, max_norm, host_step=True, world=1):
+        """torch.nn.utils.clip_grad_norm_(parameters, max_norm) + optimizer.step() (train_seq2seq.py:48-49).  world > 1 (data parallel): the
+        arena holds the SUM of the ranks' gradients; the norm of their mean is |sum| / world, so the sum is clipped against max_norm * world
+        and the mean is taken inside Adam (grad_scale = 1 / world)."""
         ws = self.ws
         ss = ws.get('opt.sumsq', (1,), torch.float64)
         ss.zero_()
         ops.sumsq(self.arena.grad, self.arena.numel, ss)
-        ops.clip_scale(self.arena.grad, self.arena.numel, ss, max_norm)
-        self.arena.adam_step(optim, grad_scale=1.0, host_step=host_step)
+        ops.clip_scale(self.arena.grad, self.arena.numel, ss, max_norm * world)
+        self.arena.adam_step(optim, grad_scale=1.0 / world, host_step=host_step)

@@ -41,7 +41,12 @@ class _Slot:
         self.static = None
 
 
-def _enqueue(args, net, eng, optim, in_text, lens_dev, Tm, target, masks, loss_buf, host_step):
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _enqueue(args, net, eng, optim, in_text, lens_dev, Tm, target, masks, loss_buf, host_step, world=1):
     dev = target.device
     B = target.shape[0]
     eng.arena.zero_grad()
@@ -51,7 +56,10 @@ def _enqueue(args, net, eng, optim, in_text, lens_dev, Tm, target, masks, loss_b
     eng.forward(in_text, lens_dev, Tm, target, True, masks, save=True)
     loss_buf.zero_()
     eng.loss_backward(target, float(args.loss_regression_weight), float(args.loss_kld_weight), float(args.loss_reg_weight), loss_buf)
-    eng.clip_and_step(optim, _MAX_NORM, host_step=host_step)
+    if world > 1:                # data parallel (train.py:93-96): sum the flat gradient arena over the ranks (NCCL; gloo in the CPU tests)
+        from train_eval.train_gan import _allreduce_grads
+        _allreduce_grads(eng.arena)
+    eng.clip_and_step(optim, _MAX_NORM, host_step=host_step, world=world)
 
 
 def train_iter_seq2seq(args, epoch, in_text, in_lengths, target_poses, net, optim):
@@ -69,7 +77,8 @@ def train_iter_seq2seq(args, epoch, in_text, in_lengths, target_poses, net, opti
     eng = net_.engine().ensure(dev, 'train_%d_%d' % (B, Tm))
     ws = eng.ws
     loss_buf = ws.get('ti.loss', (1,), torch.float64)
-    use_graph = config.graphs() and masks is None and not _lib.TRACE_ONLY and torch.cuda.is_available()
+    world = _world()
+    use_graph = config.graphs() and masks is None and not _lib.TRACE_ONLY and torch.cuda.is_available() and world == 1   # the collective runs eagerly
     done = False
     if use_graph:
         g = optim.param_groups[0]
@@ -102,5 +111,5 @@ def train_iter_seq2seq(args, epoch, in_text, in_lengths, target_poses, net, opti
                 eng.arena.note_steps(1)
                 done = True
     if not done:
-        _enqueue(args, net_, eng, optim, in_text.contiguous(), lens_dev, Tm, target, masks, loss_buf, host_step=True)
+        _enqueue(args, net_, eng, optim, in_text.contiguous(), lens_dev, Tm, target, masks, loss_buf, host_step=True, world=world)
     return {'loss': float(loss_buf.cpu()[0])}

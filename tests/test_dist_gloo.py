@@ -167,6 +167,15 @@ def test_data_parallel_train_iter_gan_world2():
 # The embedding-model trainers under data parallelism, world 2 (plans on the emulator, gradients over gloo)
 # ----------------------------------------------------------------------------------------------------------------------
 def _embed_dp_worker(rank, world, port, q):
+    try:
+        _embed_dp_worker_body(rank, world, port, q)
+    except BaseException as exc:          # report instead of leaving the peer blocked in a collective until the timeout
+        import traceback
+        q.put((rank, {'error': ''.join(traceback.format_exception(type(exc), exc, exc.__traceback__))[-1500:]}))
+        os._exit(1)
+
+
+def _embed_dp_worker_body(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'gesture-generation-from-trimodal-context_b200'))
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -228,6 +237,41 @@ def _embed_dp_worker(rank, world, port, q):
                     dist.broadcast(ref, src=0)
                     same = same and torch.equal(flat, ref)
             res['joint'] = bool(same)
+            # ---- seq2seq: clip_grad_norm_ acts on the MEAN gradient: update == Adam(clip(mean over ranks of the rank-local raw gradients))
+            import test_gpu_seq2seq as GS
+            from oracle import seq2seq_oracle as S
+            from train_eval.train_seq2seq import train_iter_seq2seq
+            s_cfg = S.Seq2SeqConfig(n_words=200)
+            s_args, s_net = GS._build(s_cfg, torch.device('cpu'))
+            s_net.train()
+            s_opt = torch.optim.Adam(s_net.parameters(), lr=s_cfg.learning_rate, betas=(0.9, 0.999))
+            inp = synth.seq2seq_inputs(s_cfg, 4, seed=60 + rank, max_len=7)
+            ssd = synth.seq2seq_state_dict(s_cfg)
+            ref = S.train_iter_seq2seq_oracle(s_cfg, ssd, inp['in_text'], inp['lengths'], inp['target'], None, step=1)
+            train_iter_seq2seq(s_args, 0, inp['in_text'], inp['lengths'], inp['target'], s_net, s_opt)
+            keys = [k for k in ref['grads']]
+            unclip = min(1.0, 5.0 / (float(ref['total_norm']) + 1e-6))
+            mean = {}
+            for k in keys:
+                g = (ref['grads'][k] / unclip).clone()           # the oracle returns the rank's CLIPPED gradient: undo its own clipping
+                dist.all_reduce(g)
+                mean[k] = g / world
+            norm = torch.sqrt(sum((g.double() ** 2).sum() for g in mean.values())).item()
+            coef = min(1.0, 5.0 / (norm + 1e-6))
+            ok = True
+            sd2 = s_net.state_dict()
+            worst = 0.0
+            for k in keys:
+                g = mean[k] * coef
+                p, _, _ = O.adam_step(ssd[k], g, torch.zeros_like(g), torch.zeros_like(g), 1, s_cfg.learning_rate, 0.9, 0.999)
+                d = (sd2[k] - p).abs()
+                ok = ok and d.max().item() <= 2.2 * s_cfg.learning_rate + 1e-6
+                if float(ref['grads'][k].norm()) > 1e-6:
+                    worst = max(worst, d.median().item())
+            flat = s_net.engine().arena.flat.clone(); refp = flat.clone()
+            dist.broadcast(refp, src=0)
+            res['seq2seq'] = bool(ok and worst < 2e-6 and torch.equal(flat, refp))
+            res['seq2seq_worst'] = worst
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -240,9 +284,15 @@ def test_data_parallel_embedding_trainers_world2():
     procs = [ctx.Process(target=_embed_dp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    for rank, r in res:
-        assert r['ae'] and r['joint'], (rank, r)
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=400))
+            assert 'error' not in res[-1][1], res[-1][1]['error']
+    finally:
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+    for rank, r in sorted(res, key=lambda t: t[0]):
+        assert r['ae'] and r['joint'] and r['seq2seq'], (rank, r)
