@@ -148,17 +148,7 @@ def _dp_worker(rank, world, port, q):
 
 
 def test_data_parallel_train_iter_gan_world2():
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = 30500 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    for rank, r in res:
+    for rank, r in _run_world2(_dp_worker, 30500):
         assert r['ok_0'] and r['ok_11'], (rank, r)
         assert r['calls_0'] == 1 and r['calls_11'] == 2, r          # warm-up: generator Adam only; afterwards D and G
 
@@ -166,13 +156,33 @@ def test_data_parallel_train_iter_gan_world2():
 # ----------------------------------------------------------------------------------------------------------------------
 # The embedding-model trainers under data parallelism, world 2 (plans on the emulator, gradients over gloo)
 # ----------------------------------------------------------------------------------------------------------------------
-def _embed_dp_worker(rank, world, port, q):
+def _guarded(body, rank, world, port, q):
     try:
-        _embed_dp_worker_body(rank, world, port, q)
+        body(rank, world, port, q)
     except BaseException as exc:          # report instead of leaving the peer blocked in a collective until the timeout
         import traceback
         q.put((rank, {'error': ''.join(traceback.format_exception(type(exc), exc, exc.__traceback__))[-1500:]}))
         os._exit(1)
+
+
+def _run_world2(body, port_base, timeout=400):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = port_base + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_guarded, args=(body, r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=timeout))
+            assert not (isinstance(res[-1][1], dict) and 'error' in res[-1][1]), res[-1][1]['error']
+    finally:
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+    return sorted(res, key=lambda t: t[0])
 
 
 def _embed_dp_worker_body(rank, world, port, q):
@@ -278,21 +288,5 @@ def _embed_dp_worker_body(rank, world, port, q):
 
 
 def test_data_parallel_embedding_trainers_world2():
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = 31500 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_embed_dp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = []
-    try:
-        for _ in procs:
-            res.append(q.get(timeout=400))
-            assert 'error' not in res[-1][1], res[-1][1]['error']
-    finally:
-        for p in procs:
-            p.join(timeout=5)
-            if p.is_alive():
-                p.terminate()
-    for rank, r in sorted(res, key=lambda t: t[0]):
+    for rank, r in _run_world2(_embed_dp_worker_body, 31500):
         assert r['ae'] and r['joint'] and r['seq2seq'], (rank, r)
