@@ -107,7 +107,10 @@ class ParamArena:
         """Makes a caller-constructed torch.optim.Adam (train.py:104-109) share our flat state so that its
         state_dict() stays meaningful while the update itself is one tg_adam_flat launch."""
         if self._bound_optim is optim:
-            return
+            st = optim.state.get(self.params[self.names[0]], None)
+            if st and 'exp_avg' in st and st['exp_avg'].data_ptr() == self.exp_avg.data_ptr() + 4 * self.offsets[self.names[0]]:
+                return
+            # optim.load_state_dict() (resume) replaced the state tensors: take the loaded moments / step count over below
         assert isinstance(optim, torch.optim.Adam), 'train_iter_gan expects the torch.optim.Adam objects of train.py:104-109'
         assert len(optim.param_groups) == 1
         g = optim.param_groups[0]

@@ -61,3 +61,27 @@ def test_emulator_is_uninstalled_afterwards():
     from tgb200 import _lib
     assert not isinstance(_lib._lib, cabi_emulator.EmuLib)
     assert _lib.TRACE_ONLY == (os.environ.get('TGB200_TRACE_ONLY', '') == '1')
+
+
+def test_resume_from_saved_model_and_optimizer_state(emu):
+    """Checkpoint / resume: the caller's torch.optim.Adam is bound to the flat arena, so optim.state_dict() holds the real moments and step
+    count; a fresh net + optimiser that load_state_dict() both continue bit-for-bit where the original continues."""
+    import copy
+    import train_feature_extractor as tfx
+    cfg, net, opt = ae_checks.build(CPU)
+    net.train()
+    batches = [synth.make_inputs(cfg, 6, seed=70 + i)['target'] for i in range(3)]
+    for b in batches[:2]:
+        tfx.train_iter(None, 0, b, net, opt)
+    saved_model, saved_opt = copy.deepcopy(net.state_dict()), copy.deepcopy(opt.state_dict())
+    assert int(saved_opt['state'][0]['step']) == 2 and float(saved_opt['state'][0]['exp_avg'].abs().sum()) > 0
+    tfx.train_iter(None, 0, batches[2], net, opt)                       # the original run goes on
+    cfg, net2, opt2 = ae_checks.build(CPU)
+    net2.train()
+    tfx.train_iter(None, 0, batches[0], net2, opt2)                     # the resumed objects have already been used (arena bound) ...
+    net2.load_state_dict(saved_model)
+    opt2.load_state_dict(saved_opt)                                     # ... then a checkpoint is loaded into them
+    tfx.train_iter(None, 0, batches[2], net2, opt2)
+    for (k, a), b in zip(net.state_dict().items(), net2.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert int(opt2.state_dict()['state'][0]['step']) == 3
