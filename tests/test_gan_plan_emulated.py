@@ -122,3 +122,43 @@ def test_other_hyper_parameters(emu_fast, kw):
         r = ref['g_grads'][k]
         if r.norm() > 1e-6:
             assert rel_l2(p.grad, r) < 1e-4, k
+
+
+def test_pretrained_frozen_word_embeddings(emu_fast):
+    """args.freeze_wordembed=True with a pre-trained embedding matrix (multimodal_context_net.py:38-41, the fastText path): the table is not
+    a trainable parameter - it stays out of the flat arena and of the optimiser, receives no scatter-add and does not move."""
+    from gpu_util import make_args, masks_to_ours
+    from conftest import rel_l2
+    from model import vocab
+    from model.multimodal_context_net import ConvDiscriminator, PoseGenerator
+    from oracle import synth
+    from oracle import trimodal_oracle as O
+    from train_eval import train_gan as TG
+    cfg = O.HotPathConfig(n_words=300, n_speakers=12)
+    args = make_args(cfg)
+    args.freeze_wordembed = True
+    spk = vocab.Vocab('vid', insert_default_tokens=False)
+    while spk.n_words < cfg.n_speakers:
+        spk.index_word('s%d' % spk.n_words)
+    gsd, dsd = synth.generator_state_dict(cfg), synth.discriminator_state_dict(cfg)
+    emb = gsd['text_encoder.embedding.weight'].numpy().copy()
+    G = PoseGenerator(args, cfg.pose_dim, cfg.n_words, cfg.wordembed_dim, emb, z_obj=spk)
+    D = ConvDiscriminator(cfg.pose_dim)
+    G.load_state_dict(synth.with_tcn_aliases(gsd), strict=True); D.load_state_dict(dsd, strict=True)
+    assert not G.text_encoder.embedding.weight.requires_grad
+    G.train(); D.train()
+    B = 3
+    inp, noise = synth.make_inputs(cfg, B, seed=3), synth.make_noise(cfg, B, seed=4, dropout=True)
+    ref = GP._oracle_step(cfg, 11, gsd, dsd, inp, noise, CPU)
+    g_opt = torch.optim.Adam([p for p in G.parameters() if p.requires_grad], lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=list(noise.eps), perm=noise.perm, g_masks=[masks_to_ours(m, CPU) for m in noise.g_masks],
+                                 d_masks=[masks_to_ours(m, CPU) for m in noise.d_masks]))
+    ret = TG.train_iter_gan(args, 11, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+    for k, v in ret.items():
+        assert abs(v - ref['losses'][k]) <= 1e-5 * abs(ref['losses'][k]) + 1e-7, k
+    assert torch.equal(G.text_encoder.embedding.weight.data, torch.from_numpy(emb))
+    assert 'tg_embedding_scatter_add' not in emu_fast.calls
+    for k, p in G.named_parameters():
+        if p.requires_grad and ref['g_grads'][k].norm() > 1e-6:
+            assert rel_l2(p.grad, ref['g_grads'][k]) < 1e-4, k
