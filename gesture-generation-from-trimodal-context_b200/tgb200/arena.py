@@ -49,6 +49,7 @@ class ParamArena:
         return True
 
     def _grads_bound(self) -> bool:
+        """Cheap per-step check (first / last parameter): optimizer.zero_grad() drops every .grad at once."""
         for n in (self.names[0], self.names[-1]):
             g = self.params[n].grad
             if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * self.offsets[n]:
@@ -56,11 +57,20 @@ class ParamArena:
         return True
 
     def bind_grads(self):
-        """Points every .grad at its slice of the flat gradient buffer (undoes optimizer.zero_grad(set_to_none=True))."""
+        """Points every .grad at its slice of the flat gradient buffer.  A parameter whose .grad was dropped - optimizer.zero_grad() sets
+        it to None by default - means "gradient zero" to autograd, which would accumulate into a fresh tensor; its slice is therefore
+        cleared before it is handed back (otherwise the previous iteration's gradient would be accumulated into)."""
+        stale = [n for n in self.names if self.params[n].grad is None
+                 or self.params[n].grad.data_ptr() != self.grad.data_ptr() + 4 * self.offsets[n]]
+        if len(stale) == len(self.names):
+            self.grad.zero_()                   # the usual case: every gradient was dropped - one memset
         for n in self.names:
             p = self.params[n]
             o, k = self.offsets[n], p.numel()
-            p.grad = self.grad[o:o + k].view(p.shape)
+            view = self.grad[o:o + k].view(p.shape)
+            if n in stale and len(stale) != len(self.names):
+                view.zero_()
+            p.grad = view
 
     def ensure(self, device) -> 'ParamArena':
         """(Re)builds the flat storage if the module was moved / re-created since the last call."""

@@ -205,3 +205,34 @@ def test_changing_batch_size_between_steps(emu_fast):
     assert abs(a['loss'] - b['loss']) <= 1e-6 * abs(b['loss']) and abs(a['KLD'] - b['KLD']) <= 1e-6 * abs(b['KLD'])
     assert abs(a['dis'] - b['dis']) <= 1e-5 * abs(b['dis'])
     assert abs(a['gen'] - b['gen']) <= 5e-2 * abs(b['gen'])
+
+
+def test_reference_style_autograd_loop_does_not_accumulate_stale_gradients(emu_fp32):
+    """The reference's own training pattern on the nn.Module API: optim.zero_grad() (which DROPS every .grad by default), forward,
+    loss.backward(), optim.step().  The .grad views into the flat arena are re-created on the next forward and must start from zero: with
+    a zero learning rate two iterations give identical gradients (they were doubled before the fix in ParamArena.bind_grads)."""
+    from gpu_util import build_ours
+    from conftest import rel_l2
+    from oracle import synth
+    from oracle import trimodal_oracle as O
+    cfg = O.HotPathConfig(n_words=300, n_speakers=12, dropout_prob=0.0, emb_dropout=0.0)
+    args, G, D, _, _ = build_ours(cfg, CPU, dropout_prob=0.0)
+    G.text_encoder.emb_dropout = 0.0
+    G.train(); D.train()
+    opt = torch.optim.SGD(list(G.parameters()) + list(D.parameters()), lr=0.0)
+    inp = synth.make_inputs(cfg, 3, seed=1)
+    pre = O.make_pre_seq(inp['target'], cfg.n_pre_poses)
+    eps = synth.make_noise(cfg, 3, seed=1).eps[0]
+    grads = []
+    for it in range(3):
+        opt.zero_grad()
+        G.set_noise(eps=eps, masks={})
+        D.set_noise(masks={})
+        poses, z, mu, logvar = G(pre, inp['in_text'], inp['in_audio'], inp['vid'])
+        loss = (poses - inp['target']).abs().mean() + 0.1 * mu.pow(2).mean() - torch.log(D(poses) + 1e-8).mean()
+        loss.backward()
+        opt.step()
+        grads.append({k: p.grad.clone() for m in (G, D) for k, p in m.named_parameters()})
+    for k, g0 in grads[0].items():
+        if g0.norm() > 1e-8:
+            assert rel_l2(grads[1][k], g0) < 1e-5 and rel_l2(grads[2][k], g0) < 1e-5, k
