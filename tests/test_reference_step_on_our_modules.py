@@ -1,0 +1,73 @@
+"""CPU (only where /root/reference is present, i.e. in the build container): the UNMODIFIED reference step function
+scripts/train_eval/train_gan.py::train_iter_gan - torch autograd, loss.backward(), the caller's torch.optim.Adam - driven over OUR
+PoseGenerator / ConvDiscriminator through their nn.Module API (launch plans on the NumPy C-ABI emulator), compared with the golden the same
+function produced on the reference's own modules (tests/golden/train_e11.npz, train_e0.npz).  This is the drop-in claim of SURVEY 8b taken
+literally: the reference code runs on our modules and computes what it computed on its own."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cabi_emulator
+import test_gpu_parity as GP
+from conftest import GOLDEN
+from gpu_util import build_ours, masks_to_ours
+from oracle import synth
+from oracle.make_golden import digest, golden_cfg
+
+REF = '/root/reference/scripts/train_eval/train_gan.py'
+CPU = torch.device('cpu')
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason='the reference tree is only present in the build container')
+@pytest.mark.parametrize('tag,epoch,use_masks', [('train_e11', 11, True), ('train_e0', 0, False)])
+def test_unmodified_reference_train_iter_gan_runs_on_our_modules(tag, epoch, use_masks):
+    from tgb200 import config
+    spec = importlib.util.spec_from_file_location('ref_train_gan', REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    orig_randperm = torch.randperm
+    try:
+        with cabi_emulator.installed():
+            cfg = golden_cfg()
+            g = np.load(os.path.join(GOLDEN, tag + '.npz'))
+            args, G, D, _, _ = build_ours(cfg, CPU)
+            G.train(); D.train()
+            inp = synth.make_inputs(cfg, 3, seed=1)
+            noise = synth.golden_noise(cfg, 3, 2, use_masks)
+            fwd_ids = [0, 1, 2] if epoch > cfg.loss_warmup else [1, 2]
+            g_queue = [(noise.eps[i], masks_to_ours(noise.g_masks[i], CPU) if noise.g_masks[i] else {}) for i in fwd_ids]
+            g_forward, d_forward = G.forward, D.forward
+
+            def g_fwd(*a, **k):                                  # the reference calls the generator two or three times per step
+                eps, masks = g_queue.pop(0)
+                G.set_noise(eps=eps, masks=masks)
+                return g_forward(*a, **k)
+
+            def d_fwd(*a, **k):
+                D.set_noise(masks={})                            # golden: GRU inter-layer dropout switched off (it cannot take a mask)
+                return d_forward(*a, **k)
+            G.forward, D.forward = g_fwd, d_fwd
+            torch.randperm = lambda n, *a, **k: noise.perm.clone()
+            g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+            d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+            ret = ref.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+            assert not g_queue
+            assert set('loss_' + k for k in ret) == set(k for k in g.files if k.startswith('loss_'))
+            for k, v in ret.items():
+                r = float(g['loss_' + k])
+                assert abs(v - r) <= GP.TOL * abs(r) + 1e-6, (k, v, r)
+            for k, p in G.named_parameters():
+                GP._digest_close(digest(p.grad), g['ggrad/' + k], 3e-4)
+            gsd, dsd = G.state_dict(), D.state_dict()
+            for k in g.files:
+                if k.startswith('gpost/'):
+                    GP._post_close(digest(gsd[k[6:]]), g[k], cfg.learning_rate, k[6:] in GP.ZERO_GRAD_KEYS)
+                if k.startswith('dpost/'):
+                    GP._post_close(digest(dsd[k[6:]]), g[k], cfg.learning_rate * cfg.discriminator_lr_weight, k[6:] in GP.ZERO_GRAD_KEYS)
+    finally:
+        torch.randperm = orig_randperm
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
