@@ -18,6 +18,37 @@ from tgb200.embed_engine import AutoEncoderTrainEngine, JointEmbeddingEngine
 from tgb200.engine import EmbeddingEngine
 
 
+class _AutoEncoderFn(torch.autograd.Function):
+    """Train-mode EmbeddingNet(mode='pose') under torch autograd (the reference's own loop: loss.backward(); optim.step(),
+    train_feature_extractor.py:54-97): forward and hand-derived backward are the launch plans of AutoEncoderTrainEngine; parameter
+    gradients are accumulated straight into the .grad views of the flat arena, like torch accumulates into .grad."""
+
+    @staticmethod
+    def forward(ctx, module, poses, *params):
+        eng = module.train_engine().ensure(poses.device)
+        mu, logvar, recon = eng.forward(poses, training=True)
+        ctx.module, ctx.device, ctx.fwd_ctx, ctx.shapes = module, poses.device, eng.ctx, (eng.enc_T, eng.dec_T)
+        ctx.gen = module._ae_gen = getattr(module, '_ae_gen', 0) + 1
+        return mu.clone(), mu.clone(), logvar.clone(), recon.clone()
+
+    @staticmethod
+    def backward(ctx, d_feat, d_mu, d_logvar, d_recon):
+        module = ctx.module
+        if module._ae_gen != ctx.gen:
+            raise RuntimeError('EmbeddingNet activations of this forward were overwritten by a later training forward before backward')
+        eng = module.train_engine().ensure(ctx.device)
+        eng.ctx, (eng.enc_T, eng.dec_T) = ctx.fwd_ctx, ctx.shapes
+        extra = None
+        for g in (d_feat, d_mu):                       # poses_feat and pose_mu are the same tensor when variational_encoding is False
+            if g is not None:
+                extra = g.contiguous().clone() if extra is None else extra + g
+        # pose_logvar: fc_logvar's backward is not part of this plan (the reference never back-propagates through it, :58-86)
+        assert d_logvar is None or not bool(d_logvar.any()), 'a loss on pose_logvar is not supported by the auto-encoder plan'
+        B, T, D = eng.ctx['B'], eng.ctx['T'], eng.ctx['D']
+        eng.backward(d_recon.contiguous().view(B * T, D) if d_recon is not None else None, extra)
+        return (None,) * (2 + len(module._ae_params))
+
+
 def reparameterize(mu, logvar):
     """embedding_net.py:10-13: mu + eps*exp(0.5*logvar), eps from the Philox kernel (CUDA tensors only)."""
     _lib.require_cuda()
@@ -167,8 +198,13 @@ class EmbeddingNet(nn.Module):
         if self.training:
             # batch-statistics forward (updates the BatchNorm running statistics like the reference's train-mode forward)
             assert not variational_encoding, 'the reference trains the auto-encoder with variational_encoding=False (train_feature_extractor.py:58)'
+            poses_c = poses.detach().contiguous().float()
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                self._ae_params = [p for p in self.parameters() if p.requires_grad]
+                feat, mu, logvar, recon = _AutoEncoderFn.apply(self, poses_c, *self._ae_params)
+                return None, None, None, feat, mu, logvar, recon
             teng = self.train_engine().ensure(poses.device)
-            mu, logvar, recon = teng.forward(poses.detach().contiguous().float(), training=True)
+            mu, logvar, recon = teng.forward(poses_c, training=True)
             return None, None, None, mu.clone(), mu.clone(), logvar.clone(), recon.clone()
         eng = self.engine().ensure(poses.device)
         poses_c = poses.detach().contiguous().float()

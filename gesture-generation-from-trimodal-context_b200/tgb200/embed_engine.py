@@ -232,8 +232,13 @@ class AutoEncoderTrainEngine(PoseEncoderPlan):
         return d_rec
 
     # ------------------------------------------------------------------------------------------------ backward
-    def backward(self, d_rec):
-        """d_rec [B*34,27] = d loss / d recon.  Accumulates every parameter gradient into the (caller-zeroed) flat gradient arena."""
+    def backward(self, d_rec, d_mu_extra=None):
+        """d_rec [B*34,27] = d loss / d recon (None: the loss does not read the reconstruction); d_mu_extra [B,32] = gradient reaching the
+        latent from outside the decoder (module-level autograd API).  Accumulates every parameter gradient into the flat gradient arena."""
+        if d_rec is None:
+            if d_mu_extra is not None:
+                self.encode_backward(d_mu_extra)
+            return
         ws, c = self.ws, self.ctx
         assert c['training'], 'backward through eval-mode BatchNorm is not on this path'
         B = c['B']
@@ -279,6 +284,8 @@ class AutoEncoderTrainEngine(PoseEncoderPlan):
         ops.linear_wgrad(ws['ae.mu'], dg0, G(d + 'pre_net.0.weight'), G(d + 'pre_net.0.bias'), M=B, K=32, N=c0)
         dmu = ws.get('ae.d_mu', (B, 32))
         ops.linear_dgrad(dg0, P(d + 'pre_net.0.weight'), dmu, M=B, K=32, N=c0)
+        if d_mu_extra is not None:
+            ops.add(dmu, d_mu_extra, dmu, dmu.numel())
         self.encode_backward(dmu)
 
 

@@ -71,3 +71,35 @@ def test_unmodified_reference_train_iter_gan_runs_on_our_modules(tag, epoch, use
     finally:
         torch.randperm = orig_randperm
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+FX = '/root/reference/scripts/train_feature_extractor.py'
+
+
+@pytest.mark.skipif(not os.path.exists(FX), reason='the reference tree is only present in the build container')
+def test_unmodified_reference_autoencoder_train_iter_runs_on_our_module():
+    """scripts/train_feature_extractor.py::train_iter and train_eval/train_joint_embed.py::train_iter_embed, unmodified (autograd +
+    torch Adam), over OUR EmbeddingNet(mode='pose'): two consecutive steps reproduce the golden the reference produced on its own module."""
+    import ae_checks
+    from oracle.make_golden_ae import reference_train_iter
+    from tgb200 import config
+    train_iter = reference_train_iter()                      # extracted from the reference source with ast, executed as is
+    spec = importlib.util.spec_from_file_location('ref_joint', '/root/reference/scripts/train_eval/train_joint_embed.py')
+    ref_joint = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_joint)
+    old_graphs = config.set_graphs(False)
+    try:
+        with cabi_emulator.installed():
+            g = np.load(os.path.join(GOLDEN, 'ae_train.npz'))
+            cfg, net, opt = ae_checks.build(CPU)
+            net.train()
+            for step in (1, 2):
+                ret = train_iter(None, 0, torch.from_numpy(g[f'fx{step}/target']), net, opt)
+                ae_checks.check_against_golden(g, f'fx{step}', net, ret['loss'], step, float(g['lr']), 2e-5)
+            cfg, net, opt = ae_checks.build(CPU)
+            net.train()
+            import argparse
+            ret = ref_joint.train_iter_embed(argparse.Namespace(n_pre_poses=cfg.n_pre_poses), 0, None, None, torch.from_numpy(g['fx1/target']), net, opt)
+            ae_checks.check_against_golden(g, 'je', net, ret['loss'], 1, float(g['lr']), 2e-5)
+    finally:
+        config.set_graphs(old_graphs)
