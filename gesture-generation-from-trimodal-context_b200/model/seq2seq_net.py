@@ -98,6 +98,30 @@ class Generator(nn.Module):
         raise RuntimeError('Generator holds parameters only; its kernels run inside Seq2SeqNet.forward (no PyTorch fallback)')
 
 
+class _Seq2SeqFn(torch.autograd.Function):
+    """Train-mode Seq2SeqNet under torch autograd (the reference's own loop, train_seq2seq.py:39-51: custom_loss in torch, loss.backward(),
+    clip_grad_norm_, optim.step()): forward and hand-derived backward are the launch plans of Seq2SeqEngine; parameter gradients are
+    accumulated into the .grad views of the flat arena."""
+
+    @staticmethod
+    def forward(ctx, module, in_text, lens_dev, Tm, poses, masks, slot, *params):
+        eng = module.engine().ensure(poses.device, slot)
+        out = eng.forward(in_text, lens_dev, Tm, poses, True, masks, save=True)
+        ctx.module, ctx.device, ctx.slot, ctx.fwd_ctx = module, poses.device, slot, eng.ctx
+        ctx.gen = module._fwd_gen = getattr(module, '_fwd_gen', 0) + 1
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        module = ctx.module
+        if module._fwd_gen != ctx.gen:
+            raise RuntimeError('Seq2SeqNet activations of this forward were overwritten by a later training forward before backward')
+        eng = module.engine().ensure(ctx.device, ctx.slot)
+        eng.ctx = ctx.fwd_ctx
+        eng.backward_from_dy(d_out.transpose(0, 1).contiguous())          # the backward sweep walks time: [T,B,D]
+        return (None,) * (7 + len(module._fn_params))
+
+
 class Seq2SeqNet(nn.Module):
     """seq2seq_net.py:217-254."""
 
@@ -130,11 +154,16 @@ class Seq2SeqNet(nn.Module):
         if not poses.is_cuda and not _lib.TRACE_ONLY:
             raise _lib.TgError('Seq2SeqNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
         dev = poses.device
-        eng = self.engine().ensure(dev, 'fwd_%d' % poses.shape[0])
         lens_dev, Tm = self.prepare_lengths(in_lengths, dev)
+        grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        slot = ('autograd_%d_%d' % (poses.shape[0], Tm)) if grad else ('fwd_%d' % poses.shape[0])
+        eng = self.engine().ensure(dev, slot)
         masks = None
         if self.training:
             masks = eng.make_masks(poses.shape[0], Tm, self._noise.seed, self._noise.offset_dev(dev))
             self._noise.advance()
+        if grad:
+            self._fn_params = [p for p in self.parameters() if p.requires_grad]
+            return _Seq2SeqFn.apply(self, in_text.contiguous(), lens_dev, Tm, poses.detach().contiguous().float(), masks, slot, *self._fn_params)
         out = eng.forward(in_text.contiguous(), lens_dev, Tm, poses.contiguous().float(), self.training, masks, save=False)
         return out.clone()

@@ -227,6 +227,16 @@ class Seq2SeqEngine:
         outputs = ws['dec.outputs']
         dy = ws.get('dec.dy', (T, B, D))
         ops.s2s_loss(outputs, target, loss_out, dy, B, T, D, w_mse, w_cont, w_var)
+        self.backward_from_dy(dy)
+
+    def backward_from_dy(self, dy):
+        """Backward through decoder and encoder from dy [T,B,D] = d loss / d outputs, TIME-major (row t = 0 is ignored: frame 0 is a copy
+        of the input pose, seq2seq_net.py:244-245); accumulates every parameter gradient into the flat gradient arena."""
+        ws, H, L, E, D, T = self.ws, self.H, self.L, self.E, self.D, self.T
+        c = self.ctx
+        B, Tm, masks, training, lengths = c['B'], c['Tm'], c['masks'], c['training'], c['lengths']
+        assert training, 'backward through eval-mode BatchNorm is not on the reference path'
+        outputs = ws['dec.outputs']
         pd = 'decoder.decoder.'
         Wa, v = self.P(pd + 'attn.attn.weight'), self.P(pd + 'attn.v')
         Wp = self.P(pd + 'pre_linear.0.weight')

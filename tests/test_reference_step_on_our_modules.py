@@ -103,3 +103,41 @@ def test_unmodified_reference_autoencoder_train_iter_runs_on_our_module():
             ae_checks.check_against_golden(g, 'je', net, ret['loss'], 1, float(g['lr']), 2e-5)
     finally:
         config.set_graphs(old_graphs)
+
+
+S2S = '/root/reference/scripts/train_eval/train_seq2seq.py'
+
+
+@pytest.mark.skipif(not os.path.exists(S2S), reason='the reference tree is only present in the build container')
+def test_unmodified_reference_train_iter_seq2seq_runs_on_our_module():
+    """scripts/train_eval/train_seq2seq.py::train_iter_seq2seq, unmodified (custom_loss in torch, loss.backward(), clip_grad_norm_,
+    torch Adam), over OUR Seq2SeqNet: two consecutive steps reproduce the golden the reference produced on its own module."""
+    import test_gpu_seq2seq as GS
+    from oracle import seq2seq_oracle as S
+    from tgb200 import config
+    spec = importlib.util.spec_from_file_location('ref_train_seq2seq', S2S)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    try:
+        with cabi_emulator.installed():
+            cfg = GS.golden_cfg()
+            g = np.load(os.path.join(GOLDEN, 'seq2seq_step.npz'))
+            args, net = GS._build(cfg, CPU)
+            inp = synth.seq2seq_inputs(cfg, 6, seed=3, max_len=9)
+            net.train()
+            optim = torch.optim.Adam(net.parameters(), lr=cfg.learning_rate, betas=(0.9, 0.999))
+            for it in range(2):
+                ret = ref.train_iter_seq2seq(args, 0, inp['in_text'], inp['lengths'], inp['target'], net, optim)
+                r = float(g[f'loss{it}'])
+                assert abs(ret['loss'] - r) <= GS.FP32_TOL * abs(r), (it, ret['loss'], r)
+                for k, p in net.named_parameters():
+                    GS._digest_close(digest(p.grad), g[f'grad{it}/' + k], 1e-3)
+                for k, v in net.state_dict().items():
+                    rr = g[f'post{it}/' + k]
+                    if k.endswith('num_batches_tracked'):
+                        assert int(v) == int(rr[1])
+                    elif S.is_param(k):
+                        GS._post_close(digest(v), rr, cfg.learning_rate, noisy=(it > 0 or k == 'decoder.decoder.pre_linear.0.bias'))
+    finally:
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
