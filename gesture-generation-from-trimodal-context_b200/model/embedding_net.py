@@ -49,6 +49,41 @@ class _AutoEncoderFn(torch.autograd.Function):
         return (None,) * (2 + len(module._ae_params))
 
 
+class _JointEmbeddingFn(torch.autograd.Function):
+    """Train-mode joint-embedding EmbeddingNet under torch autograd (the reference's loop, train_joint_embed.py:5-51).  Only the
+    reconstruction carries a gradient there; the decoder and the encoder whose latent was decoded receive it.  The other encoder's
+    parameters get NO gradient in the reference (.grad stays None and torch.optim.Adam skips them): their .grad views are dropped again
+    after the backward so that the caller's optimiser behaves the same."""
+
+    @staticmethod
+    def forward(ctx, module, in_text, in_audio, pre_poses, poses, branch, *params):
+        eng = module.joint_engine().ensure(pre_poses.device)
+        r = eng.forward(in_text, in_audio, pre_poses, poses, branch, True)
+        ctx.module, ctx.device, ctx.st, ctx.pose_ctx = module, pre_poses.device, eng.st, getattr(eng.pose, 'ctx', None)
+        ctx.gen = module._joint_gen = getattr(module, '_joint_gen', 0) + 1
+        ctx.present = [r[k] is not None for k in ('c_feat', 'c_mu', 'c_lv', 'p_mu', 'p_mu', 'p_lv')]
+        outs = [r[k].clone() if r[k] is not None else None for k in ('c_feat', 'c_mu', 'c_lv', 'p_mu', 'p_mu', 'p_lv')]
+        return tuple(outs) + (r['out'].clone(),)
+
+    @staticmethod
+    def backward(ctx, d_cf, d_cmu, d_clv, d_pf, d_pmu, d_plv, d_out):
+        module = ctx.module
+        if module._joint_gen != ctx.gen:
+            raise RuntimeError('EmbeddingNet activations of this forward were overwritten by a later training forward before backward')
+        for g in (d_cf, d_cmu, d_clv, d_pf, d_pmu, d_plv):
+            assert g is None or not bool(g.any()), 'only a loss on the reconstruction is supported by the joint-embedding plan'
+        eng = module.joint_engine().ensure(ctx.device)
+        eng.st = ctx.st
+        if ctx.pose_ctx is not None:
+            eng.pose.ctx = ctx.pose_ctx
+        B = eng.st['B']
+        eng.backward(d_out.contiguous().view(B * eng.T, eng.D))
+        unused = module.pose_encoder if eng.st['branch'] == 'speech' else module.context_encoder
+        for p in unused.parameters():
+            p.grad = None
+        return (None,) * (6 + len(module._joint_params))
+
+
 def reparameterize(mu, logvar):
     """embedding_net.py:10-13: mu + eps*exp(0.5*logvar), eps from the Philox kernel (CUDA tensors only)."""
     _lib.require_cuda()
@@ -170,6 +205,13 @@ class EmbeddingNet(nn.Module):
         if input_mode == 'random':
             input_mode = 'speech' if random.random() > 0.5 else 'pose'                # embedding_net.py:295-296
         assert input_mode in ('speech', 'pose')
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            assert in_text is not None and in_audio is not None and poses is not None
+            self._joint_params = [p for p in self.parameters() if p.requires_grad]
+            c_feat, c_mu, c_lv, p_feat, p_mu, p_lv, out = _JointEmbeddingFn.apply(
+                self, in_text.contiguous(), in_audio.detach().contiguous().float(), pre_poses.detach().contiguous().float(),
+                poses.detach().contiguous().float(), input_mode, *self._joint_params)
+            return c_feat, c_mu, c_lv, p_feat, p_mu, p_lv, out
         eng = self.joint_engine().ensure(ref.device)
         r = eng.forward(in_text, in_audio, pre_poses, poses, input_mode, self.training)
         cl = lambda t: None if t is None else t.clone()

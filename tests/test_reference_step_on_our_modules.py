@@ -141,3 +141,50 @@ def test_unmodified_reference_train_iter_seq2seq_runs_on_our_module():
                         GS._post_close(digest(v), rr, cfg.learning_rate, noisy=(it > 0 or k == 'decoder.decoder.pre_linear.0.bias'))
     finally:
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+@pytest.mark.skipif(not os.path.exists(FX), reason='the reference tree is only present in the build container')
+def test_unmodified_reference_train_iter_embed_runs_on_our_joint_embedding_module():
+    """train_joint_embed.py::train_iter_embed(mode='random'), unmodified, over OUR EmbeddingNet(mode='random') with the coin patched to
+    'speech' then 'pose' (as the golden): losses, gradients, post-Adam weights and - the subtle part - torch.optim.Adam leaving the
+    parameters of the branch that was not decoded alone."""
+    import random
+    import joint_checks
+    from oracle.make_golden import digest as dg
+    from test_oracle_ae_golden import digest_close, post_close
+    from test_oracle_joint_golden import is_zero_grad
+    from tgb200 import config
+    spec = importlib.util.spec_from_file_location('ref_joint2', '/root/reference/scripts/train_eval/train_joint_embed.py')
+    ref_joint = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_joint)
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    coins = [0.9, 0.1]
+    orig = random.random
+    random.random = lambda: coins.pop(0)
+    try:
+        with cabi_emulator.installed():
+            g = np.load(os.path.join(GOLDEN, 'joint_embed.npz'))
+            cfg, args, net, opt = joint_checks.build(CPU)
+            net.train()
+            for step in (1, 2):
+                noise = synth.golden_noise(cfg, joint_checks.B, 70 + step, True)
+                e = noise.eps[0].repeat(1, 2)[:, :32].contiguous()
+                net.joint_engine().noise = dict(eps=e, masks=masks_to_ours(noise.g_masks[0], CPU), gru_masks=[None] * 4)
+                data = synth.make_inputs(cfg, joint_checks.B, seed=63 + step)
+                ret = ref_joint.train_iter_embed(args, 0, data['in_text'], data['in_audio'], data['target'], net, opt, mode='random')
+                tag = f'step{step}'
+                r = float(g[f'{tag}/loss'])
+                assert abs(ret['loss'] - r) <= (2e-5 if step == 1 else 4e-4) * abs(r), (tag, ret['loss'], r)
+                for k, p in net.named_parameters():
+                    assert (p.grad is not None) == bool(g[f'{tag}/hasgrad/{k}']) or k.startswith('pose_encoder.fc_logvar'), (tag, k)
+                    if p.grad is None or is_zero_grad(k) or not bool(g[f'{tag}/hasgrad/{k}']):
+                        continue
+                    digest_close(dg(p.grad), g[f'{tag}/grad/{k}'], 1e-4 if step == 1 else 5e-3)
+                for k, v in net.state_dict().items():
+                    if ('.tcn.network.' in k and ('.net.0.' in k or '.net.4.' in k)) or is_zero_grad(k) or 'running' in k or k.endswith('num_batches_tracked'):
+                        continue
+                    post_close(dg(v), g[f'{tag}/post/{k}'], float(g['lr']), step)
+        assert not coins
+    finally:
+        random.random = orig
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
