@@ -188,3 +188,37 @@ def test_unmodified_reference_train_iter_embed_runs_on_our_joint_embedding_modul
     finally:
         random.random = orig
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/scripts/synthesize.py'), reason='the reference tree is only present in the build container')
+def test_unmodified_reference_generate_gestures_drives_our_generator():
+    """scripts/synthesize.py::generate_gestures (extracted with ast, executed as is: one forward per window, per-window .cpu()) calling OUR
+    PoseGenerator at the synthesize.py:131 call site gives what OUR long-form driver gives for the same clip: both draw the same Philox
+    noise sequence (one eval forward per window on a fresh, identically seeded module)."""
+    import contextlib
+    import io
+    from oracle import trimodal_oracle as O
+    from oracle.make_golden_synthesize import golden_args, reference_generate_gestures
+    from oracle.synthesize_stub import StubVocab, make_clip
+    from synthesize import generate_gestures
+    from tgb200 import config
+    gg = reference_generate_gestures()
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    try:
+        with cabi_emulator.installed():
+            cfg = O.HotPathConfig(n_words=300, n_speakers=12)
+            audio, words, seed = make_clip(4.4, seed=77)                         # two windows
+            outs = []
+            for driver in (gg, generate_gestures):
+                torch.manual_seed(11)                                             # module noise seed
+                args, G, D, _, _ = build_ours(cfg, CPU)
+                a = golden_args()
+                for k in ('n_poses', 'n_pre_poses', 'motion_resampling_framerate', 'mean_dir_vec', 'model', 'z_type'):
+                    setattr(args, k, getattr(a, k))
+                G.eval()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    outs.append(np.asarray(driver(args, G, StubVocab(), audio, words, vid=5, seed_seq=seed, fade_out=True)))
+            assert outs[0].shape == outs[1].shape and outs[0].shape[0] > 34 and np.isfinite(outs[0]).all()
+            assert np.abs(outs[0] - outs[1]).max() < 2e-6, np.abs(outs[0] - outs[1]).max()
+    finally:
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
