@@ -222,3 +222,52 @@ def test_unmodified_reference_generate_gestures_drives_our_generator():
             assert np.abs(outs[0] - outs[1]).max() < 2e-6, np.abs(outs[0] - outs[1]).max()
     finally:
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+ESE = '/root/reference/scripts/model/embedding_space_evaluator.py'
+
+
+@pytest.mark.skipif(not os.path.exists(ESE), reason='the reference tree is only present in the build container')
+def test_unmodified_reference_embedding_space_evaluator_uses_our_embedding_net(tmp_path):
+    """scripts/model/embedding_space_evaluator.py, unmodified (its `from model.embedding_net import EmbeddingNet` resolves to OUR module):
+    constructor from a checkpoint file (:16-28), push_samples (:45-61), get_scores (:74-101) -> the golden FGD of the reference run."""
+    import argparse
+    import sys
+    import types
+    from scipy import linalg as sl
+    from tgb200 import config
+    sys.modules.setdefault('umap', types.ModuleType('umap'))                      # imported at module top, only used for visualisation
+    spec = importlib.util.spec_from_file_location('ref_ese', ESE)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    import model.embedding_net as ours
+    assert ref.EmbeddingNet is ours.EmbeddingNet
+
+    class _L:                                                                     # SciPy >= 1.18 dropped disp= (SURVEY 8c shim 3)
+        @staticmethod
+        def sqrtm(a, disp=True):
+            r = sl.sqrtm(a)
+            return r if disp else (r, 0.0)
+    ref.linalg = _L
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'embedding_fgd.npz'))
+    path = str(tmp_path / 'embed_net.bin')
+    torch.save({'pose_dim': cfg.pose_dim, 'gen_dict': synth.embedding_net_state_dict(cfg)}, path)
+    args = argparse.Namespace(n_pre_poses=cfg.n_pre_poses, n_poses=cfg.n_poses, wordembed_dim=cfg.wordembed_dim, hidden_size=cfg.hidden_size,
+                              n_layers=cfg.n_layers, dropout_prob=0.3, freeze_wordembed=False)
+    lang = argparse.Namespace(n_words=cfg.n_words, word_embedding_weights=None)
+    rng = np.random.Generator(np.random.PCG64(77))
+    real = torch.from_numpy((0.5 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim))).astype(np.float32))
+    fake = torch.from_numpy((1.0 * rng.standard_normal((256, cfg.n_poses, cfg.pose_dim)) + 0.3).astype(np.float32))
+    old_graphs = config.set_graphs(False)
+    try:
+        with cabi_emulator.installed(), torch.no_grad():
+            ev = ref.EmbeddingSpaceEvaluator(args, path, lang, CPU)
+            for i in range(0, 256, 64):
+                ev.push_samples(None, None, fake[i:i + 64], real[i:i + 64])
+            fgd, feat_dist = ev.get_scores()
+    finally:
+        config.set_graphs(old_graphs)
+    assert ev.get_no_of_samples() == 4
+    assert abs(fgd - float(g['fgd'])) <= 1e-3 * abs(float(g['fgd'])), (fgd, float(g['fgd']))
+    assert abs(feat_dist - float(g['feat_dist'])) <= 1e-4 * abs(float(g['feat_dist']))
