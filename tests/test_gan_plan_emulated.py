@@ -236,3 +236,54 @@ def test_reference_style_autograd_loop_does_not_accumulate_stale_gradients(emu_f
     for k, g0 in grads[0].items():
         if g0.norm() > 1e-8:
             assert rel_l2(grads[1][k], g0) < 1e-5 and rel_l2(grads[2][k], g0) < 1e-5, k
+
+
+def run_train_variant(dev, ctx, zm, tol=1e-4):
+    """One train_iter_gan step (epoch 11, dropout off) of OUR modules built with the other constructor variants / args.z_type values vs the
+    reference's own run of the same step (tests/golden/train_variants.npz, oracle/make_golden_variants.py)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from gpu_util import make_args
+    from model import vocab
+    from model.multimodal_context_net import ConvDiscriminator, PoseGenerator
+    from oracle import synth
+    from oracle.make_golden import digest, golden_cfg
+    from train_eval import train_gan as TG
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'train_variants.npz'))
+    tag = f'{ctx}_{zm}'
+    args = make_args(cfg)
+    args.input_context, args.z_type = ctx, {'speaker': 'speaker', 'random': 'random', None: 'none'}[zm]
+    z_obj = None
+    if zm == 'speaker':
+        z_obj = vocab.Vocab('vid', insert_default_tokens=False)
+        while z_obj.n_words < cfg.n_speakers:
+            z_obj.index_word('spk%d' % z_obj.n_words)
+    elif zm == 'random':
+        z_obj = 1
+    G = PoseGenerator(args, cfg.pose_dim, cfg.n_words, cfg.wordembed_dim, None, z_obj=z_obj)
+    D = ConvDiscriminator(cfg.pose_dim)
+    G.load_state_dict(synth.with_tcn_aliases(synth.generator_state_dict_variant(cfg, ctx, zm)), strict=True)
+    D.load_state_dict(synth.discriminator_state_dict(cfg), strict=True)
+    G, D = G.to(dev).train(), D.to(dev).train()
+    inp = {k: v.to(dev) for k, v in synth.make_inputs(cfg, 3, seed=1).items()}
+    noise = synth.golden_noise(cfg, 3, 2, False)
+    g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+    TG.inject_noise(TG.StepNoise(eps=[e.to(dev) for e in noise.eps], perm=noise.perm.to(dev), g_masks=[{}, {}, {}], d_masks=[{}, {}, {}]))
+    ret = TG.train_iter_gan(args, 11, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'] if zm == 'speaker' else None, G, D, g_opt, d_opt)
+    want = {k[len(tag) + 6:]: float(g[k]) for k in g.files if k.startswith(tag + '/loss_')}
+    assert set(ret) == set(want), (ret, want)
+    for k, v in ret.items():
+        assert abs(v - want[k]) <= tol * abs(want[k]) + 1e-6, (tag, k, v, want[k])
+    for k, p in G.named_parameters():
+        if not bool(g[f'{tag}/hasgrad/{k}']) or k in GP.ZERO_GRAD_KEYS:
+            continue
+        ref = g[f'{tag}/ggrad/{k}']
+        GP._digest_close(digest(p.grad.cpu())[:34], ref, 3 * tol)
+
+
+@pytest.mark.parametrize('ctx,zm', [('audio', 'speaker'), ('text', 'random'), ('none', None), ('both', 'random'), ('none', 'speaker')])
+def test_train_iter_gan_constructor_variants(emu_fp32, ctx, zm):
+    run_train_variant(CPU, ctx, zm)

@@ -75,3 +75,16 @@ def test_noise_is_drawn_on_the_device_and_cpu_tensors_are_refused(dev, tf32):
 
 def test_fast_mode_batch32_vs_fp64_oracle(dev, tf32):
     joint_checks.run_batch_vs_fp64_oracle(dev, Bn=32, tol=1e-2, gtol=0.3)       # 0.09 predicted by the TF32-truncation model of the emulator
+
+
+@pytest.mark.parametrize('ctx,zm', [('audio', 'speaker'), ('text', 'random'), ('none', None), ('both', 'random'), ('none', 'speaker')])
+def test_train_iter_gan_constructor_variants_vs_reference_golden(dev, fp32, ctx, zm):
+    """The generator's other constructor variants / args.z_type values through a full TRAINING step (the step function branches on
+    z_type, train_gan.py:58-86) vs the reference's own run; added after this round's last GPU call - green on the emulated plan."""
+    from tgb200 import config
+    from test_gan_plan_emulated import run_train_variant
+    old = config.set_graphs(False)
+    try:
+        run_train_variant(dev, ctx, zm)
+    finally:
+        config.set_graphs(old)
