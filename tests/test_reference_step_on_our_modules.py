@@ -271,3 +271,61 @@ def test_unmodified_reference_embedding_space_evaluator_uses_our_embedding_net(t
     assert ev.get_no_of_samples() == 4
     assert abs(fgd - float(g['fgd'])) <= 1e-3 * abs(float(g['fgd'])), (fgd, float(g['fgd']))
     assert abs(feat_dist - float(g['feat_dist'])) <= 1e-4 * abs(float(g['feat_dist']))
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason='the reference tree is only present in the build container')
+@pytest.mark.parametrize('gan_w,reg_w,epoch', [(0.0, 0.05, 11), (5.0, 0.0, 11), (0.0, 0.0, 11), (0.0, 0.0, 0)])
+def test_native_step_equals_reference_step_for_other_loss_weight_settings(gan_w, reg_w, epoch):
+    """train_gan.py:27,58,88 branch on loss_gan_weight / loss_reg_weight / the warm-up: our native train_iter_gan and the UNMODIFIED
+    reference train_iter_gan (autograd over our modules) must agree on which losses are returned, their values and every gradient."""
+    from conftest import rel_l2
+    from tgb200 import config
+    from train_eval import train_gan as TG
+    spec = importlib.util.spec_from_file_location('ref_train_gan2', REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    orig_randperm = torch.randperm
+    try:
+        with cabi_emulator.installed():
+            cfg = golden_cfg()
+            inp = synth.make_inputs(cfg, 3, seed=1)
+            noise = synth.golden_noise(cfg, 3, 2, False)
+            results = []
+            for native in (True, False):
+                args, G, D, _, _ = build_ours(cfg, CPU)
+                args.loss_gan_weight, args.loss_reg_weight = gan_w, reg_w
+                G.train(); D.train()
+                g_opt = torch.optim.Adam(G.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.999))
+                d_opt = torch.optim.Adam(D.parameters(), lr=cfg.learning_rate * cfg.discriminator_lr_weight, betas=(0.5, 0.999))
+                after, do_d, do_div, _ = TG._flags(args, epoch)
+                fwd_ids = ([0] if do_d else []) + [1] + ([2] if do_div else [])
+                if native:
+                    TG.inject_noise(TG.StepNoise(eps=[noise.eps[i] for i in fwd_ids], perm=noise.perm, g_masks=[{}] * len(fwd_ids), d_masks=[{}, {}, {}]))
+                    ret = TG.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+                else:
+                    queue = [noise.eps[i] for i in fwd_ids]
+                    g_forward, d_forward = G.forward, D.forward
+
+                    def g_fwd(*a, **k):
+                        G.set_noise(eps=queue.pop(0), masks={})
+                        return g_forward(*a, **k)
+
+                    def d_fwd(*a, **k):
+                        D.set_noise(masks={})
+                        return d_forward(*a, **k)
+                    G.forward, D.forward = g_fwd, d_fwd
+                    torch.randperm = lambda n, *a, **k: noise.perm.clone()
+                    ret = ref.train_iter_gan(args, epoch, inp['in_text'], inp['in_audio'], inp['target'], inp['vid'], G, D, g_opt, d_opt)
+                    assert not queue
+                results.append((ret, {k: p.grad.clone() for k, p in G.named_parameters()}))
+            (a, ga), (b, gb) = results
+            assert set(a) == set(b), (a, b)
+            for k in a:
+                assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]) + 1e-7, (k, a[k], b[k])
+            for k in ga:
+                if gb[k].norm() > 1e-6 and k not in GP.ZERO_GRAD_KEYS:
+                    assert rel_l2(ga[k], gb[k]) < 1e-4, k
+    finally:
+        torch.randperm = orig_randperm
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
