@@ -182,3 +182,21 @@ def test_checkpoint_layout_round_trip(tmp_path):
     D2.load_state_dict(ck['dis_dict'])
     assert all(torch.equal(a, b) for a, b in zip(G.state_dict().values(), G2.state_dict().values()))
     assert G2.z_obj is ck['speaker_model']                   # what utils.train_utils.get_speaker_model(generator) returns (:152-164)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle on the host cores) prints ONE JSON line with the contract's keys; no GPU involved."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--batch', '8'],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j['impl'] == 'reference' and j['metric'] == 'G+D train samples/s' and j['unit'] == 'samples/s' and j['higher_is_better'] is True
+    assert j['value'] > 0 and j['steps'] == 1 and j['n_gpus'] == 1 and 'workload' in j['config']
+    assert j['cpu_baseline']['kind'] == 'port' and j['cpu_baseline']['cores'] >= 1 and j['cpu_baseline']['value'] == j['value']
+    assert j['e2e'] == {'value': j['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
