@@ -329,3 +329,76 @@ def test_native_step_equals_reference_step_for_other_loss_weight_settings(gan_w,
     finally:
         torch.randperm = orig_randperm
         config.set_mode(old_mode); config.set_graphs(old_graphs)
+
+
+TRAIN = '/root/reference/scripts/train.py'
+
+
+@pytest.mark.skipif(not os.path.exists(TRAIN), reason='the reference tree is only present in the build container')
+@pytest.mark.parametrize('model', ['multimodal_context', 'seq2seq'])
+def test_unmodified_reference_evaluate_testset_agrees_with_ours(model):
+    """scripts/train.py::evaluate_testset (extracted with ast together with the reference's AverageMeter, get_speaker_model and
+    convert_dir_vec_to_pose; the module itself imports matplotlib / lmdb) run over OUR generator and OUR EmbeddingSpaceEvaluator, vs OUR
+    device-side evaluate_testset on fresh, identically seeded modules: same loss, joint MAE, FGD and feature distance."""
+    import argparse
+    import ast
+    import logging
+    import random
+    import time
+    import torch.nn.functional as F
+    import test_gpu_seq2seq as GS
+    from model import vocab
+    from model.embedding_net import EmbeddingNet
+    from model.embedding_space_evaluator import EmbeddingSpaceEvaluator
+    from oracle import seq2seq_oracle as S
+    from oracle import trimodal_oracle as O
+    from oracle.make_golden_eval import MEAN_DIR_VEC, reference_convert
+    from tgb200 import config
+    from train_eval.evaluate import evaluate_testset as ours
+    from train_eval.train_joint_embed import eval_embed
+
+    def extract(path, names, ns):
+        tree = ast.parse(open(path).read())
+        keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+        assert len(keep) == len(names), names
+        exec(compile(ast.Module(body=keep, type_ignores=[]), path, 'exec'), ns)
+        return ns
+    um = extract('/root/reference/scripts/utils/train_utils.py', ['get_speaker_model'], {'vocab': vocab})
+    am = extract('/root/reference/scripts/utils/average_meter.py', ['AverageMeter'], {})
+    utils_ns = argparse.Namespace(train_utils=argparse.Namespace(get_speaker_model=um['get_speaker_model']))
+    ns = extract(TRAIN, ['evaluate_testset'], {'torch': torch, 'np': np, 'F': F, 'time': time, 'random': random, 'logging': logging, 'device': CPU,
+                                                'AverageMeter': am['AverageMeter'], 'utils': utils_ns, 'eval_embed': eval_embed,
+                                                'convert_dir_vec_to_pose': reference_convert()})
+    ref_eval = ns['evaluate_testset']
+    old_mode, old_graphs = config.set_mode('fp32'), config.set_graphs(False)
+    try:
+        with cabi_emulator.installed():
+            cfg = O.HotPathConfig(n_words=200, n_speakers=12)
+            s_cfg = S.Seq2SeqConfig(n_words=200)
+            batches = []
+            for i, B in enumerate((5, 3)):                                       # unequal batch sizes: the averages are sample-weighted
+                inp = synth.make_inputs(cfg, B, seed=40 + i)
+                s2s = synth.seq2seq_inputs(s_cfg, B, seed=50 + i, max_len=7)
+                batches.append((s2s['in_text'], s2s['lengths'], inp['in_text'], None, inp['target'], inp['in_audio'], torch.zeros(B, 2, 2), None))
+            results = []
+            for fn in (ref_eval, ours):
+                torch.manual_seed(5); random.seed(5)
+                if model == 'multimodal_context':
+                    args, G, _, _, _ = build_ours(cfg, CPU)
+                    loss_fn = None
+                else:
+                    args, G = GS._build(s_cfg, CPU)
+                    loss_fn = torch.nn.L1Loss()
+                args.model, args.n_poses, args.n_pre_poses, args.mean_dir_vec = model, cfg.n_poses, cfg.n_pre_poses, MEAN_DIR_VEC
+                enet = EmbeddingNet(None, cfg.pose_dim, cfg.n_poses, None, None, None, 'pose')
+                enet.load_state_dict(synth.embedding_net_state_dict(cfg), strict=True)
+                ev = EmbeddingSpaceEvaluator.from_net(enet, cfg.n_pre_poses, CPU)
+                G.train()
+                results.append(fn([tuple(t.clone() if torch.is_tensor(t) else t for t in b) for b in batches], G, loss_fn, ev, args))
+                assert G.training
+            a, b = results
+            assert set(a) == set(b) == {'loss', 'joint_mae', 'frechet', 'feat_dist'}
+            for k in a:
+                assert abs(a[k] - b[k]) <= 2e-4 * abs(a[k]) + 1e-7, (k, a[k], b[k])
+    finally:
+        config.set_mode(old_mode); config.set_graphs(old_graphs)
