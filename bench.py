@@ -212,6 +212,19 @@ def aux_workloads(dev, timed):
         out['autoencoder_train_ms_per_step'] = ms / 50
     except Exception as exc:                                          # a side measurement must never take the headline line down
         out['autoencoder_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
+    # joint-embedding training step, batch 128, eager: measured in a CHILD process (tests/bench_joint.py) - its tf32-mode
+    # backward had not run on hardware when this was written, and a CUDA fault in a child cannot poison this process's context
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'bench_joint.py')], capture_output=True, text=True, timeout=180, cwd=ROOT)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+        if r.returncode == 0 and line:
+            j = json.loads(line[-1])
+            out['joint_embed_train_samples_per_s'] = j['tf32']['samples_per_s']
+            out['joint_embed_train'] = j
+        else:
+            out['joint_embed_train_error'] = (r.stderr.strip().splitlines() or ['rc=%d' % r.returncode])[-1][:300]
+    except Exception as exc:
+        out['joint_embed_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
     return out
 
 
