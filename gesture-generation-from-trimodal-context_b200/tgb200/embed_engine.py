@@ -385,7 +385,10 @@ class JointEmbeddingEngine:
         return self
 
     def _tc(self):
-        return config.fast()
+        """Recurrence kernel family of ContextEncoder.gru.  The strict-fp32 persistent kernels in BOTH arithmetic modes: this GRU is tiny
+        (2 layers, H=256), so the tensor-core recurrence buys nothing measurable, and H=256 is a boundary of the tensor-core backward
+        kernel's tiling (one vs two N halves) that has not been exercised on hardware, while the fp32 family has (forward and backward)."""
+        return False
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, in_text, in_audio, pre_poses, poses, branch, training):

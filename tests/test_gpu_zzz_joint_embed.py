@@ -6,7 +6,8 @@ import torch
 
 import joint_checks
 
-pytestmark = pytest.mark.gpu
+# the cases below that have not run on hardware yet get a hard per-test limit: a hung persistent kernel must not hang the whole GPU run
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method='thread')]
 
 
 @pytest.fixture(scope='module')
