@@ -152,7 +152,7 @@ def workload_config(a, world):
             'l2': 'per-step working set (~1.5 GB of activations) exceeds the 126 MB L2; inputs rotate over 8 distinct batches'}
 
 
-def aux_workloads(dev, timed):
+def aux_workloads(dev, timed, joint=False):
     """Side measurements of the other BASELINE.json configs on one GPU (reported next to the headline, not part of it):
     configs[3] seq2seq training step at batch 128, configs[4] FGD over 10k synthetic clip pairs."""
     out = {}
@@ -212,8 +212,11 @@ def aux_workloads(dev, timed):
         out['autoencoder_train_ms_per_step'] = ms / 50
     except Exception as exc:                                          # a side measurement must never take the headline line down
         out['autoencoder_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
-    # joint-embedding training step, batch 128, eager: measured in a CHILD process (tests/bench_joint.py) - its tf32-mode
-    # backward had not run on hardware when this was written, and a CUDA fault in a child cannot poison this process's context
+    # joint-embedding training step, batch 128, eager: opt-in (--aux-joint) and measured in a CHILD process
+    # (tests/bench_joint.py) - its batch-128 path had not run on hardware when this was written, and a CUDA fault in a child cannot
+    # poison this process's context
+    if not joint:
+        return out
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'bench_joint.py')], capture_output=True, text=True, timeout=180, cwd=ROOT)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
@@ -238,6 +241,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
+    ap.add_argument('--aux-joint', action='store_true', help='also time the joint-embedding training step (child process, tests/bench_joint.py)')
     ap.add_argument('--no-aux', action='store_true', help='skip the seq2seq / FGD side measurements (BASELINE.json configs[3], configs[4])')
     a = ap.parse_args()
     if a.impl == 'reference':
@@ -355,7 +359,7 @@ def main():
     G.train()
     aux = {}
     if world == 1 and not a.no_aux:
-        aux = aux_workloads(dev, timed)
+        aux = aux_workloads(dev, timed, joint=a.aux_joint)
 
     kt = None
     if not a.no_kernel_profile:
