@@ -78,3 +78,30 @@ def test_seq2seq_batch128_plan_vs_fp64_oracle(mode):
             GS.test_seq2seq_step_batch128_vs_fp64_oracle(CPU, mode, 1e-4)      # the emulator does not round to TF32: fp32-class agreement in both
     finally:
         config.set_graphs(old)
+
+
+@pytest.mark.parametrize('kw', [dict(hidden_size=64, n_layers=1), dict(hidden_size=96, n_layers=3), dict(n_pre_poses=2)],
+                         ids=lambda kw: ','.join('%s=%s' % it for it in kw.items()))
+def test_seq2seq_other_hyper_parameters(emu_fp32, kw):
+    """The seq2seq plan is not hard-wired to config/seq2seq.yml: other layer counts, hidden widths and seed-pose counts vs the fp64 oracle."""
+    import argparse
+    from conftest import rel_l2
+    from model.seq2seq_net import Seq2SeqNet
+    from oracle import seq2seq_oracle as S
+    from oracle import synth
+    from train_eval.train_seq2seq import train_iter_seq2seq
+    cfg = S.Seq2SeqConfig(n_words=150, dropout_prob=0.0, **kw)
+    args = argparse.Namespace(hidden_size=cfg.hidden_size, n_layers=cfg.n_layers, dropout_prob=0.0, n_pre_poses=cfg.n_pre_poses, GAN_noise_size=0,
+                              loss_regression_weight=250.0, loss_kld_weight=0.1, loss_reg_weight=25.0)
+    net = Seq2SeqNet(args, cfg.pose_dim, cfg.n_poses, cfg.n_words, cfg.wordembed_dim, None)
+    sd = synth.seq2seq_state_dict(cfg)
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    inp = synth.seq2seq_inputs(cfg, 5, seed=2, max_len=7)
+    ref = S.train_iter_seq2seq_oracle(cfg, {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, inp['in_text'], inp['lengths'],
+                                      inp['target'].double(), None, step=1)
+    ret = train_iter_seq2seq(args, 0, inp['in_text'], inp['lengths'], inp['target'], net, torch.optim.Adam(net.parameters(), lr=cfg.learning_rate))
+    assert abs(ret['loss'] - float(ref['loss'])) <= 1e-5 * abs(float(ref['loss']))
+    for k, p in net.named_parameters():
+        if float(ref['grads'][k].norm()) > 1e-6:
+            assert rel_l2(p.grad, ref['grads'][k]) < 1e-4, k
