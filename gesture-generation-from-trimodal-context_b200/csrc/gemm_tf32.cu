@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for ptxas (feeds uniform registers)
   if (threadIdx.x == 0) stamp(p.trace, 1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < iters; ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = idesc_tf32(BM, BN, 0, 0);
       for (int it = 0; it < iters; ++it) {
         const int s = it % NSTAGE;

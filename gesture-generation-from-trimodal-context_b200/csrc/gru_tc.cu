@@ -302,182 +302,6 @@ __global__ void __launch_bounds__(576, 1) gru_fwd_tc_kernel(const __grid_constan
 }
 
 // =====================================================================================================================
-// forward, thread-block-cluster variant (opt-in: TGB200_GRU_CLUSTER=1; EXPERIMENTAL until validated on the GPU)
-//
-// The UC = 8 unit-chunk CTAs of one (batch tile, direction) group form one cluster.  Instead of publishing h_t to global memory
-// (store -> __threadfence -> L2 counter -> poll -> TMA reload of the operand tile: ~5 us of the 8.3 us step chain), every thread owns
-// (clip, 4 consecutive hidden units) for all T steps, keeps h in registers and writes its 16-byte slice straight into the K-major
-// 128B-swizzled operand tile of all 8 CTAs through distributed shared memory; two cluster barriers per step order the exchange:
-//   B1 "every CTA has finished reading its gate scratch (which aliases the operand tile)"  ->  DSMEM writes  ->  fence.proxy.async
-//   B2 (arrive.release / wait.acquire) "every slice of h_t has landed"                      ->  the MMA of step t+1 may be issued.
-// Clusters are independent of each other: no grid-wide co-residency requirement, no cooperative launch.
-// =====================================================================================================================
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-template <int BT>
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(576, 1)
-    gru_fwd_cl_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const FwdP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int W_CHUNK = 128 * 128;          // 128 rows x 128 B
-  constexpr int H_CHUNK = BT * 128;
-  constexpr int GS = BT + 1;
-  const int nkc = p.nkc;
-  uint8_t* Wt = smem;                          // [nkc][128 rows][128 B]
-  uint8_t* Ht = smem + (size_t)nkc * W_CHUNK;  // [nkc][BT rows][128 B]; aliased by ghs[128][GS] between the MMA and barrier B1
-  float* ghs = reinterpret_cast<float*>(Ht);
-  size_t ht_bytes = (size_t)nkc * H_CHUNK;
-  if (ht_bytes < (size_t)128 * GS * 4) ht_bytes = (size_t)128 * GS * 4;
-  ht_bytes = (ht_bytes + 15) & ~(size_t)15;
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(Ht + ht_bytes);
-  uint64_t* tmem_full = w_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x, by = blockIdx.y, dir = blockIdx.z;      // c == rank in the cluster (cluster = the 8 CTAs along x)
-  const int H = p.H, T = p.T, u = p.u;
-  const int u0 = c * u;
-  const CUtensorMap* tmW = dir ? &tmW1 : &tmW0;
-  constexpr uint32_t TMEM_COLS = BT <= 32 ? 32 : 64;
-
-  // operand regions start finite: K-padding columns of the last chunk meet zero weights, 0 * garbage must not be NaN
-  for (int i = threadIdx.x; i < (int)(((size_t)nkc * W_CHUNK + ht_bytes) / 16); i += blockDim.x)
-    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmW);
-    mbar_init(w_full, 1);
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp == 0 && lane == 0) {
-    mbar_expect_tx(w_full, (uint32_t)(nkc * 3 * u * 128));
-    for (int kc = 0; kc < nkc; ++kc)
-      for (int g = 0; g < 3; ++g) tma_load_2d(Wt + (size_t)kc * W_CHUNK + (size_t)g * u * 128, tmW, w_full, kc * 32, g * H + u0);
-  }
-  if (warp == 1 && lane == 0) mbar_wait(w_full, 0);
-  cluster_arrive();          // every CTA of the cluster has zeroed its operand tile before any peer writes into it
-  cluster_wait();
-
-  // ---- ownership: epilogue thread etid < BT * u/4 owns (clip bb, units 4*quad .. 4*quad+3) of this CTA's chunk for all steps
-  const int etid = (int)threadIdx.x - 64;
-  const int nquad = u >> 2;
-  const bool epi = etid >= 0;
-  const bool owner = epi && etid < BT * nquad;
-  const int bb = owner ? etid / nquad : 0;
-  const int quad = owner ? etid - bb * nquad : 0;
-  const int b = by * BT + bb;
-  const int unit0 = u0 + quad * 4;
-  const bool live = owner && b < p.B && unit0 < H;                  // H % 4 == 0: a quad is entirely valid or entirely out of range
-  const float* bhh = p.bhh[dir];
-  float4 bh_r = make_float4(0.f, 0.f, 0.f, 0.f), bh_z = bh_r, bh_n = bh_r;
-  if (live) { bh_r = ldv_nc4(bhh + unit0); bh_z = ldv_nc4(bhh + H + unit0); bh_n = ldv_nc4(bhh + 2 * H + unit0); }
-  float hreg[4] = {0.f, 0.f, 0.f, 0.f};
-  // destination of this thread's slice inside a CTA's operand tile (same offset in every peer): chunk, swizzled 16-byte unit
-  const int k0 = unit0;
-  const uint32_t slice_off = (uint32_t)((k0 >> 5) * H_CHUNK + (bb >> 3) * 1024 + (bb & 7) * 128 + ((((k0 & 31) >> 2) ^ (bb & 7)) << 4));
-  const uint32_t ht_saddr = smem_u32(Ht);
-  const int q = warp & 3;
-  const int lr = q * 32 + lane;
-  const long long row2H = 2ll * H;
-  constexpr uint32_t idesc = idesc_tf32(128, BT, 0, 0);
-
-  for (int s = 0; s < T; ++s) {
-    const int t = dir == 0 ? s : T - 1 - s;
-    float4 gi_r = make_float4(0.f, 0.f, 0.f, 0.f), gi_z = gi_r, gi_n = gi_r;
-    if (live) {                                                     // issued before the MMA wait: in flight during it
-      const float* gip = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + unit0;
-      gi_r = ldv_nc4(gip); gi_z = ldv_nc4(gip + H); gi_n = ldv_nc4(gip + 2 * H);
-    }
-    if (s > 0) {
-      if (warp == 1 && lane == 0) {                                 // h_{t-1} tile complete (barrier B2 of the previous step)
-        tc_fence_after();
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t sa = smem_u32(Wt + (size_t)kc * W_CHUNK);
-          const uint32_t sb = smem_u32(Ht + (size_t)kc * H_CHUNK);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            mma_tf32(tmem_base, smem_desc_sw128(sa + k4 * 32, 16, 1024), smem_desc_sw128(sb + k4 * 32, 16, 1024), idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
-        }
-        tc_commit(tmem_full);
-      }
-      if (epi) {
-        if (warp < 6) {                                             // warps 2-5: accumulator TMEM -> gate scratch (thread = gate row)
-          mbar_wait(tmem_full, (uint32_t)((s - 1) & 1));
-          tc_fence_after();
-          float v[BT];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-          if constexpr (BT == 16) { tmem_ld16(taddr, v); }
-          else if constexpr (BT == 32) { tmem_ld32(taddr, v); }
-          else { tmem_ld32(taddr, v); tmem_ld16(taddr + 32, v + 32); }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < BT; ++j) ghs[lr * GS + j] = v[j];
-          tc_fence_before();
-        }
-        epi_bar512();
-      }
-    }
-    float rr[4], zz[4], nn[4], hn[4];
-    if (live) {
-      const float gir[4] = {gi_r.x, gi_r.y, gi_r.z, gi_r.w}, giz[4] = {gi_z.x, gi_z.y, gi_z.z, gi_z.w}, gin[4] = {gi_n.x, gi_n.y, gi_n.z, gi_n.w};
-      const float br[4] = {bh_r.x, bh_r.y, bh_r.z, bh_r.w}, bz[4] = {bh_z.x, bh_z.y, bh_z.z, bh_z.w}, bn[4] = {bh_n.x, bh_n.y, bh_n.z, bh_n.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int jj = quad * 4 + e;
-        float ghr = br[e], ghz = bz[e], ghn = bn[e];
-        if (s > 0) { ghr += ghs[jj * GS + bb]; ghz += ghs[(u + jj) * GS + bb]; ghn += ghs[(2 * u + jj) * GS + bb]; }
-        rr[e] = sigmoidf_(gir[e] + ghr);
-        zz[e] = sigmoidf_(giz[e] + ghz);
-        nn[e] = tanhf_(gin[e] + rr[e] * ghn);
-        hn[e] = ghn;
-        hreg[e] = (1.f - zz[e]) * nn[e] + zz[e] * hreg[e];
-      }
-    }
-    if (s + 1 < T) {
-      cluster_arrive();        // B1: this CTA no longer reads its gate scratch, peers may overwrite the operand tile
-      cluster_wait();
-      if (owner) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) st_cluster_v4(mapa_cluster(ht_saddr + slice_off, (uint32_t)r), hreg[0], hreg[1], hreg[2], hreg[3]);
-      }
-      fence_proxy_async_all();  // generic-proxy (DSMEM) writes -> visible to the async proxy (tcgen05.mma operand reads)
-      cluster_arrive();        // B2 (release): h_t slices of this CTA are out ...
-    }
-    if (live) {                // ... the global stores for the next layer / the backward pass sit between arrive and wait
-      const long long o = ((long long)b * T + t) * row2H + dir * H + unit0;
-      *reinterpret_cast<float4*>(p.out + o) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
-      if (p.saved) {
-        *reinterpret_cast<float4*>(p.saved + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-        *reinterpret_cast<float4*>(p.saved + p.saved_qstride + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-        *reinterpret_cast<float4*>(p.saved + 2 * p.saved_qstride + o) = make_float4(nn[0], nn[1], nn[2], nn[3]);
-        *reinterpret_cast<float4*>(p.saved + 3 * p.saved_qstride + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-      }
-    }
-    if (s + 1 < T) cluster_wait();   // B2 (acquire): every slice of h_t has landed in this CTA's operand tile
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-  cluster_arrive();            // no CTA exits while a peer might still address its shared memory
-  cluster_wait();
-}
-
-// =====================================================================================================================
 // backward
 // =====================================================================================================================
 struct BwdP {
@@ -788,29 +612,22 @@ int launch_fwd(const CUtensorMap* maps, const FwdP& p, const FwdPlan& pl, cudaSt
   return 0;
 }
 
-template <int BT>
-int launch_fwd_cluster(const CUtensorMap* maps, const FwdP& p, const FwdPlan& pl, cudaStream_t s) {
-  size_t ht = (size_t)pl.nkc * BT * 128;
-  if (ht < (size_t)128 * (BT + 1) * 4) ht = (size_t)128 * (BT + 1) * 4;
-  ht = (ht + 15) & ~(size_t)15;
-  const size_t smem = (size_t)pl.nkc * 128 * 128 + ht + 4 * 8 + 16 + 1024;
-  if (smem > (size_t)tg_max_smem_optin()) { tg_set_error("tg_gru_layer_fwd_tf32(cluster): %zu B of shared memory needed", smem); return -3; }
-  cudaError_t e = cudaFuncSetAttribute(gru_fwd_cl_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32(cluster): smem attr: %s", cudaGetErrorString(e)); return -3; }
-  dim3 grid(8, pl.ntiles, 2);                 // __cluster_dims__(8,1,1): the 8 unit chunks of a (tile, direction) are one cluster
-  gru_fwd_cl_kernel<BT><<<grid, 576, smem, s>>>(maps[0], maps[1], p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32(cluster): launch (8,%d,2) smem %zu: %s", pl.ntiles, smem, cudaGetErrorString(e)); return -2; }
-  return 0;
-}
-
-bool use_cluster_gru() {
+bool use_legacy_gru() {          // TGB200_GRU_LEGACY=1: the L2-counter-stepped kernels of this file even where a cluster plan exists
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TGB200_GRU_CLUSTER"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("TGB200_GRU_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 
 }  // namespace
+
+// cluster / multicast kernels (gru_cl.cu): the default wherever they have a plan (H <= 320)
+struct TgGruClPlan { int u, bt_f, bt_b, ntiles_f, ntiles_b; };
+bool tg_gru_cl_plan(int B, int H, TgGruClPlan* pl);
+size_t tg_gru_cl_xchg_floats(int B, int H);
+int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r, float* out, float* saved,
+                  long long saved_qstride, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s);
+int tg_gru_cl_bwd(const float* dout, const float* out, const float* saved, long long saved_qstride, const float* whhT_f, const float* whhT_r,
+                  float* dgi, float* dgh, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s);
 
 extern "C" int tg_debug_gru_trace(long long* device_buf) {
   g_trace = device_buf;
@@ -821,15 +638,20 @@ extern "C" int tg_gru_tf32_sync_ints(int B, int H) {
   FwdPlan pl;
   if (fwd_plan(B, H, &pl)) return -1;
   int nb_bwd = tg_ceil_div(B, 32);
-  return 2 * (pl.NB > nb_bwd ? pl.NB : nb_bwd);
+  const size_t legacy = (size_t)2 * (pl.NB > nb_bwd ? pl.NB : nb_bwd);
+  const size_t xchg = tg_gru_cl_xchg_floats(B, H);      // the cluster kernels use the same scratch as their exchange images
+  return (int)(legacy > xchg ? legacy : xchg);
 }
 
 extern "C" int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
                                      float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream) {
   TG_REQUIRE(gi && whh_f && whh_r && bhh_f && bhh_r && out && sync && T > 0 && B > 0, "tg_gru_layer_fwd_tf32");
+  cudaStream_t s = (cudaStream_t)stream;
+  TgGruClPlan cpl;
+  if (!use_legacy_gru() && tg_gru_cl_plan(B, H, &cpl))
+    return tg_gru_cl_fwd(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, reinterpret_cast<float*>(sync), B, T, H, g_trace, s);
   FwdPlan pl;
   TG_REQUIRE(fwd_plan(B, H, &pl) == 0, "tg_gru_layer_fwd_tf32");
-  cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: memset: %s", cudaGetErrorString(e)); return -2; }
   CUtensorMap maps[4];
@@ -842,12 +664,6 @@ extern "C" int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const 
   p.gi = gi; p.bhh[0] = bhh_f; p.bhh[1] = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.sync = sync;
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.UC = pl.UC; p.NB = pl.NB; p.ntiles = pl.ntiles; p.nkc = pl.nkc;
   p.trace = g_trace;
-  if (use_cluster_gru() && pl.UC == 8 && (pl.u & 3) == 0) {
-    // experimental cluster / DSMEM variant: one tile per cluster, any number of tiles (clusters are independent)
-    if (pl.BT == 16) return launch_fwd_cluster<16>(maps, p, pl, s);
-    if (pl.BT == 32) return launch_fwd_cluster<32>(maps, p, pl, s);
-    return launch_fwd_cluster<48>(maps, p, pl, s);
-  }
   if (pl.BT == 16) return launch_fwd<16>(maps, p, pl, s);
   if (pl.BT == 32) return launch_fwd<32>(maps, p, pl, s);
   return launch_fwd<48>(maps, p, pl, s);
@@ -885,6 +701,10 @@ extern "C" int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const 
                                      int B, int T, int H, tg_stream stream) {
   TG_REQUIRE(dout && out && saved && whhT_f && whhT_r && dgi && dgh && partial && sync && T > 0 && B > 0, "tg_gru_layer_bwd_tf32");
   TG_REQUIRE(H >= 32 && H <= 384 && (H & 3) == 0, "tg_gru_layer_bwd_tf32");
+  TgGruClPlan cpl;
+  if (!use_legacy_gru() && tg_gru_cl_plan(B, H, &cpl))
+    return tg_gru_cl_bwd(dout, out, saved, saved_qstride, whhT_f, whhT_r, dgi, dgh, reinterpret_cast<float*>(sync), B, T, H, g_trace,
+                         (cudaStream_t)stream);
   BwdP p;
   p.UC = tg_ceil_div(H, BU);
   const int RB = bwd_rows_per_cta(B, H);

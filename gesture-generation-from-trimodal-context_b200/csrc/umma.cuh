@@ -8,6 +8,15 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Branching on elect.sync (not on `lane == 0`) tells ptxas that exactly one thread runs the region, so
+// the TMA / tcgen05 operands (descriptors, coordinates, TMEM addresses) are computed on the uniform datapath.  With `lane == 0` every
+// UTCHMMA / UTMALDG was wrapped in an ELECT + R2UR.BROADCAST + branch "waterfall" loop: ~140 cycles per issued MMA (measured, round 2).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(320, MINB) wgrad_tf32_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for ptxas (feeds uniform registers)
 
   if (iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int it = 0; it < iters; ++it) {
           const int s = it % NSTAGE;
           const uint32_t ph = (it / NSTAGE) & 1;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(320, MINB) wgrad_tf32_kernel(const __grid_cons
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr uint32_t idesc = idesc_tf32(128, 128, 1, 1);
         for (int it = 0; it < iters; ++it) {
           const int s = it % NSTAGE;

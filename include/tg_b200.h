@@ -276,6 +276,11 @@ int tg_pose_eval_metrics(const float* out, const float* target, int B, int T, in
 int tg_copy_bytes(void* dst, const void* src, long long nbytes, int max_ctas, tg_stream stream);
 
 int tg_debug_gru_trace(long long* device_buf);
+/* development aid: how many 8-CTA clusters of the tensor-core recurrence (forward kernel, batch tile BT in {16,32,48}, hidden size H) the
+ * device keeps resident at once (cudaOccupancyMaxActiveClusters); a B200 is expected to answer 16 = one wave for 8 tiles x 2 directions */
+int tg_debug_gru_cluster_occupancy(int H, int BT);
+/* development aid: the batch tiles the cluster recurrence picks for B clips, packed as forward_tile * 1000 + backward_tile (-1: no plan) */
+int tg_debug_gru_cluster_tiles(int B, int H);
 /* development aid: %globaltimer stamps of CTA (0,0) of the next tg_gemm_tf32 launches (7 slots; NULL disables) */
 int tg_debug_gemm_trace(long long* device_buf);
 size_t tg_gru_bwd_tf32_scratch_floats(int B, int H);
