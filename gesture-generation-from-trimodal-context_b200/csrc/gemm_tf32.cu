@@ -109,12 +109,8 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + A_STAGE_BYTES;
         const uint32_t dcol = tmem_base + (uint32_t)(tap * BN);
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t ad = smem_desc_sw128(sa + k4 * 32, 16, 1024);
-          const uint64_t bd = smem_desc_sw128(sb + k4 * 32, 16, 1024);
-          mma_tf32(dcol, ad, bd, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
-        }
+        constexpr uint32_t hi = desc_hi(1024, 2);                // SWIZZLE_128B; the 4 K-steps of a stage walk the 128-byte row: +32 B each
+        mma_tf32_seq<4, 2>(dcol, desc_lo(sa, 16), hi, desc_lo(sb, 16), hi, idesc, kb > 0 ? 1u : 0u);
         tc_commit(&empty_bar[s]);
       }
       tc_commit(tmem_full_bar);

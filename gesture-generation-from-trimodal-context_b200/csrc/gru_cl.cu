@@ -100,17 +100,6 @@ struct KLay {
   int tail_ksteps;    // K-steps of the tail chunk
   int gsz, ngf;       // full chunks per multicast group, number of full groups (ngf + (tail_w > 0) <= 8)
 };
-// shared-memory matrix descriptor of a K-major tile whose rows are `row_bytes` (128 / 64 / 32) wide and swizzled at that width
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, int row_bytes) {
-  const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;      // SWIZZLE_128B / 64B / 32B
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                                   // LBO (unused for swizzled K-major): 16 bytes
-  d |= (uint64_t)(((uint32_t)(8 * row_bytes) >> 4) & 0x3FFF) << 32;   // SBO: 8 rows
-  d |= (uint64_t)1 << 46;                                   // version = 1 (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
-}
 // byte offset of float k of row `row` inside the IMAGE of a B operand tile: [nfull][rows][128 B] then [rows][tail_w * 4 B]; every
 // 16-byte unit j of a row sits at j ^ (row bits selected by the swizzle width)
 __device__ __forceinline__ uint32_t image_off(int row, int k, int rows, const KLay& L) {
@@ -123,20 +112,29 @@ __device__ __forceinline__ uint32_t image_off(int row, int k, int rows, const KL
   return base + (uint32_t)(row * 32 + (((kl >> 2) ^ ((row >> 2) & 1)) << 4) + (kl & 3) * 4);
 }
 
-// One elected thread: MMAs of full-chunk group g (or of the tail chunk) of D[tmem] (+)= A * B.
-// a_chunk / b_chunk = bytes per full chunk of the A / B tile; tails live at a_tail / b_tail.
+// One elected thread: MMAs of full-chunk group g (or of the tail chunk) of D[tmem] (+)= A * B.  a_chunk / b_chunk = bytes per full chunk of
+// the A / B tile; K-major operands, descriptor halves per umma.cuh (lo walks the tile: +2 per 8-float K-step, + chunk bytes / 16 per chunk).
+template <int NK>
+__device__ __forceinline__ void issue_ksteps(int nk, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  if (nk == 4) mma_tf32_seq<4, 2>(tmem_d, a_lo, hi, b_lo, hi, idesc, acc);
+  else if (nk == 3) mma_tf32_seq<3, 2>(tmem_d, a_lo, hi, b_lo, hi, idesc, acc);
+  else if (nk == 2) mma_tf32_seq<2, 2>(tmem_d, a_lo, hi, b_lo, hi, idesc, acc);
+  else mma_tf32_seq<1, 2>(tmem_d, a_lo, hi, b_lo, hi, idesc, acc);
+}
 __device__ __forceinline__ void issue_full_group(uint32_t tmem_d, uint32_t a_base, uint32_t a_chunk, uint32_t b_base, uint32_t b_chunk, int g,
                                                  const KLay& L, uint32_t idesc) {
-  const int kc_hi = min(L.nfull, (g + 1) * L.gsz);
-  for (int kc = g * L.gsz; kc < kc_hi; ++kc) {
-    const uint32_t sa = a_base + (uint32_t)kc * a_chunk, sb = b_base + (uint32_t)kc * b_chunk;
-    const int kn = kc == L.nfull - 1 ? L.last_ksteps : 4;
-    for (int k4 = 0; k4 < kn; ++k4) mma_tf32(tmem_d, kdesc(sa + k4 * 32, 128), kdesc(sb + k4 * 32, 128), idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
+  constexpr uint32_t hi = desc_hi(1024, 2);                 // SWIZZLE_128B, 8 rows x 128 B between row groups
+  const int kc_lo = g * L.gsz, kc_hi = min(L.nfull, (g + 1) * L.gsz);
+  uint32_t a_lo = desc_lo(a_base + (uint32_t)kc_lo * a_chunk, 16), b_lo = desc_lo(b_base + (uint32_t)kc_lo * b_chunk, 16);
+  for (int kc = kc_lo; kc < kc_hi; ++kc, a_lo += a_chunk >> 4, b_lo += b_chunk >> 4) {
+    if (kc < L.nfull - 1) mma_tf32_seq<4, 2>(tmem_d, a_lo, hi, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
+    else issue_ksteps<0>(L.last_ksteps, tmem_d, a_lo, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
   }
 }
 __device__ __forceinline__ void issue_tail(uint32_t tmem_d, uint32_t a_tail, uint32_t b_tail, const KLay& L, uint32_t idesc) {
-  const int rb = L.tail_w * 4;
-  for (int k4 = 0; k4 < L.tail_ksteps; ++k4) mma_tf32(tmem_d, kdesc(a_tail + k4 * 32, rb), kdesc(b_tail + k4 * 32, rb), idesc, (L.nfull > 0 || k4 > 0) ? 1u : 0u);
+  // rows of tail_w floats: 64-byte swizzle (layout 4, SBO 512) for 16 floats, 32-byte swizzle (layout 6, SBO 256) for 8
+  const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
+  issue_ksteps<0>(L.tail_ksteps, tmem_d, desc_lo(a_tail, 16), desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),

@@ -93,6 +93,36 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One MMA with each operand descriptor handed over as its two 32-bit halves (lo = start address >> 4 | LBO << 16, hi = SBO | version |
+// layout): a sequence of MMAs that walks an operand only has to add to `lo` (shared memory is < 256 KB: the 14-bit field never carries).
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// NK back-to-back MMAs: descriptor k = {lo + k * STEP16, hi}.  The first overwrites D when `accumulate` is 0, the others accumulate.
+// Two uniform adds per MMA instead of rebuilding two 64-bit descriptors: with ONE thread issuing, the ~18 dependent uniform-datapath
+// instructions of the descriptor arithmetic cost ~120 cycles per MMA (measured in the recurrence kernels, round 2) - more than a
+// 128 x 64 x 8 MMA takes to execute.
+template <int NK, int STEP16>
+__device__ __forceinline__ void mma_tf32_seq(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) mma_tf32_lohi(d_tmem, a_lo + k * STEP16, a_hi, b_lo + k * STEP16, b_hi, idesc, k == 0 ? accumulate : 1u);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit)
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29); }
+
 // 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);

@@ -85,10 +85,16 @@ __global__ void __launch_bounds__(320, MINB) wgrad_tf32_kernel(const __grid_cons
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE);
           const uint32_t sb = sa + OPER;
-#pragma unroll
-          for (int k8 = 0; k8 < TK / 8; ++k8)
-            mma_tf32(tmem_base, smem_desc_mn_tf32(sa + k8 * 1024, BOX, 512), smem_desc_mn_tf32(sb + k8 * 1024, BOX, 512), idesc,
-                     (it > 0 || k8 > 0) ? 1u : 0u);
+          // MN-major 32-bit atoms (layout 1 = SWIZZLE_128B_BASE32B): LBO = BOX bytes between 32-element groups, SBO = 512 B between
+          // 4-row K groups; each K-step of 8 rows advances the start address by 1024 B (64 x 16 B)
+          constexpr uint32_t hi = desc_hi(512, 1);
+          static_assert(TK % 8 == 0 && TK / 8 >= 1 && TK / 8 <= 8, "K-steps per stage");
+          if constexpr (TK / 8 <= 4) {
+            mma_tf32_seq<TK / 8, 64>(tmem_base, desc_lo(sa, BOX), hi, desc_lo(sb, BOX), hi, idesc, it > 0 ? 1u : 0u);
+          } else {
+            mma_tf32_seq<4, 64>(tmem_base, desc_lo(sa, BOX), hi, desc_lo(sb, BOX), hi, idesc, it > 0 ? 1u : 0u);
+            mma_tf32_seq<TK / 8 - 4, 64>(tmem_base, desc_lo(sa + 4096, BOX), hi, desc_lo(sb + 4096, BOX), hi, idesc, 1u);
+          }
           tc_commit(&empty_bar[s]);
         }
         tc_commit(tmem_full);

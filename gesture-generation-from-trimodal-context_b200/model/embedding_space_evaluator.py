@@ -3,7 +3,7 @@
 push_samples runs the EmbeddingNet kernels on the real and the generated clips and folds the 32-d features straight
 into fp64 sufficient statistics on the device (count, sum x, sum x x^T, sum |real-gen|), so nothing is copied to the host
 per batch (the reference does 2 x .cpu().numpy() + 2 x .item() per batch, :55-60).  get_scores makes ONE device->host
-copy, (all-)reduces across ranks when torch.distributed is initialised, forms mean / covariance (ddof=1, == np.cov) in
+copy, optionally (reduce=True) sums the statistics of the ranks' shards first, forms mean / covariance (ddof=1, == np.cov) in
 float64 and evaluates the 32x32 matrix square root on the host with SciPy exactly like the reference (:138-156)."""
 import numpy as np
 import torch
@@ -74,13 +74,18 @@ class EmbeddingSpaceEvaluator:
         cov = (sxx - n * np.outer(mu, mu)) / (n - 1.0)
         return mu, cov
 
-    def get_scores(self):
+    def get_scores(self, reduce=False):
+        """reduce=False (default, like the reference's purely local getter, :74-101): scores of what THIS process pushed.
+        reduce=True: every rank of the default process group must call it, each having pushed its own SHARD of the test set; the fp64
+        sufficient statistics are summed across ranks first (one all-reduce of 2 x 1057 + 4 doubles), so all ranks return the scores of
+        the union.  Do not use it when every rank pushed the full set (the counts would be multiplied by the world size)."""
         acc = torch.stack([self.acc_real, self.acc_gen])
         misc = self.acc_misc.clone()
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(acc)
-            dist.all_reduce(misc)
+        if reduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(acc)
+                dist.all_reduce(misc)
         acc = acc.cpu().numpy()
         misc = misc.cpu().numpy()
         b_mu, b_sigma = self._moments(acc[0], self.F)      # real

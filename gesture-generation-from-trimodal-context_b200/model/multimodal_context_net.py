@@ -64,8 +64,17 @@ class _NoiseSource:
     """Philox stream state of one module: a device-resident offset so CUDA-graph replays draw fresh numbers."""
 
     def __init__(self, seed):
-        self.seed = seed
+        self.base_seed = seed
         self.offset = None
+
+    @property
+    def seed(self):
+        """Data-parallel ranks draw INDEPENDENT dropout masks / reparameterisation noise / speaker permutations (like the per-replica
+        generators of nn.DataParallel, train.py:93-96): the rank is mixed into the Philox key at use time, so identical weights no
+        longer have to come from identical RNG seeds (the flat arena is broadcast from rank 0 once, train_gan._dp_sync_once)."""
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return (self.base_seed ^ (rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
 
     def offset_dev(self, device):
         if self.offset is None or self.offset.device != device:

@@ -181,7 +181,26 @@ def _generate_seq2seq(args, pose_decoder, lang_model, audio, words, audio_sr, se
             windows[i] = out[0]
             poses[0, 0:n_pre] = out[0, -n_pre:]
     out_dir_vec = _crossfade_and_stack(windows.cpu().numpy(), n_pre)
+    out_dir_vec = _smooth_window_joins(out_dir_vec, n_sub, n_frames, n_pre)
     return _fade_out(out_dir_vec, args, end_padding, audio_sr) if fade_out else out_dir_vec
+
+
+def _smooth_window_joins(out_dir_vec, n_sub, n_frames, n_pre):
+    """seq2seq only (synthesize.py:163-185): around the start of every window the stacked sequence is replaced, in place and window after
+    window, by its own least-squares cubic over 3 * n_pre frames beginning n_pre frames before the join (2 * n_pre frames from frame 0
+    for the first window).  The fit is unweighted (the reference builds end weights but never hands them to polyfit)."""
+    stride = n_frames - n_pre
+    for i in range(n_sub):
+        lo = n_pre + i * stride - n_pre
+        hi = lo + (3 if lo >= 0 else 2) * n_pre
+        lo = max(lo, 0)
+        seg = out_dir_vec[lo:hi]
+        if len(seg) == 0:
+            continue
+        x = np.arange(len(seg), dtype=np.float64)
+        coeffs = np.polyfit(x, seg, 3)                                          # one cubic per pose dimension: [4, D]
+        out_dir_vec[lo:hi] = np.vander(x, 4) @ coeffs
+    return out_dir_vec
 
 
 def generate_gestures(args, pose_decoder, lang_model, audio, words, audio_sr=16000, vid=None, seed_seq=None, fade_out=False):

@@ -36,6 +36,7 @@ class DevicePrefetcher:
         self._pin = {}
         self._dev = {}
         self._free = [None] * (depth + 1)          # per ring slot: event after which the consumer no longer reads the slot's buffers
+        self._copied = [None] * (depth + 1)        # per ring slot: event after which the slot's pinned staging buffers may be refilled
 
     def _to_device(self, t):
         self._k += 1
@@ -57,12 +58,15 @@ class DevicePrefetcher:
 
     def _issue(self, batch, slot):
         self._slot, self._k = slot, 0
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()       # the previous host->device copy out of this slot's pinned staging buffers has finished
         with torch.cuda.stream(self.stream):
             if self._free[slot] is not None:
                 self.stream.wait_event(self._free[slot])
             dev_batch = _map(batch, self._to_device)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+            self._copied[slot] = ev
         return dev_batch, ev, slot
 
     def __iter__(self):

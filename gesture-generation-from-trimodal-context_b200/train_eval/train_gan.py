@@ -64,6 +64,20 @@ def _allreduce_grads(arena, bucket_floats=4 << 20):
         w.wait()
 
 
+def _dp_sync_once(module, arena):
+    """First data-parallel step of a (module, flat arena): rank 0's parameters and buffers become everybody's (what nn.DataParallel's
+    replicate-from-device-0 does every forward, train.py:93-96), so identical initial weights do not depend on identical RNG seeds."""
+    import torch.distributed as dist
+    key = arena.flat.data_ptr()
+    if getattr(arena, '_dp_synced', None) == key or torch.cuda.is_current_stream_capturing():
+        return
+    dist.broadcast(arena.flat, 0)
+    for b in module.buffers():
+        if b.is_floating_point():
+            dist.broadcast(b, 0)
+    arena._dp_synced = key
+
+
 class _GraphSlot:
     """One captured CUDA graph of the whole iteration for a fixed (modules, batch shape, schedule, hyper-parameters)."""
 
@@ -74,7 +88,6 @@ class _GraphSlot:
         self.static = None
 
 
-_graph_slots = {}
 _GRAPH_WARMUP = 2          # eager iterations (allocate every workspace) before the iteration is captured
 
 
@@ -111,7 +124,12 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
                G.training, D.training, config.mode(), config.overlap(), world, float(gg['lr']), float(dg['lr']), tuple(gg['betas']), tuple(dg['betas']),
                float(args.loss_regression_weight), float(args.loss_gan_weight), float(args.loss_kld_weight), float(args.loss_reg_weight),
                int(args.n_pre_poses))
-        slot = _graph_slots.setdefault(key, _GraphSlot())
+        ge0, de0 = G.engine(), D.engine()
+        key = key + (ge0.arena.flat.data_ptr() if ge0.arena.flat is not None else 0, de0.arena.flat.data_ptr() if de0.arena.flat is not None else 0)
+        slots = ge0.__dict__.setdefault('_gan_graph_slots', {})      # dies with the generator's engine: no stale graph can outlive its workspaces
+        for k in [k for k in slots if k[-2:] != key[-2:]]:
+            del slots[k]                                              # the arenas were rebuilt: graphs captured on the old storage are dead
+        slot = slots.setdefault(key, _GraphSlot())
         slot.calls += 1
         if not slot.failed and slot.calls > _GRAPH_WARMUP and G.engine().arena.is_current() and D.engine().arena.is_current():
             sc = _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim)
@@ -220,6 +238,8 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     ge = G.engine().ensure(dev, 'train_%d' % B)
     de = D.engine().ensure(dev, 'train_%d' % B)
     ws = ge.ws
+    if world > 1:
+        _dp_sync_once(G, ge.arena); _dp_sync_once(D, de.arena)
 
     # ---- pass list: [D-step forward] + G-step forward + [permuted-speaker forward]
     passes = (['d'] if do_d else []) + ['g'] + (['r'] if do_div else [])

@@ -12,7 +12,6 @@ from tgb200 import _lib, config, ops
 
 _MAX_NORM = 5.0            # train_seq2seq.py:48
 _GRAPH_WARMUP = 2
-_graph_slots = {}
 _injected_masks: Optional[dict] = None
 
 
@@ -84,7 +83,11 @@ def train_iter_seq2seq(args, epoch, in_text, in_lengths, target_poses, net, opti
         g = optim.param_groups[0]
         key = (id(net_), id(optim), dev.index, B, Tm, tuple(in_text.shape), config.mode(), float(g['lr']), tuple(g['betas']),
                float(args.loss_regression_weight), float(args.loss_kld_weight), float(args.loss_reg_weight))
-        slot = _graph_slots.setdefault(key, _Slot())
+        key = key + (eng.arena.flat.data_ptr() if eng.arena.flat is not None else 0,)
+        slots = eng.__dict__.setdefault('_graph_slots', {})          # lives and dies with the engine (no id() reuse across re-created models)
+        for k in [k for k in slots if k[-1] != key[-1]]:
+            del slots[k]
+        slot = slots.setdefault(key, _Slot())
         slot.calls += 1
         if not slot.failed and slot.calls > _GRAPH_WARMUP and eng.arena.is_current():
             if slot.static is None:

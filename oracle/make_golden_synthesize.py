@@ -19,7 +19,7 @@ import torch
 
 from .make_golden import OUT
 from .make_golden_eval import MEAN_DIR_VEC
-from .synthesize_stub import StubGenerator, StubVocab, make_clip
+from .synthesize_stub import StubGenerator, StubSeq2Seq, StubVocab, make_clip
 
 SYN = '/root/reference/scripts/synthesize.py'
 DPP = '/root/reference/scripts/data_loader/data_preprocessor.py'
@@ -55,6 +55,14 @@ def main():
         audio, words, seed = make_clip(seconds, seed=len(tag))
         with contextlib.redirect_stdout(io.StringIO()):
             out = gg(args, StubGenerator(), StubVocab(), audio, words, vid=7, seed_seq=seed, fade_out=fade)
+        store[tag] = np.asarray(out)
+        print(tag, np.asarray(out).shape)
+    # the seq2seq baseline takes the same driver with its own call form and an extra cubic smoothing pass over every window boundary (:163-185)
+    args.model = 'seq2seq'
+    for tag, seconds, fade in (('s2s_short', 1.7, False), ('s2s_long', 9.3, False), ('s2s_fade', 6.1, True)):
+        audio, words, seed = make_clip(seconds, seed=len(tag))
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = gg(args, StubSeq2Seq(), StubVocab(), audio, words, vid=1, seed_seq=seed, fade_out=fade)
         store[tag] = np.asarray(out)
         print(tag, np.asarray(out).shape)
     np.savez(os.path.join(OUT, 'synthesize_driver.npz'), **store)

@@ -37,6 +37,26 @@ class StubGenerator:
         return iter([torch.zeros(1)])
 
 
+class StubSeq2Seq:
+    """seq2seq call form (synthesize.py:134-136): (in_text [1,L] ragged, lengths, seed poses [1,>=4,D], None) -> [1,T,D].  The per-window
+    offset (word ids, sentence length) makes consecutive windows disagree at their boundary, which is what the seq2seq-only cubic
+    smoothing of synthesize.py:163-185 acts on."""
+    n_frames, pose_dim = 34, 27
+
+    def __call__(self, in_text, lengths, poses, _):
+        dev = in_text.device
+        T, D = self.n_frames, self.pose_dim
+        t = torch.arange(T, device=dev, dtype=torch.float32).view(1, T, 1)
+        d = torch.arange(D, device=dev, dtype=torch.float32).view(1, 1, D)
+        base = 0.1 * torch.sin(0.29 * t + 0.4 * d) + 0.002 * t * torch.cos(0.9 * d)
+        seed = 0.5 * poses[:, :4].float().mean(dim=1, keepdim=True)
+        w = (in_text.float().sum() % 13.0) * 0.01 + 0.003 * float(in_text.shape[1])
+        return base + seed + w
+
+    def parameters(self):
+        return iter([torch.zeros(1)])
+
+
 def make_clip(seconds, seed=0, sr=16000):
     rng = np.random.Generator(np.random.PCG64(100 + seed))
     n = int(seconds * sr)

@@ -49,7 +49,7 @@ def _worker(rank, world, port, q):
         for acc, f in ((ev.acc_real, feats_r), (ev.acc_gen, feats_g)):
             acc[0] = f.shape[0]; acc[1:33] = f.sum(0); acc[33:] = (f.t() @ f).reshape(-1)
         ev.acc_misc[0] = (feats_r - feats_g).abs().sum()
-        fgd, fdist = ev.get_scores()
+        fgd, fdist = ev.get_scores(reduce=True)
         q.put((rank, bool(ok), float(fgd), float(fdist)))
     finally:
         dist.destroy_process_group()

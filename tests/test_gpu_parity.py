@@ -319,7 +319,7 @@ def test_cuda_graph_replay_matches_eager(dev):
         hist[use_graph] = (rets, {k: v.detach().clone() for k, v in G.state_dict().items()}, int(g_opt.state_dict()['state'][0]['step']))
         config.set_graphs(old)
     if use_graph:
-        slots = [s for s in TG._graph_slots.values() if s.graph is not None]
+        slots = [s for s in G.engine()._gan_graph_slots.values() if s.graph is not None]
         assert slots, 'the iteration was never captured into a CUDA graph'
     # atomically-accumulated gradients are not bit-reproducible and a GAN amplifies round-off from step to step:
     # the first replayed steps must agree tightly, later ones loosely

@@ -113,7 +113,7 @@ def test_seq2seq_step_batch128_vs_fp64_oracle(dev, mode, tol):
 
 def test_seq2seq_graph_replay_and_eval(dev):
     """The captured iteration keeps training (loss decreases over replays) and eval-mode forward runs at batch 128."""
-    from train_eval.train_seq2seq import train_iter_seq2seq, _graph_slots
+    from train_eval.train_seq2seq import train_iter_seq2seq
     cfg = S.Seq2SeqConfig(n_words=2000)
     args, net = _build(cfg, dev, dropout=cfg.dropout_prob)
     inp = synth.seq2seq_inputs(cfg, 128, seed=6, max_len=10)
@@ -121,7 +121,7 @@ def test_seq2seq_graph_replay_and_eval(dev):
     net.train()
     optim = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
     losses = [train_iter_seq2seq(args, 0, text, inp['lengths'], target, net, optim)['loss'] for _ in range(12)]
-    assert any(s.graph is not None for s in _graph_slots.values()), 'the iteration was never captured into a CUDA graph'
+    assert any(s.graph is not None for s in net.engine()._graph_slots.values()), 'the iteration was never captured into a CUDA graph'
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     assert int(optim.state_dict()['state'][0]['step']) == 12
     net.eval()

@@ -8,7 +8,7 @@ import torch
 
 from conftest import GOLDEN
 from oracle.make_golden_synthesize import golden_args
-from oracle.synthesize_stub import StubGenerator, StubVocab, make_clip
+from oracle.synthesize_stub import StubGenerator, StubSeq2Seq, StubVocab, make_clip
 
 CASES = (('short', 1.7, False), ('long', 9.3, False), ('fade', 6.1, True))
 
@@ -19,6 +19,20 @@ def test_driver_matches_reference_execution(tag, seconds, fade):
     g = np.load(os.path.join(GOLDEN, 'synthesize_driver.npz'))
     audio, words, seed = make_clip(seconds, seed=len(tag))
     out = generate_gestures(golden_args(), StubGenerator(), StubVocab(), audio, words, vid=7, seed_seq=seed, fade_out=fade)
+    assert out.shape == g[tag].shape
+    assert np.abs(out - g[tag]).max() < 2e-6, np.abs(out - g[tag]).max()
+
+
+@pytest.mark.parametrize('tag,seconds,fade', (('s2s_short', 1.7, False), ('s2s_long', 9.3, False), ('s2s_fade', 6.1, True)))
+def test_seq2seq_driver_matches_reference_execution(tag, seconds, fade):
+    """args.model == 'seq2seq': ragged word-id input, seed hand-off, cross-fade AND the seq2seq-only cubic smoothing of every window join
+    (synthesize.py:134-136,163-185) vs the executed reference driver."""
+    from synthesize import generate_gestures
+    g = np.load(os.path.join(GOLDEN, 'synthesize_driver.npz'))
+    audio, words, seed = make_clip(seconds, seed=len(tag))
+    args = golden_args()
+    args.model = 'seq2seq'
+    out = generate_gestures(args, StubSeq2Seq(), StubVocab(), audio, words, vid=1, seed_seq=seed, fade_out=fade)
     assert out.shape == g[tag].shape
     assert np.abs(out - g[tag]).max() < 2e-6, np.abs(out - g[tag]).max()
 

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from torch.profiler import ProfilerActivity, profile
 from model.seq2seq_net import Seq2SeqNet
-from train_eval.train_seq2seq import train_iter_seq2seq, _graph_slots
+from train_eval.train_seq2seq import train_iter_seq2seq
 dev = torch.device('cuda:0')
 a = argparse.Namespace(hidden_size=200, n_layers=2, dropout_prob=0.1, n_pre_poses=4, GAN_noise_size=0, loss_regression_weight=250.0,
                        loss_kld_weight=0.1, loss_reg_weight=25.0)
@@ -22,7 +22,7 @@ target = (0.1 * torch.randn(128, 34, 27)).to(dev)
 f = lambda: train_iter_seq2seq(a, 0, text, lens, target, net, opt)
 for i in range(6):
     f()
-print('graph captured:', any(s.graph is not None for s in _graph_slots.values()))
+print('graph captured:', any(s.graph is not None for s in net.engine()._graph_slots.values()))
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for i in range(10):
     f()
