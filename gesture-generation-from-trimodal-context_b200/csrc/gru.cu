@@ -273,84 +273,77 @@ __global__ void __launch_bounds__(256, 1) gru_bwd_kernel(const GruBwdP p) {
 
 
 // =====================================================================================================================
-// Small hidden size (H <= 64: the ConvDiscriminator's GRU, multimodal_context_net.py:221-222).  The whole W_hh of one
-// direction fits in one CTA's shared memory, so a CTA owns a 16-clip batch tile for all T steps: no inter-CTA exchange,
-// only __syncthreads per step; gi / saved-gate loads of step s are issued before the matmul of that step so their
-// latency hides behind the FFMA loop.
+// Small hidden size (H <= 64: the ConvDiscriminator's GRU, multimodal_context_net.py:221-222).  A CTA owns SB = 2 clips of one
+// direction for all T steps (B/2 x 2 CTAs: one wave for 128 clips), no inter-CTA exchange.  The recurrent weights live in REGISTERS:
+// thread r < 3H keeps row r of W_hh (forward) / column j of one gate block of W_hh (backward) - 64 floats - so the per-step product is
+// 64 FMAs per clip fed by broadcast LDS.128 of the 256-byte state vector, instead of streaming 48 KB of weights from shared memory every
+// step (the first version: 1.3 us / 2.1 us per step, LDS-bound; ncu r01).  Two __syncthreads per step; the gi / saved-gate loads of a
+// step are issued before the product so their latency hides behind it.
 // =====================================================================================================================
-constexpr int SB = 4;             // clips per CTA: B/4 x 2 CTAs spread the (transcendental-heavy) gate math over the chip
-constexpr int SBP = SB + 1;
-constexpr int KS = 4;             // the per-step matmul reduction is split 4 ways across the 256 threads
+constexpr int SB = 2;             // clips per CTA
+constexpr int HS = 64;            // register-resident weights per thread (H <= 64, zero padded)
+constexpr int SMALL_NT = 192;     // 3 * 64 row threads
 
 struct GruSmallFwdP {
   const float* gi; const float* whhT[2]; const float* bhh[2]; float* out; float* saved; long long saved_qstride;
   int B, T, H;
 };
 
-__global__ void __launch_bounds__(256) gru_small_fwd_kernel(const GruSmallFwdP p) {
-  extern __shared__ __align__(16) float smem[];
+__global__ void __launch_bounds__(SMALL_NT) gru_small_fwd_kernel(const GruSmallFwdP p) {
+  __shared__ __align__(16) float hs[SB][HS];          // h_{t-1}
+  __shared__ __align__(16) float ghs[SB][3 * HS];     // W_hh h_{t-1}
   const int H = p.H, T = p.T, G3 = 3 * H;
-  const int WS = ((G3 + 3) & ~3) + 4;                 // row pitch of Ws (floats), multiple of 4
-  float* Ws = smem;                                   // [H][WS]    Ws[k][g*H + unit]
-  float* hs = Ws + (size_t)H * WS;                    // [H][SBP]   h_{t-1}
-  float* ghp = hs + (size_t)H * SBP;                  // [KS][192][SBP] partial gh per reduction slice
   const int tid = threadIdx.x;
   const int dir = blockIdx.y, b0 = blockIdx.x * SB;
-  const float* wT = p.whhT[dir];
-  for (int i = tid; i < H * G3; i += 256) { const int k = i / G3, r = i - k * G3; Ws[k * WS + r] = __ldg(wT + i); }
-  for (int i = tid; i < H * SBP; i += 256) hs[i] = 0.f;
-  __syncthreads();
-  const int ks = tid >> 6, w = tid & 63;
-  const int rg = w >> 2, bcol = w & 3;                // matmul: rows rg*12 .. +11, clip bcol, k in [ks*KQ, +KQ)
-  const int KQ = (H + KS - 1) / KS;
-  const float* bhh = p.bhh[dir];
+  const float* wT = dir ? p.whhT[1] : p.whhT[0];      // [H][3H]: wT[k][r] = W_hh[r][k]
+  float w[HS];
+#pragma unroll
+  for (int k = 0; k < HS; ++k) w[k] = (tid < G3 && k < H) ? __ldg(wT + (long long)k * G3 + tid) : 0.f;
+  for (int i = tid; i < SB * HS; i += SMALL_NT) (&hs[0][0])[i] = 0.f;
+  const float* bhh = dir ? p.bhh[1] : p.bhh[0];
   const long long row2H = 2ll * H;
-  // the (clip, unit) pair this thread owns in the gate phase (H <= 64 -> SB*H <= 256 pairs)
+  // the (clip, unit) pair this thread owns in the gate phase
   const int pbb = tid / H, punit = tid - pbb * H;
   const int pb = b0 + pbb;
   const bool pok = tid < SB * H && pb < p.B;
   float b_r = 0.f, b_z = 0.f, b_n = 0.f;
   if (pok) { b_r = __ldg(bhh + punit); b_z = __ldg(bhh + H + punit); b_n = __ldg(bhh + 2 * H + punit); }
+  __syncthreads();
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
-    float gir = 0.f, giz = 0.f, gin = 0.f;            // input projections: issued now, consumed after the matmul
+    float gir = 0.f, giz = 0.f, gin = 0.f;            // input projections: issued now, consumed after the product
     if (pok) {
       const float* gp = p.gi + ((long long)pb * T + t) * 6 * H + dir * 3 * H + punit;
       gir = __ldg(gp); giz = __ldg(gp + H); gin = __ldg(gp + 2 * H);
     }
-    float acc[12];
+    if (s > 0) {
+      float acc[SB];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-    if (s > 0 && rg * 12 < G3) {
-      const int k1 = min(H, (ks + 1) * KQ);
-#pragma unroll 4
-      for (int k = ks * KQ; k < k1; ++k) {
-        const float hv = hs[k * SBP + bcol];
-        const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12);
-        const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12 + 4);
-        const float4 w2 = *reinterpret_cast<const float4*>(Ws + k * WS + rg * 12 + 8);
-        acc[0] = fmaf(w0.x, hv, acc[0]); acc[1] = fmaf(w0.y, hv, acc[1]); acc[2] = fmaf(w0.z, hv, acc[2]); acc[3] = fmaf(w0.w, hv, acc[3]);
-        acc[4] = fmaf(w1.x, hv, acc[4]); acc[5] = fmaf(w1.y, hv, acc[5]); acc[6] = fmaf(w1.z, hv, acc[6]); acc[7] = fmaf(w1.w, hv, acc[7]);
-        acc[8] = fmaf(w2.x, hv, acc[8]); acc[9] = fmaf(w2.y, hv, acc[9]); acc[10] = fmaf(w2.z, hv, acc[10]); acc[11] = fmaf(w2.w, hv, acc[11]);
+      for (int c = 0; c < SB; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < HS; k += 4) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+          const float4 h4 = *reinterpret_cast<const float4*>(&hs[c][k]);      // same address in every lane: one broadcast wavefront
+          acc[c] = fmaf(w[k], h4.x, acc[c]); acc[c] = fmaf(w[k + 1], h4.y, acc[c]);
+          acc[c] = fmaf(w[k + 2], h4.z, acc[c]); acc[c] = fmaf(w[k + 3], h4.w, acc[c]);
+        }
       }
-    }
+      if (tid < G3) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) ghp[(ks * 192 + rg * 12 + i) * SBP + bcol] = acc[i];
-    __syncthreads();
+        for (int c = 0; c < SB; ++c) ghs[c][tid] = acc[c];
+      }
+      __syncthreads();
+    }
     if (pok) {
       float ghr = b_r, ghz = b_z, ghn = b_n;
-#pragma unroll
-      for (int q = 0; q < KS; ++q) {
-        ghr += ghp[(q * 192 + punit) * SBP + pbb];
-        ghz += ghp[(q * 192 + H + punit) * SBP + pbb];
-        ghn += ghp[(q * 192 + 2 * H + punit) * SBP + pbb];
-      }
-      const float hprev = hs[punit * SBP + pbb];
+      if (s > 0) { ghr += ghs[pbb][punit]; ghz += ghs[pbb][H + punit]; ghn += ghs[pbb][2 * H + punit]; }
+      const float hprev = hs[pbb][punit];
       const float r = sigmoidf_(gir + ghr);
       const float z = sigmoidf_(giz + ghz);
       const float n = tanhf(gin + r * ghn);
       const float h = (1.f - z) * n + z * hprev;
-      hs[punit * SBP + pbb] = h;
+      hs[pbb][punit] = h;
       const long long o = ((long long)pb * T + t) * row2H + dir * H + punit;
       p.out[o] = h;
       if (p.saved) {
@@ -366,29 +359,27 @@ struct GruSmallBwdP {
   float* dgi; float* dgh; int B, T, H;
 };
 
-__global__ void __launch_bounds__(256) gru_small_bwd_kernel(const GruSmallBwdP p) {
-  extern __shared__ __align__(16) float smem[];
-  const int H = p.H, T = p.T, G3 = 3 * H;
-  const int WP = H + 4;
-  float* Wb = smem;                                   // [3H][WP]   W_hh rows as stored
-  float* ds = Wb + (size_t)G3 * WP;                   // [3H][SBP]  dgh of the tile
-  float* dhp = ds + (size_t)G3 * SBP;                 // [KS][SB][H+1] partial dh carried to the previous step
+__global__ void __launch_bounds__(SMALL_NT) gru_small_bwd_kernel(const GruSmallBwdP p) {
+  __shared__ __align__(16) float ds[SB][3 * HS];      // dgh of the tile: [clip][gate block g][unit], gate blocks HS apart
+  __shared__ float dhp[3][SB][HS];                    // per-gate-block partial of W_hh^T dgh
+  const int H = p.H, T = p.T;
   const int tid = threadIdx.x;
   const int dir = blockIdx.y, b0 = blockIdx.x * SB;
-  const float* W = p.whh[dir];
-  for (int i = tid; i < G3 * H; i += 256) { const int r = i / H, k = i - r * H; Wb[r * WP + k] = __ldg(W + i); }
-  for (int i = tid; i < G3 * SBP; i += 256) ds[i] = 0.f;
-  for (int i = tid; i < KS * SB * (H + 1); i += 256) dhp[i] = 0.f;
-  __syncthreads();
-  const int ks = tid >> 6, w = tid & 63;
-  const int kq = w & 15, mb = w >> 4;                 // matmul: columns kq*4..+3, clip mb, rows i in [ks*IQ, +IQ)
-  const int IQ = (G3 + KS - 1) / KS;
+  const float* W = dir ? p.whh[1] : p.whh[0];         // [3H][H] as stored
+  // product thread (g, j): partial_g[c][j] = sum_r' W_hh[g*H + r'][j] * dgh[c][g*H + r']
+  const int g = tid / HS, j = tid - g * HS;
+  float w[HS];
+#pragma unroll
+  for (int r = 0; r < HS; ++r) w[r] = (j < H && r < H) ? __ldg(W + ((long long)g * H + r) * H + j) : 0.f;
+  for (int i = tid; i < SB * 3 * HS; i += SMALL_NT) (&ds[0][0])[i] = 0.f;
+  for (int i = tid; i < 3 * SB * HS; i += SMALL_NT) (&dhp[0][0][0])[i] = 0.f;
   const long long row2H = 2ll * H;
   const int pbb = tid / H, punit = tid - pbb * H;
   const int pb = b0 + pbb;
   const bool pin = tid < SB * H;
   const bool pok = pin && pb < p.B;
   float dhz = 0.f;                                    // dh * z carried by the owner of the (clip, unit) pair
+  __syncthreads();
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? T - 1 - s : s;
     const int tp = dir == 0 ? t - 1 : t + 1;
@@ -402,9 +393,7 @@ __global__ void __launch_bounds__(256) gru_small_bwd_kernel(const GruSmallBwdP p
         const float l_do = __ldg(p.dout + o), r = __ldg(p.saved + o), z = __ldg(p.saved + p.saved_qstride + o);
         const float n = __ldg(p.saved + 2 * p.saved_qstride + o), hn = __ldg(p.saved + 3 * p.saved_qstride + o);
         const float hprev = tp_ok ? __ldg(p.out + ((long long)pb * T + tp) * row2H + dir * H + punit) : 0.f;
-        float dh = l_do + dhz;
-#pragma unroll
-        for (int q = 0; q < KS; ++q) dh += dhp[(q * SB + pbb) * (H + 1) + punit];
+        const float dh = l_do + dhz + dhp[0][pbb][punit] + dhp[1][pbb][punit] + dhp[2][pbb][punit];
         const float dn = dh * (1.f - z) * (1.f - n * n);
         dzp = dh * (hprev - n) * z * (1.f - z);
         drp = dn * hn * r * (1.f - r);
@@ -415,23 +404,24 @@ __global__ void __launch_bounds__(256) gru_small_bwd_kernel(const GruSmallBwdP p
         float* hp = p.dgh + row * 6 * H + dir * 3 * H + punit;
         hp[0] = drp; hp[H] = dzp; hp[2 * H] = dnr;
       }
-      ds[punit * SBP + pbb] = drp; ds[(H + punit) * SBP + pbb] = dzp; ds[(2 * H + punit) * SBP + pbb] = dnr;
+      ds[pbb][punit] = drp; ds[pbb][HS + punit] = dzp; ds[pbb][2 * HS + punit] = dnr;
     }
     __syncthreads();
     if (s + 1 < T) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (kq * 4 < H) {
-        const int i1 = min(G3, (ks + 1) * IQ);
-#pragma unroll 4
-        for (int i = ks * IQ; i < i1; ++i) {
-          const float d = ds[i * SBP + mb];
-          const float4 wv = *reinterpret_cast<const float4*>(Wb + i * WP + kq * 4);
-          acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]); acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
-        }
+      float acc[SB];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (kq * 4 + e < H) dhp[(ks * SB + mb) * (H + 1) + kq * 4 + e] = acc[e];
+      for (int c = 0; c < SB; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int r = 0; r < HS; r += 4) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+          const float4 d4 = *reinterpret_cast<const float4*>(&ds[c][g * HS + r]);   // warp-uniform address (one gate block per warp pair)
+          acc[c] = fmaf(w[r], d4.x, acc[c]); acc[c] = fmaf(w[r + 1], d4.y, acc[c]);
+          acc[c] = fmaf(w[r + 2], d4.z, acc[c]); acc[c] = fmaf(w[r + 3], d4.w, acc[c]);
+        }
       }
+#pragma unroll
+      for (int c = 0; c < SB; ++c) dhp[g][c][j] = acc[c];
     }
     __syncthreads();
   }
@@ -510,11 +500,7 @@ extern "C" int tg_gru_layer_fwd(const float* gi, const float* whhT_f, const floa
     GruSmallFwdP q;
     q.gi = gi; q.whhT[0] = whhT_f; q.whhT[1] = whhT_r; q.bhh[0] = bhh_f; q.bhh[1] = bhh_r; q.out = out; q.saved = saved;
     q.saved_qstride = saved_qstride; q.B = B; q.T = T; q.H = H;
-    const int WS = ((3 * H + 3) & ~3) + 4;
-    const size_t smem = ((size_t)H * WS + (size_t)H * SBP + (size_t)KS * 192 * SBP) * sizeof(float);
-    cudaError_t e2 = cudaFuncSetAttribute(gru_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e2 != cudaSuccess) { tg_set_error("tg_gru_layer_fwd(small): smem attr: %s", cudaGetErrorString(e2)); return -3; }
-    gru_small_fwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), 256, smem, s>>>(q);
+    gru_small_fwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), SMALL_NT, 0, s>>>(q);
     TG_CHECK_LAUNCH("tg_gru_layer_fwd(small)");
     return 0;
   }
@@ -550,10 +536,7 @@ extern "C" int tg_gru_layer_bwd(const float* dout, const float* out, const float
     GruSmallBwdP q;
     q.dout = dout; q.out = out; q.saved = saved; q.saved_qstride = saved_qstride; q.whh[0] = whh_f; q.whh[1] = whh_r;
     q.dgi = dgi; q.dgh = dgh; q.B = B; q.T = T; q.H = H;
-    const size_t smem = ((size_t)3 * H * (H + 4) + (size_t)3 * H * SBP + (size_t)KS * SB * (H + 1)) * sizeof(float);
-    cudaError_t e2 = cudaFuncSetAttribute(gru_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e2 != cudaSuccess) { tg_set_error("tg_gru_layer_bwd(small): smem attr: %s", cudaGetErrorString(e2)); return -3; }
-    gru_small_bwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), 256, smem, s>>>(q);
+    gru_small_bwd_kernel<<<dim3(tg_ceil_div(B, SB), 2), SMALL_NT, 0, s>>>(q);
     TG_CHECK_LAUNCH("tg_gru_layer_bwd(small)");
     return 0;
   }

@@ -136,6 +136,29 @@ __device__ __forceinline__ void issue_tail(uint32_t tmem_d, uint32_t a_tail, uin
   const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
   issue_ksteps<0>(L.tail_ksteps, tmem_d, desc_lo(a_tail, 16), desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
 }
+// the same with the A operand resident in tensor memory: K-step k of the whole reduction reads A columns a_tmem + 8k
+template <int DUMMY>
+__device__ __forceinline__ void issue_ksteps_ts(int nk, uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  if (nk == 4) mma_tf32_ts_seq<4>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
+  else if (nk == 3) mma_tf32_ts_seq<3>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
+  else if (nk == 2) mma_tf32_ts_seq<2>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
+  else mma_tf32_ts_seq<1>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
+}
+__device__ __forceinline__ void issue_full_group_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_base, uint32_t b_chunk, int g, const KLay& L,
+                                                    uint32_t idesc) {
+  constexpr uint32_t hi = desc_hi(1024, 2);
+  const int kc_lo = g * L.gsz, kc_hi = min(L.nfull, (g + 1) * L.gsz);
+  uint32_t b_lo = desc_lo(b_base + (uint32_t)kc_lo * b_chunk, 16);
+  uint32_t a = a_tmem + (uint32_t)kc_lo * 32;
+  for (int kc = kc_lo; kc < kc_hi; ++kc, a += 32, b_lo += b_chunk >> 4) {
+    if (kc < L.nfull - 1) mma_tf32_ts_seq<4>(tmem_d, a, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
+    else issue_ksteps_ts<0>(L.last_ksteps, tmem_d, a, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
+  }
+}
+__device__ __forceinline__ void issue_tail_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_tail, const KLay& L, uint32_t idesc) {
+  const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
+  issue_ksteps_ts<0>(L.tail_ksteps, tmem_d, a_tmem + (uint32_t)L.nfull * 32, desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),
                "r"(bar_saddr)
@@ -160,18 +183,16 @@ __device__ __forceinline__ void issue_loads(uint32_t b_base, uint32_t b_chunk, u
   }
 }
 
-// shared-memory offset of the barrier block = size of the operand regions, including what the MMA reads past the packed A rows
+// shared-memory offset of the barrier block = size of the operand regions
+// forward: [h full chunks | gate scratch][h tail] - the recurrent weights live in tensor memory
 __host__ __device__ inline size_t fwd_bar_off(const KLay& L, int u, int BT) {
+  (void)u;
   size_t hreg = (size_t)L.nfull * BT * 128;
   if (hreg < (size_t)128 * (BT + 1) * 4) hreg = (size_t)128 * (BT + 1) * 4;
   hreg = (hreg + 1023) & ~(size_t)1023;
-  const size_t w_full_bytes = (size_t)L.nfull * 3 * u * 128;
-  const size_t wtail_off = w_full_bytes + hreg;
-  size_t end = wtail_off + (size_t)(3 * u + BT) * L.tail_w * 4;
-  if (L.nfull > 0 && w_full_bytes - (size_t)3 * u * 128 + 128 * 128 > end) end = w_full_bytes - (size_t)3 * u * 128 + 128 * 128;
-  if (wtail_off + (size_t)128 * L.tail_w * 4 > end) end = wtail_off + (size_t)128 * L.tail_w * 4;
-  return (end + 1023) & ~(size_t)1023;
+  return (hreg + (size_t)BT * L.tail_w * 4 + 1023) & ~(size_t)1023;
 }
+// backward: [W^T full chunks][dgh full chunks][W^T tail][dgh tail], including what the M = 64 MMA reads past the u packed A rows
 __host__ __device__ inline size_t bwd_bar_off(const KLay& L, int u, int BT) {
   size_t greg = (size_t)L.nfull * BT * 128;
   if (greg < (size_t)64 * 128) greg = (size_t)64 * 128;
@@ -188,7 +209,8 @@ __host__ __device__ inline size_t bwd_bar_off(const KLay& L, int u, int BT) {
 // forward
 // =====================================================================================================================
 struct FwdP {
-  const float* gi; const float* bhh0; const float* bhh1; float* out; float* saved; long long saved_qstride; float* xchg;
+  const float* gi; const float* whh0; const float* whh1; const float* bhh0; const float* bhh1; float* out; float* saved; long long saved_qstride;
+  float* xchg;
   int B, T, H, u, flags;      // flags bit 0: every CTA loads the whole tile itself (unicast) instead of the 8-way multicast
   KLay L;
   long long* trace;
@@ -199,10 +221,16 @@ template <int BT> struct FwdCfg {
   static constexpr int NT = 64 + 32 * EPI_WARPS;
 };
 
+constexpr uint32_t FWD_A0 = 64;       // first tensor-memory column of the resident weights (the accumulator owns columns 0 .. BT-1 <= 63)
+__host__ __device__ inline uint32_t fwd_tmem_cols(int H) {
+  const uint32_t need = FWD_A0 + (uint32_t)((H + 7) / 8) * 8;
+  uint32_t c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
 template <int BT>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
-    gru_fwd_cl_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmV0,
-                      const __grid_constant__ CUtensorMap tmV1, const FwdP p) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) gru_fwd_cl_kernel(const FwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = FwdCfg<BT>::NT, EPI = 32 * FwdCfg<BT>::EPI_WARPS;
   constexpr int H_CHUNK = BT * 128;
@@ -210,20 +238,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
   constexpr int CPP = BT / 4;                  // accumulator columns moved by one staging warp
   const KLay L = p.L;
   const int H = p.H, T = p.T, u = p.u;
-  const int a_rows = 3 * u;                    // packed gate rows r | z | n (the M = 128 MMA reads on into the next region: ignored lanes)
-  const uint32_t w_chunk = (uint32_t)a_rows * 128;
-  // [W full chunks][h full chunks | gate scratch][W tail][h tail][pad][barriers]
+  // [h full chunks | gate scratch][h tail][barriers]
   size_t hreg_bytes = (size_t)L.nfull * H_CHUNK;
   if (hreg_bytes < (size_t)128 * GS * 4) hreg_bytes = (size_t)128 * GS * 4;
   hreg_bytes = (hreg_bytes + 1023) & ~(size_t)1023;
-  uint8_t* Wt = smem;
-  uint8_t* Ht = Wt + (size_t)L.nfull * w_chunk;
+  uint8_t* Ht = smem;
   float* ghs = reinterpret_cast<float*>(Ht);
-  uint8_t* Wtail = Ht + hreg_bytes;
-  uint8_t* Htail = Wtail + (size_t)a_rows * L.tail_w * 4;
-  const size_t bar_off = fwd_bar_off(L, u, BT);   // clears every byte the M = 128 MMA reads past the 3u packed rows of the last A chunk / tail
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + bar_off);
-  uint64_t* h_full = w_full + 1;               // [ngf + tail <= 8]
+  uint8_t* Htail = Ht + hreg_bytes;
+  const size_t bar_off = fwd_bar_off(L, u, BT);
+  uint64_t* h_full = reinterpret_cast<uint64_t*>(smem + bar_off);   // [ngf + tail <= 8]
   uint64_t* tmem_full = h_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
@@ -231,43 +254,52 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
   const int rank = (int)cluster_ctarank();     // == blockIdx.x (grid.x == CL)
   const int tile = blockIdx.y, dir = blockIdx.z;
   const int u0 = rank * u;
-  constexpr uint32_t TMEM_COLS = BT <= 32 ? 32 : 64;
+  const uint32_t tmem_cols = fwd_tmem_cols(H);
   const size_t img_bytes = (size_t)L.nfull * H_CHUNK + (size_t)BT * L.tail_w * 4;
   // image of this cluster's operand tile in global memory: [parity][full chunks][tail]
   uint8_t* img = reinterpret_cast<uint8_t*>(p.xchg) + ((size_t)dir * gridDim.y + tile) * 2 * img_bytes;
 
   if (smem_u32(smem) & 1023) __trap();
-  // operand regions start finite (rows the MMA reads but nobody writes); the image starts zero (K padding, dead clips)
+  // the operand tile starts finite; the image starts zero (K padding, dead clips)
   for (int i = threadIdx.x; i < (int)(bar_off / 16); i += NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   {
     const int n16 = (int)(2 * img_bytes / 16);
     for (int i = rank * NT + threadIdx.x; i < n16; i += CL * NT) reinterpret_cast<float4*>(img)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (warp == 0 && elect_one()) {
-    mbar_init(w_full, 1);
     for (int g = 0; g < 8; ++g) mbar_init(&h_full[g], 1);
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async_all();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  if (warp == 0 && elect_one()) {
-    const CUtensorMap* tmW = dir ? &tmW1 : &tmW0;
-    const CUtensorMap* tmV = dir ? &tmV1 : &tmV0;
-    tma_prefetch_desc(tmW);
-    // resident recurrent weights: rows [g*H + u0, +u) of W_hh for g = r, z, n  ->  A rows [g*u, +u)
-    mbar_expect_tx(w_full, (uint32_t)(L.nfull * 3 * u * 128 + 3 * u * L.tail_w * 4));
-    for (int kc = 0; kc < L.nfull; ++kc)
-      for (int g = 0; g < 3; ++g) tma_load_2d(Wt + (size_t)kc * w_chunk + (size_t)g * u * 128, tmW, w_full, kc * 32, g * H + u0);
-    if (L.tail_w > 0)
-      for (int g = 0; g < 3; ++g) tma_load_2d(Wtail + (size_t)g * u * L.tail_w * 4, tmV, w_full, L.nfull * 32, g * H + u0);
+  if (warp >= 2 && warp < 6) {
+    // resident recurrent weights -> tensor memory, once: TMEM lane lr = g*u + jj holds row g*H + u0 + jj of W_hh (g = r, z, n), one
+    // column per k; lanes >= 3u, units >= H and columns >= H are zero.  Each thread streams its own 1.2 KB row (L2-resident).
+    const int lr0 = (warp & 3) * 32 + lane;
+    const int g = lr0 / u, jj = lr0 - g * u;
+    const bool row_live = lr0 < 3 * u && u0 + jj < H;
+    const float* wrow = (dir ? p.whh1 : p.whh0) + ((long long)g * H + u0 + jj) * H;
+    const int kcols = ((H + 7) / 8) * 8;
+    for (int k0 = 0; k0 < kcols; k0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_live && k0 + e < H) x = ldv_nc4(wrow + k0 + e);
+        v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+      }
+      tmem_st16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + FWD_A0 + (uint32_t)k0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
   }
-  __syncwarp();
-  if (warp == 1) mbar_wait(w_full, 0);
+  __syncthreads();
+  tc_fence_after();
   cluster_arrive();          // every CTA's barriers are initialised and the image is zero before any peer multicasts / writes
   cluster_wait();
 
@@ -291,7 +323,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
   const int lr = q * 32 + lane;
   const long long row2H = 2ll * H;
   constexpr uint32_t idesc = idesc_tf32(128, BT, 0, 0);
-  const uint32_t wt_s = smem_u32(Wt), ht_s = smem_u32(Ht), wtail_s = smem_u32(Wtail), htail_s = smem_u32(Htail), hbar_s = smem_u32(h_full);
+  const uint32_t ht_s = smem_u32(Ht), htail_s = smem_u32(Htail), hbar_s = smem_u32(h_full);
   const int ngroups = L.ngf + (L.tail_w > 0 ? 1 : 0);
 
   for (int s = 0; s < T; ++s) {
@@ -308,8 +340,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
           tc_fence_after();
           if (elect_one()) {
             stamp(p.trace, s, 8 + g);
-            if (g < L.ngf) issue_full_group(tmem_base, wt_s, w_chunk, ht_s, H_CHUNK, g, L, idesc);
-            else issue_tail(tmem_base, wtail_s, htail_s, L, idesc);
+            if (g < L.ngf) issue_full_group_ts(tmem_base, tmem_base + FWD_A0, ht_s, H_CHUNK, g, L, idesc);
+            else issue_tail_ts(tmem_base, tmem_base + FWD_A0, htail_s, L, idesc);
           }
           __syncwarp();
         }
@@ -378,7 +410,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
   cluster_arrive();            // no CTA exits while a peer's multicast may still address its shared memory / barriers
   cluster_wait();
 }
@@ -634,7 +666,13 @@ KLay klay(int K) {
   return L;
 }
 
-size_t fwd_smem(int H, int u, int BT) { return fwd_bar_off(klay(H), u, BT) + 10 * 8 + 16; }
+// the forward kernel holds up to 512 tensor-memory columns for its whole life: ask for 180 KB of shared memory so that no second CTA
+// (of this kernel or of a concurrently running tensor-core GEMM, all > 48 KB) is ever placed on the same SM, where it would spin in
+// tcgen05.alloc until this kernel ends
+size_t fwd_smem(int H, int u, int BT) {
+  const size_t need = fwd_bar_off(klay(H), u, BT) + 10 * 8 + 16;
+  return need > (size_t)180 * 1024 ? need : (size_t)180 * 1024;
+}
 size_t bwd_smem(int H, int u, int BT) { return bwd_bar_off(klay(3 * H), u, BT) + 10 * 8 + 16; }
 
 template <typename Kern>
@@ -663,11 +701,11 @@ int max_resident_clusters() {
 }
 
 template <int BT>
-int launch_fwd(const CUtensorMap* maps, const FwdP& p, int ntiles, cudaStream_t s) {
+int launch_fwd(const FwdP& p, int ntiles, cudaStream_t s) {
   const size_t smem = fwd_smem(p.H, p.u, BT);
   cudaError_t e = cudaFuncSetAttribute(gru_fwd_cl_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return -3; }
-  gru_fwd_cl_kernel<BT><<<dim3(CL, ntiles, 2), FwdCfg<BT>::NT, smem, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+  gru_fwd_cl_kernel<BT><<<dim3(CL, ntiles, 2), FwdCfg<BT>::NT, smem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: cluster launch (8,%d,2) smem %zu: %s", ntiles, smem, cudaGetErrorString(e)); return -2; }
   return 0;
@@ -732,24 +770,16 @@ int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const
   TgGruClPlan pl;
   if (!tg_gru_cl_plan(B, H, &pl)) { tg_set_error("tg_gru_layer_fwd_tf32: no cluster plan for B=%d H=%d", B, H); return -1; }
   if (reinterpret_cast<uintptr_t>(xchg) & 127) { tg_set_error("tg_gru_layer_fwd_tf32: exchange scratch must be 128-byte aligned"); return -1; }
+  if ((reinterpret_cast<uintptr_t>(whh_f) | reinterpret_cast<uintptr_t>(whh_r)) & 15) { tg_set_error("tg_gru_layer_fwd_tf32: W_hh must be 16-byte aligned"); return -1; }
   FwdP p;
   p.L = klay(H);
-  CUtensorMap maps[4];
-  int rc;
-  if ((rc = map_2d(&maps[0], whh_f, 3ll * H, H, H, 32, pl.u, "tg_gru_layer_fwd_tf32(W)"))) return rc;
-  if ((rc = map_2d(&maps[1], whh_r, 3ll * H, H, H, 32, pl.u, "tg_gru_layer_fwd_tf32(W)"))) return rc;
-  maps[2] = maps[0]; maps[3] = maps[1];
-  if (p.L.tail_w > 0) {
-    if ((rc = map_2d(&maps[2], whh_f, 3ll * H, H, H, p.L.tail_w, pl.u, "tg_gru_layer_fwd_tf32(W tail)"))) return rc;
-    if ((rc = map_2d(&maps[3], whh_r, 3ll * H, H, H, p.L.tail_w, pl.u, "tg_gru_layer_fwd_tf32(W tail)"))) return rc;
-  }
-  p.gi = gi; p.bhh0 = bhh_f; p.bhh1 = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.xchg = xchg;
+  p.gi = gi; p.whh0 = whh_f; p.whh1 = whh_r; p.bhh0 = bhh_f; p.bhh1 = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.xchg = xchg;
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.flags = cl_flags();
   p.trace = trace;
-  if (pl.bt_f == 16) return launch_fwd<16>(maps, p, pl.ntiles_f, s);
-  if (pl.bt_f == 32) return launch_fwd<32>(maps, p, pl.ntiles_f, s);
-  if (pl.bt_f == 48) return launch_fwd<48>(maps, p, pl.ntiles_f, s);
-  return launch_fwd<64>(maps, p, pl.ntiles_f, s);
+  if (pl.bt_f == 16) return launch_fwd<16>(p, pl.ntiles_f, s);
+  if (pl.bt_f == 32) return launch_fwd<32>(p, pl.ntiles_f, s);
+  if (pl.bt_f == 48) return launch_fwd<48>(p, pl.ntiles_f, s);
+  return launch_fwd<64>(p, pl.ntiles_f, s);
 }
 
 int tg_gru_cl_bwd(const float* dout, const float* out, const float* saved, long long saved_qstride, const float* whhT_f, const float* whhT_r,

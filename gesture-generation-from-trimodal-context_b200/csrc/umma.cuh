@@ -119,6 +119,39 @@ __device__ __forceinline__ void mma_tf32_seq(uint32_t d_tmem, uint32_t a_lo, uin
 #pragma unroll
   for (int k = 0; k < NK; ++k) mma_tf32_lohi(d_tmem, a_lo + k * STEP16, a_hi, b_lo + k * STEP16, b_hi, idesc, k == 0 ? accumulate : 1u);
 }
+// A operand in TENSOR MEMORY (row i of the M = 128 tile in lane i, one 32-bit column per tf32 element, K = 8 columns per MMA), B from shared
+// memory.  With A in shared memory every MMA re-reads M x 32 bytes of it (~96 cycles for M = 128, measured: the recurrence kernels were
+// A-read bound at N <= 64); from TMEM the instruction runs at the tensor pipe's own rate.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int NK>
+__device__ __forceinline__ void mma_tf32_ts_seq(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) mma_tf32_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, b_hi, idesc, k == 0 ? accumulate : 1u);
+}
+// 32 lanes x 16 consecutive columns <- 16 registers per thread (thread = TMEM lane of its warp's quarter)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.alloc with a run-time column count (power of two >= 32)
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) { tmem_alloc(dst_smem, ncols); }
+
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
 // layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit)
 __host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29); }

@@ -69,7 +69,7 @@ def _dp_sync_once(module, arena):
     replicate-from-device-0 does every forward, train.py:93-96), so identical initial weights do not depend on identical RNG seeds."""
     import torch.distributed as dist
     key = arena.flat.data_ptr()
-    if getattr(arena, '_dp_synced', None) == key or torch.cuda.is_current_stream_capturing():
+    if getattr(arena, '_dp_synced', None) == key or (arena.flat.is_cuda and torch.cuda.is_current_stream_capturing()):
         return
     dist.broadcast(arena.flat, 0)
     for b in module.buffers():
