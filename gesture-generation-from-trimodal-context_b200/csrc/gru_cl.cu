@@ -136,28 +136,41 @@ __device__ __forceinline__ void issue_tail(uint32_t tmem_d, uint32_t a_tail, uin
   const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
   issue_ksteps<0>(L.tail_ksteps, tmem_d, desc_lo(a_tail, 16), desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
 }
-// the same with the A operand resident in tensor memory: K-step k of the whole reduction reads A columns a_tmem + 8k
-template <int DUMMY>
-__device__ __forceinline__ void issue_ksteps_ts(int nk, uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
-  if (nk == 4) mma_tf32_ts_seq<4>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
-  else if (nk == 3) mma_tf32_ts_seq<3>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
-  else if (nk == 2) mma_tf32_ts_seq<2>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
-  else mma_tf32_ts_seq<1>(tmem_d, a_tmem, b_lo, hi, idesc, acc);
-}
-__device__ __forceinline__ void issue_full_group_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_base, uint32_t b_chunk, int g, const KLay& L,
-                                                    uint32_t idesc) {
-  constexpr uint32_t hi = desc_hi(1024, 2);
-  const int kc_lo = g * L.gsz, kc_hi = min(L.nfull, (g + 1) * L.gsz);
-  uint32_t b_lo = desc_lo(b_base + (uint32_t)kc_lo * b_chunk, 16);
-  uint32_t a = a_tmem + (uint32_t)kc_lo * 32;
-  for (int kc = kc_lo; kc < kc_hi; ++kc, a += 32, b_lo += b_chunk >> 4) {
-    if (kc < L.nfull - 1) mma_tf32_ts_seq<4>(tmem_d, a, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
-    else issue_ksteps_ts<0>(L.last_ksteps, tmem_d, a, b_lo, hi, idesc, kc > 0 ? 1u : 0u);
+// The same with the A operand resident in tensor memory: K-step ks of the whole reduction reads A columns a_tmem + 8 ks and accumulates
+// into accumulator ks % nacc (accumulators 64 columns apart; the epilogue adds them).  Spreading consecutive K-steps over independent
+// accumulators lets the tensor pipe overlap MMAs that would otherwise wait on the same 128 x N tile.
+__device__ __forceinline__ void issue_ts(uint32_t tmem_base, uint32_t a_tmem, int ks_lo, int ks_hi, uint32_t b_lo, uint32_t hi, uint32_t idesc, int nacc) {
+  int ai = ks_lo % nacc;
+  for (int ks = ks_lo; ks < ks_hi; ++ks, b_lo += 2) {
+    mma_tf32_ts(tmem_base + 64u * ai, a_tmem + 8u * ks, b_lo, hi, idesc, ks >= nacc ? 1u : 0u);
+    if (++ai == nacc) ai = 0;
   }
 }
-__device__ __forceinline__ void issue_tail_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_tail, const KLay& L, uint32_t idesc) {
+template <int NK>
+__device__ __forceinline__ void issue_ts_fixed(uint32_t tmem_base, uint32_t a_tmem, int ks0, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  mma_tf32_ts_seq<NK>(tmem_base, a_tmem + 8u * ks0, b_lo, hi, idesc, ks0 > 0 ? 1u : 0u);
+}
+__device__ __forceinline__ void issue_ts_n(int nk, uint32_t tmem_base, uint32_t a_tmem, int ks0, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  if (nk == 4) issue_ts_fixed<4>(tmem_base, a_tmem, ks0, b_lo, hi, idesc);
+  else if (nk == 3) issue_ts_fixed<3>(tmem_base, a_tmem, ks0, b_lo, hi, idesc);
+  else if (nk == 2) issue_ts_fixed<2>(tmem_base, a_tmem, ks0, b_lo, hi, idesc);
+  else issue_ts_fixed<1>(tmem_base, a_tmem, ks0, b_lo, hi, idesc);
+}
+__device__ __forceinline__ void issue_full_group_ts(uint32_t tmem_base, uint32_t a_tmem, uint32_t b_base, uint32_t b_chunk, int g, const KLay& L,
+                                                    uint32_t idesc, int nacc) {
+  constexpr uint32_t hi = desc_hi(1024, 2);
+  const int kc_lo = g * L.gsz, kc_hi = min(L.nfull, (g + 1) * L.gsz);
+  for (int kc = kc_lo; kc < kc_hi; ++kc) {
+    const uint32_t b_lo = desc_lo(b_base + (uint32_t)kc * b_chunk, 16);
+    const int nk = kc < L.nfull - 1 ? 4 : L.last_ksteps;
+    if (nacc == 1) issue_ts_n(nk, tmem_base, a_tmem, kc * 4, b_lo, hi, idesc);       // straight-line issue: the generic loop below costs 2x per MMA
+    else issue_ts(tmem_base, a_tmem, kc * 4, kc * 4 + nk, b_lo, hi, idesc, nacc);
+  }
+}
+__device__ __forceinline__ void issue_tail_ts(uint32_t tmem_base, uint32_t a_tmem, uint32_t b_tail, const KLay& L, uint32_t idesc, int nacc) {
   const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
-  issue_ksteps_ts<0>(L.tail_ksteps, tmem_d, a_tmem + (uint32_t)L.nfull * 32, desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
+  if (nacc == 1) issue_ts_n(L.tail_ksteps, tmem_base, a_tmem, L.nfull * 4, desc_lo(b_tail, 16), hi, idesc);
+  else issue_ts(tmem_base, a_tmem, L.nfull * 4, L.nfull * 4 + L.tail_ksteps, desc_lo(b_tail, 16), hi, idesc, nacc);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),
@@ -212,6 +225,7 @@ struct FwdP {
   const float* gi; const float* whh0; const float* whh1; const float* bhh0; const float* bhh1; float* out; float* saved; long long saved_qstride;
   float* xchg;
   int B, T, H, u, flags;      // flags bit 0: every CTA loads the whole tile itself (unicast) instead of the 8-way multicast
+  int nacc;                   // independent accumulators the K-steps rotate over (1..3)
   KLay L;
   long long* trace;
 };
@@ -221,9 +235,9 @@ template <int BT> struct FwdCfg {
   static constexpr int NT = 64 + 32 * EPI_WARPS;
 };
 
-constexpr uint32_t FWD_A0 = 64;       // first tensor-memory column of the resident weights (the accumulator owns columns 0 .. BT-1 <= 63)
-__host__ __device__ inline uint32_t fwd_tmem_cols(int H) {
-  const uint32_t need = FWD_A0 + (uint32_t)((H + 7) / 8) * 8;
+// tensor-memory columns: nacc accumulators of 64 columns (BT <= 64 used), then the resident weights (one column per k, 16-column stores)
+__host__ __device__ inline uint32_t fwd_tmem_cols(int H, int nacc) {
+  const uint32_t need = 64u * nacc + (uint32_t)((H + 15) / 16) * 16;
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
@@ -254,7 +268,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
   const int rank = (int)cluster_ctarank();     // == blockIdx.x (grid.x == CL)
   const int tile = blockIdx.y, dir = blockIdx.z;
   const int u0 = rank * u;
-  const uint32_t tmem_cols = fwd_tmem_cols(H);
+  const int nacc = p.nacc;
+  const uint32_t FWD_A0 = 64u * nacc;
+  const uint32_t tmem_cols = fwd_tmem_cols(H, nacc);
   const size_t img_bytes = (size_t)L.nfull * H_CHUNK + (size_t)BT * L.tail_w * 4;
   // image of this cluster's operand tile in global memory: [parity][full chunks][tail]
   uint8_t* img = reinterpret_cast<uint8_t*>(p.xchg) + ((size_t)dir * gridDim.y + tile) * 2 * img_bytes;
@@ -340,8 +356,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
           tc_fence_after();
           if (elect_one()) {
             stamp(p.trace, s, 8 + g);
-            if (g < L.ngf) issue_full_group_ts(tmem_base, tmem_base + FWD_A0, ht_s, H_CHUNK, g, L, idesc);
-            else issue_tail_ts(tmem_base, tmem_base + FWD_A0, htail_s, L, idesc);
+            if (g < L.ngf) issue_full_group_ts(tmem_base, tmem_base + FWD_A0, ht_s, H_CHUNK, g, L, idesc, nacc);
+            else issue_tail_ts(tmem_base, tmem_base + FWD_A0, htail_s, L, idesc, nacc);
           }
           __syncwarp();
         }
@@ -356,6 +372,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
           tc_fence_after();
           float v[CPP];
           tmem_ld_cols<CPP>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * CPP), v);
+          for (int ai = 1; ai < nacc; ++ai) {
+            float v2[CPP];
+            tmem_ld_cols<CPP>(tmem_base + ((uint32_t)(q * 32) << 16) + 64u * ai + (uint32_t)(part * CPP), v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CPP; ++j) v[j] += v2[j];
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < CPP; ++j) ghs[lr * GS + part * CPP + j] = v[j];
@@ -625,6 +648,254 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1)
   cluster_wait();
 }
 
+// =====================================================================================================================
+// backward, K-split ("own gates") variant
+//
+// dh_t[clip, j] needs sum_r dgh_{t+1}[clip, r] * W_hh[r, j] over all 3H gate rows r.  Instead of all-gathering dgh (3H values per clip,
+// above), CTA c keeps the product for ITS OWN gate rows only - the 3u rows of the u hidden units whose gate gradients its threads have
+// just computed - but for ALL H outputs j:  P_c[j, clip] = sum_{r in R_c} W_hh[r, j] * dgh[clip, r].  That is a [ceil(H/128) x 128] x BT
+// x 3u product whose A operand (W_hh^T restricted to R_c: H x 3u) fits TENSOR MEMORY next to the accumulators, so no recurrent weight
+// sits in shared memory at all and the B operand (BT x 3u) never leaves the CTA.  The partials are then reduce-scattered: the thread
+// holding accumulator row j pushes its BT values straight into the shared memory of the CTA that owns unit j (st.shared::cluster),
+// one hardware cluster barrier per step publishes them, and the owner adds the 8 contributions.
+// =====================================================================================================================
+struct BwdKsP {
+  const float* dout; const float* out; const float* saved; long long saved_qstride; const float* whhT0; const float* whhT1;
+  float* dgi; float* dgh;
+  int B, T, H, u;
+  long long* trace;
+};
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+constexpr int KS_ACC_STRIDE = 32;     // tensor-memory columns reserved per accumulator tile (BT <= 32)
+__host__ __device__ inline int ks_ka(int u) { return ((3 * u + 15) / 16) * 16; }          // A columns per M tile (16-column stores)
+__host__ __device__ inline uint32_t ks_tmem_cols(int H, int u) {
+  const uint32_t need = (uint32_t)((H + 127) / 128) * (KS_ACC_STRIDE + ks_ka(u));
+  uint32_t c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+// shared memory: [B tile: ceil(3u/32) chunks x BT rows x 128 B][slots: 2 parities x 8 sources x u rows x (BT+4) floats][barrier]
+__host__ __device__ inline size_t ks_btile_bytes(int u, int BT) { return (size_t)((3 * u + 31) / 32) * BT * 128; }
+__host__ __device__ inline size_t ks_slots_off(int u, int BT) { return (ks_btile_bytes(u, BT) + 1023) & ~(size_t)1023; }
+__host__ __device__ inline size_t ks_bar_off(int u, int BT) { return (ks_slots_off(u, BT) + (size_t)2 * CL * u * (BT + 4) * 4 + 15) & ~(size_t)15; }
+
+template <int BT>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_ks_kernel(const BwdKsP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  static_assert(BT == 16 || BT == 32, "batch tile");
+  constexpr int SP = BT + 4;                   // slot row pitch (floats): 16-byte aligned rows, conflict-free LDS.128 / remote STS.128
+  constexpr int CG = BT / 4;                   // clip groups of 4
+  const int H = p.H, T = p.T, u = p.u;
+  const int K = 3 * u;                         // own gate rows: k = g*u + jl  <->  W_hh row g*H + u0 + jl
+  const int ksteps = K >> 3;                   // u % 8 == 0
+  const int nmt = (H + 127) >> 7;              // accumulator row tiles (M = 128 each)
+  const int ka = ks_ka(u);
+  uint8_t* Bt = smem;
+  float* slots = reinterpret_cast<float*>(smem + ks_slots_off(u, BT));
+  uint64_t* tmem_full = reinterpret_cast<uint64_t*>(smem + ks_bar_off(u, BT));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile = blockIdx.y, dir = blockIdx.z;
+  const int u0 = rank * u;
+  const uint32_t tmem_cols = ks_tmem_cols(H, u);
+  const uint32_t a_col0 = (uint32_t)nmt * KS_ACC_STRIDE;              // accumulators first, then the nmt A tiles of ka columns
+
+  if (smem_u32(smem) & 1023) __trap();
+  for (int i = threadIdx.x; i < (int)(ks_bar_off(u, BT) / 16); i += BWD_NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == 0 && elect_one()) { mbar_init(tmem_full, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  fence_proxy_async_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int etid = (int)threadIdx.x - 64;
+  const bool epi = etid >= 0;
+  const int q = warp & 3, mt = epi ? (warp - 2) >> 2 : 0;               // epilogue warp (q, mt): TMEM lanes 32q.., accumulator / A tile mt
+  const bool tile_warp = epi && mt < nmt;
+  const int jrow = mt * 128 + q * 32 + lane;                            // output unit j held in this thread's TMEM lane
+  if (tile_warp) {
+    // resident weights -> tensor memory, once: lane j of tile mt, column k = g*u + jl holds W_hh[g*H + u0 + jl][j] = whhT[j][g*H + u0 + jl]
+    const float* wrow = (dir ? p.whhT1 : p.whhT0) + (long long)jrow * 3 * H;
+    for (int k0 = 0; k0 < ka; k0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const int k = k0 + e, g = k / u, jl = k - g * u;               // u % 4 == 0: a group of 4 never straddles two gates
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jrow < H && k < K && u0 + jl < H) x = ldv_nc4(wrow + (long long)g * H + u0 + jl);
+        v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+      }
+      tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(mt * ka + k0), v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  cluster_arrive();          // every CTA's slots are zeroed before any peer pushes into them
+  cluster_wait();
+
+  // ---- elementwise ownership: epilogue thread etid < CG * u owns (hidden unit u0 + jl, clips 4cg .. 4cg+3 of the tile)
+  const int cg = epi ? etid / u : 0, jl = epi ? etid - cg * u : 0;
+  const int unit = u0 + jl;
+  const bool own = epi && cg < CG && unit < H;
+  const long long row2H = 2ll * H;
+  float dhc[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t idesc = idesc_tf32(128, BT, 0, 0);
+  constexpr uint32_t hi = desc_hi(1024, 2);
+  const uint32_t bt_lo = desc_lo(smem_u32(Bt), 16);
+  const uint32_t slots_s = smem_u32(slots);
+  // where this thread's accumulator row goes: owner CTA of unit jrow, its slot [parity][source = this rank][row jrow - owner*u]
+  const int owner = jrow / u, jo = jrow - owner * u;
+  const uint32_t push0 = mapa_cluster(slots_s + (uint32_t)(((rank * u + jo) * SP) * 4), (uint32_t)(owner < CL ? owner : 0));
+  const uint32_t par_bytes = (uint32_t)(CL * u * SP * 4);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    const bool tp_ok = tp >= 0 && tp < T;
+    float v_do[4], v_r[4], v_z[4], v_n[4], v_hn[4], v_hp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v_do[i] = v_r[i] = v_z[i] = v_n[i] = v_hn[i] = v_hp[i] = 0.f;
+      const int b = tile * BT + cg * 4 + i;
+      if (own && b < p.B) {
+        const long long o = ((long long)b * T + t) * row2H + dir * H + unit;
+        v_do[i] = ldv_nc(p.dout + o);
+        v_r[i] = ldv_nc(p.saved + o);
+        v_z[i] = ldv_nc(p.saved + p.saved_qstride + o);
+        v_n[i] = ldv_nc(p.saved + 2 * p.saved_qstride + o);
+        v_hn[i] = ldv_nc(p.saved + 3 * p.saved_qstride + o);
+        if (tp_ok) v_hp[i] = ldv_nc(p.out + ((long long)b * T + tp) * row2H + dir * H + unit);
+      }
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (s > 0) {
+      cluster_wait();          // acquire: all 8 partial slices of this step are in slots[s & 1]
+      if (etid == 0) stamp(p.trace, s, 5);
+      if (own) {
+        const float* sl = slots + (size_t)(s & 1) * CL * u * SP + (size_t)jl * SP + cg * 4;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) {
+          const float4 x = *reinterpret_cast<const float4*>(sl + (size_t)src * u * SP);
+          acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+        }
+      }
+    }
+    float dr[4], dz[4], dn[4], dnr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dh = v_do[i] + dhc[i] + acc[i];
+      const float dnv = dh * (1.f - v_z[i]) * (1.f - v_n[i] * v_n[i]);
+      dz[i] = dh * (v_hp[i] - v_n[i]) * v_z[i] * (1.f - v_z[i]);
+      dr[i] = dnv * v_hn[i] * v_r[i] * (1.f - v_r[i]);
+      dn[i] = dnv;
+      dnr[i] = dnv * v_r[i];
+      dhc[i] = dh * v_z[i];
+    }
+    if (etid == 0) stamp(p.trace, s, 3);
+    if (s + 1 < T) {
+      if (epi) {
+        if (own) {
+          // B operand of the next product: this CTA's own gate gradients, K-major [clip][k = g*u + jl], 128-byte swizzle
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = cg * 4 + i;
+            const uint32_t rowoff = (uint32_t)((c >> 3) * 1024 + (c & 7) * 128);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              const int k = g * u + jl;
+              const float val = g == 0 ? dr[i] : g == 1 ? dz[i] : dnr[i];
+              *reinterpret_cast<float*>(Bt + (size_t)(k >> 5) * BT * 128 + rowoff + ((((k & 31) >> 2) ^ (c & 7)) << 4) + (k & 3) * 4) = val;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      if (warp >= 1) {
+        tc_fence_before();
+        asm volatile("bar.sync 1, 544;" ::: "memory");     // 16 epilogue warps + the MMA warp: the B tile is complete
+      }
+      if (warp == 1) {
+        tc_fence_after();
+        if (elect_one()) {
+          stamp(p.trace, s, 6);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t b_lo = bt_lo + (uint32_t)(ks >> 2) * (BT * 128 / 16) + (uint32_t)(ks & 3) * 2;
+            const uint32_t a_k = tmem_base + a_col0 + 8u * ks;
+            const uint32_t acc_on = ks > 0 ? 1u : 0u;
+            // consecutive MMAs go to DIFFERENT accumulator tiles: independent, so the tensor pipe can overlap them
+            mma_tf32_ts(tmem_base, a_k, b_lo, hi, idesc, acc_on);
+            if (nmt > 1) mma_tf32_ts(tmem_base + KS_ACC_STRIDE, a_k + (uint32_t)ka, b_lo, hi, idesc, acc_on);
+            if (nmt > 2) mma_tf32_ts(tmem_base + 2 * KS_ACC_STRIDE, a_k + 2u * ka, b_lo, hi, idesc, acc_on);
+          }
+          tc_commit(tmem_full);
+          stamp(p.trace, s, 7);
+        }
+        __syncwarp();
+      }
+    }
+    if (own) {                 // stores for the weight-gradient GEMMs: overlap the MMAs
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = tile * BT + cg * 4 + i;
+        if (b < p.B) {
+          const long long row = (long long)b * T + t;
+          float* gp = p.dgi + row * 6 * H + dir * 3 * H + unit;
+          float* hp = p.dgh + row * 6 * H + dir * 3 * H + unit;
+          gp[0] = dr[i]; gp[H] = dz[i]; gp[2 * H] = dn[i];
+          hp[0] = dr[i]; hp[H] = dz[i]; hp[2 * H] = dnr[i];
+        }
+      }
+    }
+    if (s + 1 < T) {
+      if (tile_warp) {
+        // partial dh of THIS CTA's gate rows for output unit jrow, all BT clips -> the owner of unit jrow
+        mbar_wait(tmem_full, (uint32_t)(s & 1));
+        if (etid == 0) stamp(p.trace, s, 1);
+        tc_fence_after();
+        float v[BT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * KS_ACC_STRIDE);
+        tmem_ld16(taddr, v);
+        if constexpr (BT == 32) tmem_ld16(taddr + 16, v + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        if (jrow < H) {
+          const uint32_t dst = push0 + (uint32_t)((s + 1) & 1) * par_bytes;
+#pragma unroll
+          for (int c4 = 0; c4 < BT / 4; ++c4) st_cluster_v4(dst + c4 * 16, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        }
+      }
+      cluster_arrive();        // release: this CTA's partials are in the owners' slots[(s + 1) & 1]
+      if (etid == 0) stamp(p.trace, s, 4);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  cluster_arrive();            // no CTA exits while a peer may still push into its shared memory
+  cluster_wait();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -721,10 +992,35 @@ int launch_bwd(const CUtensorMap* maps, const BwdP& p, int ntiles, cudaStream_t 
   return 0;
 }
 
+int cl_nacc() {              // TGB200_GRU_NACC=1..3: accumulators the forward K-steps rotate over
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TGB200_GRU_NACC"); v = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 1; }
+  return v;
+}
 int cl_flags() {             // TGB200_GRU_UNICAST=1: A/B switch of the operand all-gather (development aid)
   static int v = -1;
   if (v < 0) { const char* e = getenv("TGB200_GRU_UNICAST"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
+}
+
+size_t ks_smem(int u, int BT) {
+  const size_t need = ks_bar_off(u, BT) + 32;
+  return need > (size_t)180 * 1024 ? need : (size_t)180 * 1024;     // holds most of tensor memory: one CTA per SM (see fwd_smem)
+}
+int cl_bwd_variant() {       // TGB200_GRU_BWD=ag: the all-gather backward kernel (default: the K-split / reduce-scatter kernel)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TGB200_GRU_BWD"); v = (e && e[0] == 'a') ? 1 : 0; }
+  return v;
+}
+template <int BT>
+int launch_bwd_ks(const BwdKsP& p, int ntiles, cudaStream_t s) {
+  const size_t smem = ks_smem(p.u, BT);
+  cudaError_t e = cudaFuncSetAttribute(gru_bwd_ks_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return -3; }
+  gru_bwd_ks_kernel<BT><<<dim3(CL, ntiles, 2), BWD_NT, smem, s>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: cluster launch (8,%d,2) smem %zu: %s", ntiles, smem, cudaGetErrorString(e)); return -2; }
+  return 0;
 }
 
 }  // namespace
@@ -775,6 +1071,9 @@ int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const
   p.L = klay(H);
   p.gi = gi; p.whh0 = whh_f; p.whh1 = whh_r; p.bhh0 = bhh_f; p.bhh1 = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.xchg = xchg;
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.flags = cl_flags();
+  p.nacc = cl_nacc();
+  if (p.nacc > (H + 7) / 8) p.nacc = 1;
+  if (fwd_tmem_cols(H, p.nacc) > 512) p.nacc = 1;
   p.trace = trace;
   if (pl.bt_f == 16) return launch_fwd<16>(p, pl.ntiles_f, s);
   if (pl.bt_f == 32) return launch_fwd<32>(p, pl.ntiles_f, s);
@@ -787,6 +1086,14 @@ int tg_gru_cl_bwd(const float* dout, const float* out, const float* saved, long 
   TgGruClPlan pl;
   if (!tg_gru_cl_plan(B, H, &pl)) { tg_set_error("tg_gru_layer_bwd_tf32: no cluster plan for B=%d H=%d", B, H); return -1; }
   if (reinterpret_cast<uintptr_t>(xchg) & 127) { tg_set_error("tg_gru_layer_bwd_tf32: exchange scratch must be 128-byte aligned"); return -1; }
+  if (!cl_bwd_variant() && ((reinterpret_cast<uintptr_t>(whhT_f) | reinterpret_cast<uintptr_t>(whhT_r)) & 15) == 0 && ks_tmem_cols(H, pl.u) <= 512) {
+    // K-split kernel: batch tile 16 when all 2 * ceil(B/16) chains fit one wave of resident clusters, else 32
+    BwdKsP k;
+    k.dout = dout; k.out = out; k.saved = saved; k.saved_qstride = saved_qstride; k.whhT0 = whhT_f; k.whhT1 = whhT_r; k.dgi = dgi; k.dgh = dgh;
+    k.B = B; k.T = T; k.H = H; k.u = pl.u; k.trace = trace;
+    if (2 * tg_ceil_div(B, 16) <= max_resident_clusters()) return launch_bwd_ks<16>(k, tg_ceil_div(B, 16), s);
+    return launch_bwd_ks<32>(k, tg_ceil_div(B, 32), s);
+  }
   BwdP p;
   p.L = klay(3 * H);
   CUtensorMap maps[4];

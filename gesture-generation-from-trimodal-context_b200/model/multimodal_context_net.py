@@ -31,7 +31,15 @@ class WavEncoder(nn.Module):
             nn.Conv1d(64, 32, 15, stride=6))
 
     def forward(self, wav_data):
-        raise RuntimeError('WavEncoder holds parameters only; its kernels run inside PoseGenerator.forward (no PyTorch fallback)')
+        """[B, L] raw audio -> [B, n_frames, 32] (multimodal_context_net.py:25-28).  Stand-alone call: forward only, no autograd graph; inside
+        PoseGenerator / ContextEncoder the parent's engine runs the same kernels together with their backward."""
+        _lib.require_cuda()
+        if not wav_data.is_cuda and not _lib.TRACE_ONLY:
+            raise _lib.TgError('WavEncoder.forward runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+        if getattr(self, '_engine', None) is None:
+            from tgb200.engine import StandaloneEncoderEngine
+            self._engine = StandaloneEncoderEngine(self, 'audio_encoder.')
+        return self._engine.ensure(wav_data.device).run_wav(wav_data)
 
 
 class TextEncoderTCN(nn.Module):
@@ -57,7 +65,20 @@ class TextEncoderTCN(nn.Module):
         self.decoder.weight.data.normal_(0, 0.01)
 
     def forward(self, input):
-        raise RuntimeError('TextEncoderTCN holds parameters only; its kernels run inside PoseGenerator.forward (no PyTorch fallback)')
+        """[B, T] word ids -> ([B, T, 32], 0) (multimodal_context_net.py:57-61; train mode draws its dropout masks from Philox).  Stand-alone
+        call: forward only, no autograd graph; inside PoseGenerator / ContextEncoder the parent's engine runs the same kernels + backward."""
+        _lib.require_cuda()
+        if not input.is_cuda and not _lib.TRACE_ONLY:
+            raise _lib.TgError('TextEncoderTCN.forward runs on CUDA tensors only (sm_100a kernels, no CPU fallback)')
+        if getattr(self, '_engine', None) is None:
+            from tgb200.engine import StandaloneEncoderEngine
+            self._engine = StandaloneEncoderEngine(self, 'text_encoder.')
+            self._noise = _NoiseSource(_module_seed() ^ 0x7E47)
+        eng = self._engine.ensure(input.device)
+        y = eng.run_text(input, self._noise.seed, self._noise.offset_dev(input.device))
+        if self.training:
+            self._noise.advance()
+        return y, 0
 
 
 class _NoiseSource:

@@ -895,3 +895,62 @@ class EmbeddingEngine:
             ops.conv1d(x, w, p[f'{d}net.{idx}.bias'], y, B=B, Tin=tin, Cin=cin, N=cout, k=k)
             x, tin, cin = y, tout, cout
         return feat, mu, logvar, x.view(B, tin, cin)
+
+
+# =====================================================================================================================
+# WavEncoder / TextEncoderTCN called on their own (multimodal_context_net.py:25-28,57-61)
+# =====================================================================================================================
+class StandaloneEncoderEngine:
+    """Forward of a stand-alone `WavEncoder()` / `TextEncoderTCN(...)` module (the reference constructs them directly in ContextEncoder,
+    embedding_net.py:225-226, and nothing stops a user from calling them).  The generator's launch plans for the two encoders run
+    unchanged on an arena over THIS module's own parameters: a parameter the plans call `audio_encoder.feat_extractor.0.weight` /
+    `text_encoder.tcn...` is this module's `feat_extractor.0.weight` / `tcn...`.  Forward only: the result carries no autograd graph
+    (training these modules goes through PoseGenerator / EmbeddingNet, whose engines own the hand-derived backward)."""
+    WAV = GeneratorEngine.WAV
+    wav_fast, wav_forward = GeneratorEngine.wav_fast, GeneratorEngine.wav_forward
+    text_forward, make_masks = GeneratorEngine.text_forward, GeneratorEngine.make_masks
+    _tcn_conv = staticmethod(GeneratorEngine._tcn_conv)
+
+    def __init__(self, module, prefix):
+        self.m, self.prefix = module, prefix
+        self.arena = ParamArena(module)
+        self.ws = None
+        self.use_text = prefix == 'text_encoder.'
+        self.use_audio = not self.use_text
+        if self.use_text:
+            self.E = module.embedding.weight.shape[1]
+            self.H = module.tcn.network[0].conv1.weight_v.shape[0]
+            self.n_tcn = len(module.tcn.network)
+            self.tcn_k = module.tcn.network[0].conv1.weight_v.shape[2]
+            self.p_emb, self.p_tcn = float(module.emb_dropout), float(module.tcn.network[0].dropout1.p)
+        self.L, self.p_gru = 1, 0.0                                       # make_masks: no GRU masks
+
+    def P(self, name):
+        assert name.startswith(self.prefix), name
+        return self.arena.params[name[len(self.prefix):]].data
+
+    def ensure(self, device):
+        if not self.arena.is_current() or self.ws is None or self.ws.device != device:
+            self.arena.ensure(device)
+            self.ws = Workspace(device)
+        self.bufs = {self.prefix + k: v for k, v in self.m.named_buffers()}
+        return self
+
+    def run_wav(self, wav):
+        B = wav.shape[0]
+        feat = self.wav_forward(wav.detach().contiguous().float(), self.m.training, 1)
+        return feat.view(B, -1, feat.shape[1]).clone()
+
+    def run_text(self, ids, seed, offset_dev):
+        B, T = ids.shape
+        ws = self.ws
+        for i in range(self.n_tcn):                                       # weight-normed filters, tap-major (+ per-tap transposes in fast mode)
+            for j in (1, 2):
+                q = f'text_encoder.tcn.network.{i}.conv{j}'
+                v = self.P(q + '.weight_v')
+                N, Cin, k = v.shape
+                wT = ws.get(f'tcn.wT{i}_{j}', (k, Cin, N)) if config.fast() else None
+                ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (k, N, Cin)), wT, ws.get(f'tcn.inv{i}_{j}', (N,)), N, Cin, k)
+        masks = self.make_masks(B, T, seed, offset_dev) if self.m.training else None
+        feat = self.text_forward(ids.contiguous(), B, T, masks)
+        return feat.view(B, T, feat.shape[1]).clone()
