@@ -136,16 +136,7 @@ __device__ __forceinline__ void issue_tail(uint32_t tmem_d, uint32_t a_tail, uin
   const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
   issue_ksteps<0>(L.tail_ksteps, tmem_d, desc_lo(a_tail, 16), desc_lo(b_tail, 16), hi, idesc, L.nfull > 0 ? 1u : 0u);
 }
-// The same with the A operand resident in tensor memory: K-step ks of the whole reduction reads A columns a_tmem + 8 ks and accumulates
-// into accumulator ks % nacc (accumulators 64 columns apart; the epilogue adds them).  Spreading consecutive K-steps over independent
-// accumulators lets the tensor pipe overlap MMAs that would otherwise wait on the same 128 x N tile.
-__device__ __forceinline__ void issue_ts(uint32_t tmem_base, uint32_t a_tmem, int ks_lo, int ks_hi, uint32_t b_lo, uint32_t hi, uint32_t idesc, int nacc) {
-  int ai = ks_lo % nacc;
-  for (int ks = ks_lo; ks < ks_hi; ++ks, b_lo += 2) {
-    mma_tf32_ts(tmem_base + 64u * ai, a_tmem + 8u * ks, b_lo, hi, idesc, ks >= nacc ? 1u : 0u);
-    if (++ai == nacc) ai = 0;
-  }
-}
+// The same with the A operand resident in tensor memory: K-step ks of the whole reduction reads A columns a_tmem + 8 ks.
 template <int NK>
 __device__ __forceinline__ void issue_ts_fixed(uint32_t tmem_base, uint32_t a_tmem, int ks0, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
   mma_tf32_ts_seq<NK>(tmem_base, a_tmem + 8u * ks0, b_lo, hi, idesc, ks0 > 0 ? 1u : 0u);
@@ -157,20 +148,18 @@ __device__ __forceinline__ void issue_ts_n(int nk, uint32_t tmem_base, uint32_t 
   else issue_ts_fixed<1>(tmem_base, a_tmem, ks0, b_lo, hi, idesc);
 }
 __device__ __forceinline__ void issue_full_group_ts(uint32_t tmem_base, uint32_t a_tmem, uint32_t b_base, uint32_t b_chunk, int g, const KLay& L,
-                                                    uint32_t idesc, int nacc) {
+                                                    uint32_t idesc) {
   constexpr uint32_t hi = desc_hi(1024, 2);
   const int kc_lo = g * L.gsz, kc_hi = min(L.nfull, (g + 1) * L.gsz);
   for (int kc = kc_lo; kc < kc_hi; ++kc) {
     const uint32_t b_lo = desc_lo(b_base + (uint32_t)kc * b_chunk, 16);
     const int nk = kc < L.nfull - 1 ? 4 : L.last_ksteps;
-    if (nacc == 1) issue_ts_n(nk, tmem_base, a_tmem, kc * 4, b_lo, hi, idesc);       // straight-line issue: the generic loop below costs 2x per MMA
-    else issue_ts(tmem_base, a_tmem, kc * 4, kc * 4 + nk, b_lo, hi, idesc, nacc);
+    issue_ts_n(nk, tmem_base, a_tmem, kc * 4, b_lo, hi, idesc);
   }
 }
-__device__ __forceinline__ void issue_tail_ts(uint32_t tmem_base, uint32_t a_tmem, uint32_t b_tail, const KLay& L, uint32_t idesc, int nacc) {
+__device__ __forceinline__ void issue_tail_ts(uint32_t tmem_base, uint32_t a_tmem, uint32_t b_tail, const KLay& L, uint32_t idesc) {
   const uint32_t hi = L.tail_w == 16 ? desc_hi(512, 4) : desc_hi(256, 6);
-  if (nacc == 1) issue_ts_n(L.tail_ksteps, tmem_base, a_tmem, L.nfull * 4, desc_lo(b_tail, 16), hi, idesc);
-  else issue_ts(tmem_base, a_tmem, L.nfull * 4, L.nfull * 4 + L.tail_ksteps, desc_lo(b_tail, 16), hi, idesc, nacc);
+  issue_ts_n(L.tail_ksteps, tmem_base, a_tmem, L.nfull * 4, desc_lo(b_tail, 16), hi, idesc);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),
@@ -225,7 +214,6 @@ struct FwdP {
   const float* gi; const float* whh0; const float* whh1; const float* bhh0; const float* bhh1; float* out; float* saved; long long saved_qstride;
   float* xchg;
   int B, T, H, u, flags;      // flags bit 0: every CTA loads the whole tile itself (unicast) instead of the 8-way multicast
-  int nacc;                   // independent accumulators the K-steps rotate over (1..3)
   KLay L;
   long long* trace;
 };
@@ -235,15 +223,17 @@ template <int BT> struct FwdCfg {
   static constexpr int NT = 64 + 32 * EPI_WARPS;
 };
 
-// tensor-memory columns: nacc accumulators of 64 columns (BT <= 64 used), then the resident weights (one column per k, 16-column stores)
-__host__ __device__ inline uint32_t fwd_tmem_cols(int H, int nacc) {
-  const uint32_t need = 64u * nacc + (uint32_t)((H + 15) / 16) * 16;
+// tensor-memory columns: the accumulator (64 columns, BT <= 64 used), then the resident weights (one column per k, 16-column stores)
+constexpr uint32_t FWD_A0 = 64;
+__host__ __device__ inline uint32_t fwd_tmem_cols(int H) {
+  const uint32_t need = FWD_A0 + (uint32_t)((H + 15) / 16) * 16;
   uint32_t c = 32;
   while (c < need) c <<= 1;
   return c;
 }
 
-template <int BT>
+// HC = compile-time hidden size (300: the generator; K layout 9 full chunks + a 16-float tail, 5 + 1 multicast groups) or 0 (any H <= 320)
+template <int BT, int HC>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) gru_fwd_cl_kernel(const FwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = FwdCfg<BT>::NT, EPI = 32 * FwdCfg<BT>::EPI_WARPS;
@@ -268,9 +258,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
   const int rank = (int)cluster_ctarank();     // == blockIdx.x (grid.x == CL)
   const int tile = blockIdx.y, dir = blockIdx.z;
   const int u0 = rank * u;
-  const int nacc = p.nacc;
-  const uint32_t FWD_A0 = 64u * nacc;
-  const uint32_t tmem_cols = fwd_tmem_cols(H, nacc);
+  const uint32_t tmem_cols = fwd_tmem_cols(H);
   const size_t img_bytes = (size_t)L.nfull * H_CHUNK + (size_t)BT * L.tail_w * 4;
   // image of this cluster's operand tile in global memory: [parity][full chunks][tail]
   uint8_t* img = reinterpret_cast<uint8_t*>(p.xchg) + ((size_t)dir * gridDim.y + tile) * 2 * img_bytes;
@@ -351,15 +339,38 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
     }
     if (s > 0) {
       if (warp == 1) {
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&h_full[g], (uint32_t)((s - 1) & 1));
-          tc_fence_after();
-          if (elect_one()) {
-            stamp(p.trace, s, 8 + g);
-            if (g < L.ngf) issue_full_group_ts(tmem_base, tmem_base + FWD_A0, ht_s, H_CHUNK, g, L, idesc, nacc);
-            else issue_tail_ts(tmem_base, tmem_base + FWD_A0, htail_s, L, idesc, nacc);
+        if constexpr (HC == 300) {
+          // straight-line issue with immediate offsets (tests/ubench/mma_issue.cu: ~34 cycles per 128 x 64 x 8 MMA, the tensor pipe's own rate;
+          // the same MMAs issued through run-time loops over chunks and K-steps took 80-110 cycles each)
+          constexpr uint32_t hi = desc_hi(1024, 2), hi_tail = desc_hi(512, 4);
+          const uint32_t a0 = tmem_base + FWD_A0, b0 = desc_lo(ht_s, 16), bt0 = desc_lo(htail_s, 16);
+#pragma unroll
+          for (int g = 0; g < 6; ++g) {
+            mbar_wait(&h_full[g], (uint32_t)((s - 1) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+              stamp(p.trace, s, 8 + g);
+              if (g < 5) {
+#pragma unroll
+                for (int kc = 2 * g; kc < (2 * g + 2 < 9 ? 2 * g + 2 : 9); ++kc)
+                  mma_tf32_ts_seq<4>(tmem_base, a0 + 32u * kc, b0 + (uint32_t)kc * (H_CHUNK / 16), hi, idesc, kc > 0 ? 1u : 0u);
+              } else {
+                mma_tf32_ts_seq<2>(tmem_base, a0 + 32u * 9, bt0, hi_tail, idesc, 1u);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
+        } else {
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(&h_full[g], (uint32_t)((s - 1) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+              stamp(p.trace, s, 8 + g);
+              if (g < L.ngf) issue_full_group_ts(tmem_base, tmem_base + FWD_A0, ht_s, H_CHUNK, g, L, idesc);
+              else issue_tail_ts(tmem_base, tmem_base + FWD_A0, htail_s, L, idesc);
+            }
+            __syncwarp();
+          }
         }
         if (elect_one()) { tc_commit(tmem_full); stamp(p.trace, s, 7); }
         __syncwarp();
@@ -372,13 +383,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
           tc_fence_after();
           float v[CPP];
           tmem_ld_cols<CPP>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * CPP), v);
-          for (int ai = 1; ai < nacc; ++ai) {
-            float v2[CPP];
-            tmem_ld_cols<CPP>(tmem_base + ((uint32_t)(q * 32) << 16) + 64u * ai + (uint32_t)(part * CPP), v2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < CPP; ++j) v[j] += v2[j];
-          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < CPP; ++j) ghs[lr * GS + part * CPP + j] = v[j];
@@ -670,9 +674,6 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -690,26 +691,61 @@ __host__ __device__ inline uint32_t ks_tmem_cols(int H, int u) {
   while (c < need) c <<= 1;
   return c;
 }
-// shared memory: [B tile: ceil(3u/32) chunks x BT rows x 128 B][slots: 2 parities x 8 sources x u rows x (BT+4) floats][barrier]
+// shared memory: [B tile: ceil(3u/32) chunks x BT rows x 128 B][stage: 2 parities x 8 destinations x u rows x (BT+4) floats]
+//                [slots: 2 parities x 8 sources x u rows x (BT+4) floats][barriers]
 __host__ __device__ inline size_t ks_btile_bytes(int u, int BT) { return (size_t)((3 * u + 31) / 32) * BT * 128; }
-__host__ __device__ inline size_t ks_slots_off(int u, int BT) { return (ks_btile_bytes(u, BT) + 1023) & ~(size_t)1023; }
+__host__ __device__ inline size_t ks_stage_off(int u, int BT) { return (ks_btile_bytes(u, BT) + 1023) & ~(size_t)1023; }
+__host__ __device__ inline size_t ks_slots_off(int u, int BT) { return ks_stage_off(u, BT) + (((size_t)2 * CL * u * (BT + 4) * 4 + 127) & ~(size_t)127); }
 __host__ __device__ inline size_t ks_bar_off(int u, int BT) { return (ks_slots_off(u, BT) + (size_t)2 * CL * u * (BT + 4) * 4 + 15) & ~(size_t)15; }
 
-template <int BT>
+// shared::cta -> shared memory of CTA `dst_saddr` lives in (a mapa address), completing `bar_raddr` (a mapa address in the same CTA)
+__device__ __forceinline__ void bulk_s2s_cluster(uint32_t dst_raddr, uint32_t src_saddr, uint32_t bytes, uint32_t bar_raddr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_raddr), "r"(src_saddr),
+               "r"(bytes), "r"(bar_raddr)
+               : "memory");
+}
+
+// the nmt x ksteps MMAs of one step, consecutive MMAs on different accumulator tiles; KSTEPS / NMT > 0: compile-time shape (straight-line
+// issue with immediate offsets: ~10 cycles per MMA instead of ~50 through run-time loops - tests/ubench/mma_issue.cu)
+template <int BT, int KSTEPS, int NMT>
+__device__ __forceinline__ void ks_issue(uint32_t tmem_base, uint32_t a_col0, int ka, uint32_t bt_lo, uint32_t idesc, int ksteps_rt, int nmt_rt) {
+  constexpr uint32_t hi = desc_hi(1024, 2);
+  if constexpr (KSTEPS > 0) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint32_t b_lo = bt_lo + (uint32_t)(ks >> 2) * (BT * 128 / 16) + (uint32_t)(ks & 3) * 2;
+#pragma unroll
+      for (int m = 0; m < NMT; ++m)
+        mma_tf32_ts(tmem_base + (uint32_t)(m * KS_ACC_STRIDE), tmem_base + a_col0 + (uint32_t)(m * ka) + 8u * ks, b_lo, hi, idesc, ks > 0 ? 1u : 0u);
+    }
+  } else {
+    for (int ks = 0; ks < ksteps_rt; ++ks) {
+      const uint32_t b_lo = bt_lo + (uint32_t)(ks >> 2) * (BT * 128 / 16) + (uint32_t)(ks & 3) * 2;
+      for (int m = 0; m < nmt_rt; ++m)
+        mma_tf32_ts(tmem_base + (uint32_t)(m * KS_ACC_STRIDE), tmem_base + a_col0 + (uint32_t)(m * ka) + 8u * ks, b_lo, hi, idesc, ks > 0 ? 1u : 0u);
+    }
+  }
+}
+
+// HC = compile-time hidden size (300: the generator) or 0 (any H <= 320)
+template <int BT, int HC>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_ks_kernel(const BwdKsP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   static_assert(BT == 16 || BT == 32, "batch tile");
-  constexpr int SP = BT + 4;                   // slot row pitch (floats): 16-byte aligned rows, conflict-free LDS.128 / remote STS.128
+  constexpr int SP = BT + 4;                   // slot / stage row pitch (floats): 16-byte aligned rows
   constexpr int CG = BT / 4;                   // clip groups of 4
-  const int H = p.H, T = p.T, u = p.u;
+  const int H = HC > 0 ? HC : p.H, T = p.T;
+  const int u = HC > 0 ? ((HC + CL - 1) / CL + 7) / 8 * 8 : p.u;
   const int K = 3 * u;                         // own gate rows: k = g*u + jl  <->  W_hh row g*H + u0 + jl
   const int ksteps = K >> 3;                   // u % 8 == 0
   const int nmt = (H + 127) >> 7;              // accumulator row tiles (M = 128 each)
   const int ka = ks_ka(u);
   uint8_t* Bt = smem;
+  float* stage = reinterpret_cast<float*>(smem + ks_stage_off(u, BT));
   float* slots = reinterpret_cast<float*>(smem + ks_slots_off(u, BT));
   uint64_t* tmem_full = reinterpret_cast<uint64_t*>(smem + ks_bar_off(u, BT));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* slot_full = tmem_full + 1;         // [2 parities]: 8 x (u x SP x 4) bytes of partials have landed in slots[parity]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -717,16 +753,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
   const int u0 = rank * u;
   const uint32_t tmem_cols = ks_tmem_cols(H, u);
   const uint32_t a_col0 = (uint32_t)nmt * KS_ACC_STRIDE;              // accumulators first, then the nmt A tiles of ka columns
+  const uint32_t slice_bytes = (uint32_t)(u * SP * 4);                // one (source, destination) slice of partials
 
   if (smem_u32(smem) & 1023) __trap();
   for (int i = threadIdx.x; i < (int)(ks_bar_off(u, BT) / 16); i += BWD_NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == 0 && elect_one()) { mbar_init(tmem_full, 1); fence_barrier_init(); }
+  if (warp == 0 && elect_one()) {
+    mbar_init(tmem_full, 1); mbar_init(&slot_full[0], 1); mbar_init(&slot_full[1], 1);
+    fence_barrier_init();
+  }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async_all();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (warp == 0 && elect_one()) {              // arm both parities for their first use (steps 1 and 2)
+    mbar_expect_tx(&slot_full[0], CL * slice_bytes);
+    mbar_expect_tx(&slot_full[1], CL * slice_bytes);
+  }
   const int etid = (int)threadIdx.x - 64;
   const bool epi = etid >= 0;
   const int q = warp & 3, mt = epi ? (warp - 2) >> 2 : 0;               // epilogue warp (q, mt): TMEM lanes 32q.., accumulator / A tile mt
@@ -751,7 +795,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
   }
   __syncthreads();
   tc_fence_after();
-  cluster_arrive();          // every CTA's slots are zeroed before any peer pushes into them
+  cluster_arrive();          // every CTA's slots are zeroed and its barriers armed before any peer copies into them
   cluster_wait();
 
   // ---- elementwise ownership: epilogue thread etid < CG * u owns (hidden unit u0 + jl, clips 4cg .. 4cg+3 of the tile)
@@ -761,13 +805,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
   const long long row2H = 2ll * H;
   float dhc[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t idesc = idesc_tf32(128, BT, 0, 0);
-  constexpr uint32_t hi = desc_hi(1024, 2);
   const uint32_t bt_lo = desc_lo(smem_u32(Bt), 16);
-  const uint32_t slots_s = smem_u32(slots);
-  // where this thread's accumulator row goes: owner CTA of unit jrow, its slot [parity][source = this rank][row jrow - owner*u]
+  const uint32_t stage_s = smem_u32(stage), slots_s = smem_u32(slots), sfull_s = smem_u32(slot_full);
+  // where this thread's accumulator row is staged: destination = owner CTA of unit jrow, row jrow - owner*u of stage[owner]
   const int owner = jrow / u, jo = jrow - owner * u;
-  const uint32_t push0 = mapa_cluster(slots_s + (uint32_t)(((rank * u + jo) * SP) * 4), (uint32_t)(owner < CL ? owner : 0));
-  const uint32_t par_bytes = (uint32_t)(CL * u * SP * 4);
+  float* stage_row = stage + ((size_t)(owner < CL ? owner : 0) * u + jo) * SP;      // + parity * CL * u * SP
+  // Both staging and slots are double buffered by step parity.  No per-step cluster barrier: a CTA overwrites stage[p] / has slots[p]
+  // overwritten two steps after their last use, and in between it has received every peer's next slice - which a peer only sends after
+  // this CTA's previous slice has fully landed there (so the copy engine is done with stage[p]) and after it consumed its own slots[p].
 
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? T - 1 - s : s;
@@ -790,7 +835,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (s > 0) {
-      cluster_wait();          // acquire: all 8 partial slices of this step are in slots[s & 1]
+      // all 8 partial slices of this step have landed in slots[s & 1] (bulk copies complete the barrier; phase (s-1)/2 of that parity)
+      mbar_wait(&slot_full[s & 1], (uint32_t)(((s - 1) >> 1) & 1));
       if (etid == 0) stamp(p.trace, s, 5);
       if (own) {
         const float* sl = slots + (size_t)(s & 1) * CL * u * SP + (size_t)jl * SP + cg * 4;
@@ -833,21 +879,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
       }
       if (warp >= 1) {
         tc_fence_before();
-        asm volatile("bar.sync 1, 544;" ::: "memory");     // 16 epilogue warps + the MMA warp: the B tile is complete
+        asm volatile("bar.sync 1, 544;" ::: "memory");     // 16 epilogue warps + the MMA warp: the B tile is complete, slots[s & 1] are consumed
       }
       if (warp == 1) {
         tc_fence_after();
         if (elect_one()) {
+          // re-arm this step's parity for its next use (step s + 2); its producers cannot send before they have this CTA's step s + 1 slice
+          if (s > 0 && s + 2 < T) mbar_expect_tx(&slot_full[s & 1], CL * slice_bytes);
           stamp(p.trace, s, 6);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t b_lo = bt_lo + (uint32_t)(ks >> 2) * (BT * 128 / 16) + (uint32_t)(ks & 3) * 2;
-            const uint32_t a_k = tmem_base + a_col0 + 8u * ks;
-            const uint32_t acc_on = ks > 0 ? 1u : 0u;
-            // consecutive MMAs go to DIFFERENT accumulator tiles: independent, so the tensor pipe can overlap them
-            mma_tf32_ts(tmem_base, a_k, b_lo, hi, idesc, acc_on);
-            if (nmt > 1) mma_tf32_ts(tmem_base + KS_ACC_STRIDE, a_k + (uint32_t)ka, b_lo, hi, idesc, acc_on);
-            if (nmt > 2) mma_tf32_ts(tmem_base + 2 * KS_ACC_STRIDE, a_k + 2u * ka, b_lo, hi, idesc, acc_on);
-          }
+          ks_issue<BT, HC == 300 ? 15 : 0, HC == 300 ? 3 : 0>(tmem_base, a_col0, ka, bt_lo, idesc, ksteps, nmt);
           tc_commit(tmem_full);
           stamp(p.trace, s, 7);
         }
@@ -868,31 +908,41 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
       }
     }
     if (s + 1 < T) {
-      if (tile_warp) {
-        // partial dh of THIS CTA's gate rows for output unit jrow, all BT clips -> the owner of unit jrow
-        mbar_wait(tmem_full, (uint32_t)(s & 1));
-        if (etid == 0) stamp(p.trace, s, 1);
-        tc_fence_after();
-        float v[BT];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * KS_ACC_STRIDE);
-        tmem_ld16(taddr, v);
-        if constexpr (BT == 32) tmem_ld16(taddr + 16, v + 16);
-        tmem_ld_wait();
-        tc_fence_before();
-        if (jrow < H) {
-          const uint32_t dst = push0 + (uint32_t)((s + 1) & 1) * par_bytes;
+      if (epi) {
+        if (tile_warp) {
+          // partial dh of THIS CTA's gate rows for output unit jrow, all BT clips -> staged per destination CTA (the owner of unit jrow)
+          mbar_wait(tmem_full, (uint32_t)(s & 1));
+          if (etid == 0) stamp(p.trace, s, 1);
+          tc_fence_after();
+          float v[BT];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * KS_ACC_STRIDE);
+          tmem_ld16(taddr, v);
+          if constexpr (BT == 32) tmem_ld16(taddr + 16, v + 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (jrow < H) {
+            float* sr = stage_row + (size_t)((s + 1) & 1) * CL * u * SP;
 #pragma unroll
-          for (int c4 = 0; c4 < BT / 4; ++c4) st_cluster_v4(dst + c4 * 16, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            for (int c4 = 0; c4 < BT / 4; ++c4) *reinterpret_cast<float4*>(sr + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          }
+          fence_proxy_async_smem();      // generic-proxy staging writes -> the bulk copies' async-proxy reads
+        }
+        asm volatile("bar.sync 2, 512;" ::: "memory");        // the 16 epilogue warps: staging complete
+        if (warp == 2 && elect_one()) {
+          // reduce-scatter: slice d of the staged partials -> CTA d's slots[(s+1) & 1][source = this rank]; each copy completes CTA d's barrier
+          const uint32_t par = (uint32_t)((s + 1) & 1);
+          for (int d = 0; d < CL; ++d)
+            bulk_s2s_cluster(mapa_cluster(slots_s + (par * CL + (uint32_t)rank) * slice_bytes, (uint32_t)d), stage_s + (par * CL + (uint32_t)d) * slice_bytes,
+                             slice_bytes, mapa_cluster(sfull_s + 8u * par, (uint32_t)d));
+          stamp(p.trace, s, 4);
         }
       }
-      cluster_arrive();        // release: this CTA's partials are in the owners' slots[(s + 1) & 1]
-      if (etid == 0) stamp(p.trace, s, 4);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
-  cluster_arrive();            // no CTA exits while a peer may still push into its shared memory
+  cluster_arrive();            // no CTA exits while a peer's copy may still address its shared memory
   cluster_wait();
 }
 
@@ -964,8 +1014,8 @@ int max_resident_clusters() {
   cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
   int n = 0;
   const size_t smem = fwd_smem(300, 40, 16);
-  if (cluster_launch_cfg(&cfg, at, gru_fwd_cl_kernel<16>, FwdCfg<16>::NT, smem, 32, nullptr) == cudaSuccess &&
-      cudaOccupancyMaxActiveClusters(&n, gru_fwd_cl_kernel<16>, &cfg) == cudaSuccess && n > 0)
+  if (cluster_launch_cfg(&cfg, at, gru_fwd_cl_kernel<16, 0>, FwdCfg<16>::NT, smem, 32, nullptr) == cudaSuccess &&
+      cudaOccupancyMaxActiveClusters(&n, gru_fwd_cl_kernel<16, 0>, &cfg) == cudaSuccess && n > 0)
     cached = n;
   else { cudaGetLastError(); cached = 15; }
   return cached;
@@ -974,9 +1024,10 @@ int max_resident_clusters() {
 template <int BT>
 int launch_fwd(const FwdP& p, int ntiles, cudaStream_t s) {
   const size_t smem = fwd_smem(p.H, p.u, BT);
-  cudaError_t e = cudaFuncSetAttribute(gru_fwd_cl_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = p.H == 300 ? gru_fwd_cl_kernel<BT, 300> : gru_fwd_cl_kernel<BT, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return -3; }
-  gru_fwd_cl_kernel<BT><<<dim3(CL, ntiles, 2), FwdCfg<BT>::NT, smem, s>>>(p);
+  kern<<<dim3(CL, ntiles, 2), FwdCfg<BT>::NT, smem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_fwd_tf32: cluster launch (8,%d,2) smem %zu: %s", ntiles, smem, cudaGetErrorString(e)); return -2; }
   return 0;
@@ -992,11 +1043,6 @@ int launch_bwd(const CUtensorMap* maps, const BwdP& p, int ntiles, cudaStream_t 
   return 0;
 }
 
-int cl_nacc() {              // TGB200_GRU_NACC=1..3: accumulators the forward K-steps rotate over
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TGB200_GRU_NACC"); v = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 1; }
-  return v;
-}
 int cl_flags() {             // TGB200_GRU_UNICAST=1: A/B switch of the operand all-gather (development aid)
   static int v = -1;
   if (v < 0) { const char* e = getenv("TGB200_GRU_UNICAST"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -1015,9 +1061,10 @@ int cl_bwd_variant() {       // TGB200_GRU_BWD=ag: the all-gather backward kerne
 template <int BT>
 int launch_bwd_ks(const BwdKsP& p, int ntiles, cudaStream_t s) {
   const size_t smem = ks_smem(p.u, BT);
-  cudaError_t e = cudaFuncSetAttribute(gru_bwd_ks_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = p.H == 300 ? gru_bwd_ks_kernel<BT, 300> : gru_bwd_ks_kernel<BT, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return -3; }
-  gru_bwd_ks_kernel<BT><<<dim3(CL, ntiles, 2), BWD_NT, smem, s>>>(p);
+  kern<<<dim3(CL, ntiles, 2), BWD_NT, smem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { tg_set_error("tg_gru_layer_bwd_tf32: cluster launch (8,%d,2) smem %zu: %s", ntiles, smem, cudaGetErrorString(e)); return -2; }
   return 0;
@@ -1071,9 +1118,6 @@ int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const
   p.L = klay(H);
   p.gi = gi; p.whh0 = whh_f; p.whh1 = whh_r; p.bhh0 = bhh_f; p.bhh1 = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.xchg = xchg;
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.flags = cl_flags();
-  p.nacc = cl_nacc();
-  if (p.nacc > (H + 7) / 8) p.nacc = 1;
-  if (fwd_tmem_cols(H, p.nacc) > 512) p.nacc = 1;
   p.trace = trace;
   if (pl.bt_f == 16) return launch_fwd<16>(p, pl.ntiles_f, s);
   if (pl.bt_f == 32) return launch_fwd<32>(p, pl.ntiles_f, s);

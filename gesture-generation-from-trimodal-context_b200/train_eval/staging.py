@@ -21,6 +21,11 @@ def _map(obj, fn):
     return obj
 
 
+# Ring buffers and copy streams outlive a DevicePrefetcher: a training loop builds one per epoch (like `for data in train_data_loader`),
+# and re-creating 3 x 19 MB of device buffers plus a stream each time cost 50-230 ms of host time on the B200 boxes (bench.py e2e, round 2)
+_POOL = {}          # (device, depth) -> dict(stream, dev buffers, pinned staging buffers)
+
+
 class DevicePrefetcher:
     """copy_ctas: CTAs of the copy kernel.  8 CTAs already move 18.6 MB in well under a step, and every additional CTA measurably slows the
     concurrently running step (resident inputs 6.16 ms/step; 4-8 CTAs 6.29-6.30; 16: 6.35; 32: 6.44; 64: 6.50 - tests/sweep_e2e_copy.py).
@@ -32,9 +37,11 @@ class DevicePrefetcher:
     def __init__(self, loader, device, depth=2, copy_ctas=8):
         assert depth >= 1
         self.loader, self.device, self.depth, self.copy_ctas = loader, torch.device(device), depth, copy_ctas
-        self.stream = torch.cuda.Stream(device=self.device)
-        self._pin = {}
-        self._dev = {}
+        pool = _POOL.setdefault((str(self.device), depth), {})
+        if 'stream' not in pool:
+            pool['stream'], pool['pin'], pool['dev'] = torch.cuda.Stream(device=self.device), {}, {}
+        self.stream, self._pin, self._dev = pool['stream'], pool['pin'], pool['dev']
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))   # whatever still reads the pooled buffers (a previous epoch's last batch)
         self._free = [None] * (depth + 1)          # per ring slot: event after which the consumer no longer reads the slot's buffers
         self._copied = [None] * (depth + 1)        # per ring slot: event after which the slot's pinned staging buffers may be refilled
 

@@ -57,6 +57,39 @@ def test_forward_eval_vs_reference_golden(dev):
     assert rel_l2(d_real, g['d_real']) < TOL and rel_l2(d_fake, g['d_fake']) < TOL
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+def test_standalone_encoders_vs_reference_golden(dev, mode):
+    """WavEncoder()(wav) and TextEncoderTCN(...)(ids) called on their own (multimodal_context_net.py:25-28,57-61; SURVEY 8b lists both
+    signatures) reproduce the features the reference generator computed from the same weights."""
+    from model.multimodal_context_net import TextEncoderTCN, WavEncoder
+    from gpu_util import make_args
+    from tgb200 import config
+    cfg = golden_cfg()
+    g = np.load(os.path.join(GOLDEN, 'forward_eval.npz'))
+    gsd = synth.with_tcn_aliases(synth.generator_state_dict(cfg))     # the reference's TemporalBlock registers conv1 / conv2 under net.0 / net.4 too
+    inp = to_dev(synth.make_inputs(cfg, 3, seed=1), dev)
+    old = config.set_mode(mode)
+    try:
+        wav = WavEncoder()
+        wav.load_state_dict({k[len('audio_encoder.'):]: v for k, v in gsd.items() if k.startswith('audio_encoder.')}, strict=True)
+        wav = wav.to(dev).eval()
+        txt = TextEncoderTCN(make_args(cfg), cfg.n_words, cfg.wordembed_dim, None, dropout=cfg.dropout_prob)
+        txt.load_state_dict({k[len('text_encoder.'):]: v for k, v in gsd.items() if k.startswith('text_encoder.')}, strict=True)
+        txt = txt.to(dev).eval()
+        tol = TOL if mode == 'fp32' else 1e-2
+        with torch.no_grad():
+            a = wav(inp['in_audio'])
+            t, zero = txt(inp['in_text'])
+        assert zero == 0 and a.shape == (3, 34, 32) and t.shape == (3, 34, 32)
+        assert rel_l2(a, g['audio_feat']) < tol, rel_l2(a, g['audio_feat'])
+        assert rel_l2(t, g['text_feat']) < tol, rel_l2(t, g['text_feat'])
+        txt.train()                                   # train mode draws Philox dropout masks: finite, different from eval, fresh per call
+        t1, _ = txt(inp['in_text']); t2, _ = txt(inp['in_text'])
+        assert torch.isfinite(t1).all() and rel_l2(t1, t) > 1e-3 and rel_l2(t1, t2) > 1e-3
+    finally:
+        config.set_mode(old)
+
+
 def _digest_close(a, ref, tol):
     a = np.asarray(a); ref = np.asarray(ref)
     scale = max(abs(ref[0]), 1e-12)
