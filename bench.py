@@ -601,8 +601,13 @@ def main():
                 'infer_clips_per_s': infer, 'aux': aux, 'last_losses': ret}
         print(json.dumps(line))
     if world > 1:
+        # A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group() behind it hung the process
+        # until the job's timeout (round-2 call L).  Order: drain the device, barrier, flush the one JSON line, leave without the teardown.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

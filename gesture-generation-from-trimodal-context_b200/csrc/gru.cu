@@ -324,21 +324,22 @@ __global__ void __launch_bounds__(SMALL_NT) gru_small_fwd_kernel(const GruSmallF
       nx_r = __ldg(gp); nx_z = __ldg(gp + H); nx_n = __ldg(gp + 2 * H);
     }
     if (s > 0) {
-      float acc[SB];
+      // four independent partial sums per clip: one accumulator per clip is a chain of 64 dependent FMAs (~260 cycles of pure latency)
+      float acc[SB][4];
 #pragma unroll
-      for (int c = 0; c < SB; ++c) acc[c] = 0.f;
+      for (int c = 0; c < SB; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
 #pragma unroll
       for (int k = 0; k < HS; k += 4) {
 #pragma unroll
         for (int c = 0; c < SB; ++c) {
           const float4 h4 = *reinterpret_cast<const float4*>(&hs[c][k]);      // same address in every lane: one broadcast wavefront
-          acc[c] = fmaf(w[k], h4.x, acc[c]); acc[c] = fmaf(w[k + 1], h4.y, acc[c]);
-          acc[c] = fmaf(w[k + 2], h4.z, acc[c]); acc[c] = fmaf(w[k + 3], h4.w, acc[c]);
+          acc[c][0] = fmaf(w[k], h4.x, acc[c][0]); acc[c][1] = fmaf(w[k + 1], h4.y, acc[c][1]);
+          acc[c][2] = fmaf(w[k + 2], h4.z, acc[c][2]); acc[c][3] = fmaf(w[k + 3], h4.w, acc[c][3]);
         }
       }
       if (tid < G3) {
 #pragma unroll
-        for (int c = 0; c < SB; ++c) ghs[c][tid] = acc[c];
+        for (int c = 0; c < SB; ++c) ghs[c][tid] = (acc[c][0] + acc[c][1]) + (acc[c][2] + acc[c][3]);
       }
       __syncthreads();
     }
@@ -420,20 +421,20 @@ __global__ void __launch_bounds__(SMALL_NT) gru_small_bwd_kernel(const GruSmallB
     }
     __syncthreads();
     if (s + 1 < T) {
-      float acc[SB];
+      float acc[SB][4];                                  // independent partial sums (see the forward kernel)
 #pragma unroll
-      for (int c = 0; c < SB; ++c) acc[c] = 0.f;
+      for (int c = 0; c < SB; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
 #pragma unroll
       for (int r = 0; r < HS; r += 4) {
 #pragma unroll
         for (int c = 0; c < SB; ++c) {
           const float4 d4 = *reinterpret_cast<const float4*>(&ds[c][g * HS + r]);   // warp-uniform address (one gate block per warp pair)
-          acc[c] = fmaf(w[r], d4.x, acc[c]); acc[c] = fmaf(w[r + 1], d4.y, acc[c]);
-          acc[c] = fmaf(w[r + 2], d4.z, acc[c]); acc[c] = fmaf(w[r + 3], d4.w, acc[c]);
+          acc[c][0] = fmaf(w[r], d4.x, acc[c][0]); acc[c][1] = fmaf(w[r + 1], d4.y, acc[c][1]);
+          acc[c][2] = fmaf(w[r + 2], d4.z, acc[c][2]); acc[c][3] = fmaf(w[r + 3], d4.w, acc[c][3]);
         }
       }
 #pragma unroll
-      for (int c = 0; c < SB; ++c) dhp[g][c][j] = acc[c];
+      for (int c = 0; c < SB; ++c) dhp[g][c][j] = (acc[c][0] + acc[c][1]) + (acc[c][2] + acc[c][3]);
     }
     __syncthreads();
   }

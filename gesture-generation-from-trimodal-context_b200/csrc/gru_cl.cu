@@ -295,7 +295,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
       for (int e = 0; e < 16; e += 4) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row_live && k0 + e < H) x = ldv_nc4(wrow + k0 + e);
-        v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+        v[e] = round_tf32(x.x); v[e + 1] = round_tf32(x.y); v[e + 2] = round_tf32(x.z); v[e + 3] = round_tf32(x.w);   // nearest, not truncated
       }
       tmem_st16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + FWD_A0 + (uint32_t)k0, v);
     }
@@ -411,7 +411,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
     if (etid == 0) stamp(p.trace, s, 3);
     if (s + 1 < T) {
       // h_t slice -> image[s & 1] (dead clips keep the zeros the image started with)
-      if (live) *reinterpret_cast<float4*>(img + (size_t)(s & 1) * img_bytes + slice_off) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
+      // the MMA operand copy of h_t is rounded to the nearest TF32 (the state carried in registers and the stored output stay fp32)
+      if (live)
+        *reinterpret_cast<float4*>(img + (size_t)(s & 1) * img_bytes + slice_off) =
+            make_float4(round_tf32(hreg[0]), round_tf32(hreg[1]), round_tf32(hreg[2]), round_tf32(hreg[3]));
       fence_proxy_async_all();   // generic-proxy writes (image; gate scratch aliasing the operand tile) -> async-proxy readers / writers
       cluster_arrive();          // release: this CTA's slice is out and it no longer reads its gate scratch
       if (etid == 0) stamp(p.trace, s, 4);
@@ -786,7 +789,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
         const int k = k0 + e, g = k / u, jl = k - g * u;               // u % 4 == 0: a group of 4 never straddles two gates
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (jrow < H && k < K && u0 + jl < H) x = ldv_nc4(wrow + (long long)g * H + u0 + jl);
-        v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+        v[e] = round_tf32(x.x); v[e + 1] = round_tf32(x.y); v[e + 2] = round_tf32(x.z); v[e + 3] = round_tf32(x.w);
       }
       tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(mt * ka + k0), v);
     }
@@ -870,7 +873,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BWD_NT, 1) gru_bwd_
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
               const int k = g * u + jl;
-              const float val = g == 0 ? dr[i] : g == 1 ? dz[i] : dnr[i];
+              const float val = round_tf32(g == 0 ? dr[i] : g == 1 ? dz[i] : dnr[i]);
               *reinterpret_cast<float*>(Bt + (size_t)(k >> 5) * BT * 128 + rowoff + ((((k & 31) >> 2) ^ (c & 7)) << 4) + (k & 3) * 4) = val;
             }
           }

@@ -17,6 +17,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// fp32 -> nearest TF32 (10-bit mantissa, ties away from zero), returned as an fp32 bit pattern.  kind::tf32 MMAs simply DROP the low 13
+// mantissa bits of whatever fp32 word they are fed (round toward zero: a biased error of up to 2^-10 relative); operands written through
+// this function lose at most 2^-11 and without bias.  Free in the epilogue that produces the operand.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -56,3 +56,38 @@ def set_graphs(v: bool) -> bool:
     global _GRAPHS
     old, _GRAPHS = _GRAPHS, bool(v)
     return old
+
+
+_WAV_FIRST = os.environ.get('TGB200_WAV_FIRST', '1') == '1'
+
+
+def wav_first() -> bool:
+    """Queue the WavEncoder forward before everything else of an iteration (default) instead of after the TextEncoderTCN chain.
+    Measured on the graph-replayed batch-128 step: audio first 4.81 ms, text first 4.93 ms (profiles/r02_bench_wav_order.txt) - the audio
+    chain's BatchNorm reductions are HBM-bound and overlap well with the tensor-core text chain when they start together."""
+    return _WAV_FIRST
+
+
+_NCCL_GRAPH = os.environ.get('TGB200_NCCL_GRAPH', '1') == '1'
+
+
+def nccl_in_graph() -> bool:
+    """Data parallel: capture the gradient all-reduces INSIDE the iteration's CUDA graph (one graph, no host-driven segment boundaries, the
+    exchange of the recurrent layers' gradients overlapped with the rest of the backward).  TGB200_NCCL_GRAPH=0: graph segments split at
+    the two collectives, NCCL launched eagerly in between (the round-1 scheme)."""
+    return _NCCL_GRAPH
+
+
+_D_FUSED = os.environ.get('TGB200_D_FUSED', '1') == '1'
+
+
+def d_fused() -> bool:
+    """ConvDiscriminator: run the 4-layer bidirectional GRU and both heads as one launch (csrc/dgru_stack.cu) instead of the per-layer
+    plan (projection GEMM + recurrence + dropout multiply per layer, then sum + two head GEMMs)."""
+    return _D_FUSED
+
+
+def set_d_fused(v: bool) -> bool:
+    global _D_FUSED
+    old, _D_FUSED = _D_FUSED, bool(v)
+    return old

@@ -204,6 +204,17 @@ class GruPlan:
         self._fwd_inputs = x
         return inp
 
+    def weight_grads(self, l, inp, dgi, dgh, out, Bb, T):
+        """Weight / bias gradients of layer l from its gate gradients, on the weight-gradient stream (off the recurrence chain)."""
+        H = self.H
+        K = self.I if l == 0 else 2 * H
+        with side.on(S_WGRAD):
+            wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
+            for d in (0, 1):
+                # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
+                wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
+                      shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
+
     def backward(self, dout, x, B_all, lo, hi, T, masks, need_dx: bool):
         """dout [(hi-lo)*T, 2H] = gradient of the last layer's output for clips [lo,hi) of a forward over B_all clips.
         Accumulates all weight grads; returns d x [(hi-lo)*T, I] (or None)."""
@@ -234,12 +245,7 @@ class GruPlan:
                 inp = ws[f'{tag}.drop{l - 1}'][r0:r1]
             else:
                 inp = ws[f'{tag}.out{l - 1}'][r0:r1]
-            with side.on(S_WGRAD):
-                wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
-                for d in (0, 1):
-                    # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
-                    wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
-                          shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
+            self.weight_grads(l, inp, dgi, dgh, out, Bb, T)
             if l > 0 or need_dx:
                 dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
                 m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
@@ -575,9 +581,10 @@ class GeneratorEngine:
         if self.use_audio:
             audio_feat = getattr(self, '_wav_feat', None)
             self._wav_feat = None
-            if audio_feat is None:
-                with side.on(S_WAV):        # the audio encoder is independent of the text / speaker branches
-                    audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
+        wav_late = self.use_audio and audio_feat is None and self.use_text and not config.wav_first()
+        if self.use_audio and audio_feat is None and not wav_late:
+            with side.on(S_WAV):            # the audio encoder is independent of the text / speaker branches
+                audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
         z = mu = logvar = None
         Z = 0
         if self.z_mode == 'speaker':
@@ -594,6 +601,11 @@ class GeneratorEngine:
             Z = 16
             z = eps
         text_feat = self.text_forward(in_text, Bt, T, masks) if self.use_text else None
+        if wav_late:
+            # queued AFTER the text chain: the TextEncoderTCN chain (8 dependent GEMMs, ~0.5 ms) is the longer of the two in front of the
+            # GRU, and a replayed CUDA graph feeds the GPU its nodes in capture order - whatever is captured first starts first
+            with side.on(S_WAV):
+                audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
         side.join(S_SPK)
         side.join(S_WAV)
         side.join(S_WGRAD)                          # side-stream mask draws, if text_forward did not already join them
@@ -631,6 +643,11 @@ class GeneratorEngine:
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'
         d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx)
+        if getattr(self, 'on_gru_grads', None) is not None:
+            # data parallel: the recurrent layers' gradients (the tail of the flat arena, 22 MB of 53) are complete once the weight-gradient
+            # stream has drained what gru.backward queued on it - their all-reduce starts now, under the text / audio encoder backward
+            with side.on(S_WGRAD):
+                self.on_gru_grads()
         if not need_dx:
             side.join(S_WGRAD)
             return
@@ -724,7 +741,20 @@ class DiscriminatorEngine:
         x, tin, cin = poses, T0, D
         scale = shift = None
         self.Ts = [T0]
-        for li, (conv, bn) in enumerate(self.CONVS):
+        self.ctx['fused_conv'] = self.fused_conv(B, T0, D)
+        if self.ctx['fused_conv']:
+            # the three convolutions and two train-mode BatchNorms in one 8-CTA-cluster launch (csrc/dconv_stack.cu)
+            y0, y1, y2 = ws.get('d.y0', (B * 32, 16)), ws.get('d.y1', (B * 30, 8)), ws.get('d.y2', (B * 28, 8))
+            st1, st2 = ws.get('d.st1', (64,)), ws.get('d.st2', (32,))
+            bf = self.bufs
+            ops.dconv_stack_fwd(poses, self.P('pre_conv.0.weight'), self.P('pre_conv.0.bias'), self.P('pre_conv.1.weight'), self.P('pre_conv.1.bias'),
+                                bf['pre_conv.1.running_mean'], bf['pre_conv.1.running_var'], bf['pre_conv.1.num_batches_tracked'],
+                                self.P('pre_conv.3.weight'), self.P('pre_conv.3.bias'), self.P('pre_conv.4.weight'), self.P('pre_conv.4.bias'),
+                                bf['pre_conv.4.running_mean'], bf['pre_conv.4.running_var'], bf['pre_conv.4.num_batches_tracked'],
+                                self.P('pre_conv.6.weight'), self.P('pre_conv.6.bias'), y0, y1, y2, st1, st2, B, T0, D, training, BN_EPS, BN_MOM)
+            x, tin, cin = y2, 28, 8
+            self.Ts = [34, 32, 30, 28]
+        for li, (conv, bn) in enumerate(() if self.ctx['fused_conv'] else self.CONVS):
             w = self.P(conv + '.weight')
             cout, k = w.shape[0], w.shape[2]
             tout = tin - k + 1
@@ -748,13 +778,44 @@ class DiscriminatorEngine:
         M = B * T
         H = self.H
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
-        out = self.gru.forward(x, B, T, gmasks, save)
         hsum = ws.get('d.hsum', (M, H)); o1 = ws.get('d.o1', (M, 1)); prob = ws.get('d.prob', (B, 1))
-        ops.sum_halves(out, hsum, M, H)
-        ops.linear(hsum, self.P('out.weight'), self.P('out.bias'), o1, M=M, K=H, N=1)
-        ops.linear(o1, self.P('out2.weight'), self.P('out2.bias'), prob, M=B, K=T, N=1, act1=ops.ACT_SIGMOID)
+        if self.fused_stack(T, cin):
+            # one launch for the 4-layer bidirectional GRU + both heads (csrc/dgru_stack.cu); writes exactly the buffers the per-layer
+            # backward plan reads (layer outputs, saved gate planes, masked layer inputs, hsum, per-frame head output)
+            L = self.L
+            outs = [ws.get(f'd.out{l}', (M, 2 * H)) for l in range(L)]
+            saved = [ws.get(f'd.saved{l}', (4, M, 2 * H)) for l in range(L)] if save else None
+            drops = [(ws.get(f'd.drop{l}', (M, 2 * H)) if (gmasks is not None and l < L - 1 and gmasks[l] is not None) else None) for l in range(L)]
+            mks = [(gmasks[l] if (gmasks is not None and l < L - 1) else None) for l in range(L)]
+            a0 = self.arena.offsets['gru.weight_ih_l0']
+            ops.dgru_stack_fwd(x, self.arena.flat[a0:], mks, outs, saved, M * 2 * H, drops, self.P('out.weight'), self.P('out.bias'),
+                               self.P('out2.weight'), self.P('out2.bias'), hsum, o1, prob, B, T, cin, H, L)
+            self.gru._fwd_inputs = x
+        else:
+            out = self.gru.forward(x, B, T, gmasks, save)
+            ops.sum_halves(out, hsum, M, H)
+            ops.linear(hsum, self.P('out.weight'), self.P('out.bias'), o1, M=M, K=H, N=1)
+            ops.linear(o1, self.P('out2.weight'), self.P('out2.bias'), prob, M=B, K=T, N=1, act1=ops.ACT_SIGMOID)
         self.ctx['T'] = T
         return prob
+
+    def fused_conv(self, B, T0, D):
+        """The fused convolution-stack kernel covers the reference's ConvDiscriminator shapes (34 frames x 27 dims, 16 / 8 / 8 channels, k = 3)
+        for up to 128 clips; TGB200_D_FUSED=0 keeps the per-operator plan."""
+        m = self.m
+        shapes = tuple(tuple(m.pre_conv[i].weight.shape) for i in (0, 3, 6))
+        return config.d_fused() and B <= 128 and T0 == 34 and D == 27 and shapes == ((16, 27, 3), (8, 16, 3), (8, 8, 3))
+
+    def fused_stack(self, T, I0):
+        """The fused recurrent-stack kernel handles the discriminator's configuration (H = 64, <= 4 layers, <= 32 frames) when the GRU
+        parameters are packed in the arena in gru_arena_order, which ParamArena guarantees; TGB200_D_FUSED=0 keeps the per-layer plan."""
+        if not config.d_fused() or self.H != 64 or self.L > 4 or T > 32 or I0 > 64:
+            return False
+        names = []
+        for l in range(self.L):
+            for kind in ('weight_ih', 'bias_ih', 'weight_hh', 'bias_hh'):
+                names += [f'gru.{kind}_l{l}', f'gru.{kind}_l{l}_reverse']
+        return all(self.arena.adjacent(a, b) for a, b in zip(names, names[1:]))
 
     def backward(self, dlogit, need_dposes: bool, param_grads: bool = True):
         """dlogit [B,1] = d loss / d (pre-sigmoid output).  Returns d poses [B,34,27] if requested."""
@@ -762,15 +823,49 @@ class DiscriminatorEngine:
         B, T, H = c['B'], c['T'], self.H
         M = B * T
         masks = c['masks']
-        do1 = ws.get('d.do1', (M, 1)); dhs = ws.get('d.dhs', (M, H)); dout = ws.get('d.dout', (M, 2 * H))
-        ops.linear_wgrad(ws['d.o1'], dlogit, self.G('out2.weight'), self.G('out2.bias'), M=B, K=T, N=1)
-        ops.linear_dgrad(dlogit, self.P('out2.weight'), do1, M=B, K=T, N=1)
-        ops.linear_wgrad(ws['d.hsum'], do1, self.G('out.weight'), self.G('out.bias'), M=M, K=H, N=1)
-        ops.linear_dgrad(do1, self.P('out.weight'), dhs, M=M, K=H, N=1)
-        ops.dup_halves(dhs, dout, M, H)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
-        dy = self.gru.backward(dout, ws['d.y2'], B, 0, B, T, gmasks, True)
+        if self.fused_stack(T, 8):
+            # one launch: heads + 4 x [recurrence backward + data gradient through W_ih]; the recurrent layers' weight gradients follow on
+            # the weight-gradient stream from the dgi / dgh it leaves behind
+            L = self.L
+            side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading dgi / dgh
+            outs = [ws[f'd.out{l}'] for l in range(L)]
+            saved = [ws[f'd.saved{l}'] for l in range(L)]
+            dgi = [ws.get(f'd.dgi{l}', (M, 6 * H)) for l in range(L)]
+            dgh = [ws.get(f'd.dgh{l}', (M, 6 * H)) for l in range(L)]
+            mks = [(gmasks[l] if (gmasks is not None and l < L - 1) else None) for l in range(L)]
+            dy = ws.get('d.dxin', (M, 8))
+            a0 = self.arena.offsets['gru.weight_ih_l0']
+            ops.dgru_stack_bwd(dlogit, self.arena.flat[a0:], mks, outs, saved, M * 2 * H, ws['d.hsum'], ws['d.o1'], self.P('out.weight'),
+                               self.P('out2.weight'), dgi, dgh, dy, self.G('out.weight'), self.G('out.bias'), self.G('out2.weight'),
+                               self.G('out2.bias'), B, T, 8, H, L)
+            for l in range(L - 1, -1, -1):
+                if l == 0:
+                    inp = ws['d.y2']
+                elif gmasks is not None and gmasks[l - 1] is not None:
+                    inp = ws[f'd.drop{l - 1}']
+                else:
+                    inp = ws[f'd.out{l - 1}']
+                self.gru.weight_grads(l, inp, dgi[l], dgh[l], outs[l], B, T)
+        else:
+            do1 = ws.get('d.do1', (M, 1)); dhs = ws.get('d.dhs', (M, H)); dout = ws.get('d.dout', (M, 2 * H))
+            ops.linear_wgrad(ws['d.o1'], dlogit, self.G('out2.weight'), self.G('out2.bias'), M=B, K=T, N=1)
+            ops.linear_dgrad(dlogit, self.P('out2.weight'), do1, M=B, K=T, N=1)
+            ops.linear_wgrad(ws['d.hsum'], do1, self.G('out.weight'), self.G('out.bias'), M=M, K=H, N=1)
+            ops.linear_dgrad(do1, self.P('out.weight'), dhs, M=M, K=H, N=1)
+            ops.dup_halves(dhs, dout, M, H)
+            dy = self.gru.backward(dout, ws['d.y2'], B, 0, B, T, gmasks, True)
         dposes = None
+        if c.get('fused_conv'):
+            assert c['training'], 'backward through eval-mode BatchNorm is not on the hot path'
+            dposes_buf = ws.get('d.da0', (B * 34, 27)) if need_dposes else None
+            ops.dconv_stack_bwd(dy, c['poses'], ws['d.y0'], ws['d.y1'], ws['d.st1'], ws['d.st2'], self.P('pre_conv.0.weight'),
+                                self.P('pre_conv.3.weight'), self.P('pre_conv.6.weight'), self.P('pre_conv.1.weight'), self.P('pre_conv.4.weight'),
+                                self.G('pre_conv.0.weight'), self.G('pre_conv.0.bias'), self.G('pre_conv.3.weight'), self.G('pre_conv.3.bias'),
+                                self.G('pre_conv.6.weight'), self.G('pre_conv.6.bias'), self.G('pre_conv.1.weight'), self.G('pre_conv.1.bias'),
+                                self.G('pre_conv.4.weight'), self.G('pre_conv.4.bias'), dposes_buf, B, 34, 27)
+            side.join(S_WGRAD)
+            return dposes_buf.view(B, 34, 27) if need_dposes else None
         for li in (2, 1, 0):
             conv, _ = self.CONVS[li]
             w = self.P(conv + '.weight')

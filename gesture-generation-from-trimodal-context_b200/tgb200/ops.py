@@ -317,6 +317,51 @@ def gru_layer_bwd_tf32(dout, out, saved, saved_qstride, whhT_f, whhT_r, dgi, dgh
                                      _p(sync), B, T, H, _s()), 'tg_gru_layer_bwd_tf32'); _count(2)
 
 
+def _ptr_array(tensors, n):
+    """ctypes array of n device pointers (None -> NULL); the C side copies it into the kernel's parameter block."""
+    import ctypes
+    arr = (ctypes.c_void_p * n)()
+    for i in range(n):
+        t = tensors[i] if (tensors is not None and i < len(tensors)) else None
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def dgru_stack_fwd(x, gru_params, masks, outs, saved, saved_qstride, drops, w_out, b_out, w_out2, b_out2, hsum, o1, prob, B, T, I0, H, L):
+    import ctypes
+    a_m = _ptr_array(masks, 4) if masks is not None else None
+    a_o = _ptr_array(outs, 4)
+    a_s = _ptr_array(saved, 4) if saved is not None else None
+    a_d = _ptr_array(drops, 4) if drops is not None else None
+    addr = lambda a: None if a is None else ctypes.cast(a, ctypes.c_void_p)
+    check(_L().tg_dgru_stack_fwd(_p(x), _p(gru_params), addr(a_m), addr(a_o), addr(a_s), saved_qstride, addr(a_d), _p(w_out), _p(b_out),
+                                 _p(w_out2), _p(b_out2), _p(hsum), _p(o1), _p(prob), B, T, I0, H, L, _s()), 'tg_dgru_stack_fwd'); _count()
+
+
+def dgru_stack_bwd(dlogit, gru_params, masks, outs, saved, saved_qstride, hsum, o1, w_out, w_out2, dgi, dgh, dx0, g_w_out, g_b_out, g_w_out2,
+                   g_b_out2, B, T, I0, H, L):
+    import ctypes
+    addr = lambda a: None if a is None else ctypes.cast(a, ctypes.c_void_p)
+    a_m = _ptr_array(masks, 4) if masks is not None else None
+    a_o, a_s, a_gi, a_gh = _ptr_array(outs, 4), _ptr_array(saved, 4), _ptr_array(dgi, 4), _ptr_array(dgh, 4)
+    check(_L().tg_dgru_stack_bwd(_p(dlogit), _p(gru_params), addr(a_m), addr(a_o), addr(a_s), saved_qstride, _p(hsum), _p(o1), _p(w_out),
+                                 _p(w_out2), addr(a_gi), addr(a_gh), _p(dx0), _p(g_w_out), _p(g_b_out), _p(g_w_out2), _p(g_b_out2),
+                                 B, T, I0, H, L, _s()), 'tg_dgru_stack_bwd'); _count()
+
+
+def dconv_stack_fwd(x, w1, b1, g1, be1, rm1, rv1, nbt1, w2, b2, g2, be2, rm2, rv2, nbt2, w3, b3, y0, y1, y2, st1, st2, B, T, D, training, eps,
+                    momentum):
+    check(_L().tg_dconv_stack_fwd(_p(x), _p(w1), _p(b1), _p(g1), _p(be1), _p(rm1), _p(rv1), _p(nbt1), _p(w2), _p(b2), _p(g2), _p(be2), _p(rm2),
+                                  _p(rv2), _p(nbt2), _p(w3), _p(b3), _p(y0), _p(y1), _p(y2), _p(st1), _p(st2), B, T, D, int(training), eps,
+                                  momentum, _s()), 'tg_dconv_stack_fwd'); _count()
+
+
+def dconv_stack_bwd(dy2, x, y0, y1, st1, st2, w1, w2, w3, g1, g2, dw1, db1, dw2, db2, dw3, db3, dg1, dbe1, dg2, dbe2, dx, B, T, D):
+    check(_L().tg_dconv_stack_bwd(_p(dy2), _p(x), _p(y0), _p(y1), _p(st1), _p(st2), _p(w1), _p(w2), _p(w3), _p(g1), _p(g2), _p(dw1), _p(db1),
+                                  _p(dw2), _p(db2), _p(dw3), _p(db3), _p(dg1), _p(dbe1), _p(dg2), _p(dbe2), _p(dx), B, T, D, _s()),
+          'tg_dconv_stack_bwd'); _count()
+
+
 # ------------------------------------------------------------------------------------------ losses / optimiser / rng
 def gen_losses(out, target, out_rand, z, z_rand, mu, logvar, B, TD, Z, w_reg, w_div, w_kld, scalars, d_out, dmu, dlogvar):
     check(_L().tg_gen_losses(_p(out), _p(target), _p(out_rand), _p(z), _p(z_rand), _p(mu), _p(logvar), B, TD, Z, w_reg, w_div, w_kld,

@@ -53,15 +53,41 @@ def _dist_world():
     return 1
 
 
-def _allreduce_grads(arena, bucket_floats=4 << 20):
-    """Bucketed NCCL all-reduce (sum) of the flat gradient arena; averaging is folded into Adam's grad_scale."""
+def _allreduce_grads(arena, lo=0, hi=None, bucket_floats=4 << 20):
+    """Bucketed all-reduce (sum) of arena.grad[lo:hi], complete on return; averaging is folded into Adam's grad_scale."""
+    for w in _allreduce_grads_async(arena, lo, hi, bucket_floats):
+        w.wait()
+
+
+def _allreduce_grads_async(arena, lo=0, hi=None, bucket_floats=4 << 20):
+    """Launches the bucketed NCCL all-reduce (sum) of arena.grad[lo:hi] and returns the work handles."""
     import torch.distributed as dist
     works = []
-    n = arena.numel
-    for o in range(0, n, bucket_floats):
-        works.append(dist.all_reduce(arena.grad[o:min(n, o + bucket_floats)], op=dist.ReduceOp.SUM, async_op=True))
-    for w in works:
-        w.wait()
+    hi = arena.numel if hi is None else hi
+    for o in range(lo, hi, bucket_floats):
+        works.append(dist.all_reduce(arena.grad[o:min(hi, o + bucket_floats)], op=dist.ReduceOp.SUM, async_op=True))
+    return works
+
+
+class _Comm:
+    """Gradient exchange of one iteration.  inline=True (eager launches, or the whole iteration captured into ONE CUDA graph with the
+    NCCL kernels inside it): the recurrent layers' gradients are all-reduced as soon as they exist (`early`, called from the generator's
+    backward on its weight-gradient stream) and the rest when the backward has finished (`finish`), so most of the exchange hides under
+    the encoder backward.  inline=False (the iteration captured as graph segments split at the collectives): one exchange per network
+    between two segments."""
+
+    def __init__(self, inline):
+        self.inline = inline
+        self.pending = {}
+
+    def early(self, arena, lo):
+        if self.inline:
+            self.pending[id(arena)] = (lo, _allreduce_grads_async(arena, lo=lo))
+
+    def finish(self, arena):
+        lo, works = self.pending.pop(id(arena), (arena.numel, []))
+        for w in works + _allreduce_grads_async(arena, hi=lo):
+            w.wait()
 
 
 def _dp_sync_once(module, arena):
@@ -86,6 +112,19 @@ class _GraphSlot:
         self.graph = None
         self.failed = False
         self.static = None
+
+
+def release_graphs(pose_decoder) -> int:
+    """Drops every captured iteration graph of this generator (they are re-captured on demand).  With data parallelism the graph holds
+    NCCL kernels of the process group's communicator: call this (and torch.cuda.synchronize()) BEFORE dist.destroy_process_group(),
+    otherwise the communicator teardown waits on the graph forever (seen on 2 x B200, round-2 call L)."""
+    ge = _unwrap(pose_decoder).engine()
+    slots = ge.__dict__.get('_gan_graph_slots', {})
+    n = len(slots)
+    for slot in slots.values():
+        slot.graph = None
+    slots.clear()
+    return n
 
 
 _GRAPH_WARMUP = 2          # eager iterations (allocate every workspace) before the iteration is captured
@@ -137,7 +176,7 @@ def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, po
         sc = _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step=True)
 
     # ---- one device->host copy for the logged scalars (train_gan.py:94-102)
-    s = sc.cpu().tolist()
+    s = sc if isinstance(sc, list) else sc.cpu().tolist()
     huber = s[0] / (B * T * Dm)
     ret: Dict[str, float] = {'loss': args.loss_regression_weight * huber}
     if do_kld:
@@ -183,19 +222,46 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
         try:
             ge.arena.bind_optimizer(g_opt); de.arena.bind_optimizer(d_opt)
             torch.cuda.synchronize()
-            out = {}
-            gen = _step_segments(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None,
-                                 _dist_world(), False, out)
+            slot.host_sc = torch.zeros(8, dtype=torch.float64).pin_memory()
+            slot.ev = torch.cuda.Event(external=True)          # an event-record NODE inside the graph: the host can wait on it after replay
+
+            def early(sc_dev):
+                slot.host_sc.copy_(sc_dev, non_blocking=True)
+                slot.ev.record()
+            out = {'early': early}
+            world = _dist_world()
             graphs, arenas = [], []
-            done = False
-            while not done:                       # one CUDA graph per collective-free stretch of the iteration
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    try:
-                        arenas.append(next(gen))
-                    except StopIteration:
-                        done = True
-                graphs.append(graph)
+            if world > 1 and config.nccl_in_graph() and not getattr(slot, 'no_inline', False):
+                # the whole iteration, NCCL kernels included, as ONE graph (possible since the recurrence kernels no longer spin on
+                # grid-wide co-residency: a cluster kernel cannot dead-lock against a co-resident NCCL kernel)
+                try:
+                    comm = _Comm(inline=True)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                        for arena in _step_segments(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None,
+                                                    world, False, out, comm):
+                            comm.finish(arena)
+                    graphs = [graph]
+                except Exception as exc:
+                    import warnings
+                    warnings.warn('tgb200: capturing NCCL inside the CUDA graph failed (%s); falling back to graph segments split at the '
+                                  'collectives' % (str(exc).splitlines()[0] if str(exc) else type(exc).__name__))
+                    slot.no_inline = True
+                    torch.cuda.synchronize()
+                    out = {'early': early}
+            if not graphs:
+                comm = _Comm(inline=False)
+                gen = _step_segments(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None,
+                                     world, False, out, comm)
+                done = False
+                while not done:                       # one CUDA graph per collective-free stretch of the iteration
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        try:
+                            arenas.append(next(gen))
+                        except StopIteration:
+                            done = True
+                    graphs.append(graph)
             slot.graph, slot.arenas, slot.sc = graphs, arenas, out['sc']
         except Exception as exc:            # capture unsupported for some launch: stay on the eager path
             slot.failed = True
@@ -210,24 +276,31 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
     for i, graph in enumerate(slot.graph):
         graph.replay()
         if i < len(slot.arenas):
-            _allreduce_grads(slot.arenas[i])      # eager NCCL call between two graph segments
+            _Comm(inline=False).finish(slot.arenas[i])      # eager NCCL call between two graph segments
     _, do_d, _, _ = _flags(args, epoch)
     ge.arena.note_steps(1)
     if do_d:
         de.arena.note_steps(1)
-    return slot.sc
+    # The logged scalars (train_gan.py:94-102) are complete once the generator losses have been evaluated - before the generator backward,
+    # its weight gradients and Adam run (~40 % of the step).  The graph copies them to pinned host memory at that point and records an
+    # external event; waiting on IT instead of on the whole step lets the caller's next iteration (input staging, graph launch) be queued
+    # while this one is still finishing, so the GPU never idles between iterations.  Stream order keeps every later read of the
+    # parameters correct.
+    slot.ev.synchronize()
+    return slot.host_sc.tolist()
 
 
 def _enqueue_step(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step):
     """Eager iteration: enqueues every kernel (no host synchronisation) and runs the gradient all-reduces in line;
     returns the fp64 scalars buffer."""
     out = {}
-    for arena in _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, out):
-        _allreduce_grads(arena)
+    comm = _Comm(inline=True)
+    for arena in _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, out, comm):
+        comm.finish(arena)
     return out['sc']
 
 
-def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, result):
+def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_optim, dis_optim, noise, world, host_step, result, comm=None):
     """Generator over the launch sequence of one iteration.  With world > 1 it yields the flat gradient arena at the two
     points where gradients must be summed across ranks (after D's backward, after G's backward): the caller performs
     the collective (NCCL) and resumes.  Each stretch between yields touches no collective, has all auxiliary streams
@@ -246,8 +319,8 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     n_pass = len(passes)
     Bt = n_pass * B
     ig = passes.index('g')
-    if ge.use_audio:
-        ge.start_wav(in_audio, G.training, n_pass)          # longest chain in front of the GRU: queue it first (side stream)
+    if ge.use_audio and (config.wav_first() or not ge.use_text):
+        ge.start_wav(in_audio, G.training, n_pass)          # eager launches are host-bound: queue the audio chain first (side stream)
     pre_seq = ws.get('ti.pre', (B, T, Dm + 1))
     ops.make_pre_seq(target, pre_seq, B, T, Dm, args.n_pre_poses)
 
@@ -335,10 +408,15 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
                    B, T * Dm, 16, float(args.loss_regression_weight), float(args.loss_reg_weight) if do_div else 0.0,
                    float(args.loss_kld_weight) if do_kld else 0.0, sc, d_out, dmu if do_kld else None, dlv if do_kld else None)
     ops.bce_sigmoid(p_gen, B, 1.0, 0.0, float(args.loss_gan_weight), sc[3:], dlogit)
+    if result.get('early') is not None:
+        result['early'](sc)          # every logged scalar is final here: the graph path reads them back before the generator backward runs
     if after:
         dposes = de.backward(dlogit, need_dposes=True)                        # D's own (stale) grads accumulate as in the reference
         ops.add(d_out, dposes, d_out, B * T * Dm)
+    gru_lo = ge.arena.offsets.get('gru.weight_ih_l0')
+    ge.on_gru_grads = (lambda: comm.early(ge.arena, gru_lo)) if (world > 1 and comm is not None and gru_lo is not None) else None
     ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
+    ge.on_gru_grads = None
     if world > 1:
         yield ge.arena
     ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world, host_step=host_step)

@@ -235,6 +235,41 @@ int tg_transpose_f32(const float* in, float* out, int R, int C, tg_stream stream
 int tg_gru_tf32_sync_ints(int B, int H);
 /* development aid: when a device buffer of >= 16*T int64 is set, CTA (0,0,0) of the tensor-core GRU kernels stamps
  * %globaltimer at its per-step phases (NULL switches it off) */
+/* ConvDiscriminator recurrent stack in one launch (multimodal_context_net.py:221-222,241-251): L-layer bidirectional GRU(I0 -> 64) over
+ * x [B,T,I0], inter-layer dropout (masks[l]: already scaled keep-masks [B*T,2H] on the output of layer l < L-1, or NULL), sum of the
+ * directions, Linear(64,1) per frame, Linear(T,1), sigmoid -> prob [B,1].  gru_params: the discriminator's GRU parameters as the flat
+ * arena stores them (per layer: weight_ih | weight_ih_reverse | bias_ih | bias_ih_reverse | weight_hh | weight_hh_reverse | bias_hh |
+ * bias_hh_reverse).  outs[l] / saved[l] (4 planes r,z,n,W_hn h + b_hn; plane stride saved_qstride) / drops[l] (masked outputs, l < L-1) /
+ * hsum [B*T,64] / o1 [B*T] are what the per-layer backward kernels read.  H == 64, L <= 4, T <= 32, I0 <= 64. */
+int tg_dgru_stack_fwd(const float* x, const float* gru_params, const float* const* masks, float* const* outs, float* const* saved,
+                      long long saved_qstride, float* const* drops, const float* w_out, const float* b_out, const float* w_out2,
+                      const float* b_out2, float* hsum, float* o1, float* prob, int B, int T, int I0, int H, int L, tg_stream stream);
+
+/* Backward of tg_dgru_stack_fwd in one launch: heads -> L x [recurrence backward + data gradient through W_ih (+ dropout mask of the layer
+ * below)].  dlogit [B] = d loss / d (pre-sigmoid output).  Writes dgi[l] / dgh[l] [B*T,6H] for the recurrent layers' weight-gradient
+ * GEMMs (which stay separate launches), dx0 [B*T,I0] (optional) = gradient w.r.t. the stack input, and ACCUMULATES the four head
+ * gradients (out.weight [64], out.bias [1], out2.weight [T], out2.bias [1]) with atomics. */
+int tg_dgru_stack_bwd(const float* dlogit, const float* gru_params, const float* const* masks, const float* const* outs,
+                      const float* const* saved, long long saved_qstride, const float* hsum, const float* o1, const float* w_out,
+                      const float* w_out2, float* const* dgi, float* const* dgh, float* dx0, float* g_w_out, float* g_b_out,
+                      float* g_w_out2, float* g_b_out2, int B, int T, int I0, int H, int L, tg_stream stream);
+
+/* ConvDiscriminator convolution stack in one launch (multimodal_context_net.py:212-220,233-236): Conv1d(27,16,3) -> BatchNorm1d(16) ->
+ * identity -> Conv1d(16,8,3) -> BatchNorm1d(8) -> identity -> Conv1d(8,8,3) on channels-last poses x [B,34,27] (B <= 128, one 8-CTA cluster,
+ * BatchNorm sums all-reduced through distributed shared memory).  Weights as stored ([N,Cin,3]).  training != 0: batch statistics, running
+ * buffers updated once (momentum, unbiased variance), num_batches_tracked += 1; else running statistics.  Outputs: y0 [B*32,16], y1 [B*30,8]
+ * (the PRE-BatchNorm conv outputs the backward needs), y2 [B*28,8], st1 [4*16] / st2 [4*8] = mean | rstd | scale | shift per BatchNorm. */
+int tg_dconv_stack_fwd(const float* x, const float* w1, const float* b1, const float* g1, const float* be1, float* rm1, float* rv1,
+                       long long* nbt1, const float* w2, const float* b2, const float* g2, const float* be2, float* rm2, float* rv2,
+                       long long* nbt2, const float* w3, const float* b3, float* y0, float* y1, float* y2, float* st1, float* st2,
+                       int B, int T, int D, int training, float eps, float momentum, tg_stream stream);
+/* Backward of tg_dconv_stack_fwd (train mode) in one launch: dy2 [B*28,8] -> ACCUMULATES the three convolutions' weight / bias gradients
+ * and both BatchNorms' gamma / beta gradients (atomics), optionally writes dx [B,34,27]. */
+int tg_dconv_stack_bwd(const float* dy2, const float* x, const float* y0, const float* y1, const float* st1, const float* st2,
+                       const float* w1, const float* w2, const float* w3, const float* g1, const float* g2, float* dw1, float* db1,
+                       float* dw2, float* db2, float* dw3, float* db3, float* dg1, float* dbe1, float* dg2, float* dbe2, float* dx,
+                       int B, int T, int D, tg_stream stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * seq2seq baseline (scripts/model/seq2seq_net.py, scripts/train_eval/train_seq2seq.py; config/seq2seq.yml).
  * The projections are GEMMs (tg_conv_gemm_f32 / tg_gemm_tf32); these are the per-step non-GEMM pieces.

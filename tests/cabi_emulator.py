@@ -431,6 +431,57 @@ class EmuLib:
                         S[q * qstride + o] = val.astype(np.float32)
         return 0
 
+    def tg_dgru_stack_fwd(self, x, params, masks, outs, saved, qstride, drops, w_out, b_out, w_out2, b_out2, hsum, o1, prob, B, T, I0, H, L,
+                          stream):
+        """csrc/dgru_stack.cu by its documented semantics: L x [gi = W_ih x + b_ih; recurrence; dropout mask] + sum of the directions +
+        Linear(64,1) per frame + Linear(T,1) + sigmoid, parameters read from the flat-arena block."""
+        self.calls.append('tg_dgru_stack_fwd')
+        assert H == 64 and 1 <= L <= 4 and 1 <= T <= 32 and 1 <= I0 <= 64, 'TG_REQUIRE of tg_dgru_stack_fwd'
+        ptrs = lambda a: [None] * 4 if not a else list(ctypes.cast(ctypes.c_void_p(a if isinstance(a, int) else a.value), ctypes.POINTER(ctypes.c_void_p * 4)).contents)
+        masks, outs, saved, drops = ptrs(masks), ptrs(outs), ptrs(saved), ptrs(drops)
+        G3, rows = 3 * H, np.arange(B) * T
+        inp = _arr(x, B * T * I0).reshape(B, T, I0).astype(np.float64)
+        off = 0
+        for l in range(L):
+            K = I0 if l == 0 else 2 * H
+            n_all = 2 * G3 * K + 2 * G3 + 2 * G3 * H + 2 * G3
+            blk = _arr(params + 4 * off, n_all).astype(np.float64)
+            off += n_all
+            wih = blk[:2 * G3 * K].reshape(2, G3, K); bih = blk[2 * G3 * K:2 * G3 * K + 2 * G3].reshape(2, G3)
+            whh = blk[2 * G3 * K + 2 * G3:2 * G3 * K + 2 * G3 + 2 * G3 * H].reshape(2, G3, H); bhh = blk[-2 * G3:].reshape(2, G3)
+            OUT = _arr(outs[l], B * T * 2 * H).reshape(B, T, 2 * H)
+            S = _arr(saved[l], 3 * qstride + B * T * 2 * H) if saved[l] else None
+            full = np.zeros((B, T, 2 * H))
+            for d in range(2):
+                gi = inp @ wih[d].T + bih[d]
+                h = np.zeros((B, H))
+                for s_ in range(T):
+                    t = s_ if d == 0 else T - 1 - s_
+                    gh = h @ whh[d].T + bhh[d]
+                    g = gi[:, t]
+                    r = self._sig(g[:, :H] + gh[:, :H]); z = self._sig(g[:, H:2 * H] + gh[:, H:2 * H])
+                    n = np.tanh(g[:, 2 * H:] + r * gh[:, 2 * H:])
+                    h = (1 - z) * n + z * h
+                    full[:, t, d * H:(d + 1) * H] = h
+                    if S is not None:
+                        o = ((rows + t) * 2 * H + d * H)[:, None] + np.arange(H)[None, :]
+                        for q, val in enumerate((r, z, n, gh[:, 2 * H:])):
+                            S[q * qstride + o] = val.astype(np.float32)
+            OUT[:] = full.astype(np.float32)
+            inp = OUT.astype(np.float64)
+            if l < L - 1 and masks[l]:
+                inp = inp * _arr(masks[l], B * T * 2 * H).reshape(B, T, 2 * H)
+                if drops[l]:
+                    _arr(drops[l], B * T * 2 * H)[:] = inp.astype(np.float32).reshape(-1)
+                    inp = _arr(drops[l], B * T * 2 * H).reshape(B, T, 2 * H).astype(np.float64)
+        hs = (inp[:, :, :H] + inp[:, :, H:]).astype(np.float32)
+        _arr(hsum, B * T * H)[:] = hs.reshape(-1)
+        o = (hs.astype(np.float64) @ _arr(w_out, H).astype(np.float64) + float(_arr(b_out, 1)[0])).astype(np.float32)
+        _arr(o1, B * T)[:] = o.reshape(-1)
+        v = o.astype(np.float64) @ _arr(w_out2, T).astype(np.float64) + float(_arr(b_out2, 1)[0])
+        _arr(prob, B)[:] = (1.0 / (1.0 + np.exp(-v))).astype(np.float32)
+        return 0
+
     def tg_gru_layer_bwd(self, dout, out, saved, qstride, whh_f, whh_r, dgi, dgh, partial, sync, B, T, H, stream):
         self.calls.append('tg_gru_layer_bwd')
         DOUT = _arr(dout, B * T * 2 * H).reshape(B, T, 2 * H).astype(np.float64)
@@ -457,6 +508,140 @@ class EmuLib:
                 gh = np.concatenate([drp, dzp, dnr], axis=1)
                 DGH[:, t, d * 3 * H:(d + 1) * 3 * H] = gh.astype(np.float32)
                 carry = dh * z + (_tf32(gh.astype(np.float32), rnd) if rnd else gh) @ W
+        return 0
+
+    def tg_dgru_stack_bwd(self, dlogit, params, masks, outs, saved, qstride, hsum, o1, w_out, w_out2, dgi, dgh, dx0, g_w_out, g_b_out, g_w_out2,
+                          g_b_out2, B, T, I0, H, L, stream):
+        """csrc/dgru_stack.cu (backward) by its documented semantics."""
+        self.calls.append('tg_dgru_stack_bwd')
+        assert H == 64 and 1 <= L <= 4 and 1 <= T <= 32 and 4 <= I0 <= 64, 'TG_REQUIRE of tg_dgru_stack_bwd'
+        ptrs = lambda a: [None] * 4 if not a else list(ctypes.cast(ctypes.c_void_p(a if isinstance(a, int) else a.value), ctypes.POINTER(ctypes.c_void_p * 4)).contents)
+        masks, outs, saved, dgi, dgh = ptrs(masks), ptrs(outs), ptrs(saved), ptrs(dgi), ptrs(dgh)
+        G3, rows = 3 * H, np.arange(B) * T
+        dl = _arr(dlogit, B).astype(np.float64)
+        O1 = _arr(o1, B * T).reshape(B, T).astype(np.float64)
+        HS = _arr(hsum, B * T * H).reshape(B, T, H).astype(np.float64)
+        w2 = _arr(w_out2, T).astype(np.float64); wo = _arr(w_out, H).astype(np.float64)
+        do1 = dl[:, None] * w2[None, :]
+        _arr(g_w_out2, T)[:] += (dl[:, None] * O1).sum(0).astype(np.float32)
+        _arr(g_b_out2, 1)[:] += np.float32(dl.sum())
+        _arr(g_b_out, 1)[:] += np.float32(do1.sum())
+        _arr(g_w_out, H)[:] += np.einsum('bt,bth->h', do1, HS).astype(np.float32)
+        dcur = np.concatenate([do1[:, :, None] * wo[None, None, :]] * 2, axis=2)          # [B,T,2H]
+        sizes = []
+        for l in range(L):
+            K = I0 if l == 0 else 2 * H
+            sizes.append(2 * G3 * K + 2 * G3 + 2 * G3 * H + 2 * G3)
+        for l in range(L - 1, -1, -1):
+            K = I0 if l == 0 else 2 * H
+            blk = _arr(params + 4 * sum(sizes[:l]), sizes[l]).astype(np.float64)
+            wih = blk[:2 * G3 * K].reshape(2 * G3, K)
+            whh = blk[2 * G3 * K + 2 * G3:2 * G3 * K + 2 * G3 + 2 * G3 * H].reshape(2, G3, H)
+            OUT = _arr(outs[l], B * T * 2 * H).reshape(B, T, 2 * H).astype(np.float64)
+            S = _arr(saved[l], 3 * qstride + B * T * 2 * H)
+            DGI = _arr(dgi[l], B * T * 6 * H).reshape(B, T, 6 * H); DGH = _arr(dgh[l], B * T * 6 * H).reshape(B, T, 6 * H)
+            for d in range(2):
+                carry = np.zeros((B, H))
+                for s_ in range(T):
+                    t = T - 1 - s_ if d == 0 else s_
+                    tp = t - 1 if d == 0 else t + 1
+                    o = ((rows + t) * 2 * H + d * H)[:, None] + np.arange(H)[None, :]
+                    r, z, n, hn = (S[q * qstride + o].astype(np.float64) for q in range(4))
+                    hprev = OUT[:, tp, d * H:(d + 1) * H] if 0 <= tp < T else np.zeros((B, H))
+                    dh = dcur[:, t, d * H:(d + 1) * H] + carry
+                    dn = dh * (1 - z) * (1 - n * n)
+                    dzp = dh * (hprev - n) * z * (1 - z)
+                    drp = dn * hn * r * (1 - r)
+                    dnr = dn * r
+                    DGI[:, t, d * 3 * H:(d + 1) * 3 * H] = np.concatenate([drp, dzp, dn], axis=1).astype(np.float32)
+                    gh = np.concatenate([drp, dzp, dnr], axis=1)
+                    DGH[:, t, d * 3 * H:(d + 1) * 3 * H] = gh.astype(np.float32)
+                    carry = dh * z + gh @ whh[d]
+            dx = DGI.astype(np.float64) @ wih                                                # [B,T,6H] x [6H,K]
+            if l > 0:
+                dcur = dx * _arr(masks[l - 1], B * T * 2 * H).reshape(B, T, 2 * H) if masks[l - 1] else dx
+            elif dx0:
+                _arr(dx0, B * T * I0)[:] = dx.astype(np.float32).reshape(-1)
+        return 0
+
+    # ---------------------------------------------------------------------------------------- fused ConvDiscriminator convolutions (csrc/dconv_stack.cu)
+    @staticmethod
+    def _conv3(a, w, b):
+        """channels-last valid convolution, k = 3: a [B,T,Cin], w [N,Cin,3] -> [B,T-2,N]"""
+        T = a.shape[1]
+        return sum(a[:, j:T - 2 + j, :] @ w[:, :, j].T for j in range(3)) + b
+
+    def tg_dconv_stack_fwd(self, x, w1, b1, g1, be1, rm1, rv1, nbt1, w2, b2, g2, be2, rm2, rv2, nbt2, w3, b3, y0, y1, y2, st1, st2, B, T, D,
+                           training, eps, momentum, stream):
+        self.calls.append('tg_dconv_stack_fwd')
+        assert 0 < B <= 128 and T == 34 and D == 27, 'TG_REQUIRE of tg_dconv_stack_fwd'
+        f = lambda p_, n: _arr(p_, n).astype(np.float64)
+        a = f(x, B * 34 * 27).reshape(B, 34, 27)
+        outs = []
+        for (w, b, cin, cout, g, be, rm, rv, nbt, st, yp) in ((w1, b1, 27, 16, g1, be1, rm1, rv1, nbt1, st1, y0), (w2, b2, 16, 8, g2, be2, rm2, rv2, nbt2, st2, y1),
+                                                          (w3, b3, 8, 8, None, None, None, None, None, None, y2)):
+            y = self._conv3(a, f(w, cout * cin * 3).reshape(cout, cin, 3), f(b, cout))
+            _arr(yp, y.size)[:] = y.astype(np.float32).reshape(-1)
+            if g is None:
+                break
+            y = _arr(yp, y.size).astype(np.float64).reshape(y.shape)
+            M = y.shape[0] * y.shape[1]
+            RM, RV = _arr(rm, cout), _arr(rv, cout)
+            if training:
+                mu = y.reshape(M, cout).mean(0); var = np.maximum((y.reshape(M, cout) ** 2).mean(0) - mu * mu, 0.0)
+                mu32 = mu.astype(np.float32)
+                RM[:] = (1.0 - np.float32(momentum)) * RM + np.float32(momentum) * mu32
+                RV[:] = (1.0 - np.float32(momentum)) * RV + np.float32(momentum) * (var * M / max(M - 1, 1)).astype(np.float32)
+                if nbt:
+                    _arr(nbt, 1, ctypes.c_longlong)[0] += 1
+                rs = (1.0 / np.sqrt(var + eps)).astype(np.float32)
+            else:
+                mu32 = RM.copy(); rs = (1.0 / np.sqrt(RV + np.float32(eps))).astype(np.float32)
+            sc = _arr(g, cout) * rs
+            sh = _arr(be, cout) - mu32 * _arr(g, cout) * rs
+            S = _arr(st, 4 * cout)
+            S[:cout] = mu32; S[cout:2 * cout] = rs; S[2 * cout:3 * cout] = sc; S[3 * cout:] = sh
+            a = y * sc.astype(np.float64) + sh.astype(np.float64)
+        return 0
+
+    def tg_dconv_stack_bwd(self, dy2, x, y0, y1, st1, st2, w1, w2, w3, g1, g2, dw1, db1, dw2, db2, dw3, db3, dg1, dbe1, dg2, dbe2, dx, B, T, D, stream):
+        self.calls.append('tg_dconv_stack_bwd')
+        assert 0 < B <= 128 and T == 34 and D == 27, 'TG_REQUIRE of tg_dconv_stack_bwd'
+        f = lambda p_, n: _arr(p_, n).astype(np.float64)
+        X = f(x, B * 34 * 27).reshape(B, 34, 27); Y0 = f(y0, B * 32 * 16).reshape(B, 32, 16); Y1 = f(y1, B * 30 * 8).reshape(B, 30, 8)
+        S1, S2 = f(st1, 64), f(st2, 32)
+        d = f(dy2, B * 28 * 8).reshape(B, 28, 8)
+
+        def conv_bwd(dy, a, w, cin, cout, dwp, dbp, need_da=True):
+            W = f(w, cout * cin * 3).reshape(cout, cin, 3)
+            Tout = dy.shape[1]
+            dW = np.stack([np.einsum('btn,btc->nc', dy, a[:, j:j + Tout, :]) for j in range(3)], axis=2)
+            _arr(dwp, dW.size)[:] += dW.astype(np.float32).reshape(-1)
+            _arr(dbp, cout)[:] += dy.sum((0, 1)).astype(np.float32)
+            if not need_da:
+                return None
+            da = np.zeros_like(a)
+            for j in range(3):
+                da[:, j:j + Tout, :] += dy @ W[:, :, j]
+            return da
+
+        def bn_bwd(da, y, S, g, C, dgp, dbp):
+            mu, rs = S[:C], S[C:2 * C]
+            xhat = (y - mu) * rs
+            M = y.shape[0] * y.shape[1]
+            s0, s1 = da.sum((0, 1)), (da * xhat).sum((0, 1))
+            _arr(dgp, C)[:] += s1.astype(np.float32); _arr(dbp, C)[:] += s0.astype(np.float32)
+            return f(g, C) * rs * (da - s0 / M - xhat * s1 / M)
+
+        a1 = Y1 * S2[16:24] + S2[24:32]
+        da1 = conv_bwd(d, a1, w3, 8, 8, dw3, db3)
+        dY1 = bn_bwd(da1, Y1, S2, g2, 8, dg2, dbe2)
+        a0 = Y0 * S1[32:48] + S1[48:64]
+        da0 = conv_bwd(dY1, a0, w2, 16, 8, dw2, db2)
+        dY0 = bn_bwd(da0, Y0, S1, g1, 16, dg1, dbe1)
+        dX = conv_bwd(dY0, X, w1, 27, 16, dw1, db1, need_da=bool(dx))
+        if dx:
+            _arr(dx, B * 34 * 27)[:] = dX.astype(np.float32).reshape(-1)
         return 0
 
     # ---------------------------------------------------------------------------------------- losses (csrc/losses.cu)

@@ -90,6 +90,46 @@ def test_standalone_encoders_vs_reference_golden(dev, mode):
         config.set_mode(old)
 
 
+def test_discriminator_fused_stack_matches_per_layer_plan(dev):
+    """csrc/dgru_stack.cu (4-layer bidirectional GRU + heads in one launch, forward and backward) against the per-layer plan it replaces:
+    same probabilities, same parameter gradients, same gradient w.r.t. the poses - with dropout masks, B = 128."""
+    from tgb200 import config, ops
+    cfg = golden_cfg()
+    B = 128
+    torch.manual_seed(3)
+    poses = (0.3 * torch.randn(B, cfg.n_poses, cfg.pose_dim)).to(dev)
+    dlogit = (0.1 * torch.randn(B, 1)).to(dev)
+    res = {}
+    for fused in (False, True):
+        old = config.set_d_fused(fused)
+        try:
+            _, _, D, _, _ = build_ours(cfg, dev)
+            D.train()
+            de = D.engine().ensure(dev, 'fused_test')
+            assert de.fused_stack(28, 8) == fused
+            de.prep_weights()
+            off = torch.zeros(1, dtype=torch.int64, device=dev)
+            masks = de.make_masks(B, cfg.n_poses - 6, 1234, off)
+            prob = de.forward(poses, True, masks).clone()
+            de.arena.zero_grad()
+            dposes = de.backward(dlogit, need_dposes=True).clone()
+            torch.cuda.synchronize()
+            res[fused] = (prob, dposes, de.arena.grad.clone(), {n: de.arena.offsets[n] for n in de.arena.names})
+        finally:
+            config.set_d_fused(old)
+    (p0, dp0, g0, offs), (p1, dp1, g1, _) = res[False], res[True]
+    assert rel_l2(p1, p0) < 1e-5, rel_l2(p1, p0)
+    assert rel_l2(dp1, dp0) < 1e-4, rel_l2(dp1, dp0)
+    names = sorted(offs, key=lambda n: offs[n])
+    for i, n in enumerate(names):
+        lo, hi = offs[n], (offs[names[i + 1]] if i + 1 < len(names) else g0.numel())
+        a, b_ = g1[lo:hi], g0[lo:hi]
+        if b_.abs().max() < 1e-9:
+            continue
+        tol = 2e-2 if config.fast() and n.startswith('gru.') else 1e-3      # tf32 weight-gradient GEMMs see the same operands: round-off only
+        assert rel_l2(a, b_) < tol, (n, rel_l2(a, b_))
+
+
 def _digest_close(a, ref, tol):
     a = np.asarray(a); ref = np.asarray(ref)
     scale = max(abs(ref[0]), 1e-12)
