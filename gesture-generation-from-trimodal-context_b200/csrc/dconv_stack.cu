@@ -6,12 +6,17 @@
 // CTAs hold bit-identical statistics).  The whole stack is ~7.5 MFLOP: the per-operator plan it replaces (3 implicit-GEMM launches +
 // 2 x [memset + column statistics + finalize] forward, 3 weight-gradient + 3 data-gradient + 2 x [reduce + apply] backward) spent its
 // time in launch latency (15-20 us per launch).
+// Version 2 (after profiles/r02_ncu_dfused_v1_*.txt: 46 us forward / 138 us backward, all of it dependent-latency chains in 8 CTAs):
+// inputs arrive by cp.async in one round trip, the statistics are reduced with warp shuffles + per-warp partials instead of contended
+// fp64 shared-memory atomics (CAS loops), every all-reduce owns its buffer (one cluster barrier each instead of two), the convolutions
+// keep four independent accumulators per thread, and the weight gradients run as (output, clip-slice) threads with a rolling 3-tap
+// window instead of one 512-long dependent chain per tap.
 #include <cuda_runtime.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int CL = 8, NT = 512, CPB = 16;            // CTAs per cluster, threads per CTA, clips per CTA
+constexpr int CL = 8, NT = 512, NW = NT / 32, CPB = 16;   // CTAs per cluster, threads per CTA, warps per CTA, clips per CTA
 constexpr int T0 = 34, C0 = 27, C1 = 16, C2 = 8, C3 = 8, KW = 3;
 constexpr int T1 = T0 - 2, T2 = T1 - 2, T3 = T2 - 2;  // 32, 30, 28
 
@@ -31,15 +36,60 @@ __device__ __forceinline__ double ld_cluster_f64(const double* local, uint32_t r
   asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
   return v;
 }
-// sum of `mine[0..n)` over the 8 CTAs of the cluster, in rank order, into tot[0..n) (every CTA gets the same bits)
-__device__ __forceinline__ void cluster_allreduce(double* mine, double* tot, int n) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// n floats global -> shared: 16-byte asynchronous copies for the aligned body (4-byte ones when the source is not 16-byte aligned: the
+// poses may be a view at any clip offset, e.g. pass 2 of a 3-clip sweep), scalar loads for a tail of < 4 floats
+__device__ __forceinline__ void stage_flat(float* dst, const float* src, int n) {
+  const int n4 = n & ~3;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (int i = threadIdx.x * 4; i < n4; i += NT * 4) cp_async16(dst + i, src + i);
+  } else {
+    for (int i = threadIdx.x; i < n4; i += NT) cp_async4(dst + i, src + i);
+  }
+  if (threadIdx.x < n - n4) dst[n4 + threadIdx.x] = __ldg(src + n4 + threadIdx.x);
+}
+// nn.Conv1d filter [N][CIN][3] -> [3][CIN][N] (tap-major, output channel fastest)
+template <int CIN, int N>
+__device__ __forceinline__ void load_filter(float* ws, const float* w) {
+  for (int i = threadIdx.x; i < KW * CIN * N; i += NT) {
+    const int j = i / (CIN * N), r = i - j * CIN * N, ci = r / N, n = r - ci * N;
+    ws[i] = __ldg(w + (n * CIN + ci) * KW + j);
+  }
+}
+// sum of `mine[0..n)` over the 8 CTAs of the cluster, in rank order, into tot[0..n) (every CTA gets the same bits).  `mine` must not be
+// written again by its owner (a peer may read it at any time up to the kernel's final cluster barrier).
+__device__ __forceinline__ void cluster_allreduce(const double* mine, double* tot, int n) {
   cluster_sync_();                                   // every CTA's partial sums are in its `mine`
   for (int i = threadIdx.x; i < n; i += NT) {
     double a = 0.0;
     for (uint32_t r = 0; r < CL; ++r) a += ld_cluster_f64(mine + i, r);
     tot[i] = a;
   }
-  cluster_sync_();                                   // nobody overwrites `mine` before every peer has read it; tot visible CTA-wide
+  __syncthreads();
+}
+// per-channel sums of a thread's (s0, s1) over the CTA: threads with equal (threadIdx.x % C) own the same channel.  Shuffle inside the
+// warp, one partial per warp in shared memory, fp64 sum over the 16 warps -> mine[0..C) (sum) and mine[C..2C) (second sum).
+template <int C>
+__device__ __forceinline__ void cta_channel_sums(float s0, float s1, float* part, double* mine) {
+#pragma unroll
+  for (int o = 16; o >= C; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < C) { part[warp * 32 + lane] = s0; part[warp * 32 + C + lane] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a += (double)part[w * 32 + threadIdx.x];
+    mine[threadIdx.x] = a;
+  }
 }
 
 struct ConvFwdP {
@@ -68,7 +118,7 @@ __device__ __forceinline__ void bn_affine(const double* tot, int C, long long M,
         const float unbiased = (float)(var * ((double)M / (double)(M > 1 ? M - 1 : 1)));
         rm[c] = (1.f - momentum) * rm[c] + momentum * mu;
         rv[c] = (1.f - momentum) * rv[c] + momentum * unbiased;
-        if (c == 0) *nbt += 1;
+        if (c == 0 && nbt) *nbt += 1;
       }
     } else {
       mu = rm[c]; rs = 1.f / sqrtf(rv[c] + eps);
@@ -77,6 +127,49 @@ __device__ __forceinline__ void bn_affine(const double* tot, int C, long long M,
     s_scale[c] = sc; s_shift[c] = sh;
     if (leader) { st[c] = mu; st[C + c] = rs; st[2 * C + c] = sc; st[3 * C + c] = sh; }
   }
+}
+
+// valid k=3 convolution of this CTA's clips from shared memory: in [nclip][TIN][CIN] -> out [nclip][TIN-2][COUT] (shared) and gout
+// (global, may be NULL).  thread = (output channel n = tid % COUT, position lane tid / COUT), four positions in flight per thread;
+// a window (3 taps x CIN) is CONTIGUOUS in the channels-last layout.  Returns the thread's sum / sum of squares of what it produced.
+template <int CIN, int COUT, int TIN>
+__device__ __forceinline__ void conv3_part(const float* in, const float* ws, float bias, int nclip, float* out, float* gout, float& s0, float& s1) {
+  constexpr int TOUT = TIN - 2, LANES = NT / COUT, WIN = KW * CIN;
+  const int n = threadIdx.x % COUT, pl = threadIdx.x / COUT;
+  const int npos = nclip * TOUT;
+  s0 = 0.f; s1 = 0.f;
+  for (int p0 = pl; p0 < npos; p0 += 4 * LANES) {
+    const float* xr[4];
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pos = min(p0 + i * LANES, npos - 1);
+      const int c = pos / TOUT, t = pos - c * TOUT;
+      xr[i] = in + (c * TIN + t) * CIN;
+      a[i] = bias;
+    }
+#pragma unroll 9
+    for (int q = 0; q < WIN; ++q) {
+      const float w = ws[q * COUT + n];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = fmaf(xr[i][q], w, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pos = p0 + i * LANES;
+      if (pos < npos) {
+        if (out) out[pos * COUT + n] = a[i];
+        if (gout) gout[(long long)pos * COUT + n] = a[i];
+        s0 += a[i]; s1 += a[i] * a[i];
+      }
+    }
+  }
+}
+// x[i] = x[i] * scale[c] + shift[c] in place over [npos][C]  (NT % C == 0: a thread keeps its channel)
+template <int C>
+__device__ __forceinline__ void affine_inplace(float* x, int npos, const float* scale, const float* shift) {
+  const float sc = scale[threadIdx.x % C], sh = shift[threadIdx.x % C];
+  for (int i = threadIdx.x; i < npos * C; i += NT) x[i] = fmaf(x[i], sc, sh);
 }
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_fwd_kernel(const ConvFwdP p) {
@@ -88,85 +181,50 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_
   float* w2s = w1s + KW * C0 * C1;                   // [3][16][8]
   float* w3s = w2s + KW * C1 * C2;                   // [3][8][8]
   float* aff = w3s + KW * C2 * C3;                   // scale1[16] shift1[16] scale2[8] shift2[8]
-  double* mine = reinterpret_cast<double*>(aff + 48);  // [32] partial sums of this CTA
-  double* tot = mine + 32;                             // [32]
+  float* part = aff + 48;                            // [16 warps][32] per-warp partial sums
+  double* mineA = reinterpret_cast<double*>(part + NW * 32);   // [32] this CTA's sums for BatchNorm 1 (read by the peers)
+  double* mineB = mineA + 32;                                  // [16] ... BatchNorm 2
+  double* tot = mineB + 16;                                    // [32]
   const int tid = threadIdx.x;
   const int rank = (int)cluster_rank_();
   const int c_lo = rank * CPB;
   const int nclip = max(0, min(CPB, p.B - c_lo));
   const bool leader = rank == 0;
 
-  for (int i = tid; i < nclip * T0 * C0; i += NT) xs[i] = __ldg(p.x + (long long)c_lo * T0 * C0 + i);
-  for (int i = tid; i < KW * C0 * C1; i += NT) { const int j = i / (C0 * C1), r = i - j * C0 * C1, ci = r / C1, n = r - ci * C1; w1s[i] = __ldg(p.w1 + (n * C0 + ci) * KW + j); }
-  for (int i = tid; i < KW * C1 * C2; i += NT) { const int j = i / (C1 * C2), r = i - j * C1 * C2, ci = r / C2, n = r - ci * C2; w2s[i] = __ldg(p.w2 + (n * C1 + ci) * KW + j); }
-  for (int i = tid; i < KW * C2 * C3; i += NT) { const int j = i / (C2 * C3), r = i - j * C2 * C3, ci = r / C3, n = r - ci * C3; w3s[i] = __ldg(p.w3 + (n * C2 + ci) * KW + j); }
-  if (tid < 32) mine[tid] = 0.0;
+  stage_flat(xs, p.x + (long long)c_lo * T0 * C0, nclip * T0 * C0);
+  load_filter<C0, C1>(w1s, p.w1);
+  load_filter<C1, C2>(w2s, p.w2);
+  load_filter<C2, C3>(w3s, p.w3);
+  cp_async_wait_all();
   __syncthreads();
 
-  // ---- conv1: thread = (output channel n = tid % 16, position lane tid / 16); x reads are broadcasts, weight reads conflict-free
-  {
-    const int n = tid & (C1 - 1), pl = tid >> 4;
-    const float bias = __ldg(p.b1 + n);
-    float s0 = 0.f, s1 = 0.f;
-    for (int pos = pl; pos < nclip * T1; pos += NT / C1) {
-      const int c = pos / T1, t = pos - c * T1;
-      const float* xr = xs + (c * T0 + t) * C0;
-      float a = bias;
-#pragma unroll
-      for (int j = 0; j < KW; ++j)
-#pragma unroll 9
-        for (int ci = 0; ci < C0; ++ci) a = fmaf(xr[j * C0 + ci], w1s[(j * C0 + ci) * C1 + n], a);
-      y0s[pos * C1 + n] = a;
-      p.y0[((long long)c_lo * T1 + pos) * C1 + n] = a;
-      s0 += a; s1 += a * a;
-    }
-    if (p.training) { atomicAdd(&mine[n], (double)s0); atomicAdd(&mine[C1 + n], (double)s1); }
+  float s0, s1;
+  // ---- conv1 (the pre-BatchNorm output goes to global memory for the backward)
+  conv3_part<C0, C1, T0>(xs, w1s, __ldg(p.b1 + (tid % C1)), nclip, y0s, p.y0 + (long long)c_lo * T1 * C1, s0, s1);
+  if (p.training) {
+    cta_channel_sums<C1>(s0, s1, part, mineA);
+    cluster_allreduce(mineA, tot, 2 * C1);
+  } else {
+    __syncthreads();
   }
-  __syncthreads();
-  if (p.training) cluster_allreduce(mine, tot, 2 * C1);
   bn_affine(tot, C1, (long long)p.B * T1, p.g1, p.be1, p.rm1, p.rv1, p.nbt1, p.st1, aff, aff + 16, p.training, p.eps, p.momentum, leader);
-  if (tid < 32) mine[tid] = 0.0;
   __syncthreads();
-
-  // ---- conv2 on a0 = scale1 * y0 + shift1 (LeakyReLU(True) is the identity): thread = (n = tid % 8, position lane tid / 8)
-  {
-    const int n = tid & (C2 - 1), pl = tid >> 3;
-    const float bias = __ldg(p.b2 + n);
-    float s0 = 0.f, s1 = 0.f;
-    for (int pos = pl; pos < nclip * T2; pos += NT / C2) {
-      const int c = pos / T2, t = pos - c * T2;
-      const float* yr = y0s + (c * T1 + t) * C1;
-      float a = bias;
-#pragma unroll
-      for (int j = 0; j < KW; ++j)
-#pragma unroll
-        for (int ci = 0; ci < C1; ++ci) a = fmaf(fmaf(yr[j * C1 + ci], aff[ci], aff[16 + ci]), w2s[(j * C1 + ci) * C2 + n], a);
-      y1s[pos * C2 + n] = a;
-      p.y1[((long long)c_lo * T2 + pos) * C2 + n] = a;
-      s0 += a; s1 += a * a;
-    }
-    if (p.training) { atomicAdd(&mine[n], (double)s0); atomicAdd(&mine[C2 + n], (double)s1); }
+  affine_inplace<C1>(y0s, nclip * T1, aff, aff + 16);          // LeakyReLU(True) has slope 1: the identity
+  __syncthreads();
+  // ---- conv2
+  conv3_part<C1, C2, T1>(y0s, w2s, __ldg(p.b2 + (tid % C2)), nclip, y1s, p.y1 + (long long)c_lo * T2 * C2, s0, s1);
+  if (p.training) {
+    cta_channel_sums<C2>(s0, s1, part, mineB);
+    cluster_allreduce(mineB, tot, 2 * C2);
+  } else {
+    __syncthreads();
   }
-  __syncthreads();
-  if (p.training) cluster_allreduce(mine, tot, 2 * C2);
   bn_affine(tot, C2, (long long)p.B * T2, p.g2, p.be2, p.rm2, p.rv2, p.nbt2, p.st2, aff + 32, aff + 40, p.training, p.eps, p.momentum, leader);
   __syncthreads();
-
-  // ---- conv3 on a1 = scale2 * y1 + shift2
-  {
-    const int n = tid & (C3 - 1), pl = tid >> 3;
-    const float bias = __ldg(p.b3 + n);
-    for (int pos = pl; pos < nclip * T3; pos += NT / C3) {
-      const int c = pos / T3, t = pos - c * T3;
-      const float* yr = y1s + (c * T2 + t) * C2;
-      float a = bias;
-#pragma unroll
-      for (int j = 0; j < KW; ++j)
-#pragma unroll
-        for (int ci = 0; ci < C2; ++ci) a = fmaf(fmaf(yr[j * C2 + ci], aff[32 + ci], aff[40 + ci]), w3s[(j * C2 + ci) * C3 + n], a);
-      p.y2[((long long)c_lo * T3 + pos) * C3 + n] = a;
-    }
-  }
+  affine_inplace<C2>(y1s, nclip * T2, aff + 32, aff + 40);
+  __syncthreads();
+  // ---- conv3
+  conv3_part<C2, C3, T2>(y1s, w3s, __ldg(p.b3 + (tid % C3)), nclip, nullptr, p.y2 + (long long)c_lo * T3 * C3, s0, s1);
   cluster_sync_();                                   // no CTA exits while a peer may still read its partial sums
 }
 
@@ -183,23 +241,52 @@ struct ConvBwdP {
   int B;
 };
 
-// dW[n][ci][j] += sum over the CTA's (clip, t) of dy[c][t][n] * a[c][t + j][ci]  (a = affine(src) if sc != NULL), db[n] += sum dy
+// dW[n][ci][j] += sum over the CTA's (clip, t) of dy[c][t][n] * a[c][t + j][ci],  db[n] += sum dy,  a = sc[ci] * src + sh[ci] (the
+// BatchNorm in front of the convolution, applied on the fly; sc == NULL: a = src).
+// thread = ((n, ci), clip slice): the three taps share a rolling window over t (one load of `a` and one of `dy` per position for three
+// FMAs on independent accumulators); the SL slices are summed through shared memory (`red`, SL * COUT*CIN*3 floats) before ONE atomic
+// per weight and CTA.
 template <int CIN, int COUT, int TIN>
-__device__ __forceinline__ void conv_wgrad_part(const float* dys, const float* src, const float* sc, const float* sh, int nclip, float* dW, float* db) {
-  constexpr int TOUT = TIN - 2;
-  for (int o = threadIdx.x; o < COUT * CIN * KW + COUT; o += NT) {
-    float a = 0.f;
-    if (o < COUT * CIN * KW) {
-      const int n = o / (CIN * KW), r = o - n * CIN * KW, ci = r / KW, j = r - ci * KW;
-      const float s = sc ? sc[ci] : 1.f, h = sc ? sh[ci] : 0.f;
-      for (int c = 0; c < nclip; ++c)
-        for (int t = 0; t < TOUT; ++t) a = fmaf(dys[(c * TOUT + t) * COUT + n], fmaf(src[(c * TIN + t + j) * CIN + ci], s, h), a);
-      atomicAdd(dW + o, a);
-    } else {
-      const int n = o - COUT * CIN * KW;
-      for (int i = 0; i < nclip * TOUT; ++i) a += dys[i * COUT + n];
-      atomicAdd(db + n, a);
+__device__ __forceinline__ void conv_wgrad_part(const float* dys, const float* src, const float* sc, const float* sh, int nclip, float* dW,
+                                                float* db, float* red) {
+  constexpr int TOUT = TIN - 2, NOUT = COUT * CIN, SL = (NT / NOUT) >= 8 ? 8 : (NT / NOUT) >= 4 ? 4 : (NT / NOUT) >= 2 ? 2 : 1, CPS = CPB / SL;
+  const int o = threadIdx.x % NOUT, sl = threadIdx.x / NOUT;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (sl < SL) {
+    const int n = o / CIN, ci = o - n * CIN;
+    const float s_ = sc ? sc[ci] : 1.f, h_ = sc ? sh[ci] : 0.f;
+    for (int c = sl * CPS; c < min(nclip, (sl + 1) * CPS); ++c) {
+      const float* sr = src + c * TIN * CIN + ci;
+      const float* dr = dys + c * TOUT * COUT + n;
+      float x0 = fmaf(sr[0], s_, h_), x1 = fmaf(sr[CIN], s_, h_);
+#pragma unroll 4
+      for (int t = 0; t < TOUT; ++t) {
+        const float x2 = fmaf(sr[(t + 2) * CIN], s_, h_), g = dr[t * COUT];
+        a0 = fmaf(g, x0, a0); a1 = fmaf(g, x1, a1); a2 = fmaf(g, x2, a2);
+        x0 = x1; x1 = x2;
+      }
     }
+  }
+  if (SL == 1) {
+    if (sl < SL) { atomicAdd(dW + o * KW, a0); atomicAdd(dW + o * KW + 1, a1); atomicAdd(dW + o * KW + 2, a2); }
+  } else {
+    __syncthreads();                                 // `red` may still be in use by the previous caller
+    if (sl < SL) { red[(sl * NOUT + o) * KW] = a0; red[(sl * NOUT + o) * KW + 1] = a1; red[(sl * NOUT + o) * KW + 2] = a2; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NOUT * KW; i += NT) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < SL; ++q) a += red[q * NOUT * KW + i];
+      atomicAdd(dW + i, a);
+    }
+  }
+  // bias gradient: one warp per output channel (COUT <= 16 warps)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < COUT) {
+    float a = 0.f;
+    for (int i = lane; i < nclip * TOUT; i += 32) a += dys[i * COUT + warp];
+    a = warp_sum(a);
+    if (lane == 0) atomicAdd(db + warp, a);
   }
 }
 // da[c][u][ci] = sum_{n, j} dy[c][u - j][n] * W[n][ci][j]   (ws: [3][CIN][COUT] tap-major copy of W)
@@ -208,41 +295,46 @@ __device__ __forceinline__ void conv_dgrad_part(const float* dys, const float* w
   constexpr int TOUT = TIN - 2;
   for (int i = threadIdx.x; i < nclip * TIN * CIN; i += NT) {
     const int ci = i % CIN, u = (i / CIN) % TIN, c = i / (CIN * TIN);
-    float a = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    {
+      const int t = u;
+      if (t < TOUT) { const float* dr = dys + (c * TOUT + t) * COUT;
 #pragma unroll
-    for (int j = 0; j < KW; ++j) {
-      const int t = u - j;
-      if (t >= 0 && t < TOUT) {
-        const float* dr = dys + (c * TOUT + t) * COUT;
-#pragma unroll
-        for (int n = 0; n < COUT; ++n) a = fmaf(dr[n], ws[(j * CIN + ci) * COUT + n], a);
-      }
+        for (int n = 0; n < COUT; ++n) a0 = fmaf(dr[n], ws[(0 * CIN + ci) * COUT + n], a0); }
     }
-    das[i] = a;
+    {
+      const int t = u - 1;
+      if (t >= 0 && t < TOUT) { const float* dr = dys + (c * TOUT + t) * COUT;
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) a1 = fmaf(dr[n], ws[(1 * CIN + ci) * COUT + n], a1); }
+    }
+    {
+      const int t = u - 2;
+      if (t >= 0) { const float* dr = dys + (c * TOUT + t) * COUT;
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) a2 = fmaf(dr[n], ws[(2 * CIN + ci) * COUT + n], a2); }
+    }
+    das[i] = a0 + a1 + a2;
   }
 }
 // BatchNorm (identity activation) backward in place on d [npos][C]: partial sums -> cluster all-reduce -> dy = g * rstd * (d - S0/M - xhat * S1/M)
 template <int C>
-__device__ __forceinline__ void bn_bwd_part(float* d, const float* ysrc, int npos, long long M, const float* st, const float* gamma, double* mine,
-                                            double* tot, float* dgamma, float* dbeta, bool leader) {
-  __syncthreads();
-  if (threadIdx.x < 2 * C) mine[threadIdx.x] = 0.0;
-  __syncthreads();
+__device__ __forceinline__ void bn_bwd_part(float* d, const float* ysrc, int npos, long long M, const float* st, const float* gamma, float* part,
+                                            double* mine, double* tot, float* dgamma, float* dbeta, bool leader) {
+  __syncthreads();                                   // d complete
+  const int c = threadIdx.x % C;
+  const float mu = st[c], rs = st[C + c];
   {
-    const int c = threadIdx.x % C;
-    const float mu = st[c], rs = st[C + c];
     float s0 = 0.f, s1 = 0.f;
     for (int i = threadIdx.x; i < npos * C; i += NT) {          // NT % C == 0: a thread keeps its channel
       const float dz = d[i];
       s0 += dz; s1 += dz * (ysrc[i] - mu) * rs;
     }
-    atomicAdd(&mine[c], (double)s0); atomicAdd(&mine[C + c], (double)s1);
+    cta_channel_sums<C>(s0, s1, part, mine);
   }
-  __syncthreads();
   cluster_allreduce(mine, tot, 2 * C);
   {
-    const int c = threadIdx.x % C;
-    const float mu = st[c], rs = st[C + c], g = gamma[c];
+    const float g = __ldg(gamma + c);
     const float m0 = (float)(tot[c] / (double)M), m1 = (float)(tot[C + c] / (double)M);
     for (int i = threadIdx.x; i < npos * C; i += NT) d[i] = g * rs * (d[i] - m0 - (ysrc[i] - mu) * rs * m1);
     if (leader && threadIdx.x < C) { dgamma[c] += (float)tot[C + c]; dbeta[c] += (float)tot[c]; }
@@ -252,9 +344,9 @@ __device__ __forceinline__ void bn_bwd_part(float* d, const float* ysrc, int npo
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_bwd_kernel(const ConvBwdP p) {
   extern __shared__ __align__(16) float sm[];
-  float* xs = sm;                                    // [CPB][34][27]
-  float* y0s = xs + CPB * T0 * C0;                   // [CPB][32][16]   y0, later reused? (kept: conv2 weight gradient needs a0)
-  float* y1s = y0s + CPB * T1 * C1;                  // [CPB][30][8]
+  float* xs = sm;                                    // [CPB][34][27]   x, later d x
+  float* y0s = xs + CPB * T0 * C0;                   // [CPB][32][16]   y0 (pre-BatchNorm)
+  float* y1s = y0s + CPB * T1 * C1;                  // [CPB][30][8]    y1
   float* d2s = y1s + CPB * T2 * C2;                  // [CPB][28][8]    dy2
   float* d1s = d2s + CPB * T3 * C3;                  // [CPB][30][8]    d a1 -> d y1
   float* d0s = d1s + CPB * T2 * C2;                  // [CPB][32][16]   d a0 -> d y0
@@ -263,50 +355,57 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_
   float* w3s = w2s + KW * C1 * C2;                   // [3][8][8]
   float* st1 = w3s + KW * C2 * C3;                   // 64 floats
   float* st2 = st1 + 64;                             // 32 floats
-  double* mine = reinterpret_cast<double*>(st2 + 32);
-  double* tot = mine + 32;
+  float* part = st2 + 32;                            // [16][32]
+  float* red = part + NW * 32;                       // [8 * 64 * 3] slice partials of the weight gradients (conv2: 4 * 128 * 3)
+  double* mineA = reinterpret_cast<double*>(red + 1536);
+  double* mineB = mineA + 32;
+  double* tot = mineB + 32;
   const int tid = threadIdx.x;
   const int rank = (int)cluster_rank_();
   const int c_lo = rank * CPB;
   const int nclip = max(0, min(CPB, p.B - c_lo));
   const bool leader = rank == 0;
 
-  for (int i = tid; i < nclip * T0 * C0; i += NT) xs[i] = __ldg(p.x + (long long)c_lo * T0 * C0 + i);
-  for (int i = tid; i < nclip * T1 * C1; i += NT) y0s[i] = __ldg(p.y0 + (long long)c_lo * T1 * C1 + i);
-  for (int i = tid; i < nclip * T2 * C2; i += NT) y1s[i] = __ldg(p.y1 + (long long)c_lo * T2 * C2 + i);
-  for (int i = tid; i < nclip * T3 * C3; i += NT) d2s[i] = __ldg(p.dy2 + (long long)c_lo * T3 * C3 + i);
-  for (int i = tid; i < KW * C0 * C1; i += NT) { const int j = i / (C0 * C1), r = i - j * C0 * C1, ci = r / C1, n = r - ci * C1; w1s[i] = __ldg(p.w1 + (n * C0 + ci) * KW + j); }
-  for (int i = tid; i < KW * C1 * C2; i += NT) { const int j = i / (C1 * C2), r = i - j * C1 * C2, ci = r / C2, n = r - ci * C2; w2s[i] = __ldg(p.w2 + (n * C1 + ci) * KW + j); }
-  for (int i = tid; i < KW * C2 * C3; i += NT) { const int j = i / (C2 * C3), r = i - j * C2 * C3, ci = r / C3, n = r - ci * C3; w3s[i] = __ldg(p.w3 + (n * C2 + ci) * KW + j); }
+  stage_flat(xs, p.x + (long long)c_lo * T0 * C0, nclip * T0 * C0);
+  stage_flat(y0s, p.y0 + (long long)c_lo * T1 * C1, nclip * T1 * C1);
+  stage_flat(y1s, p.y1 + (long long)c_lo * T2 * C2, nclip * T2 * C2);
+  stage_flat(d2s, p.dy2 + (long long)c_lo * T3 * C3, nclip * T3 * C3);
+  load_filter<C0, C1>(w1s, p.w1);
+  load_filter<C1, C2>(w2s, p.w2);
+  load_filter<C2, C3>(w3s, p.w3);
   if (tid < 64) st1[tid] = __ldg(p.st1 + tid);
   if (tid < 32) st2[tid] = __ldg(p.st2 + tid);
+  cp_async_wait_all();
   __syncthreads();
 
   const long long M1 = (long long)p.B * T1, M2 = (long long)p.B * T2;
   // conv3: weight gradient on a1 = affine2(y1), data gradient -> d a1
-  conv_wgrad_part<C2, C3, T2>(d2s, y1s, st2 + 2 * C2, st2 + 3 * C2, nclip, p.dw3, p.db3);
+  conv_wgrad_part<C2, C3, T2>(d2s, y1s, st2 + 2 * C2, st2 + 3 * C2, nclip, p.dw3, p.db3, red);
   conv_dgrad_part<C2, C3, T2>(d2s, w3s, nclip, d1s);
-  bn_bwd_part<C2>(d1s, y1s, nclip * T2, M2, st2, p.g2, mine, tot, p.dg2, p.dbe2, leader);
+  bn_bwd_part<C2>(d1s, y1s, nclip * T2, M2, st2, p.g2, part, mineA, tot, p.dg2, p.dbe2, leader);
   // conv2
-  conv_wgrad_part<C1, C2, T1>(d1s, y0s, st1 + 2 * C1, st1 + 3 * C1, nclip, p.dw2, p.db2);
+  conv_wgrad_part<C1, C2, T1>(d1s, y0s, st1 + 2 * C1, st1 + 3 * C1, nclip, p.dw2, p.db2, red);
   conv_dgrad_part<C1, C2, T1>(d1s, w2s, nclip, d0s);
-  bn_bwd_part<C1>(d0s, y0s, nclip * T1, M1, st1, p.g1, mine, tot, p.dg1, p.dbe1, leader);
+  bn_bwd_part<C1>(d0s, y0s, nclip * T1, M1, st1, p.g1, part, mineB, tot, p.dg1, p.dbe1, leader);
   // conv1
-  conv_wgrad_part<C0, C1, T0>(d0s, xs, nullptr, nullptr, nclip, p.dw1, p.db1);
+  conv_wgrad_part<C0, C1, T0>(d0s, xs, nullptr, nullptr, nclip, p.dw1, p.db1, red);
   if (p.dx) {
+    __syncthreads();                                 // x is no longer needed once its weight gradient is done
+    conv_dgrad_part<C0, C1, T0>(d0s, w1s, nclip, xs);
     __syncthreads();
-    float* dxs = xs;                                 // x is no longer needed once its weight gradient is done
-    __syncthreads();
-    conv_dgrad_part<C0, C1, T0>(d0s, w1s, nclip, dxs);
-    __syncthreads();
-    for (int i = tid; i < nclip * T0 * C0; i += NT) p.dx[(long long)c_lo * T0 * C0 + i] = dxs[i];
+    const int n = nclip * T0 * C0;
+    float* gx = p.dx + (long long)c_lo * T0 * C0;
+    for (int i = tid; i < n; i += NT) gx[i] = xs[i];
   }
   cluster_sync_();
 }
 
-size_t fwd_smem() { return (size_t)(CPB * T0 * C0 + CPB * T1 * C1 + CPB * T2 * C2 + KW * C0 * C1 + KW * C1 * C2 + KW * C2 * C3 + 48) * 4 + 64 * 8; }
+size_t fwd_smem() {
+  return (size_t)(CPB * T0 * C0 + CPB * T1 * C1 + CPB * T2 * C2 + KW * C0 * C1 + KW * C1 * C2 + KW * C2 * C3 + 48 + NW * 32) * 4 + (32 + 16 + 32) * 8;
+}
 size_t bwd_smem() {
-  return (size_t)(CPB * T0 * C0 + 2 * CPB * T1 * C1 + 2 * CPB * T2 * C2 + CPB * T3 * C3 + KW * C0 * C1 + KW * C1 * C2 + KW * C2 * C3 + 96) * 4 + 64 * 8;
+  return (size_t)(CPB * T0 * C0 + 2 * CPB * T1 * C1 + 2 * CPB * T2 * C2 + CPB * T3 * C3 + KW * C0 * C1 + KW * C1 * C2 + KW * C2 * C3 + 96 + NW * 32 +
+                  1536) * 4 + (32 + 32 + 32) * 8;
 }
 
 }  // namespace

@@ -127,6 +127,115 @@ __global__ void bn_bwd_apply_kernel(const float* dy, const float* __restrict__ x
   }
 }
 
+// ---- float4 variants of the BatchNorm passes for power-of-two channel counts (WavEncoder: 16 / 32 / 64 channels over up to 1M rows).
+// A thread's grid stride (gridDim * 256 * 4 elements) is a multiple of C, so it keeps the SAME four channels for its whole loop: the
+// per-channel constants live in registers and every memory instruction is a 16-byte access (the scalar kernels above reach 31-47 % of
+// the HBM peak, limited by instruction issue: one 4-byte access + an integer modulo per element).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) col_reduce_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long n4, int C,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                                                            double* __restrict__ sums) {
+  __shared__ double sh[256][8];
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int c0 = (int)((i0 * 4) % C);
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, sc = mu, sf = mu;
+  if (BWD) { mu = ldg4(mean + c0); rs = ldg4(rstd + c0); sc = ldg4(scale + c0); sf = ldg4(shift + c0); }
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = i0; i < n4; i += stride) {
+    const float4 v = ldg4(x + 4 * i);
+    if (BWD) {
+      const float4 g = ldg4(dy + 4 * i);
+      const float d0 = g.x * (v.x * sc.x + sf.x >= 0.f ? 1.f : slope), d1 = g.y * (v.y * sc.y + sf.y >= 0.f ? 1.f : slope);
+      const float d2 = g.z * (v.z * sc.z + sf.z >= 0.f ? 1.f : slope), d3 = g.w * (v.w * sc.w + sf.w >= 0.f ? 1.f : slope);
+      f[0] += d0; f[1] += d1; f[2] += d2; f[3] += d3;
+      f[4] += d0 * (v.x - mu.x) * rs.x; f[5] += d1 * (v.y - mu.y) * rs.y; f[6] += d2 * (v.z - mu.z) * rs.z; f[7] += d3 * (v.w - mu.w) * rs.w;
+    } else {
+      f[0] += v.x; f[1] += v.y; f[2] += v.z; f[3] += v.w;
+      f[4] += v.x * v.x; f[5] += v.y * v.y; f[6] += v.z * v.z; f[7] += v.w * v.w;
+    }
+    if (++cnt == 64) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] += f[k]; f[k] = 0.f; }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = a[k] + (double)f[k];
+  __syncthreads();
+  // threads tid, tid + C/4, tid + 2C/4, ... hold the same four channels
+  const int lanes = C / 4;
+  for (int o = threadIdx.x; o < lanes * 8; o += 256) {
+    const int l = o >> 3, k = o & 7;
+    double t = 0.0;
+    for (int q = l; q < 256; q += lanes) t += sh[q][k];
+    const int c = (int)(((long long)blockIdx.x * 256 + l) * 4 % C) + (k & 3);
+    atomicAdd(sums + (k < 4 ? 0 : C) + c, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) affine_lrelu_v4_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int C,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift, float slope) {
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int c0 = (int)((i0 * 4) % C);
+  const float4 sc = ldg4(scale + c0), sf = ldg4(shift + c0);
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = i0; i < n4; i += stride) {
+    const float4 v = ldg4(x + 4 * i);
+    float4 o;
+    o.x = v.x * sc.x + sf.x; o.y = v.y * sc.y + sf.y; o.z = v.z * sc.z + sf.z; o.w = v.w * sc.w + sf.w;
+    o.x = o.x >= 0.f ? o.x : o.x * slope; o.y = o.y >= 0.f ? o.y : o.y * slope;
+    o.z = o.z >= 0.f ? o.z : o.z * slope; o.w = o.w >= 0.f ? o.w : o.w * slope;
+    *reinterpret_cast<float4*>(y + 4 * i) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(const float* dy, const float* __restrict__ x, float* dx, long long n4, long long M,
+                                                              int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                                                              const float* __restrict__ gamma, const double* __restrict__ sums, float* dgamma,
+                                                              float* dbeta) {
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int c0 = (int)((i0 * 4) % C);
+  const double invM = 1.0 / (double)M;
+  const float4 mu = ldg4(mean + c0), rs = ldg4(rstd + c0), sc = ldg4(scale + c0), sf = ldg4(shift + c0);
+  const float4 g = gamma ? ldg4(gamma + c0) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float m0x = (float)(sums[c0] * invM), m0y = (float)(sums[c0 + 1] * invM), m0z = (float)(sums[c0 + 2] * invM), m0w = (float)(sums[c0 + 3] * invM);
+  const float m1x = (float)(sums[C + c0] * invM), m1y = (float)(sums[C + c0 + 1] * invM), m1z = (float)(sums[C + c0 + 2] * invM),
+              m1w = (float)(sums[C + c0 + 3] * invM);
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = i0; i < n4; i += stride) {
+    const float4 v = ldg4(x + 4 * i);
+    const float4 d = *reinterpret_cast<const float4*>(dy + 4 * i);         // dx may alias dy: plain load
+    float4 o;
+    o.x = g.x * rs.x * (d.x * (v.x * sc.x + sf.x >= 0.f ? 1.f : slope) - m0x - (v.x - mu.x) * rs.x * m1x);
+    o.y = g.y * rs.y * (d.y * (v.y * sc.y + sf.y >= 0.f ? 1.f : slope) - m0y - (v.y - mu.y) * rs.y * m1y);
+    o.z = g.z * rs.z * (d.z * (v.z * sc.z + sf.z >= 0.f ? 1.f : slope) - m0z - (v.z - mu.z) * rs.z * m1z);
+    o.w = g.w * rs.w * (d.w * (v.w * sc.w + sf.w >= 0.f ? 1.f : slope) - m0w - (v.w - mu.w) * rs.w * m1w);
+    *reinterpret_cast<float4*>(dx + 4 * i) = o;
+  }
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dgamma) dgamma[c] += (float)sums[C + c];
+      if (dbeta) dbeta[c] += (float)sums[c];
+    }
+  }
+}
+
+// the float4 variants apply to: contiguous rows, C a power of two in [4, 256], 16-byte aligned pointers
+static inline bool v4_ok(int C, int ld, const void* a, const void* b = nullptr, const void* c = nullptr) {
+  return ld == C && C >= 4 && C <= 256 && (C & (C - 1)) == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+static inline int v4_blocks(long long n4) {
+  long long b = (n4 + 255) / 256, cap = (long long)tg_num_sms() * 8;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
 // ------------------------------------------------------------------ embedding
 __global__ void embedding_gather_kernel(const float* __restrict__ table, const long long* __restrict__ idx, int idx_mod,
                                         const float* __restrict__ mask, float* __restrict__ out, long long M, int E) {
@@ -448,6 +557,12 @@ static int next_pow2(int c) { int p = 1; while (p < c) p <<= 1; return p; }
 
 extern "C" int tg_col_stats_f64(const float* x, int ld, long long M, int C, double* sums, tg_stream stream) {
   TG_REQUIRE(x && sums && C > 0 && C <= 256 && M > 0, "tg_col_stats_f64");
+  if (v4_ok(C, ld, x) && M * C >= 4096) {
+    const long long n4 = M * C / 4;
+    col_reduce_v4_kernel<false><<<v4_blocks(n4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, n4, C, nullptr, nullptr, nullptr, nullptr, 0.f, sums);
+    TG_CHECK_LAUNCH("tg_col_stats_f64");
+    return 0;
+  }
   const int CP = next_pow2(C), RL = 256 / CP;
   long long blocks = (M + RL * 16 - 1) / (RL * 16);
   if (blocks > tg_num_sms() * 8) blocks = tg_num_sms() * 8;
@@ -468,6 +583,12 @@ extern "C" int tg_bn_finalize(const double* sums, long long M, int C, float eps,
 extern "C" int tg_affine_lrelu(const float* x, float* y, long long M, int C, const float* scale, const float* shift, float slope,
                                tg_stream stream) {
   TG_REQUIRE(x && y && scale && shift, "tg_affine_lrelu");
+  if (v4_ok(C, C, x, y, scale) && (((uintptr_t)shift) & 15) == 0 && M * C >= 4096) {
+    const long long n4 = M * C / 4;
+    affine_lrelu_v4_kernel<<<v4_blocks(n4), 256, 0, (cudaStream_t)stream>>>(x, y, n4, C, scale, shift, slope);
+    TG_CHECK_LAUNCH("tg_affine_lrelu");
+    return 0;
+  }
   affine_lrelu_kernel<<<ew_blocks(M * C), 256, 0, (cudaStream_t)stream>>>(x, y, M * C, C, scale, shift, slope);
   TG_CHECK_LAUNCH("tg_affine_lrelu");
   return 0;
@@ -475,6 +596,12 @@ extern "C" int tg_affine_lrelu(const float* x, float* y, long long M, int C, con
 extern "C" int tg_bn_bwd_reduce(const float* dy, const float* x, long long M, int C, const float* mean, const float* rstd,
                                 const float* scale, const float* shift, float slope, double* sums, tg_stream stream) {
   TG_REQUIRE(dy && x && sums && C > 0 && C <= 256, "tg_bn_bwd_reduce");
+  if (v4_ok(C, C, x, dy, mean) && M * C >= 4096 && ((((uintptr_t)rstd | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0)) {
+    const long long n4 = M * C / 4;
+    col_reduce_v4_kernel<true><<<v4_blocks(n4), 256, 0, (cudaStream_t)stream>>>(x, dy, n4, C, mean, rstd, scale, shift, slope, sums);
+    TG_CHECK_LAUNCH("tg_bn_bwd_reduce");
+    return 0;
+  }
   const int CP = next_pow2(C), RL = 256 / CP;
   long long blocks = (M + RL * 16 - 1) / (RL * 16);
   if (blocks > tg_num_sms() * 8) blocks = tg_num_sms() * 8;
@@ -487,6 +614,14 @@ extern "C" int tg_bn_bwd_apply(const float* dy, const float* x, float* dx, long 
                                const float* scale, const float* shift, float slope, const float* gamma, const double* sums,
                                float* dgamma, float* dbeta, tg_stream stream) {
   TG_REQUIRE(dy && x && dx && sums, "tg_bn_bwd_apply");
+  if (v4_ok(C, C, x, dy, dx) && M * C >= 4096 && mean && rstd && scale && shift &&
+      ((((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)gamma) & 15) == 0)) {
+    const long long n4 = M * C / 4;
+    bn_bwd_apply_v4_kernel<<<v4_blocks(n4), 256, 0, (cudaStream_t)stream>>>(dy, x, dx, n4, M, C, mean, rstd, scale, shift, slope, gamma, sums,
+                                                                            dgamma, dbeta);
+    TG_CHECK_LAUNCH("tg_bn_bwd_apply");
+    return 0;
+  }
   bn_bwd_apply_kernel<<<ew_blocks(M * C), 256, 0, (cudaStream_t)stream>>>(dy, x, dx, M, C, mean, rstd, scale, shift, slope, gamma, sums,
                                                                        dgamma, dbeta);
   TG_CHECK_LAUNCH("tg_bn_bwd_apply");

@@ -789,7 +789,7 @@ class DiscriminatorEngine:
             mks = [(gmasks[l] if (gmasks is not None and l < L - 1) else None) for l in range(L)]
             a0 = self.arena.offsets['gru.weight_ih_l0']
             ops.dgru_stack_fwd(x, self.arena.flat[a0:], mks, outs, saved, M * 2 * H, drops, self.P('out.weight'), self.P('out.bias'),
-                               self.P('out2.weight'), self.P('out2.bias'), hsum, o1, prob, B, T, cin, H, L)
+                               self.P('out2.weight'), self.P('out2.bias'), hsum, o1, prob, B, T, cin, H, L, fast=config.fast())
             self.gru._fwd_inputs = x
         else:
             out = self.gru.forward(x, B, T, gmasks, save)
@@ -809,7 +809,7 @@ class DiscriminatorEngine:
     def fused_stack(self, T, I0):
         """The fused recurrent-stack kernel handles the discriminator's configuration (H = 64, <= 4 layers, <= 32 frames) when the GRU
         parameters are packed in the arena in gru_arena_order, which ParamArena guarantees; TGB200_D_FUSED=0 keeps the per-layer plan."""
-        if not config.d_fused() or self.H != 64 or self.L > 4 or T > 32 or I0 > 64:
+        if not config.d_fused() or self.H != 64 or self.L > 4 or T > 32 or I0 > 32 or I0 % 4:
             return False
         names = []
         for l in range(self.L):

@@ -327,7 +327,8 @@ def _ptr_array(tensors, n):
     return arr
 
 
-def dgru_stack_fwd(x, gru_params, masks, outs, saved, saved_qstride, drops, w_out, b_out, w_out2, b_out2, hsum, o1, prob, B, T, I0, H, L):
+def dgru_stack_fwd(x, gru_params, masks, outs, saved, saved_qstride, drops, w_out, b_out, w_out2, b_out2, hsum, o1, prob, B, T, I0, H, L,
+                   fast=False):
     import ctypes
     a_m = _ptr_array(masks, 4) if masks is not None else None
     a_o = _ptr_array(outs, 4)
@@ -335,7 +336,7 @@ def dgru_stack_fwd(x, gru_params, masks, outs, saved, saved_qstride, drops, w_ou
     a_d = _ptr_array(drops, 4) if drops is not None else None
     addr = lambda a: None if a is None else ctypes.cast(a, ctypes.c_void_p)
     check(_L().tg_dgru_stack_fwd(_p(x), _p(gru_params), addr(a_m), addr(a_o), addr(a_s), saved_qstride, addr(a_d), _p(w_out), _p(b_out),
-                                 _p(w_out2), _p(b_out2), _p(hsum), _p(o1), _p(prob), B, T, I0, H, L, _s()), 'tg_dgru_stack_fwd'); _count()
+                                 _p(w_out2), _p(b_out2), _p(hsum), _p(o1), _p(prob), B, T, I0, H, L, 1 if fast else 0, _s()), 'tg_dgru_stack_fwd'); _count()
 
 
 def dgru_stack_bwd(dlogit, gru_params, masks, outs, saved, saved_qstride, hsum, o1, w_out, w_out2, dgi, dgh, dx0, g_w_out, g_b_out, g_w_out2,

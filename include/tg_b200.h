@@ -240,10 +240,11 @@ int tg_gru_tf32_sync_ints(int B, int H);
  * directions, Linear(64,1) per frame, Linear(T,1), sigmoid -> prob [B,1].  gru_params: the discriminator's GRU parameters as the flat
  * arena stores them (per layer: weight_ih | weight_ih_reverse | bias_ih | bias_ih_reverse | weight_hh | weight_hh_reverse | bias_hh |
  * bias_hh_reverse).  outs[l] / saved[l] (4 planes r,z,n,W_hn h + b_hn; plane stride saved_qstride) / drops[l] (masked outputs, l < L-1) /
- * hsum [B*T,64] / o1 [B*T] are what the per-layer backward kernels read.  H == 64, L <= 4, T <= 32, I0 <= 64. */
+ * hsum [B*T,64] / o1 [B*T] are what the per-layer backward kernels read.  H == 64, L <= 4, T <= 32, I0 <= 32, I0 % 4 == 0; x, gru_params
+ * and the masks 16-byte aligned.  fast != 0 (the tensor-core arithmetic mode): sigmoid / tanh through ex2.approx / rcp.approx. */
 int tg_dgru_stack_fwd(const float* x, const float* gru_params, const float* const* masks, float* const* outs, float* const* saved,
                       long long saved_qstride, float* const* drops, const float* w_out, const float* b_out, const float* w_out2,
-                      const float* b_out2, float* hsum, float* o1, float* prob, int B, int T, int I0, int H, int L, tg_stream stream);
+                      const float* b_out2, float* hsum, float* o1, float* prob, int B, int T, int I0, int H, int L, int fast, tg_stream stream);
 
 /* Backward of tg_dgru_stack_fwd in one launch: heads -> L x [recurrence backward + data gradient through W_ih (+ dropout mask of the layer
  * below)].  dlogit [B] = d loss / d (pre-sigmoid output).  Writes dgi[l] / dgh[l] [B*T,6H] for the recurrent layers' weight-gradient

@@ -432,7 +432,7 @@ class EmuLib:
         return 0
 
     def tg_dgru_stack_fwd(self, x, params, masks, outs, saved, qstride, drops, w_out, b_out, w_out2, b_out2, hsum, o1, prob, B, T, I0, H, L,
-                          stream):
+                          fast, stream):
         """csrc/dgru_stack.cu by its documented semantics: L x [gi = W_ih x + b_ih; recurrence; dropout mask] + sum of the directions +
         Linear(64,1) per frame + Linear(T,1) + sigmoid, parameters read from the flat-arena block."""
         self.calls.append('tg_dgru_stack_fwd')

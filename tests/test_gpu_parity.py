@@ -90,14 +90,18 @@ def test_standalone_encoders_vs_reference_golden(dev, mode):
         config.set_mode(old)
 
 
-def test_discriminator_fused_stack_matches_per_layer_plan(dev):
-    """csrc/dgru_stack.cu (4-layer bidirectional GRU + heads in one launch, forward and backward) against the per-layer plan it replaces:
-    same probabilities, same parameter gradients, same gradient w.r.t. the poses - with dropout masks, B = 128."""
+@pytest.mark.parametrize('B', [128, 21, 5])
+def test_discriminator_fused_stack_matches_per_layer_plan(dev, B):
+    """csrc/dgru_stack.cu (4-layer bidirectional GRU + heads in one launch, forward and backward) and csrc/dconv_stack.cu (the three
+    convolutions + two train-mode BatchNorms in one 8-CTA-cluster launch) against the per-layer plan they replace: same probabilities,
+    same parameter gradients, same gradient w.r.t. the poses - with dropout masks; B = 128 (every CTA of the cluster full), 21 (a ragged
+    second CTA, six idle ones), 5 (odd clip count: the unaligned tail of the asynchronous copies)."""
     from tgb200 import config, ops
     cfg = golden_cfg()
-    B = 128
     torch.manual_seed(3)
-    poses = (0.3 * torch.randn(B, cfg.n_poses, cfg.pose_dim)).to(dev)
+    # B = 5: the poses are a VIEW that starts 8 bytes off a 16-byte boundary (what D(fake) gets: clips [B, 2B) of the generator's 3B sweep)
+    poses = (0.3 * torch.randn(B + 1, cfg.n_poses, cfg.pose_dim)).to(dev)[1:] if B == 5 else (0.3 * torch.randn(B, cfg.n_poses, cfg.pose_dim)).to(dev)
+    assert B != 5 or poses.data_ptr() % 16 != 0
     dlogit = (0.1 * torch.randn(B, 1)).to(dev)
     res = {}
     for fused in (False, True):
@@ -118,15 +122,19 @@ def test_discriminator_fused_stack_matches_per_layer_plan(dev):
         finally:
             config.set_d_fused(old)
     (p0, dp0, g0, offs), (p1, dp1, g1, _) = res[False], res[True]
-    assert rel_l2(p1, p0) < 1e-5, rel_l2(p1, p0)
-    assert rel_l2(dp1, dp0) < 1e-4, rel_l2(dp1, dp0)
+    # fast mode: the fused kernel evaluates sigmoid / tanh with ex2.approx / rcp.approx (as the generator's recurrence does), the per-layer
+    # kernels with expf / tanhf - the difference is far inside the mode's 1e-2
+    fast = config.fast()
+    assert rel_l2(p1, p0) < (2e-4 if fast else 1e-5), rel_l2(p1, p0)
+    assert rel_l2(dp1, dp0) < (2e-3 if fast else 1e-4), rel_l2(dp1, dp0)
     names = sorted(offs, key=lambda n: offs[n])
     for i, n in enumerate(names):
         lo, hi = offs[n], (offs[names[i + 1]] if i + 1 < len(names) else g0.numel())
         a, b_ = g1[lo:hi], g0[lo:hi]
-        if b_.abs().max() < 1e-9:
+        if b_.abs().max() < 1e-9 or n in ('pre_conv.0.bias', 'pre_conv.3.bias', 'pre_conv.1.bias'):
+            assert a.abs().max() < 1e-5, (n, a.abs().max())          # analytically zero (a bias in front of a train-mode BatchNorm): round-off only
             continue
-        tol = 2e-2 if config.fast() and n.startswith('gru.') else 1e-3      # tf32 weight-gradient GEMMs see the same operands: round-off only
+        tol = 2e-2 if fast and n.startswith('gru.') else (5e-3 if fast else 1e-3)   # tf32 weight-gradient GEMMs see the same operands: round-off only
         assert rel_l2(a, b_) < tol, (n, rel_l2(a, b_))
 
 
@@ -192,12 +200,12 @@ def _oracle_step(cfg, epoch, gsd, dsd, inp, noise, dev):
                                    i64['in_text'], i64['in_audio'], i64['target'], i64['vid'], n64)
 
 
-@pytest.mark.parametrize('B,epoch', [(128, 11), (16, 0)])
-def test_train_iter_full_size_vs_oracle(dev, B, epoch):
+@pytest.mark.parametrize('B,epoch,n_words,n_speakers', [(128, 11, 2000, 50), (16, 0, 2000, 50), (128, 11, 20000, 1370)])
+def test_train_iter_full_size_vs_oracle(dev, B, epoch, n_words, n_speakers):
     """BASELINE.json configs[1]: batch 128, every dropout mask injected (incl. GRU inter-layer masks, which the
-    reference itself cannot take - hence the oracle)."""
+    reference itself cannot take - hence the oracle).  Third case: bench.py's vocabulary (20 000 words, 1 370 speakers)."""
     from train_eval import train_gan as TG
-    cfg = O.HotPathConfig(n_words=2000, n_speakers=50)
+    cfg = O.HotPathConfig(n_words=n_words, n_speakers=n_speakers)
     args, G, D, gsd, dsd = build_ours(cfg, dev)
     G.train(); D.train()
     inp = to_dev(synth.make_inputs(cfg, B, seed=3), dev)
@@ -337,12 +345,18 @@ def test_fast_mode_forward_eval_vs_reference_golden(dev):
     assert rel_l2(d_fake, g['d_fake']) < TOL_FAST
 
 
-@pytest.mark.parametrize('B,epoch', [(128, 11), (16, 0)])
-def test_fast_mode_train_iter_full_size_vs_oracle(dev, B, epoch):
+@pytest.mark.parametrize('B,epoch,n_words,n_speakers', [(128, 11, 2000, 50), (16, 0, 2000, 50), (128, 11, 20000, 1370)])
+def test_fast_mode_train_iter_full_size_vs_oracle(dev, B, epoch, n_words, n_speakers):
+    """Tensor-core mode at BASELINE's batch 128 against the fp64 oracle; the third case is bench.py's vocabulary (20 000 words / 1 370
+    speakers: the embedding table and its sparse gradient at full size).  Tolerance 1e-2 (north_star's fast-mode figure) on the poses,
+    on every logged loss and on the generator's GRADIENT AS A WHOLE; per tensor the bound is 5e-2: TF32 operands (10-bit mantissa) leave
+    ~1e-3 per product, and tensors whose gradient is a cancelling sum over ~1e6 terms (BatchNorm beta / gamma of the WavEncoder) amplify
+    that - the operand-rounding model (tests/cabi_emulator.py tf32_round) predicts 2.1e-2 for them even with every
+    operand rounded to nearest."""
     from tgb200 import config
     from train_eval import train_gan as TG
     config.set_mode('tf32')
-    cfg = O.HotPathConfig(n_words=2000, n_speakers=50)
+    cfg = O.HotPathConfig(n_words=n_words, n_speakers=n_speakers)
     args, G, D, gsd, dsd = build_ours(cfg, dev)
     G.train(); D.train()
     inp = to_dev(synth.make_inputs(cfg, B, seed=3), dev)
@@ -363,12 +377,21 @@ def test_fast_mode_train_iter_full_size_vs_oracle(dev, B, epoch):
     e = rel_l2(out, ref['out'])
     assert e < TOL_FAST, e
     worst = ('', 0.0)
+    num = den = 0.0
+    over = []
     for k, p in G.named_parameters():
         r = ref['g_grads'][k]
+        num += float((p.grad.double() - r.double().to(p.grad.device)).pow(2).sum()); den += float(r.double().pow(2).sum())
         if r.norm() < 1e-6:
             continue
-        worst = max(worst, (k, rel_l2(p.grad, r)), key=lambda t: t[1])
-    print('fast-mode pose rel-L2 %.2e, worst gradient rel-L2 %s %.2e' % (e, worst[0], worst[1]))
+        ek = rel_l2(p.grad, r)
+        if ek >= TOL_FAST:
+            over.append((k, float('%.2e' % ek)))
+        worst = max(worst, (k, ek), key=lambda t: t[1])
+    whole = (num / den) ** 0.5
+    print('fast-mode pose rel-L2 %.2e, whole generator gradient rel-L2 %.2e, worst gradient rel-L2 %s %.2e, tensors over 1e-2: %s'
+          % (e, whole, worst[0], worst[1], over))
+    assert whole < TOL_FAST, whole
     assert worst[1] < 5e-2, worst
 
 
