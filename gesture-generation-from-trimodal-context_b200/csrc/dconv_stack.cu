@@ -64,6 +64,14 @@ __device__ __forceinline__ void load_filter(float* ws, const float* w) {
     ws[i] = __ldg(w + (n * CIN + ci) * KW + j);
   }
 }
+// nn.Conv1d filter [N][CIN][3] -> [3][N][CIN] (tap-major, INPUT channel fastest): the data gradient's threads differ in the input channel
+template <int CIN, int N>
+__device__ __forceinline__ void load_filter_dg(float* wd, const float* w) {
+  for (int i = threadIdx.x; i < KW * CIN * N; i += NT) {
+    const int j = i / (CIN * N), r = i - j * CIN * N, n = r / CIN, ci = r - n * CIN;
+    wd[i] = __ldg(w + (n * CIN + ci) * KW + j);
+  }
+}
 // sum of `mine[0..n)` over the 8 CTAs of the cluster, in rank order, into tot[0..n) (every CTA gets the same bits).  `mine` must not be
 // written again by its owner (a peer may read it at any time up to the kernel's final cluster barrier).
 __device__ __forceinline__ void cluster_allreduce(const double* mine, double* tot, int n) {
@@ -289,7 +297,8 @@ __device__ __forceinline__ void conv_wgrad_part(const float* dys, const float* s
     if (lane == 0) atomicAdd(db + warp, a);
   }
 }
-// da[c][u][ci] = sum_{n, j} dy[c][u - j][n] * W[n][ci][j]   (ws: [3][CIN][COUT] tap-major copy of W)
+// da[c][u][ci] = sum_{n, j} dy[c][u - j][n] * W[n][ci][j]   (ws: [3][COUT][CIN] copy of W - consecutive threads = consecutive input
+// channels read consecutive words; the first version read [3][CIN][COUT] at a 64-byte stride: 16-way bank conflicts, 70 % of the kernel)
 template <int CIN, int COUT, int TIN>
 __device__ __forceinline__ void conv_dgrad_part(const float* dys, const float* ws, int nclip, float* das) {
   constexpr int TOUT = TIN - 2;
@@ -300,19 +309,19 @@ __device__ __forceinline__ void conv_dgrad_part(const float* dys, const float* w
       const int t = u;
       if (t < TOUT) { const float* dr = dys + (c * TOUT + t) * COUT;
 #pragma unroll
-        for (int n = 0; n < COUT; ++n) a0 = fmaf(dr[n], ws[(0 * CIN + ci) * COUT + n], a0); }
+        for (int n = 0; n < COUT; ++n) a0 = fmaf(dr[n], ws[(0 * COUT + n) * CIN + ci], a0); }
     }
     {
       const int t = u - 1;
       if (t >= 0 && t < TOUT) { const float* dr = dys + (c * TOUT + t) * COUT;
 #pragma unroll
-        for (int n = 0; n < COUT; ++n) a1 = fmaf(dr[n], ws[(1 * CIN + ci) * COUT + n], a1); }
+        for (int n = 0; n < COUT; ++n) a1 = fmaf(dr[n], ws[(1 * COUT + n) * CIN + ci], a1); }
     }
     {
       const int t = u - 2;
       if (t >= 0) { const float* dr = dys + (c * TOUT + t) * COUT;
 #pragma unroll
-        for (int n = 0; n < COUT; ++n) a2 = fmaf(dr[n], ws[(2 * CIN + ci) * COUT + n], a2); }
+        for (int n = 0; n < COUT; ++n) a2 = fmaf(dr[n], ws[(2 * COUT + n) * CIN + ci], a2); }
     }
     das[i] = a0 + a1 + a2;
   }
@@ -350,7 +359,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_
   float* d2s = y1s + CPB * T2 * C2;                  // [CPB][28][8]    dy2
   float* d1s = d2s + CPB * T3 * C3;                  // [CPB][30][8]    d a1 -> d y1
   float* d0s = d1s + CPB * T2 * C2;                  // [CPB][32][16]   d a0 -> d y0
-  float* w1s = d0s + CPB * T1 * C1;                  // [3][27][16]
+  float* w1s = d0s + CPB * T1 * C1;                  // [3][16][27]  (data-gradient layout: input channel fastest)
   float* w2s = w1s + KW * C0 * C1;                   // [3][16][8]
   float* w3s = w2s + KW * C1 * C2;                   // [3][8][8]
   float* st1 = w3s + KW * C2 * C3;                   // 64 floats
@@ -370,9 +379,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) dconv_stack_
   stage_flat(y0s, p.y0 + (long long)c_lo * T1 * C1, nclip * T1 * C1);
   stage_flat(y1s, p.y1 + (long long)c_lo * T2 * C2, nclip * T2 * C2);
   stage_flat(d2s, p.dy2 + (long long)c_lo * T3 * C3, nclip * T3 * C3);
-  load_filter<C0, C1>(w1s, p.w1);
-  load_filter<C1, C2>(w2s, p.w2);
-  load_filter<C2, C3>(w3s, p.w3);
+  load_filter_dg<C0, C1>(w1s, p.w1);
+  load_filter_dg<C1, C2>(w2s, p.w2);
+  load_filter_dg<C2, C3>(w3s, p.w3);
   if (tid < 64) st1[tid] = __ldg(p.st1 + tid);
   if (tid < 32) st2[tid] = __ldg(p.st2 + tid);
   cp_async_wait_all();

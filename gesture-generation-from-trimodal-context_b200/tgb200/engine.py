@@ -838,7 +838,7 @@ class DiscriminatorEngine:
             a0 = self.arena.offsets['gru.weight_ih_l0']
             ops.dgru_stack_bwd(dlogit, self.arena.flat[a0:], mks, outs, saved, M * 2 * H, ws['d.hsum'], ws['d.o1'], self.P('out.weight'),
                                self.P('out2.weight'), dgi, dgh, dy, self.G('out.weight'), self.G('out.bias'), self.G('out2.weight'),
-                               self.G('out2.bias'), B, T, 8, H, L)
+                               self.G('out2.bias'), B, T, 8, H, L, fast=config.fast())
             for l in range(L - 1, -1, -1):
                 if l == 0:
                     inp = ws['d.y2']

@@ -340,14 +340,14 @@ def dgru_stack_fwd(x, gru_params, masks, outs, saved, saved_qstride, drops, w_ou
 
 
 def dgru_stack_bwd(dlogit, gru_params, masks, outs, saved, saved_qstride, hsum, o1, w_out, w_out2, dgi, dgh, dx0, g_w_out, g_b_out, g_w_out2,
-                   g_b_out2, B, T, I0, H, L):
+                   g_b_out2, B, T, I0, H, L, fast=False):
     import ctypes
     addr = lambda a: None if a is None else ctypes.cast(a, ctypes.c_void_p)
     a_m = _ptr_array(masks, 4) if masks is not None else None
     a_o, a_s, a_gi, a_gh = _ptr_array(outs, 4), _ptr_array(saved, 4), _ptr_array(dgi, 4), _ptr_array(dgh, 4)
     check(_L().tg_dgru_stack_bwd(_p(dlogit), _p(gru_params), addr(a_m), addr(a_o), addr(a_s), saved_qstride, _p(hsum), _p(o1), _p(w_out),
                                  _p(w_out2), addr(a_gi), addr(a_gh), _p(dx0), _p(g_w_out), _p(g_b_out), _p(g_w_out2), _p(g_b_out2),
-                                 B, T, I0, H, L, _s()), 'tg_dgru_stack_bwd'); _count()
+                                 B, T, I0, H, L, 1 if fast else 0, _s()), 'tg_dgru_stack_bwd'); _count()
 
 
 def dconv_stack_fwd(x, w1, b1, g1, be1, rm1, rv1, nbt1, w2, b2, g2, be2, rm2, rv2, nbt2, w3, b3, y0, y1, y2, st1, st2, B, T, D, training, eps,

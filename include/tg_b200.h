@@ -249,11 +249,12 @@ int tg_dgru_stack_fwd(const float* x, const float* gru_params, const float* cons
 /* Backward of tg_dgru_stack_fwd in one launch: heads -> L x [recurrence backward + data gradient through W_ih (+ dropout mask of the layer
  * below)].  dlogit [B] = d loss / d (pre-sigmoid output).  Writes dgi[l] / dgh[l] [B*T,6H] for the recurrent layers' weight-gradient
  * GEMMs (which stay separate launches), dx0 [B*T,I0] (optional) = gradient w.r.t. the stack input, and ACCUMULATES the four head
- * gradients (out.weight [64], out.bias [1], out2.weight [T], out2.bias [1]) with atomics. */
+ * gradients (out.weight [64], out.bias [1], out2.weight [T], out2.bias [1]) with atomics.  fast != 0: the per-clip GEMMs (data gradient
+ * through W_ih) run on warp-level TF32 tensor-core tiles (mma.sync m16n8k8), as the forward's input projections do. */
 int tg_dgru_stack_bwd(const float* dlogit, const float* gru_params, const float* const* masks, const float* const* outs,
                       const float* const* saved, long long saved_qstride, const float* hsum, const float* o1, const float* w_out,
                       const float* w_out2, float* const* dgi, float* const* dgh, float* dx0, float* g_w_out, float* g_b_out,
-                      float* g_w_out2, float* g_b_out2, int B, int T, int I0, int H, int L, tg_stream stream);
+                      float* g_w_out2, float* g_b_out2, int B, int T, int I0, int H, int L, int fast, tg_stream stream);
 
 /* ConvDiscriminator convolution stack in one launch (multimodal_context_net.py:212-220,233-236): Conv1d(27,16,3) -> BatchNorm1d(16) ->
  * identity -> Conv1d(16,8,3) -> BatchNorm1d(8) -> identity -> Conv1d(8,8,3) on channels-last poses x [B,34,27] (B <= 128, one 8-CTA cluster,

@@ -511,7 +511,7 @@ class EmuLib:
         return 0
 
     def tg_dgru_stack_bwd(self, dlogit, params, masks, outs, saved, qstride, hsum, o1, w_out, w_out2, dgi, dgh, dx0, g_w_out, g_b_out, g_w_out2,
-                          g_b_out2, B, T, I0, H, L, stream):
+                          g_b_out2, B, T, I0, H, L, fast, stream):
         """csrc/dgru_stack.cu (backward) by its documented semantics."""
         self.calls.append('tg_dgru_stack_bwd')
         assert H == 64 and 1 <= L <= 4 and 1 <= T <= 32 and 4 <= I0 <= 64, 'TG_REQUIRE of tg_dgru_stack_bwd'

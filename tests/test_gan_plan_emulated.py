@@ -36,7 +36,7 @@ def test_forward_eval_plan_vs_reference_golden(emu_fp32):
 
 def test_train_iter_gan_all_dropout_masks_vs_fp64_oracle(emu_fp32):
     """Every dropout mask injected, incl. the GRU inter-layer masks the reference cannot take (hence the fp64 oracle); small batch."""
-    GP.test_train_iter_full_size_vs_oracle(CPU, 4, 11)
+    GP.test_train_iter_full_size_vs_oracle(CPU, 4, 11, 2000, 50)
 
 
 def test_module_api_autograd_plan(emu_fp32):
@@ -68,7 +68,7 @@ def test_fast_mode_plans(emu_fast):
     """The DEFAULT (tf32) mode routes the large GEMMs, weight gradients, the generator GRU and WavEncoder conv2-4 through the
     tensor-core entries (window views, two-tap causal GEMM, col2im, MN-major weight gradients): same goldens / oracle, other plan."""
     GP.test_fast_mode_forward_eval_vs_reference_golden(CPU)
-    GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11)
+    GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11, 2000, 50)
     for sym in ('tg_gemm_tf32', 'tg_wgrad_tf32', 'tg_gru_layer_fwd_tf32', 'tg_gru_layer_bwd_tf32', 'tg_col2im', 'tg_conv1_wgrad'):
         assert sym in emu_fast.calls, sym
 
@@ -77,7 +77,7 @@ def test_fast_mode_plans(emu_fast):
 def test_small_and_odd_batches(emu_fast, B):
     """Edge cases of the launch plan: a single clip (every 'batch' statistic is over one clip's frames) and a batch that is not a multiple
     of any tile size, full G+D iteration with every dropout mask vs the fp64 oracle."""
-    GP.test_train_iter_full_size_vs_oracle(CPU, B, 11)
+    GP.test_train_iter_full_size_vs_oracle(CPU, B, 11, 2000, 50)
 
 
 def test_fast_mode_error_budget_under_tf32_operand_truncation():
@@ -88,7 +88,7 @@ def test_fast_mode_error_budget_under_tf32_operand_truncation():
     old_mode, old_graphs = config.set_mode('tf32'), config.set_graphs(False)
     try:
         with cabi_emulator.installed(tf32_round='trunc'):
-            GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 8, 11)       # asserts losses / poses <= 1e-2, worst gradient <= 5e-2
+            GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 8, 11, 2000, 50)       # asserts losses / poses <= 1e-2, worst gradient <= 5e-2
     finally:
         config.set_mode(old_mode); config.set_graphs(old_graphs)
 
