@@ -10,6 +10,7 @@
 // tap accumulates in a second TMEM accumulator and is masked per row in the epilogue (t + shift outside the clip),
 // so the shifted operand is a plain 2-D TMA load with a row offset - no im2col, no padded copy, no chomp.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -317,6 +318,11 @@ extern "C" int tg_debug_gemm_trace(long long* device_buf) {
   g_trace = device_buf;
   return 0;
 }
+long long* tg_gemm_trace_ptr() { return g_trace; }
+
+// gemm_tcn.cu: the two-tap case as a one-accumulator clip-group kernel
+bool tg_gemm_tcn_applies(const tg_gemm_tf32_t& g);
+int tg_gemm_tcn_launch(const tg_gemm_tf32_t& g, cudaStream_t s);
 
 extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   const tg_gemm_tf32_t& g = *gp;
@@ -326,6 +332,8 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   TG_REQUIRE(g.act1 >= 0 && g.act1 <= 2 && (g.act1 != 2 || (g.slope1 >= 0.f && g.slope1 <= 1.f)) && (g.act2 == 0 || g.act2 == 1), "tg_gemm_tf32(activation)");
   TG_REQUIRE(g.clip_rows == 0 || (g.clip_rows > 0 && g.taps == 1 && g.M % g.clip_rows == 0 && g.a_clip_pitch > 0), "tg_gemm_tf32(clip mode)");
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool tcn_old = getenv("TGB200_TCN_TWO_ACC") != nullptr;      // A/B switch: keep the two-accumulator tiles for taps == 2
+  if (!tcn_old && tg_gemm_tcn_applies(g)) return tg_gemm_tcn_launch(g, s);
   // tile width: minimise padded N, prefer wider tiles on ties (fewer A re-reads)
   int bn;
   if (g.N <= 32) bn = 32;

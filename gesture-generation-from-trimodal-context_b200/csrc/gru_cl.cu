@@ -212,6 +212,7 @@ __host__ __device__ inline size_t bwd_bar_off(const KLay& L, int u, int BT) {
 // =====================================================================================================================
 struct FwdP {
   const float* gi; const float* whh0; const float* whh1; const float* bhh0; const float* bhh1; float* out; float* saved; long long saved_qstride;
+  const float* mask; float* drop;      // optional: drop = out * mask (the inter-layer dropout, stored beside `out`; was a separate 19 us pass)
   float* xchg;
   int B, T, H, u, flags;      // flags bit 0: every CTA loads the whole tile itself (unicast) instead of the 8-way multicast
   KLay L;
@@ -337,6 +338,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
       const float* gip = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + unit0;
       gi_r = ldv_nc4(gip); gi_z = ldv_nc4(gip + H); gi_n = ldv_nc4(gip + 2 * H);
     }
+    float4 mk4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (live && p.mask) mk4 = ldv_nc4(p.mask + ((long long)b * T + t) * row2H + dir * H + unit0);
     if (s > 0) {
       if (warp == 1) {
         if constexpr (HC == 300) {
@@ -422,6 +425,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FwdCfg<BT>::NT, 1) 
     if (live) {                  // stores for the next layer / the backward pass: between arrive and wait, off the step chain
       const long long o = ((long long)b * T + t) * row2H + dir * H + unit0;
       *reinterpret_cast<float4*>(p.out + o) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
+      if (p.drop) *reinterpret_cast<float4*>(p.drop + o) = make_float4(hreg[0] * mk4.x, hreg[1] * mk4.y, hreg[2] * mk4.z, hreg[3] * mk4.w);
       if (p.saved) {
         *reinterpret_cast<float4*>(p.saved + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
         *reinterpret_cast<float4*>(p.saved + p.saved_qstride + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
@@ -1112,7 +1116,7 @@ size_t tg_gru_cl_xchg_floats(int B, int H) {
 }
 
 int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r, float* out, float* saved,
-                  long long saved_qstride, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s) {
+                  long long saved_qstride, const float* mask, float* drop, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s) {
   TgGruClPlan pl;
   if (!tg_gru_cl_plan(B, H, &pl)) { tg_set_error("tg_gru_layer_fwd_tf32: no cluster plan for B=%d H=%d", B, H); return -1; }
   if (reinterpret_cast<uintptr_t>(xchg) & 127) { tg_set_error("tg_gru_layer_fwd_tf32: exchange scratch must be 128-byte aligned"); return -1; }
@@ -1120,6 +1124,8 @@ int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const
   FwdP p;
   p.L = klay(H);
   p.gi = gi; p.whh0 = whh_f; p.whh1 = whh_r; p.bhh0 = bhh_f; p.bhh1 = bhh_r; p.out = out; p.saved = saved; p.saved_qstride = saved_qstride; p.xchg = xchg;
+  p.mask = (mask && drop) ? mask : nullptr; p.drop = (mask && drop) ? drop : nullptr;
+  if ((reinterpret_cast<uintptr_t>(p.mask) | reinterpret_cast<uintptr_t>(p.drop)) & 15) { tg_set_error("tg_gru_layer_fwd_tf32: mask / drop must be 16-byte aligned"); return -1; }
   p.B = B; p.T = T; p.H = H; p.u = pl.u; p.flags = cl_flags();
   p.trace = trace;
   if (pl.bt_f == 16) return launch_fwd<16>(p, pl.ntiles_f, s);

@@ -625,7 +625,7 @@ struct TgGruClPlan { int u, bt_f, bt_b, ntiles_f, ntiles_b; };
 bool tg_gru_cl_plan(int B, int H, TgGruClPlan* pl);
 size_t tg_gru_cl_xchg_floats(int B, int H);
 int tg_gru_cl_fwd(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r, float* out, float* saved,
-                  long long saved_qstride, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s);
+                  long long saved_qstride, const float* mask, float* drop, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s);
 int tg_gru_cl_bwd(const float* dout, const float* out, const float* saved, long long saved_qstride, const float* whhT_f, const float* whhT_r,
                   float* dgi, float* dgh, float* xchg, int B, int T, int H, long long* trace, cudaStream_t s);
 
@@ -643,13 +643,28 @@ extern "C" int tg_gru_tf32_sync_ints(int B, int H) {
   return (int)(legacy > xchg ? legacy : xchg);
 }
 
+extern "C" int tg_gru_layer_fwd_tf32_drop(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
+                                          float* out, float* saved, long long saved_qstride, const float* mask, float* drop, int* sync, int B,
+                                          int T, int H, tg_stream stream) {
+  TG_REQUIRE(mask && drop, "tg_gru_layer_fwd_tf32_drop");
+  TgGruClPlan cpl;
+  if (!use_legacy_gru() && tg_gru_cl_plan(B, H, &cpl)) {
+    TG_REQUIRE(gi && whh_f && whh_r && bhh_f && bhh_r && out && sync && T > 0 && B > 0, "tg_gru_layer_fwd_tf32_drop");
+    return tg_gru_cl_fwd(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, mask, drop, reinterpret_cast<float*>(sync), B, T, H, g_trace,
+                         (cudaStream_t)stream);
+  }
+  const int rc = tg_gru_layer_fwd_tf32(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, sync, B, T, H, stream);
+  return rc ? rc : tg_mul(out, mask, drop, (long long)B * T * 2 * H, stream);
+}
+
 extern "C" int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
                                      float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream) {
   TG_REQUIRE(gi && whh_f && whh_r && bhh_f && bhh_r && out && sync && T > 0 && B > 0, "tg_gru_layer_fwd_tf32");
   cudaStream_t s = (cudaStream_t)stream;
   TgGruClPlan cpl;
   if (!use_legacy_gru() && tg_gru_cl_plan(B, H, &cpl))
-    return tg_gru_cl_fwd(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, reinterpret_cast<float*>(sync), B, T, H, g_trace, s);
+    return tg_gru_cl_fwd(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, nullptr, nullptr, reinterpret_cast<float*>(sync), B, T, H,
+                         g_trace, s);
   FwdPlan pl;
   TG_REQUIRE(fwd_plan(B, H, &pl) == 0, "tg_gru_layer_fwd_tf32");
   cudaError_t e = cudaMemsetAsync(sync, 0, sizeof(int) * 2 * pl.NB, s);

@@ -53,6 +53,8 @@ class _Overlap:
     def join(self, i):
         if not self.enabled():
             return
+        if i == S_WGRAD:
+            self.join(S_BIAS)             # the bias-gradient column sums forked off the weight-gradient stream
         cur = torch.cuda.current_stream()
         key = (cur.device.index, i)
         if key not in self._active or self._streams[key] == cur:
@@ -64,7 +66,7 @@ class _Overlap:
 
 
 side = _Overlap()
-S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK = 1, 2, 3, 4, 5
+S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS = 1, 2, 3, 4, 5, 6
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -120,7 +122,12 @@ def wgrad(X, G, dW, *, B, T, N, Cin, shift=0, ldx=None, ldg=None, ldw=None, dbia
     ldg = N if ldg is None else ldg
     if (config.fast() and Cin >= 8 and Cin % 4 == 0 and N >= 16 and ldx % 4 == 0 and ldg % 4 == 0 and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0
             and (shift == 0 or T <= 40)):
-        ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=ldx, ldw=ldw, dbias=dbias)
+        if dbias is not None:
+            # ~3 us column-sum launches: on their own stream they run beside the weight-gradient GEMMs instead of between them (60 per
+            # iteration; they owned 89 us of the step when serialised on the weight-gradient stream, profiles/r02_timeline_step_ownership.txt)
+            with side.on(S_BIAS):
+                ops.col_sum(G, ldg, B * T, N, dbias)
+        ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=ldx, ldw=ldw, dbias=None)
     else:
         ops.conv_wgrad(X, G, dW, B=B, Tin=T, Tout=T, N=N, Cin=Cin, taps=1, pad=-shift, lda=ldx, ldg=ldg, ldw=Cin if ldw is None else ldw,
                        dbias=dbias)
@@ -188,15 +195,21 @@ class GruPlan:
             mm_nt(inp, self._w('weight_ih', l), gi, M=M, N=6 * H, K=K, bias=self._w('bias_ih', l))
             out = ws.get(f'{tag}.out{l}', (M, 2 * H))
             saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
-            if tc:
+            mk = masks[l] if (masks is not None and l < self.L - 1) else None
+            drop = ws.get(f'{tag}.drop{l}', (M, 2 * H)) if mk is not None else None
+            if tc and mk is not None:
+                # the inter-layer dropout rides on the recurrence kernel's output store (was a separate 94 MB elementwise pass per layer)
+                ops.gru_layer_fwd_tf32_drop(gi, self._w('weight_hh', l), self._w('weight_hh', l, True), self._w('bias_hh', l),
+                                            self._w('bias_hh', l, True), out, saved, M * 2 * H, mk, drop, sync, B, T, H)
+            elif tc:
                 ops.gru_layer_fwd_tf32(gi, self._w('weight_hh', l), self._w('weight_hh', l, True), self._w('bias_hh', l),
                                        self._w('bias_hh', l, True), out, saved, M * 2 * H, sync, B, T, H)
             else:
                 ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
                                   out, saved, M * 2 * H, sync, B, T, H)
-            if masks is not None and l < self.L - 1 and masks[l] is not None:
-                drop = ws.get(f'{tag}.drop{l}', (M, 2 * H))
-                ops.mul(out, masks[l], drop, M * 2 * H)
+            if mk is not None:
+                if not tc:
+                    ops.mul(out, mk, drop, M * 2 * H)
                 inp = drop
             else:
                 inp = out

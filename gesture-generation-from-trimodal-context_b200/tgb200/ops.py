@@ -312,6 +312,17 @@ def gru_layer_fwd_tf32(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride
                                      B, T, H, _s()), 'tg_gru_layer_fwd_tf32'); _count(2)
 
 
+def col_sum(g, ld, M, N, out):
+    """out[n] += sum_m g[m*ld + n]"""
+    check(_L().tg_col_sum_f32(_p(g), ld, M, N, _p(out), _s()), 'tg_col_sum_f32'); _count()
+
+
+def gru_layer_fwd_tf32_drop(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, saved_qstride, mask, drop, sync, B, T, H):
+    """tg_gru_layer_fwd_tf32 + drop = out * mask written by the recurrence kernel itself"""
+    check(_L().tg_gru_layer_fwd_tf32_drop(_p(gi), _p(whh_f), _p(whh_r), _p(bhh_f), _p(bhh_r), _p(out), _p(saved), saved_qstride, _p(mask),
+                                          _p(drop), _p(sync), B, T, H, _s()), 'tg_gru_layer_fwd_tf32_drop'); _count(2)
+
+
 def gru_layer_bwd_tf32(dout, out, saved, saved_qstride, whhT_f, whhT_r, dgi, dgh, partial, sync, B, T, H):
     check(_L().tg_gru_layer_bwd_tf32(_p(dout), _p(out), _p(saved), saved_qstride, _p(whhT_f), _p(whhT_r), _p(dgi), _p(dgh), _p(partial),
                                      _p(sync), B, T, H, _s()), 'tg_gru_layer_bwd_tf32'); _count(2)

@@ -323,6 +323,11 @@ int tg_debug_gemm_trace(long long* device_buf);
 size_t tg_gru_bwd_tf32_scratch_floats(int B, int H);
 int tg_gru_layer_fwd_tf32(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
                           float* out, float* saved, long long saved_qstride, int* sync, int B, int T, int H, tg_stream stream);
+/* tg_gru_layer_fwd_tf32 + the inter-layer dropout of nn.GRU(dropout=p) (multimodal_context_net.py:98-99): drop [B*T,2H] = out * mask, stored
+ * by the recurrence kernel beside `out` (mask: already scaled keep-mask [B*T,2H]; both 16-byte aligned) */
+int tg_gru_layer_fwd_tf32_drop(const float* gi, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
+                               float* out, float* saved, long long saved_qstride, const float* mask, float* drop, int* sync, int B, int T,
+                               int H, tg_stream stream);
 int tg_gru_layer_bwd_tf32(const float* dout, const float* out, const float* saved, long long saved_qstride,
                           const float* whhT_f, const float* whhT_r, float* dgi, float* dgh, float* partial, int* sync,
                           int B, int T, int H, tg_stream stream);

@@ -958,6 +958,15 @@ class EmuLib:
         self.calls[-1] = 'tg_gru_layer_fwd_tf32'
         return rc
 
+    def tg_gru_layer_fwd_tf32_drop(self, gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, qstride, mask, drop, sync, B, T, H, stream):
+        """tg_gru_layer_fwd_tf32 + drop = out * mask"""
+        assert mask and drop and mask % 16 == 0 and drop % 16 == 0, 'tg_gru_layer_fwd_tf32_drop: mask / drop'
+        rc = self.tg_gru_layer_fwd_tf32(gi, whh_f, whh_r, bhh_f, bhh_r, out, saved, qstride, sync, B, T, H, stream)
+        self.calls[-1] = 'tg_gru_layer_fwd_tf32_drop'
+        n = B * T * 2 * H
+        _arr(drop, n)[:] = _arr(out, n) * _arr(mask, n)
+        return rc
+
     def tg_gru_layer_bwd_tf32(self, dout, out, saved, qstride, whhT_f, whhT_r, dgi, dgh, partial, sync, B, T, H, stream):
         """Takes the transposed recurrent weights [H,3H]."""
         assert 32 <= H <= 384 and H % 4 == 0 and whhT_f % 16 == 0 and whhT_r % 16 == 0, 'tg_gru_layer_bwd_tf32: H range / TMA alignment'

@@ -42,9 +42,11 @@ def test_gemm_tf32_plain(dev, M, N, K):
 
 
 @pytest.mark.parametrize('d', [1, 2, 4, 8])
-@pytest.mark.parametrize('B', [3, 128])
+@pytest.mark.parametrize('B', [3, 128, 384])
 def test_gemm_tf32_causal_two_tap(dev, B, d):
-    """TCN conv (k=2, dilation d, causal) and its anti-causal data gradient as two-accumulator GEMMs."""
+    """TCN conv (k=2, dilation d, causal) and its anti-causal data gradient as two-tap GEMMs (csrc/gemm_tcn.cu: clip-group tiles, the
+    shifted tap zero-filled per clip by the TMA unit).  B = 3: one ragged tile, N split over two CTAs; 128: 43 tiles, the last one with two
+    of its three clips; 384: 128 tiles with the whole N = 300 in one 304-column accumulator (the forward sweep's shape)."""
     from tgb200 import ops
     T, C = 34, 300
     x = _rand(B, T, C, dev=dev); w = _rand(C, C, 2, dev=dev, seed=1, scale=(2 * C) ** -0.5); b = _rand(C, dev=dev, seed=2)
@@ -62,6 +64,30 @@ def test_gemm_tf32_causal_two_tap(dev, B, d):
     dx = torch.full((B * T, C), float('nan'), device=dev)
     ops.gemm_tf32(dc.view(B * T, C), wtt.view(2 * C, C), dx, M=B * T, N=C, K=C, taps=2, shift0=d, T=T)
     assert rel_l2(dx.view(B, T, C), xr.grad.transpose(1, 2)) < 2 * TF32_TOL
+
+
+@pytest.mark.parametrize('B,T,H', [(384, 34, 300), (5, 7, 200)])
+def test_gru_layer_tensor_core_fwd_fused_dropout(dev, B, T, H):
+    """tg_gru_layer_fwd_tf32_drop: same recurrence, and the masked copy of the output (nn.GRU's inter-layer dropout) written by the kernel."""
+    from test_gpu_kernels import _gru_params
+    from tgb200 import ops
+    p = _gru_params(16, H, dev)
+    M = B * T
+    gi = _rand(M, 6 * H, dev=dev)
+    mask = (torch.rand(M, 2 * H, generator=torch.Generator().manual_seed(5)) > 0.3).float().div(0.7).to(dev)
+    sync = torch.zeros(max(ops.gru_tf32_sync_ints(B, H), 1), dtype=torch.int32, device=dev)
+    outs = []
+    for fused in (False, True):
+        out = torch.full((M, 2 * H), float('nan'), device=dev); saved = torch.empty(4, M, 2 * H, device=dev)
+        drop = torch.full((M, 2 * H), float('nan'), device=dev)
+        if fused:
+            ops.gru_layer_fwd_tf32_drop(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, mask, drop, sync, B, T, H)
+        else:
+            ops.gru_layer_fwd_tf32(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, sync, B, T, H)
+        torch.cuda.synchronize()
+        outs.append((out, saved, drop))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[1][2], outs[1][0] * mask)
 
 
 @pytest.mark.parametrize('B,T,I,H', [(3, 34, 108, 300), (128, 34, 108, 300), (384, 34, 40, 300), (128, 28, 8, 64), (5, 7, 16, 200), (600, 5, 16, 300)])
