@@ -283,26 +283,33 @@ __global__ void weight_norm_fwd_kernel(const float* __restrict__ v, const float*
   }
   if (lane == 0) inv_norm[row] = inv;
 }
-__global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
-                                       const float* __restrict__ inv_norm, float* dv, float* dg, int N, int Cin, int taps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= N) return;
+// one 128-thread block per output row (was one warp per row: 19 dependent load round trips per pass, 12-27 us for a 300 x 600 filter on
+// 38 CTAs; the TCN's eight filters sit on the tail of the iteration)
+__global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
+                                                              const float* __restrict__ inv_norm, float* dv, float* dg, int N, int Cin, int taps) {
+  __shared__ float red[4];
+  const int row = blockIdx.x, tid = threadIdx.x;
   const int K = Cin * taps;
   const float* vr = v + (long long)row * K;
   float dot = 0.f;
-  for (int k = lane; k < K; k += 32) {
+#pragma unroll 4
+  for (int k = tid; k < K; k += 128) {
     const int c = k / taps, j = k - c * taps;
-    dot += dw[((long long)j * N + row) * Cin + c] * vr[k];
+    dot = fmaf(dw[((long long)j * N + row) * Cin + c], vr[k], dot);
   }
   dot = warp_sum(dot);
+  if ((tid & 31) == 0) red[tid >> 5] = dot;
+  __syncthreads();
+  dot = (red[0] + red[1]) + (red[2] + red[3]);
   const float inv = inv_norm[row], gg = g[row];
   // w = g v / |v| : dg = dot/|v| ; dv = g/|v| * (dw - v * dot / |v|^2)
   const float c1 = gg * inv, c2 = dot * inv * inv;
-  for (int k = lane; k < K; k += 32) {
+#pragma unroll 4
+  for (int k = tid; k < K; k += 128) {
     const int c = k / taps, j = k - c * taps;
     dv[(long long)row * K + k] += c1 * (dw[((long long)j * N + row) * Cin + c] - vr[k] * c2);
   }
-  if (lane == 0) dg[row] += dot * inv;
+  if (tid == 0) dg[row] += dot * inv;
 }
 
 // ------------------------------------------------------------------ small elementwise
@@ -651,7 +658,7 @@ extern "C" int tg_weight_norm_fwd(const float* v, const float* g, float* w, floa
 extern "C" int tg_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int N,
                                   int Cin, int taps, tg_stream stream) {
   TG_REQUIRE(dw && v && g && inv_norm && dv && dg && taps > 0, "tg_weight_norm_bwd");
-  weight_norm_bwd_kernel<<<tg_ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, N, Cin, taps);
+  weight_norm_bwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, N, Cin, taps);
   TG_CHECK_LAUNCH("tg_weight_norm_bwd");
   return 0;
 }

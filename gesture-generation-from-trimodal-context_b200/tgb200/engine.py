@@ -55,6 +55,8 @@ class _Overlap:
             return
         if i == S_WGRAD:
             self.join(S_BIAS)             # the bias-gradient column sums forked off the weight-gradient stream
+            self.join(S_WGRAD2)           # the second / third weight-gradient streams (independent filters round-robin over them)
+            self.join(S_WGRAD3)
         cur = torch.cuda.current_stream()
         key = (cur.device.index, i)
         if key not in self._active or self._streams[key] == cur:
@@ -66,7 +68,7 @@ class _Overlap:
 
 
 side = _Overlap()
-S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS = 1, 2, 3, 4, 5, 6
+S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3 = 1, 2, 3, 4, 5, 6, 7, 8
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -560,14 +562,16 @@ class GeneratorEngine:
             ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                      # through the block's final ReLU
             ops.relu_mask_bwd(dpre, y2, m2, dc2, Mb * H)                       # dropout2 + relu2
             wT = lambda j: ws.t.get(f'tcn.wT{i}_{j}') if config.fast() else None
-            with side.on(S_WGRAD):
+            # each filter's gradient chain (zero, two tap GEMMs, weight-norm backward: ~50 us of small launches) on one of three streams:
+            # serialised on a single stream the eight chains outlasted the data-gradient chain by ~120 us at the end of the iteration
+            with side.on((S_WGRAD, S_WGRAD2, S_WGRAD3)[(2 * i) % 3]):
                 dw = ws.get(f'tcn.dw{i}_2', (k * H * H,)); dw.zero_()                 # tap-major [k][H][cin]
                 self._tcn_wgrad(y1, dc2, dw, self.G(q + '.conv2.bias'), Bb, T, H, H, k, d)
                 ops.weight_norm_bwd(dw, self.P(q + '.conv2.weight_v'), self.P(q + '.conv2.weight_g'), ws[f'tcn.inv{i}_2'],
                                     self.G(q + '.conv2.weight_v'), self.G(q + '.conv2.weight_g'), H, H, k)
             self._tcn_dgrad(dc2, ws[f'tcn.w{i}_2'], wT(2), dy1, Bb, T, H, H, k, d)
             ops.relu_mask_bwd(dy1, y1, m1, dc1, Mb * H)                        # dropout1 + relu1
-            with side.on(S_WGRAD):
+            with side.on((S_WGRAD, S_WGRAD2, S_WGRAD3)[(2 * i + 1) % 3]):
                 dw = ws.get(f'tcn.dw{i}_1', (k * H * cin,)); dw.zero_()
                 self._tcn_wgrad(xin, dc1, dw, self.G(q + '.conv1.bias'), Bb, T, cin, H, k, d)
                 ops.weight_norm_bwd(dw, self.P(q + '.conv1.weight_v'), self.P(q + '.conv1.weight_g'), ws[f'tcn.inv{i}_1'],
