@@ -36,6 +36,9 @@ struct GemmP {
   float* C; int ldc;
   int M, N, K, taps, shift0, T;
   int clip_rows, tiles_per_clip;     // clip mode (clip_rows > 0): tile = 128 rows of one clip; C row = clip*clip_rows + t
+  int ksplit;                        // > 1: blockIdx.z owns a contiguous share of the K blocks and ADDS its partial tile to a zeroed C with
+                                     // red.global.add (long-K, few-tile problems: the GRU data gradient [4352 x 600] x K 1800 ran 57
+                                     // dependent stages on 170 CTAs, 72 us for 31 us worth of operand traffic)
   const float* escale; const float* bias; int act1; float slope1;
   const float* mask; int ldmask; const float* residual; int ldres; int act2; int accumulate;
 };
@@ -60,7 +63,11 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
   const int m0 = clip * p.clip_rows + t0;                    // first output row of the tile
   const int m_end = p.clip_rows > 0 ? clip * p.clip_rows + p.clip_rows : p.M;
   const int n0 = blockIdx.y * BN;
-  const int nkb = (p.K + BKF - 1) / BKF;
+  const int nkb_all = (p.K + BKF - 1) / BKF;
+  // split-K (taps == 1 only): this CTA's K blocks are [kb_lo, kb_lo + nkb)
+  const int kb_per = p.ksplit > 1 ? (nkb_all + p.ksplit - 1) / p.ksplit : nkb_all;
+  const int kb_lo = p.ksplit > 1 ? (int)blockIdx.z * kb_per : 0;
+  const int nkb = p.ksplit > 1 ? max(0, min(kb_per, nkb_all - kb_lo)) : nkb_all;
   const int iters = nkb * p.taps;
   constexpr uint32_t TMEM_COLS_1 = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS_2 = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -93,8 +100,8 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * BKF, t0 + shift, clip);
-        tma_load_2d(sb, &tmB, &full_bar[s], kb * BKF, tap * p.N + n0);
+        tma_load_3d(sa, &tmA, &full_bar[s], (kb_lo + kb) * BKF, t0 + shift, clip);
+        tma_load_2d(sb, &tmB, &full_bar[s], (kb_lo + kb) * BKF, tap * p.N + n0);
       }
     }
   } else if (warp == 1) {
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
         if (n < p.N) {                            // N % 4 == 0: the lane's four columns are all valid or all invalid
           float4 es = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.escale) es = __ldg(reinterpret_cast<const float4*>(p.escale + n));
-          if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (p.bias && (p.ksplit <= 1 || blockIdx.z == 0)) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           float* crow = p.C + (long long)row0 * p.ldc + n;
           const float* mrow = p.mask ? p.mask + (long long)row0 * p.ldmask + n : nullptr;
           const float* rrow = p.residual ? p.residual + (long long)row0 * p.ldres + n : nullptr;
@@ -199,7 +206,10 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
                 const float4 t4 = *reinterpret_cast<const float4*>(crow + i * cstep);
                 x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
               }
-              *reinterpret_cast<float4*>(crow + i * cstep) = x;
+              if (p.ksplit > 1)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i * cstep), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+              else
+                *reinterpret_cast<float4*>(crow + i * cstep) = x;
             }
           }
         }
@@ -299,6 +309,26 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   p.residual = g.residual; p.ldres = g.ldres; p.act2 = g.act2; p.accumulate = g.accumulate;
   p.clip_rows = clipm ? g.clip_rows : 0;
   p.tiles_per_clip = clipm ? tg_ceil_div(g.clip_rows, BM) : 0;
+  // split-K: a linear epilogue (scale / bias / mask only), vector-aligned contiguous C, few tiles and a long K loop
+  p.ksplit = 1;
+  {
+    const int tiles = tg_ceil_div(g.M, BM) * tg_ceil_div(g.N, BN), nkb_all = tg_ceil_div(g.K, BKF);
+    const bool linear = g.taps == 1 && !clipm && g.act1 == 0 && g.act2 == 0 && !g.residual && !g.accumulate;
+    const bool vec = (g.N & 3) == 0 && g.ldc == g.N && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+                     (!g.mask || ((g.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
+    static const bool off = getenv("TGB200_NO_SPLITK") != nullptr;
+    if (!off && linear && vec && nkb_all >= 24 && tiles < 2 * tg_num_sms()) {
+      int ks = (3 * tg_num_sms() + tiles - 1) / tiles;         // aim at ~3 resident CTAs' worth of tiles per SM pair
+      if (ks > 4) ks = 4;
+      if (ks > nkb_all / 8) ks = nkb_all / 8;
+      while (ks > 1 && ((nkb_all + ks - 1) / ks) * (ks - 1) >= nkb_all) --ks;      // every share non-empty
+      if (ks > 1) {
+        p.ksplit = ks;
+        cudaError_t e = cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.N, s);
+        if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: memset: %s", cudaGetErrorString(e)); return -2; }
+      }
+    }
+  }
   constexpr size_t smem = (size_t)NSTAGE * (A_STAGE_BYTES + BN * 128) + (2 * NSTAGE + 1) * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -306,7 +336,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
     if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
     attr_done = true;
   }
-  dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN));
+  dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN), p.ksplit);
   gemm_tf32_kernel<BN, NSTAGE><<<grid, 320, smem, s>>>(ta, tb, p);
   TG_CHECK_LAUNCH("tg_gemm_tf32");
   return 0;

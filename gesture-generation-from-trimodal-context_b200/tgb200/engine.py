@@ -57,6 +57,7 @@ class _Overlap:
             self.join(S_BIAS)             # the bias-gradient column sums forked off the weight-gradient stream
             self.join(S_WGRAD2)           # the second / third weight-gradient streams (independent filters round-robin over them)
             self.join(S_WGRAD3)
+            self.join(S_SCALARS)          # the early read-back of the logged scalars (train_gan.py)
         cur = torch.cuda.current_stream()
         key = (cur.device.index, i)
         if key not in self._active or self._streams[key] == cur:
@@ -68,7 +69,7 @@ class _Overlap:
 
 
 side = _Overlap()
-S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3 = 1, 2, 3, 4, 5, 6, 7, 8
+S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3, S_SCALARS = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -219,18 +220,18 @@ class GruPlan:
         self._fwd_inputs = x
         return inp
 
-    def weight_grads(self, l, inp, dgi, dgh, out, Bb, T):
-        """Weight / bias gradients of layer l from its gate gradients, on the weight-gradient stream (off the recurrence chain)."""
+    def weight_grads(self, l, inp, dgi, dgh, out, Bb, T, stream=S_WGRAD):
+        """Weight / bias gradients of layer l from its gate gradients, on a weight-gradient stream (off the recurrence chain)."""
         H = self.H
         K = self.I if l == 0 else 2 * H
-        with side.on(S_WGRAD):
+        with side.on(stream):
             wgrad(inp, dgi, self._g('weight_ih', l), B=Bb, T=T, N=6 * H, Cin=K, dbias=self._g('bias_ih', l))
             for d in (0, 1):
                 # dW_hh[d] += dgh_d^T h_prev ; h_prev(t) = out(t-1) (fwd) / out(t+1) (rev), zero outside the clip
                 wgrad(out[:, d * H:], dgh[:, d * 3 * H:], self._g('weight_hh', l, bool(d)), B=Bb, T=T, N=3 * H, Cin=H,
                       shift=(-1 if d == 0 else 1), ldx=2 * H, ldg=6 * H, dbias=self._g('bias_hh', l, bool(d)))
 
-    def backward(self, dout, x, B_all, lo, hi, T, masks, need_dx: bool):
+    def backward(self, dout, x, B_all, lo, hi, T, masks, need_dx: bool, join_first: bool = True):
         """dout [(hi-lo)*T, 2H] = gradient of the last layer's output for clips [lo,hi) of a forward over B_all clips.
         Accumulates all weight grads; returns d x [(hi-lo)*T, I] (or None)."""
         H, ws, tag = self.H, self.ws, self.tag
@@ -238,7 +239,8 @@ class GruPlan:
         Mb, M_all = Bb * T, B_all * T
         r0, r1 = lo * T, hi * T
         tc = self.tc()
-        side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading dgi / dgh
+        if join_first:
+            side.join(S_WGRAD)  # weight-gradient launches of an earlier backward may still be reading dgi / dgh
         partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_tf32_scratch_floats(Bb, H) if tc else ops.gru_bwd_scratch_floats(Bb, H), 1),))
         sync = ws.get(f'{tag}.bsync', (max(ops.gru_tf32_sync_ints(Bb, H) if tc else ops.gru_sync_ints(Bb, H), 1),), torch.int32)
         dx = None
@@ -652,14 +654,17 @@ class GeneratorEngine:
         H, D = self.H, m.pose_dim
         d_poses = d_poses.reshape(Mb, D)
         dy1 = ws.get('g.dy1', (Mb, H // 2)); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
-        ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
+        side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading the scratch buffers below
+        with side.on(S_WGRAD):  # the head's weight gradients are fp32 CUDA-core kernels (150 columns: no TMA pitch): off the chain to the GRU
+            ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
         ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)          # K = 27 reduction: fp32 kernel
-        wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=H // 2, Cin=H, dbias=self.G('out.0.bias'))
+        with side.on(S_WGRAD2):
+            wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=H // 2, Cin=H, dbias=self.G('out.0.bias'))
         mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=H // 2, K=H)
         ops.dup_halves(dhs, dout, Mb, H)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'
-        d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx)
+        d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx, join_first=False)      # joined above, before the head's forks
         if getattr(self, 'on_gru_grads', None) is not None:
             # data parallel: the recurrent layers' gradients (the tail of the flat arena, 22 MB of 53) are complete once the weight-gradient
             # stream has drained what gru.backward queued on it - their all-reduce starts now, under the text / audio encoder backward
@@ -738,7 +743,9 @@ class DiscriminatorEngine:
         return self.arena.gview(name)
 
     def prep_weights(self):
-        self.gru.prep()
+        # the fused stack reads the arena's GRU block directly; the per-layer plan's transposed recurrent matrices (12 launches per
+        # optimiser step) are produced on first use by a forward that does not take the fused path
+        self._gru_prep_stale = True
 
     def make_masks(self, B, T, seed, offset_dev, sid0=0, tag=''):
         masks = {}
@@ -809,6 +816,9 @@ class DiscriminatorEngine:
                                self.P('out2.weight'), self.P('out2.bias'), hsum, o1, prob, B, T, cin, H, L, fast=config.fast())
             self.gru._fwd_inputs = x
         else:
+            if getattr(self, '_gru_prep_stale', True):
+                self.gru.prep()
+                self._gru_prep_stale = False
             out = self.gru.forward(x, B, T, gmasks, save)
             ops.sum_halves(out, hsum, M, H)
             ops.linear(hsum, self.P('out.weight'), self.P('out.bias'), o1, M=M, K=H, N=1)
@@ -863,7 +873,8 @@ class DiscriminatorEngine:
                     inp = ws[f'd.drop{l - 1}']
                 else:
                     inp = ws[f'd.out{l - 1}']
-                self.gru.weight_grads(l, inp, dgi[l], dgh[l], outs[l], B, T)
+                # all layers' gate gradients exist at once here (one launch produced them): the 12 small GEMMs go round-robin over three streams
+                self.gru.weight_grads(l, inp, dgi[l], dgh[l], outs[l], B, T, stream=(S_WGRAD, S_WGRAD2, S_WGRAD3)[l % 3])
         else:
             do1 = ws.get('d.do1', (M, 1)); dhs = ws.get('d.dhs', (M, H)); dout = ws.get('d.dout', (M, 2 * H))
             ops.linear_wgrad(ws['d.o1'], dlogit, self.G('out2.weight'), self.G('out2.bias'), M=B, K=T, N=1)

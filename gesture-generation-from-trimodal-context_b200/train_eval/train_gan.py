@@ -226,8 +226,12 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
             slot.ev = torch.cuda.Event(external=True)          # an event-record NODE inside the graph: the host can wait on it after replay
 
             def early(sc_dev):
-                slot.host_sc.copy_(sc_dev, non_blocking=True)
-                slot.ev.record()
+                # on a side branch of the graph: as a node of the main chain the 64-byte device-to-host copy held up the discriminator's
+                # backward by ~36 us (profiles/r02_timeline_step.txt)
+                from tgb200.engine import side, S_SCALARS
+                with side.on(S_SCALARS):
+                    slot.host_sc.copy_(sc_dev, non_blocking=True)
+                    slot.ev.record()
             out = {'early': early}
             world = _dist_world()
             graphs, arenas = [], []

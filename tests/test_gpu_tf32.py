@@ -39,6 +39,10 @@ def test_gemm_tf32_plain(dev, M, N, K):
     ops.gemm_tf32(a, w, c2, M=M, N=N, K=K, bias=b, act1=ops.ACT_RELU, mask=mask, residual=res, act2=ops.ACT_RELU, accumulate=True)
     ref2 = torch.relu(torch.relu(ref) * mask.double() + res.double()) + 1.0
     assert rel_l2(c2, ref2) < TF32_TOL, rel_l2(c2, ref2)
+    # linear epilogue (bias + mask): the shape class that runs split-K with red.global.add when K is long and the tiles are few
+    c3 = torch.full((M, N), float('nan'), device=dev)
+    ops.gemm_tf32(a, w, c3, M=M, N=N, K=K, bias=b, mask=mask)
+    assert rel_l2(c3, ref * mask.double()) < TF32_TOL, rel_l2(c3, ref * mask.double())
 
 
 @pytest.mark.parametrize('d', [1, 2, 4, 8])
