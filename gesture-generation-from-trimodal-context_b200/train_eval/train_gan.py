@@ -104,6 +104,19 @@ def _dp_sync_once(module, arena):
     arena._dp_synced = key
 
 
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(device):
+    """The iteration is captured on a HIGH-priority stream, the forked weight-gradient / bias / mask streams keep the default (lowest)
+    priority: kernel nodes inherit it, so when the data-gradient GEMM that the next recurrence waits for and that layer's weight-gradient
+    GEMMs are runnable at the same time, the block scheduler fills free SMs with the critical chain first."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _CAPTURE_STREAMS[key]
+
+
 class _GraphSlot:
     """One captured CUDA graph of the whole iteration for a fixed (modules, batch shape, schedule, hyper-parameters)."""
 
@@ -241,7 +254,7 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
                 try:
                     comm = _Comm(inline=True)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                    with torch.cuda.graph(graph, stream=_capture_stream(target.device), capture_error_mode='thread_local'):
                         for arena in _step_segments(args, epoch, st['in_text'], st['in_audio'], st['target'], st['vid'], G, D, g_opt, d_opt, None,
                                                     world, False, out, comm):
                             comm.finish(arena)
@@ -260,7 +273,7 @@ def _run_graphed(slot, args, epoch, in_text, in_audio, target, vid, G, D, g_opt,
                 done = False
                 while not done:                       # one CUDA graph per collective-free stretch of the iteration
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, stream=_capture_stream(target.device)):
                         try:
                             arenas.append(next(gen))
                         except StopIteration:
@@ -358,13 +371,24 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         else:
             g_masks = ge.make_masks(Bt, T, seed, off, split=True)
 
+    d_drawn = {}
+    if D.training and not (noise is not None and noise.d_masks is not None):
+        # the masks of the two discriminator passes that follow the generator sweep, and the zeroing of the generator's gradient arena, are
+        # queued now on the speaker stream (joined by ge.forward): as nodes of the main chain they sat between D's Adam and D(G(x))
+        with side.on(S_SPK):
+            for i in ((1, 2) if do_d else (2,)):
+                d_drawn[i] = de.make_masks(B, T - 6, D._noise.seed, D._noise.offset_dev(dev), sid0=16 * i, tag=str(i))
+    with side.on(S_SPK):
+        ge.arena.zero_grad()
+
     def d_masks_for(i):
         if not D.training:
             return None
         if noise is not None and noise.d_masks is not None:
             return noise.d_masks[i]
-        m = de.make_masks(B, T - 6, D._noise.seed, D._noise.offset_dev(dev), sid0=16 * i)
-        return m
+        if i in d_drawn:
+            return d_drawn[i]
+        return de.make_masks(B, T - 6, D._noise.seed, D._noise.offset_dev(dev), sid0=16 * i, tag=str(i))
 
     sc = ws.get('ti.scalars', (8,), torch.float64)
     sc.zero_()
@@ -397,8 +421,7 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         de.arena.adam_step(dis_optim, grad_scale=1.0 / world, host_step=host_step)
         de.prep_weights()
 
-    # ---- train G (train_gan.py:45-92)
-    ge.arena.zero_grad()
+    # ---- train G (train_gan.py:45-92); the generator's gradient arena was zeroed on a side stream at the top of the iteration
     out = poses[ig * B:(ig + 1) * B]
     p_gen = de.forward(out, D.training, d_masks_for(2))                       # runs in warm-up too (updates D's BN statistics)
     if D.training:
