@@ -339,6 +339,33 @@ __global__ void relu_mask_bwd_kernel(const float* __restrict__ dy, const float* 
     dx[i] = v;
   }
 }
+// float4 variants of the small elementwise kernels on the TextEncoderTCN / head chains (n % 4 == 0, 16-byte aligned): one 16-byte access
+// per array per thread instead of four scalar ones
+__global__ void relu_mask_bwd_v4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, const float4* __restrict__ mask,
+                                        float4* __restrict__ dx, long long n4) {
+  GRID_STRIDE(i, n4) {
+    const float4 g = dy[i], a = y[i];
+    float4 v = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+    if (mask) { const float4 m = mask[i]; v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+    dx[i] = v;
+  }
+}
+__global__ void sum_halves_v4_kernel(const float4* __restrict__ x, float4* __restrict__ o, long long M, int H4) {
+  const long long n = M * H4;
+  GRID_STRIDE(i, n) {
+    const long long m = i / H4; const int h = (int)(i - m * H4);
+    const float4 a = x[m * 2 * H4 + h], b = x[m * 2 * H4 + H4 + h];
+    o[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+__global__ void dup_halves_v4_kernel(const float4* __restrict__ d, float4* __restrict__ dx, long long M, int H4) {
+  const long long n = M * H4;
+  GRID_STRIDE(i, n) {
+    const long long m = i / H4; const int h = (int)(i - m * H4);
+    const float4 v = d[i];
+    dx[m * 2 * H4 + h] = v; dx[m * 2 * H4 + H4 + h] = v;
+  }
+}
 __global__ void sum_halves_kernel(const float* __restrict__ x, float* __restrict__ o, long long M, int H) {
   const long long n = M * H;
   GRID_STRIDE(i, n) {
@@ -678,15 +705,25 @@ extern "C" int tg_add(const float* a, const float* b, float* out, long long n, i
   TG_CHECK_LAUNCH("tg_add"); return 0;
 }
 extern "C" int tg_relu_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, tg_stream stream) {
-  relu_mask_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, mask, dx, n);
+  if ((n & 3) == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)mask | (uintptr_t)dx) & 15) == 0)
+    relu_mask_bwd_v4_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y),
+                                                                               reinterpret_cast<const float4*>(mask), reinterpret_cast<float4*>(dx), n / 4);
+  else
+    relu_mask_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, mask, dx, n);
   TG_CHECK_LAUNCH("tg_relu_mask_bwd"); return 0;
 }
 extern "C" int tg_sum_halves(const float* x, float* out, long long M, int H, tg_stream stream) {
-  sum_halves_kernel<<<ew_blocks(M * H), 256, 0, (cudaStream_t)stream>>>(x, out, M, H);
+  if ((H & 3) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0)
+    sum_halves_v4_kernel<<<ew_blocks(M * H / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), M, H / 4);
+  else
+    sum_halves_kernel<<<ew_blocks(M * H), 256, 0, (cudaStream_t)stream>>>(x, out, M, H);
   TG_CHECK_LAUNCH("tg_sum_halves"); return 0;
 }
 extern "C" int tg_dup_halves(const float* d, float* dx, long long M, int H, tg_stream stream) {
-  dup_halves_kernel<<<ew_blocks(M * H), 256, 0, (cudaStream_t)stream>>>(d, dx, M, H);
+  if ((H & 3) == 0 && (((uintptr_t)d | (uintptr_t)dx) & 15) == 0)
+    dup_halves_v4_kernel<<<ew_blocks(M * H / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d), reinterpret_cast<float4*>(dx), M, H / 4);
+  else
+    dup_halves_kernel<<<ew_blocks(M * H), 256, 0, (cudaStream_t)stream>>>(d, dx, M, H);
   TG_CHECK_LAUNCH("tg_dup_halves"); return 0;
 }
 extern "C" int tg_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, long long n, tg_stream stream) {

@@ -102,6 +102,75 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
   }
 }
 
+// Register-tiled version for the WavEncoder's actual conv1 (15 taps, stride 5): thread = (chunk of 32 consecutive output frames, channel
+// quad) keeps ALL 15 x 4 weight-gradient partial sums in registers and slides a 15-sample window of the waveform along its frames (5 new
+// samples per frame), so a frame costs one 16-byte load of dy + 5 cached waveform loads for 60 FMAs and nothing is staged through shared
+// memory.  The tile-staging kernel above spends its time waiting on its own load -> __syncthreads -> compute rounds (2 CTAs per SM):
+// 82-130 us for 83 MB of traffic, the last kernel of the iteration's audio chain.
+template <int TAPS, int STRIDE>
+__global__ void __launch_bounds__(256) conv1_wgrad_reg_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dW,
+                                                              float* __restrict__ dbias, int Tin, int Tout, int pad, int chunks_per_clip,
+                                                              long long total_chunks) {
+  constexpr int FPC = 32, NV = TAPS * 4 + 4;
+  __shared__ float red[8][4][NV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = tid & 3;
+  const long long chunk = (long long)blockIdx.x * 64 + (tid >> 2);
+  float acc[TAPS][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < TAPS; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  if (chunk < total_chunks) {
+    const int b = (int)(chunk / chunks_per_clip), f0 = (int)(chunk - (long long)b * chunks_per_clip) * FPC;
+    const int nf = min(FPC, Tout - f0);
+    const float* xb = x + (long long)b * Tin;
+    const float* dyp = dy + ((long long)b * Tout + f0) * 16 + quad * 4;
+    const int xi0 = f0 * STRIDE - pad;
+    auto ldx = [&](int xi) { return (xi >= 0 && xi < Tin) ? __ldg(xb + xi) : 0.f; };
+    float win[TAPS];
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) win[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TAPS - STRIDE; ++j) win[j + STRIDE] = ldx(xi0 + j);
+#pragma unroll 3
+    for (int f = 0; f < nf; ++f) {
+#pragma unroll
+      for (int j = 0; j < TAPS - STRIDE; ++j) win[j] = win[j + STRIDE];
+#pragma unroll
+      for (int j = TAPS - STRIDE; j < TAPS; ++j) win[j] = ldx(xi0 + f * STRIDE + j);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dyp + (long long)f * 16));
+#pragma unroll
+      for (int j = 0; j < TAPS; ++j) {
+        acc[j][0] = fmaf(g.x, win[j], acc[j][0]); acc[j][1] = fmaf(g.y, win[j], acc[j][1]);
+        acc[j][2] = fmaf(g.z, win[j], acc[j][2]); acc[j][3] = fmaf(g.w, win[j], acc[j][3]);
+      }
+      accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
+    }
+  }
+  // lanes with equal (lane & 3) hold the same channel quad: sum the warp's 8 chunks, then the block's 8 warps, then one atomic per value
+#pragma unroll
+  for (int j = 0; j < TAPS; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = acc[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) red[warp][lane][j * 4 + e] = v;
+    }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v = accb[e];
+    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 4) red[warp][lane][TAPS * 4 + e] = v;
+  }
+  __syncthreads();
+  for (int o = tid; o < 4 * NV; o += 256) {
+    const int qd = o / NV, idx = o - qd * NV;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][qd][idx];
+    if (idx < TAPS * 4) atomicAdd(dW + (qd * 4 + (idx & 3)) * TAPS + (idx >> 2), v);
+    else if (dbias) atomicAdd(dbias + qd * 4 + (idx - TAPS * 4), v);
+  }
+}
+
 inline int ew_grid(long long n, int per_block = 256) {
   long long b = (n + per_block - 1) / per_block;
   const long long cap = (long long)tg_num_sms() * 16;
@@ -137,6 +206,13 @@ extern "C" int tg_conv1_wgrad(const float* x, const float* dy, float* dW, float*
   TG_REQUIRE(x && dy && dW && B > 0 && Tin > 0 && Tout > 0, "tg_conv1_wgrad");
   TG_REQUIRE(N == 16 && taps >= 1 && taps <= 15 && stride >= 1 && stride <= 8, "tg_conv1_wgrad(shape)");
   TG_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "tg_conv1_wgrad(alignment)");
+  if (taps == 15 && stride == 5) {
+    const int cpc = tg_ceil_div(Tout, 32);
+    const long long total = (long long)B * cpc;
+    conv1_wgrad_reg_kernel<15, 5><<<(unsigned)((total + 63) / 64), 256, 0, (cudaStream_t)stream>>>(x, dy, dW, dbias, Tin, Tout, pad, cpc, total);
+    TG_CHECK_LAUNCH("tg_conv1_wgrad");
+    return 0;
+  }
   const size_t smem = (size_t)(C1_TT * 16 + C1_TT * stride + 16) * sizeof(float);
   const int tiles = B * tg_ceil_div(Tout, C1_TT);
   int grid = 2 * tg_num_sms();
