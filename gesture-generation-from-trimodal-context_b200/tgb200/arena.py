@@ -162,6 +162,25 @@ class ParamArena:
         ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.numel, float(g['lr']), float(b1), float(b2),
                       float(g['eps']), float(grad_scale), self.step_dev)
 
+    def adam_begin(self, optim: torch.optim.Optimizer, host_step: bool = True):
+        """First half of a SPLIT update: binds the optimiser and advances the step counters; follow with adam_range() calls that
+        together cover [0, numel) exactly once."""
+        self.bind_optimizer(optim)
+        if host_step:
+            self.step += 1
+            self._step_tensor.fill_(float(self.step))
+        ops.increment_i64(self.step_dev, 1)
+
+    def adam_range(self, optim: torch.optim.Optimizer, lo: int, hi: int, grad_scale: float = 1.0):
+        """Adam update of the flat range [lo, hi) (lo 16-byte aligned: a tensor boundary) at the step adam_begin() set."""
+        if hi <= lo:
+            return
+        assert lo % 4 == 0
+        g = optim.param_groups[0]
+        b1, b2 = g['betas']
+        ops.adam_flat(self.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], hi - lo, float(g['lr']), float(b1),
+                      float(b2), float(g['eps']), float(grad_scale), self.step_dev)
+
     def note_steps(self, n: int):
         self.step += n
         if getattr(self, '_step_tensor', None) is not None:

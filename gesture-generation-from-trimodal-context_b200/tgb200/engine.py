@@ -669,6 +669,7 @@ class GeneratorEngine:
             # data parallel: the recurrent layers' gradients (the tail of the flat arena, 22 MB of 53) are complete once the weight-gradient
             # stream has drained what gru.backward queued on it - their all-reduce starts now, under the text / audio encoder backward
             with side.on(S_WGRAD):
+                side.join(S_BIAS)       # the bias gradients' column sums run on their own stream
                 self.on_gru_grads()
         if not need_dx:
             side.join(S_WGRAD)

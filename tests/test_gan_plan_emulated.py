@@ -26,7 +26,8 @@ def emu_fp32():
 @pytest.mark.parametrize('tag,epoch,use_masks', [('train_e11', 11, True), ('train_e0', 0, False)])
 def test_train_iter_gan_plan_vs_reference_golden(emu_fp32, tag, epoch, use_masks):
     GP.test_train_iter_vs_reference_golden(CPU, tag, epoch, use_masks)
-    assert emu_fp32.calls.count('tg_adam_flat') == (2 if epoch > 10 else 1)
+    # the generator's Adam is two launches (the recurrent layers' range as soon as their gradients are final, the rest at the end), D's is one
+    assert emu_fp32.calls.count('tg_adam_flat') == (3 if epoch > 10 else 2)
     assert 'tg_gru_layer_bwd' in emu_fp32.calls and 'tg_gen_losses' in emu_fp32.calls
 
 
