@@ -145,25 +145,36 @@ __global__ void __launch_bounds__(256) col_reduce_v4_kernel(const float* __restr
   if (BWD) { mu = ldg4(mean + c0); rs = ldg4(rstd + c0); sc = ldg4(scale + c0); sf = ldg4(shift + c0); }
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int cnt = 0;
   const long long stride = (long long)gridDim.x * 256;
-  for (long long i = i0; i < n4; i += stride) {
-    const float4 v = ldg4(x + 4 * i);
-    if (BWD) {
-      const float4 g = ldg4(dy + 4 * i);
-      const float d0 = g.x * (v.x * sc.x + sf.x >= 0.f ? 1.f : slope), d1 = g.y * (v.y * sc.y + sf.y >= 0.f ? 1.f : slope);
-      const float d2 = g.z * (v.z * sc.z + sf.z >= 0.f ? 1.f : slope), d3 = g.w * (v.w * sc.w + sf.w >= 0.f ? 1.f : slope);
-      f[0] += d0; f[1] += d1; f[2] += d2; f[3] += d3;
-      f[4] += d0 * (v.x - mu.x) * rs.x; f[5] += d1 * (v.y - mu.y) * rs.y; f[6] += d2 * (v.z - mu.z) * rs.z; f[7] += d3 * (v.w - mu.w) * rs.w;
-    } else {
-      f[0] += v.x; f[1] += v.y; f[2] += v.z; f[3] += v.w;
-      f[4] += v.x * v.x; f[5] += v.y * v.y; f[6] += v.z * v.z; f[7] += v.w * v.w;
-    }
-    if (++cnt == 64) {
+  // batches of 4 independent 16-byte loads per array (the loads of a batch are issued before the first one is consumed); fp32 partial sums
+  // are flushed into the fp64 accumulators every 16 batches
+  long long i = i0;
+  while (i < n4) {
+#pragma unroll 1
+    for (int batch = 0; batch < 16 && i < n4; ++batch) {
+      float4 v[4], g[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] += f[k]; f[k] = 0.f; }
-      cnt = 0;
+      for (int u = 0; u < 4; ++u) {
+        const long long iu = i + u * stride;
+        v[u] = iu < n4 ? ldg4(x + 4 * iu) : make_float4(BWD ? mu.x : 0.f, BWD ? mu.y : 0.f, BWD ? mu.z : 0.f, BWD ? mu.w : 0.f);
+        if (BWD) g[u] = iu < n4 ? ldg4(dy + 4 * iu) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (BWD) {
+          const float d0 = g[u].x * (v[u].x * sc.x + sf.x >= 0.f ? 1.f : slope), d1 = g[u].y * (v[u].y * sc.y + sf.y >= 0.f ? 1.f : slope);
+          const float d2 = g[u].z * (v[u].z * sc.z + sf.z >= 0.f ? 1.f : slope), d3 = g[u].w * (v[u].w * sc.w + sf.w >= 0.f ? 1.f : slope);
+          f[0] += d0; f[1] += d1; f[2] += d2; f[3] += d3;
+          f[4] += d0 * (v[u].x - mu.x) * rs.x; f[5] += d1 * (v[u].y - mu.y) * rs.y; f[6] += d2 * (v[u].z - mu.z) * rs.z; f[7] += d3 * (v[u].w - mu.w) * rs.w;
+        } else {
+          f[0] += v[u].x; f[1] += v[u].y; f[2] += v[u].z; f[3] += v[u].w;
+          f[4] += v[u].x * v[u].x; f[5] += v[u].y * v[u].y; f[6] += v[u].z * v[u].z; f[7] += v[u].w * v[u].w;
+        }
+      }
+      i += 4 * stride;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] += f[k]; f[k] = 0.f; }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = a[k] + (double)f[k];

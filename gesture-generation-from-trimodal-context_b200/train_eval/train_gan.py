@@ -59,13 +59,16 @@ def _allreduce_grads(arena, lo=0, hi=None, bucket_floats=4 << 20):
         w.wait()
 
 
-def _allreduce_grads_async(arena, lo=0, hi=None, bucket_floats=4 << 20):
-    """Launches the bucketed NCCL all-reduce (sum) of arena.grad[lo:hi] and returns the work handles."""
+def _allreduce_grads_async(arena, lo=0, hi=None, bucket_floats=4 << 20, ranges=None):
+    """Launches the bucketed NCCL all-reduce (sum) of arena.grad[lo:hi] and returns the work handles (ranges: a list that receives the
+    (start, end) of every bucket, in launch order)."""
     import torch.distributed as dist
     works = []
     hi = arena.numel if hi is None else hi
     for o in range(lo, hi, bucket_floats):
         works.append(dist.all_reduce(arena.grad[o:min(hi, o + bucket_floats)], op=dist.ReduceOp.SUM, async_op=True))
+        if ranges is not None:
+            ranges.append((o, min(hi, o + bucket_floats)))
     return works
 
 
@@ -79,6 +82,7 @@ class _Comm:
     def __init__(self, inline):
         self.inline = inline
         self.pending = {}
+        self.on_bucket = None         # callable(arena, lo, hi) run as soon as a bucket of the final exchange has been reduced
 
     def early(self, arena, lo, wait=False):
         if self.inline:
@@ -90,8 +94,14 @@ class _Comm:
 
     def finish(self, arena):
         lo, works = self.pending.pop(id(arena), (arena.numel, []))
-        for w in works + _allreduce_grads_async(arena, hi=lo):
+        ranges = []
+        rest = _allreduce_grads_async(arena, hi=lo, bucket_floats=(2 << 20) if self.on_bucket else (4 << 20), ranges=ranges)
+        for w in works:
             w.wait()
+        for w, (o, e) in zip(rest, ranges):          # pipelined: bucket k's consumer (Adam of that range) runs under bucket k+1's exchange
+            w.wait()
+            if self.on_bucket is not None:
+                self.on_bucket(arena, o, e)
 
 
 def _dp_sync_once(module, arena):
@@ -461,9 +471,20 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         ge.on_gru_grads = None
     ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
     ge.on_gru_grads = None
+    done = []
     if world > 1:
+        if split:
+            def on_bucket(arena, o, e):
+                if arena is ge.arena:
+                    ge.arena.adam_range(pose_dec_optim, o, e, grad_scale=1.0 / world)
+                    done.append((o, e))
+            comm.on_bucket = on_bucket
         yield ge.arena
-    if split:
+        if comm is not None:
+            comm.on_bucket = None
+    if split and done:
+        assert done[0][0] == 0 and done[-1][1] == gru_lo and all(a[1] == b[0] for a, b in zip(done, done[1:])), done
+    elif split:
         ge.arena.adam_range(pose_dec_optim, 0, gru_lo, grad_scale=1.0 / world)
     else:
         ge.arena.adam_step(pose_dec_optim, grad_scale=1.0 / world, host_step=host_step)
