@@ -13,6 +13,7 @@ What differs is the schedule on the device (B200-first, results identical):
   * with torch.distributed initialised (one process per GPU), gradients are averaged with NCCL all-reduce over
     the flat gradient arena before Adam - the data-parallel equivalent of nn.DataParallel (train.py:93-96).
 """
+import os
 from typing import Dict, Optional
 
 import torch
@@ -473,7 +474,9 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     ge.on_gru_grads = None
     done = []
     if world > 1:
-        if split:
+        if split and os.environ.get('TGB200_DP_PIPELINE', '0') == '1':
+            # opt-in: 8 MB buckets with Adam of bucket k under the exchange of bucket k+1.  Measured on 2 x B200: 4.38 ms/step against 4.32
+            # with one wait and one Adam launch for the whole range (four more NCCL launches cost more than the overlap returns)
             def on_bucket(arena, o, e):
                 if arena is ge.arena:
                     ge.arena.adam_range(pose_dec_optim, o, e, grad_scale=1.0 / world)
