@@ -473,3 +473,56 @@ def copy_bytes(dst, src, max_ctas=64):
     nbytes = dst.numel() * dst.element_size()
     assert nbytes == src.numel() * src.element_size()
     check(_L().tg_copy_bytes(dst.data_ptr(), src.data_ptr(), nbytes, max_ctas, _s()), 'tg_copy_bytes'); _count()
+
+
+# ---- Speech2Gesture pieces (csrc/s2g.cu)
+def im2col2d(x, col, B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo):
+    check(_L().tg_im2col2d(_p(x), _p(col), B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, _s()), 'tg_im2col2d'); _count()
+
+
+def col2im2d(col, dx, B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo):
+    check(_L().tg_col2im2d(_p(col), _p(dx), B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, _s()), 'tg_col2im2d'); _count()
+
+
+def resize_bilinear_fwd(x, y, B, H, W, C, Ho, Wo):
+    check(_L().tg_resize_bilinear_fwd(_p(x), _p(y), B, H, W, C, Ho, Wo, _s()), 'tg_resize_bilinear_fwd'); _count()
+
+
+def resize_bilinear_bwd(dy, dx, B, H, W, C, Ho, Wo):
+    check(_L().tg_resize_bilinear_bwd(_p(dy), _p(dx), B, H, W, C, Ho, Wo, _s()), 'tg_resize_bilinear_bwd'); _count()
+
+
+def upsample2_add_fwd(x1, x2, y, B, T1, T2, C):
+    check(_L().tg_upsample2_add_fwd(_p(x1), _p(x2), _p(y), B, T1, T2, C, _s()), 'tg_upsample2_add_fwd'); _count()
+
+
+def upsample2_bwd(dy, dx1, B, T1, T2, C, accumulate=False):
+    check(_L().tg_upsample2_bwd(_p(dy), _p(dx1), B, T1, T2, C, 1 if accumulate else 0, _s()), 'tg_upsample2_bwd'); _count()
+
+
+def time_diff_fwd(x, y, B, T, D):
+    check(_L().tg_time_diff_fwd(_p(x), _p(y), B, T, D, _s()), 'tg_time_diff_fwd'); _count()
+
+
+def time_diff_bwd(dy, dx, B, T, D, accumulate=False):
+    check(_L().tg_time_diff_bwd(_p(dy), _p(dx), B, T, D, 1 if accumulate else 0, _s()), 'tg_time_diff_bwd'); _count()
+
+
+def concat_bcast_fwd(a, p, y, B, T, Ca, Cp):
+    check(_L().tg_concat_bcast_fwd(_p(a), _p(p), _p(y), B, T, Ca, Cp, _s()), 'tg_concat_bcast_fwd'); _count()
+
+
+def concat_bcast_bwd(d, da, dp, B, T, Ca, Cp):
+    check(_L().tg_concat_bcast_bwd(_p(d), _p(da), _p(dp), B, T, Ca, Cp, _s()), 'tg_concat_bcast_bwd'); _count()
+
+
+def lrelu_bwd(dy, x, dx, n, slope):
+    check(_L().tg_lrelu_bwd(_p(dy), _p(x), _p(dx), n, float(slope), _s()), 'tg_lrelu_bwd'); _count()
+
+
+def mse_const(x, n, target, w, scalar, dx):
+    check(_L().tg_mse_const(_p(x), n, float(target), float(w), _p(scalar), _p(dx), _s()), 'tg_mse_const'); _count()
+
+
+def l1_loss(x, y, n, w, scalar, dx):
+    check(_L().tg_l1_loss(_p(x), _p(y), n, float(w), _p(scalar), _p(dx), _s()), 'tg_l1_loss'); _count()

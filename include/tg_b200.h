@@ -273,6 +273,36 @@ int tg_dconv_stack_bwd(const float* dy2, const float* x, const float* y0, const 
                        int B, int T, int D, tg_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Speech2Gesture baseline (scripts/model/speech2gesture.py, scripts/train_eval/train_speech2gesture.py): the non-GEMM pieces.
+ * Conv2d_tf / Conv1d_tf (speech2gesture.py:9-101) = tg_im2col2d -> tg_gemm_tf32 / tg_conv_gemm_f32 (forward), tg_wgrad_tf32 on the
+ * column matrix (weight gradient), column GEMM -> tg_col2im2d (data gradient).  Activations channels-last [B,H,W,C]; a sequence is H = 1.
+ * --------------------------------------------------------------------------------------------------------- */
+/* col[((b*Ho+ho)*Wo+wo), (i*kw+j)*C + c] = x[b, ho*sh+i-pt, wo*sw+j-pl, c], zero outside the image (TF "SAME": pt / pl = total_pad / 2) */
+int tg_im2col2d(const float* x, float* col, int B, int H, int W, int C, int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo,
+                tg_stream stream);
+/* adjoint of tg_im2col2d: dx[b,h,w,c] = sum of the column entries that were gathered from it (no atomics) */
+int tg_col2im2d(const float* col, float* dx, int B, int H, int W, int C, int kh, int kw, int sh, int sw, int pt, int pl, int Ho, int Wo,
+                tg_stream stream);
+/* torch.nn.Upsample(size=(Ho,Wo), mode='bilinear', align_corners=False) (speech2gesture.py:147,172) and its adjoint (dx is overwritten) */
+int tg_resize_bilinear_fwd(const float* x, float* y, int B, int H, int W, int C, int Ho, int Wo, tg_stream stream);
+int tg_resize_bilinear_bwd(const float* dy, float* dx, int B, int H, int W, int C, int Ho, int Wo, tg_stream stream);
+/* UnetUp (speech2gesture.py:120-130): y[b,t,:] = x1[b,t/2,:] + x2[b,t,:], t < T2 <= 2*T1; backward w.r.t. x1 (w.r.t. x2 it is dy itself) */
+int tg_upsample2_add_fwd(const float* x1, const float* x2, float* y, int B, int T1, int T2, int C, tg_stream stream);
+int tg_upsample2_bwd(const float* dy, float* dx1, int B, int T1, int T2, int C, int accumulate, tg_stream stream);
+/* x[:, 1:] - x[:, :-1] over [B,T,D] (train_speech2gesture.py:12-13) and its adjoint */
+int tg_time_diff_fwd(const float* x, float* y, int B, int T, int D, tg_stream stream);
+int tg_time_diff_bwd(const float* dy, float* dx, int B, int T, int D, int accumulate, tg_stream stream);
+/* torch.cat((a, p.unsqueeze(2).repeat(1,1,T)), dim=1) in channels-last form (speech2gesture.py:219-221) and its adjoint */
+int tg_concat_bcast_fwd(const float* a, const float* p, float* y, int B, int T, int Ca, int Cp, tg_stream stream);
+int tg_concat_bcast_bwd(const float* d, float* da, float* dp, int B, int T, int Ca, int Cp, tg_stream stream);
+/* LeakyReLU backward without a BatchNorm in front (speech2gesture.py:237): dx = dy * (x >= 0 ? 1 : slope) */
+int tg_lrelu_bwd(const float* dy, const float* x, float* dx, long long n, float slope, tg_stream stream);
+/* F.mse_loss(full_like(x, target), x) (train_speech2gesture.py:20,30): *scalar += mean (fp64); dx (optional) = w * d mean / dx */
+int tg_mse_const(const float* x, long long n, float target, float w, double* scalar, float* dx, tg_stream stream);
+/* torch.nn.L1Loss (train.py:62): *scalar += mean |x - y|; dx (optional) = w * sign(x - y) / n */
+int tg_l1_loss(const float* x, const float* y, long long n, float w, double* scalar, float* dx, tg_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * seq2seq baseline (scripts/model/seq2seq_net.py, scripts/train_eval/train_seq2seq.py; config/seq2seq.yml).
  * The projections are GEMMs (tg_conv_gemm_f32 / tg_gemm_tf32); these are the per-step non-GEMM pieces.
  * --------------------------------------------------------------------------------------------------------- */
