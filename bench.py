@@ -248,6 +248,26 @@ def aux_workloads(dev, timed, joint=False):
         out['autoencoder_train_ms_per_step'] = ms / 50
     except Exception as exc:                                          # a side measurement must never take the headline line down
         out['autoencoder_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
+    # training step of the Speech2Gesture baseline (train_iter_speech2gesture), batch 128, eager launches
+    try:
+        from model.speech2gesture import Discriminator as S2GD, Generator as S2GG
+        from train_eval.train_speech2gesture import train_iter_speech2gesture
+        sg, sd_ = S2GG(T, POSE_DIM, 4).to(dev).train(), S2GD(POSE_DIM).to(dev).train()
+        sgo = torch.optim.Adam(sg.parameters(), lr=1e-3, betas=(0.5, 0.999)); sdo = torch.optim.Adam(sd_.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        sa = argparse.Namespace(n_pre_poses=4, loss_regression_weight=100.0, loss_gan_weight=10.0)
+        gsp = torch.Generator().manual_seed(5)
+        spec = (torch.randn(128, 128, 70, generator=gsp) * 20.0 - 40.0).to(dev)
+        tg2 = [synth_batch(128, 120 + i)['target'].to(dev) for i in range(2)]
+        fs = lambda i: train_iter_speech2gesture(sa, spec, tg2[i % 2], sg, sd_, sgo, sdo, None)
+        for i in range(3):
+            fs(i)
+        ms, _, _, _ = timed(fs, 10)
+        out['speech2gesture_train_samples_per_s'] = 128 * 10 / (ms / 1e3)
+        out['speech2gesture_train_ms_per_step'] = ms / 10
+        del sg, sd_, sgo, sdo
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out['speech2gesture_train_error'] = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
     if not joint:
         return out
     try:

@@ -1,7 +1,7 @@
 """init_model / train_epoch - the model switch and the per-batch dispatch of scripts/train.py:36-68,166-226 around the step functions.
 
-`init_model` is the reference's constructor switch for the four model families built here (multimodal_context, joint_embedding,
-gesture_autoencoder, seq2seq; speech2gesture needs Conv2d and is not built).  `train_epoch` is the inner loop of train_epochs
+`init_model` is the reference's constructor switch for all five model families (multimodal_context, joint_embedding, gesture_autoencoder,
+seq2seq, speech2gesture).  `train_epoch` is the inner loop of train_epochs
 (train.py:166-226): batches come through train_eval.staging.DevicePrefetcher (the copy of batch i+1 overlaps step i; the reference does a
 blocking `.to(device)` per tensor, and copies the unused spectrogram too, :171-176), speaker ids are looked up like :178-183, the step
 function is chosen by args.model like :186-203, and the loss meters are fed like :205-209.  Tensorboard, checkpoints, sample videos and
@@ -12,10 +12,12 @@ from model import vocab
 from model.embedding_net import EmbeddingNet
 from model.multimodal_context_net import ConvDiscriminator, PoseGenerator
 from model.seq2seq_net import Seq2SeqNet
+from model import speech2gesture
 from tgb200 import _lib
 from train_eval.train_gan import train_iter_gan
 from train_eval.train_joint_embed import train_iter_embed
 from train_eval.train_seq2seq import train_iter_seq2seq
+from train_eval.train_speech2gesture import train_iter_speech2gesture
 
 LOSS_NAMES = ('loss', 'var_loss', 'gen', 'dis', 'KLD', 'DIV_REG')           # train.py:72-73
 
@@ -37,8 +39,12 @@ def init_model(args, lang_model, speaker_model, pose_dim, _device):
     elif args.model == 'seq2seq':
         generator = Seq2SeqNet(args, pose_dim, n_frames, lang_model.n_words, args.wordembed_dim, lang_model.word_embedding_weights).to(_device)
         loss_fn = torch.nn.L1Loss()
+    elif args.model == 'speech2gesture':                                                                 # train.py:59-62
+        generator = speech2gesture.Generator(n_frames, pose_dim, args.n_pre_poses).to(_device)
+        discriminator = speech2gesture.Discriminator(pose_dim).to(_device)
+        loss_fn = torch.nn.L1Loss()
     else:
-        raise NotImplementedError('model %r is not built on the B200 path (speech2gesture needs Conv2d)' % (args.model,))
+        raise NotImplementedError('unknown model %r' % (args.model,))
     return generator, discriminator, loss_fn
 
 
@@ -67,16 +73,16 @@ def train_epoch(args, epoch, train_data_loader, generator, discriminator, gen_op
     device = torch.device(device)
     meters = {n: Meter(n) for n in LOSS_NAMES}
 
-    def strip(data):                      # the spectrogram is never read by these model families: do not ship it (train.py:175)
+    def strip(data):                      # the spectrogram is read by speech2gesture only: do not ship it otherwise (train.py:175)
         in_text, text_lengths, in_text_padded, _, target_vec, in_audio, in_spec, aux_info = data
-        return in_text, text_lengths, in_text_padded, None, target_vec, in_audio, None, aux_info
+        return in_text, text_lengths, in_text_padded, None, target_vec, in_audio, in_spec if args.model == 'speech2gesture' else None, aux_info
 
     batches = (strip(d) for d in train_data_loader)
     if device.type == 'cuda' and not _lib.TRACE_ONLY:
         from train_eval.staging import DevicePrefetcher
         batches = DevicePrefetcher(batches, device)
     for iter_idx, data in enumerate(batches):
-        in_text, text_lengths, in_text_padded, _, target_vec, in_audio, _, aux_info = data
+        in_text, text_lengths, in_text_padded, _, target_vec, in_audio, in_spec, aux_info = data
         batch_size = target_vec.size(0)
         vid_indices = []
         if speaker_model and isinstance(speaker_model, vocab.Vocab):                                    # :178-183
@@ -91,6 +97,8 @@ def train_epoch(args, epoch, train_data_loader, generator, discriminator, gen_op
         elif args.model == 'seq2seq':
             lengths = text_lengths.cpu() if torch.is_tensor(text_lengths) else text_lengths              # pack_padded_sequence wants host lengths
             loss = train_iter_seq2seq(args, epoch, in_text, lengths, target_vec, generator, gen_optimizer)
+        elif args.model == 'speech2gesture':                                                             # :199-201
+            loss = train_iter_speech2gesture(args, in_spec, target_vec, generator, discriminator, gen_optimizer, dis_optimizer, None)
         else:
             raise NotImplementedError(args.model)
         for name, val in loss.items():                                                                   # :205-209

@@ -7,6 +7,7 @@ from typing import Dict
 import torch
 
 from tgb200 import _lib, ops
+from tgb200.engine import S_WGRAD, side
 
 
 def _unwrap(m):
@@ -45,6 +46,7 @@ def train_iter_speech2gesture(args, in_spec, target_poses, pose_decoder, discrim
     ops.mse_const(s_fake, n, 0.0, 1.0, sc[0:], g_fake)
     de.backward(g_real.view(n, 1), need_dposes=False, ctx=ctx_r)
     de.backward(g_fake.view(n, 1), need_dposes=False, ctx=ctx_f)
+    side.join(S_WGRAD)          # bias column sums of the tensor-core weight-gradient path run on their own stream
     de.arena.adam_step(dis_optim)
 
     # ---- train G (:28-35): w_reg * L1(out, target) + w_gan * mse(1, D(fake))
@@ -58,6 +60,7 @@ def train_iter_speech2gesture(args, in_spec, target_poses, pose_decoder, discrim
     d_om = de.backward(g_gen.view(n, 1), need_dposes=True, param_grads=False)
     ops.time_diff_bwd(d_om, d_out, B, T, Dm, accumulate=True)
     ge.backward(d_out)
+    side.join(S_WGRAD)
     ge.arena.adam_step(pose_dec_optim)
 
     s = sc.cpu().tolist()

@@ -311,3 +311,26 @@ def joint_embedding_state_dict(cfg: HotPathConfig, seed: int = 0) -> Dict[str, t
     _lin(sd, rng, 'decoder.out.0', (150, 300), 300)
     _lin(sd, rng, 'decoder.out.2', (cfg.pose_dim, 150), 150)
     return sd
+
+
+
+def s2g_state_dict(template, seed):
+    """Deterministic Speech2Gesture weights (tests / goldens): a value for every entry of `template` (a state_dict of the reference's or
+    of our Generator / Discriminator - same keys and shapes), drawn from a seeded generator in key order, fan-in scaled."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in template.items():
+        if k.endswith('num_batches_tracked'):
+            out[k] = torch.zeros_like(v)
+        elif k.endswith('running_mean'):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith('running_var'):
+            out[k] = 1.0 + 0.2 * torch.rand(v.shape, generator=g)
+        elif v.dim() == 1 and k.endswith('weight'):                 # BatchNorm gamma
+            out[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif v.dim() == 1:                                          # biases, BatchNorm beta
+            out[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            fan_in = v[0].numel()
+            out[k] = torch.randn(v.shape, generator=g) * (1.4 / fan_in ** 0.5)
+    return out

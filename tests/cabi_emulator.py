@@ -644,6 +644,126 @@ class EmuLib:
             _arr(dx, B * 34 * 27)[:] = dX.astype(np.float32).reshape(-1)
         return 0
 
+    # ---------------------------------------------------------------------------------------- Speech2Gesture pieces (csrc/s2g.cu)
+    @staticmethod
+    def _im2col_index(B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo):
+        ho, wo, i, j = np.meshgrid(np.arange(Ho), np.arange(Wo), np.arange(kh), np.arange(kw), indexing='ij')
+        h = ho * sh + i - pt; w = wo * sw + j - pl
+        valid = (h >= 0) & (h < H) & (w >= 0) & (w < W)
+        return np.where(valid, h, 0), np.where(valid, w, 0), valid
+
+    def tg_im2col2d(self, x, col, B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, stream):
+        self.calls.append('tg_im2col2d')
+        X = _arr(x, B * H * W * C).reshape(B, H, W, C)
+        h, w, valid = self._im2col_index(B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo)
+        out = X[:, h, w, :] * valid[None, ..., None]                       # [B,Ho,Wo,kh,kw,C]
+        _arr(col, B * Ho * Wo * kh * kw * C)[:] = out.reshape(-1)
+        return 0
+
+    def tg_col2im2d(self, col, dx, B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo, stream):
+        self.calls.append('tg_col2im2d')
+        Cm = _arr(col, B * Ho * Wo * kh * kw * C).reshape(B, Ho, Wo, kh, kw, C).astype(np.float64)
+        h, w, valid = self._im2col_index(B, H, W, C, kh, kw, sh, sw, pt, pl, Ho, Wo)
+        out = np.zeros((B, H, W, C))
+        np.add.at(out, (slice(None), h, w, slice(None)), Cm * valid[None, ..., None])
+        _arr(dx, B * H * W * C)[:] = out.astype(np.float32).reshape(-1)
+        return 0
+
+    @staticmethod
+    def _bilin(o, n_in, n_out):
+        s = np.maximum((o + 0.5) * (np.float32(n_in) / np.float32(n_out)) - 0.5, 0.0).astype(np.float32)
+        i0 = np.minimum(s.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        return i0, i1, (s - i0).astype(np.float64)
+
+    def _bilin_weights(self, H, W, Ho, Wo):
+        h0, h1, lh = self._bilin(np.arange(Ho), H, Ho)
+        w0, w1, lw = self._bilin(np.arange(Wo), W, Wo)
+        return h0, h1, lh, w0, w1, lw
+
+    def tg_resize_bilinear_fwd(self, x, y, B, H, W, C, Ho, Wo, stream):
+        self.calls.append('tg_resize_bilinear_fwd')
+        X = _arr(x, B * H * W * C).reshape(B, H, W, C).astype(np.float64)
+        h0, h1, lh, w0, w1, lw = self._bilin_weights(H, W, Ho, Wo)
+        lh = lh[None, :, None, None]; lw = lw[None, None, :, None]
+        g = lambda hh, ww: X[:, hh][:, :, ww]
+        out = (1 - lh) * ((1 - lw) * g(h0, w0) + lw * g(h0, w1)) + lh * ((1 - lw) * g(h1, w0) + lw * g(h1, w1))
+        _arr(y, B * Ho * Wo * C)[:] = out.astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_resize_bilinear_bwd(self, dy, dx, B, H, W, C, Ho, Wo, stream):
+        self.calls.append('tg_resize_bilinear_bwd')
+        G = _arr(dy, B * Ho * Wo * C).reshape(B, Ho, Wo, C).astype(np.float64)
+        h0, h1, lh, w0, w1, lw = self._bilin_weights(H, W, Ho, Wo)
+        out = np.zeros((B, H, W, C))
+        for hh, wh in ((h0, 1 - lh), (h1, lh)):
+            for ww, wl in ((w0, 1 - lw), (w1, lw)):
+                np.add.at(out, (slice(None), hh[:, None], ww[None, :], slice(None)), G * wh[None, :, None, None] * wl[None, None, :, None])
+        _arr(dx, B * H * W * C)[:] = out.astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_upsample2_add_fwd(self, x1, x2, y, B, T1, T2, C, stream):
+        self.calls.append('tg_upsample2_add_fwd')
+        X1 = _arr(x1, B * T1 * C).reshape(B, T1, C); X2 = _arr(x2, B * T2 * C).reshape(B, T2, C)
+        _arr(y, B * T2 * C)[:] = (np.repeat(X1, 2, axis=1)[:, :T2] + X2).reshape(-1)
+        return 0
+
+    def tg_upsample2_bwd(self, dy, dx1, B, T1, T2, C, accumulate, stream):
+        self.calls.append('tg_upsample2_bwd')
+        G = np.zeros((B, 2 * T1, C), np.float32); G[:, :T2] = _arr(dy, B * T2 * C).reshape(B, T2, C)
+        v = G.reshape(B, T1, 2, C).sum(2)
+        out = _arr(dx1, B * T1 * C)
+        out[:] = (out.reshape(B, T1, C) + v if accumulate else v).reshape(-1)
+        return 0
+
+    def tg_time_diff_fwd(self, x, y, B, T, D, stream):
+        self.calls.append('tg_time_diff_fwd')
+        X = _arr(x, B * T * D).reshape(B, T, D)
+        _arr(y, B * (T - 1) * D)[:] = (X[:, 1:] - X[:, :-1]).reshape(-1)
+        return 0
+
+    def tg_time_diff_bwd(self, dy, dx, B, T, D, accumulate, stream):
+        self.calls.append('tg_time_diff_bwd')
+        G = _arr(dy, B * (T - 1) * D).reshape(B, T - 1, D)
+        v = np.zeros((B, T, D), np.float32); v[:, 1:] += G; v[:, :-1] -= G
+        out = _arr(dx, B * T * D)
+        out[:] = (out.reshape(B, T, D) + v if accumulate else v).reshape(-1)
+        return 0
+
+    def tg_concat_bcast_fwd(self, a, p, y, B, T, Ca, Cp, stream):
+        self.calls.append('tg_concat_bcast_fwd')
+        A = _arr(a, B * T * Ca).reshape(B, T, Ca); P = _arr(p, B * Cp).reshape(B, 1, Cp)
+        _arr(y, B * T * (Ca + Cp))[:] = np.concatenate([A, np.broadcast_to(P, (B, T, Cp))], axis=2).reshape(-1)
+        return 0
+
+    def tg_concat_bcast_bwd(self, d, da, dp, B, T, Ca, Cp, stream):
+        self.calls.append('tg_concat_bcast_bwd')
+        Dd = _arr(d, B * T * (Ca + Cp)).reshape(B, T, Ca + Cp)
+        _arr(da, B * T * Ca)[:] = Dd[:, :, :Ca].reshape(-1)
+        _arr(dp, B * Cp)[:] = Dd[:, :, Ca:].astype(np.float64).sum(1).astype(np.float32).reshape(-1)
+        return 0
+
+    def tg_lrelu_bwd(self, dy, x, dx, n, slope, stream):
+        self.calls.append('tg_lrelu_bwd')
+        _arr(dx, n)[:] = _arr(dy, n) * np.where(_arr(x, n) >= 0, np.float32(1), np.float32(slope))
+        return 0
+
+    def tg_mse_const(self, x, n, target, w, scalar, dx, stream):
+        self.calls.append('tg_mse_const')
+        e = _arr(x, n).astype(np.float64) - target
+        _arr(scalar, 1, ctypes.c_double)[0] += (e * e).mean()
+        if dx:
+            _arr(dx, n)[:] = (w * 2.0 * e / n).astype(np.float32)
+        return 0
+
+    def tg_l1_loss(self, x, y, n, w, scalar, dx, stream):
+        self.calls.append('tg_l1_loss')
+        e = _arr(x, n).astype(np.float64) - _arr(y, n)
+        _arr(scalar, 1, ctypes.c_double)[0] += np.abs(e).mean()
+        if dx:
+            _arr(dx, n)[:] = (w * np.sign(e) / n).astype(np.float32)
+        return 0
+
     # ---------------------------------------------------------------------------------------- losses (csrc/losses.cu)
     @staticmethod
     def _huber(x, y, beta):

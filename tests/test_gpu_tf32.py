@@ -88,7 +88,8 @@ def test_gru_layer_tensor_core_fwd_fused_dropout(dev, B, T, H):
             ops.gru_layer_fwd_tf32_drop(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, mask, drop, sync, B, T, H)
         else:
             ops.gru_layer_fwd_tf32(gi, p['whh'][0], p['whh'][1], p['bhh'][0], p['bhh'][1], out, saved, M * 2 * H, sync, B, T, H)
-        torch.cuda.synchronize()
+        if dev.type == 'cuda':
+            torch.cuda.synchronize()
         outs.append((out, saved, drop))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[1][2], outs[1][0] * mask)

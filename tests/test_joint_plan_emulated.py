@@ -82,7 +82,9 @@ def test_long_form_driver_joint_embedding_and_seq2seq(emu):
     audio, words, seed = make_clip(4.4, seed=52)
     out = generate_gestures(s_args, s_net, StubVocab(), audio, words, seed_seq=seed, fade_out=True)
     assert out.ndim == 2 and out.shape[1] == 27 and np.isfinite(out).all() and out.shape[0] >= 34
-    assert np.allclose(out[0], seed[0], atol=1e-6)                                            # frame 0 of window 0 is the first seed pose
+    # (frame 0 is no longer the first seed pose itself: the reference's seq2seq-only cubic smoothing, synthesize.py:163-185, refits frames
+    # [0, 2 * n_pre) of the first window - checked against the executed reference driver in tests/test_synthesize_driver.py)
+    assert np.abs(out[0] - seed[0]).max() < 1.0
 
 
 def test_fast_mode_error_budget_under_tf32_operand_truncation():

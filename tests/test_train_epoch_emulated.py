@@ -66,6 +66,9 @@ def test_init_model_and_train_epoch(emu, model):
     assert set(ret) == want and all(np.isfinite(v) for v in ret.values())
     assert abs(ret['loss'] - np.mean([s[1]['loss'] for s in steps])) < 1e-9 * abs(ret['loss'])
     assert any(not torch.equal(before[k], v) for k, v in G.state_dict().items() if v.is_floating_point())      # the optimiser moved the weights
+    args.model = 'speech2gesture'                                  # train.py:59-62: the fifth family is constructed too
+    g2, d2, l2 = train.init_model(args, Lang(cfg.n_words), None, cfg.pose_dim, torch.device('cpu'))
+    assert type(g2).__name__ == 'Generator' and type(d2).__name__ == 'Discriminator' and isinstance(l2, torch.nn.L1Loss)
     with pytest.raises(NotImplementedError):
-        args.model = 'speech2gesture'
+        args.model = 'no_such_model'
         train.init_model(args, Lang(cfg.n_words), None, cfg.pose_dim, torch.device('cpu'))
