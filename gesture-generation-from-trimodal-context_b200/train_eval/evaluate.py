@@ -37,7 +37,7 @@ class PoseMetrics:
 
 
 def evaluate_testset(test_data_loader, generator, loss_fn, embed_space_evaluator, args):
-    """train.py:234-329 for args.model in {'multimodal_context', 'seq2seq', 'joint_embedding', 'gesture_autoencoder'}.  `loss_fn` is
+    """train.py:234-329 for args.model in {'multimodal_context', 'seq2seq', 'speech2gesture', 'joint_embedding', 'gesture_autoencoder'}.  `loss_fn` is
     accepted for signature compatibility; like the reference's multimodal_context branch the reported loss is the L1 distance of the
     direction vectors (for the two embedding models that IS eval_embed's loss: the batch mean of per-sample means over equal-sized samples)."""
     _lib.require_cuda()
@@ -69,6 +69,8 @@ def evaluate_testset(test_data_loader, generator, loss_fn, embed_space_evaluator
                 out_dir_vec, *_ = generator(pre_seq, in_text_padded.to(dev), in_audio.to(dev), vid_indices)
             elif model == 'seq2seq':
                 out_dir_vec = generator(in_text.to(dev), text_lengths, target, None)
+            elif model == 'speech2gesture':                                     # train.py:277-279
+                out_dir_vec = generator(in_spec.to(dev), target[:, 0:args.n_pre_poses])
             elif model == 'joint_embedding':                                    # train.py:269-271: decode the speech latent
                 from train_eval.train_joint_embed import eval_embed
                 _, out_dir_vec = eval_embed(in_text_padded.to(dev), in_audio.to(dev), target[:, 0:args.n_pre_poses], target, generator, mode='speech')
