@@ -43,12 +43,17 @@ struct GemmP {
   const float* mask; int ldmask; const float* residual; int ldres; int act2; int accumulate;
 };
 
-template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                           const GemmP p) {
+// MH = 2 (flat single-tap problems with wide outputs): the CTA owns 256 rows as two 128-row accumulators fed by the same B tile, so a
+// 256 x 240 x 32 block costs (256 + 240) x 128 bytes of operand fetch where two 128-row CTAs pay (256 + 480) x 128 - these GEMMs run at
+// the L2 -> SM fabric's ~10 TB/s, not at the tensor pipe's rate.  Both accumulators fill tensor memory (2 x 256 columns), one CTA per
+// SM, 16 epilogue warps; the epilogue of one SM overlaps the main loops of the others.
+template <int BN, int NSTAGE, int MH>
+__global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                                        const __grid_constant__ CUtensorMap tmB, const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = MH * A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;          // TMEM column offset of the second 128-row accumulator (MH == 2)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NSTAGE;
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
   // flat mode: tile rows m0.. of the [M,K] matrix (A map = {K, a_rows, 1}); clip mode: rows t0.. of clip `clip`
   // (A map = {K, clip_rows, clips} with its own row / clip pitches, e.g. overlapping convolution windows)
   const int clip = p.clip_rows > 0 ? blockIdx.x / p.tiles_per_clip : 0;
-  const int t0 = p.clip_rows > 0 ? (blockIdx.x - clip * p.tiles_per_clip) * BM : blockIdx.x * BM;
+  const int t0 = p.clip_rows > 0 ? (blockIdx.x - clip * p.tiles_per_clip) * BM : blockIdx.x * (BM * MH);
   const int m0 = clip * p.clip_rows + t0;                    // first output row of the tile
   const int m_end = p.clip_rows > 0 ? clip * p.clip_rows + p.clip_rows : p.M;
   const int n0 = blockIdx.y * BN;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
   const int iters = nkb * p.taps;
   constexpr uint32_t TMEM_COLS_1 = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS_2 = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  const uint32_t tmem_cols = p.taps == 2 ? TMEM_COLS_2 : TMEM_COLS_1;
+  const uint32_t tmem_cols = MH == 2 ? 2 * ACC_STRIDE : (p.taps == 2 ? TMEM_COLS_2 : TMEM_COLS_1);
 
   if (threadIdx.x == 0) stamp(p.trace, 0);
   if (warp == 0 && lane == 0) {
@@ -98,9 +103,10 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
         const int tap = it / nkb, kb = it - tap * nkb;
         const int shift = (p.taps == 2 && tap == 0) ? p.shift0 : 0;
         uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
+        uint8_t* sb = sa + MH * A_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_3d(sa, &tmA, &full_bar[s], (kb_lo + kb) * BKF, t0 + shift, clip);
+        if (MH == 2) tma_load_3d(sa + A_STAGE_BYTES, &tmA, &full_bar[s], (kb_lo + kb) * BKF, t0 + BM, clip);      // rows past the matrix: zero fill
         tma_load_2d(sb, &tmB, &full_bar[s], (kb_lo + kb) * BKF, tap * p.N + n0);
       }
     }
@@ -115,32 +121,34 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
         if (it == 0) stamp(p.trace, 2);
         const int tap = it / nkb, kb = it - tap * nkb;
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t sb = sa + MH * A_STAGE_BYTES;
         const uint32_t dcol = tmem_base + (uint32_t)(tap * BN);
         constexpr uint32_t hi = desc_hi(1024, 2);                // SWIZZLE_128B; the 4 K-steps of a stage walk the 128-byte row: +32 B each
         mma_tf32_seq<4, 2>(dcol, desc_lo(sa, 16), hi, desc_lo(sb, 16), hi, idesc, kb > 0 ? 1u : 0u);
+        if (MH == 2) mma_tf32_seq<4, 2>(dcol + ACC_STRIDE, desc_lo(sa + A_STAGE_BYTES, 16), hi, desc_lo(sb, 16), hi, idesc, kb > 0 ? 1u : 0u);
         tc_commit(&empty_bar[s]);
       }
       tc_commit(tmem_full_bar);
       stamp(p.trace, 3);
     }
   } else {
-    // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4) .. +31, so warps w and w+4 share a lane quarter and
-    // split its 32-column chunks (even / odd).  One epilogue warp per scheduler cannot hide its own instruction latency, so
+    // ---- epilogue: 8 warps (16 with two accumulators).  Warp w may only touch TMEM lanes 32*(w%4) .. +31, so the warps of one lane
+    // quarter split its (accumulator, 32-column chunk) items round-robin.  One epilogue warp per scheduler cannot hide its own instruction latency, so
     // the per-element work is kept branch-free: act(v) = max(v, v*s) (s = 1 none, 0 relu, slope leaky), every option folded
     // into per-chunk constants, row addresses advanced by pointer increments.
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    constexpr int NGRP = MH == 2 ? 4 : 2, NCHUNK = (BN + 31) / 32;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) stamp(p.trace, 4);
-    const int m = m0 + q * 32 + lane;
+    const int m = m0 + q * 32 + lane;          // (two-tap mode is MH == 1)
     bool tap0_ok = true;
     if (p.taps == 2) {
       const int t = m % p.T;
       const int ts = t + p.shift0;
       tap0_ok = ts >= 0 && ts < p.T;
     }
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_addr0 = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec_ok = (p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                         (!p.mask || ((p.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) &&
                         (!p.residual || ((p.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
@@ -153,12 +161,15 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const float s1 = p.act1 == 0 ? 1.f : (p.act1 == 1 ? 0.f : p.slope1);
     const float s2 = p.act2 == 0 ? 1.f : 0.f;
-    const int row0 = m0 + q * 32 + rsub;             // this lane's first row; it handles rows row0 + 4*i
-    const int rows_left = m_end - row0;              // row i is valid iff 4*i < rows_left
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+    for (int item = grp; item < MH * NCHUNK; item += NGRP) {
+      const int h = MH == 2 ? item / NCHUNK : 0;
+      const int c0 = (item - h * NCHUNK) * 32;
       const int nb = n0 + c0;
-      if (nb >= p.N) break;
+      if (nb >= p.N) continue;
+      const uint32_t lane_addr = lane_addr0 + (uint32_t)(h * ACC_STRIDE);
+      const int row0 = m0 + h * BM + q * 32 + rsub;    // this lane's first row; it handles rows row0 + 4*i
+      const int rows_left = m_end - row0;              // row i is valid iff 4*i < rows_left
       float v[32];
       if (p.taps == 2) {
         float v0[32];
@@ -177,7 +188,8 @@ __global__ void __launch_bounds__(320, 2) gemm_tf32_kernel(const __grid_constant
       for (int j4 = 0; j4 < 32; j4 += 4) *reinterpret_cast<float4*>(stg + lane * SP + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
       __syncwarp();
       const int n = nb + c4;                      // this lane's 4 columns
-      if (vec_ok) {
+      if (BN % 32 != 0 && c0 + c4 >= BN) {        // BN = 240: the last 32-column chunk is half a tile wide
+      } else if (vec_ok) {
         if (n < p.N) {                            // N % 4 == 0: the lane's four columns are all valid or all invalid
           float4 es = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.escale) es = __ldg(reinterpret_cast<const float4*>(p.escale + n));
@@ -291,7 +303,7 @@ int make_map_a(CUtensorMap* m, const float* base, long long clips, long long row
   return 0;
 }
 
-template <int BN, int NSTAGE>
+template <int BN, int NSTAGE, int MH = 1>
 int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   CUtensorMap ta, tb;
   const bool clipm = g.clip_rows > 0;
@@ -312,7 +324,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   // split-K: a linear epilogue (scale / bias / mask only), vector-aligned contiguous C, few tiles and a long K loop
   p.ksplit = 1;
   {
-    const int tiles = tg_ceil_div(g.M, BM) * tg_ceil_div(g.N, BN), nkb_all = tg_ceil_div(g.K, BKF);
+    const int tiles = tg_ceil_div(g.M, BM * MH) * tg_ceil_div(g.N, BN), nkb_all = tg_ceil_div(g.K, BKF);
     const bool linear = g.taps == 1 && !clipm && g.act1 == 0 && g.act2 == 0 && !g.residual && !g.accumulate;
     const bool vec = (g.N & 3) == 0 && g.ldc == g.N && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
                      (!g.mask || ((g.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
@@ -329,15 +341,16 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
       }
     }
   }
-  constexpr size_t smem = (size_t)NSTAGE * (A_STAGE_BYTES + BN * 128) + (2 * NSTAGE + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)NSTAGE * (MH * A_STAGE_BYTES + BN * 128) + (2 * NSTAGE + 1) * 8 + 16 + 1024;
+  static_assert(MH == 1 || (size_t)NSTAGE * (MH * A_STAGE_BYTES + BN * 128) >= 16 * 32 * 36 * 4, "epilogue staging lives in the pipeline stages");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, NSTAGE, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return -3; }
     attr_done = true;
   }
-  dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM), tg_ceil_div(g.N, BN), p.ksplit);
-  gemm_tf32_kernel<BN, NSTAGE><<<grid, 320, smem, s>>>(ta, tb, p);
+  dim3 grid(clipm ? (unsigned)(clips * p.tiles_per_clip) : tg_ceil_div(g.M, BM * MH), tg_ceil_div(g.N, BN), p.ksplit);
+  gemm_tf32_kernel<BN, NSTAGE, MH><<<grid, MH == 2 ? 576 : 320, smem, s>>>(ta, tb, p);
   TG_CHECK_LAUNCH("tg_gemm_tf32");
   return 0;
 }
@@ -369,8 +382,13 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   if (g.N <= 32) bn = 32;
   else if (g.N <= 64) bn = 64;
   else {
-    const int p128 = tg_ceil_div(g.N, 128) * 128, p160 = tg_ceil_div(g.N, 160) * 160;
+    const int p128 = tg_ceil_div(g.N, 128) * 128, p160 = tg_ceil_div(g.N, 160) * 160, p240 = tg_ceil_div(g.N, 240) * 240;
     bn = (p160 < p128) ? 160 : 128;
+    // wide outputs (the GRU input projections, N = 1800): a tile's operand fetch, (128 + BN) x 128 bytes per 128 x BN x 32 block, is what
+    // bounds these GEMMs (an SM ingests ~46 bytes/clk from L2 while a 128 x 128 block needs 128 bytes per MMA clock), so take the widest
+    // tile that does not add padding: 240 columns with two stages still leaves two CTAs per SM for the epilogue overlap
+    static const bool no240 = getenv("TGB200_NO_BN240") != nullptr;
+    if (!no240 && g.taps == 1 && g.N >= 960 && p240 <= (bn == 160 ? p160 : p128)) bn = 240;
   }
   // 3-4 stages keep two CTAs resident per SM (shared memory and 2 x 256 TMEM columns), so one CTA's epilogue overlaps
   // the other's main loop; the two-accumulator mode is limited to BN <= 128 for the same reason (2 x 2 x 128 = 512 columns)
@@ -378,5 +396,10 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   if (bn == 32) return launch<32, 4>(g, s);
   if (bn == 64) return launch<64, 4>(g, s);
   if (bn == 128) return launch<128, 3>(g, s);
+  if (bn == 240) {
+    static const bool no256 = getenv("TGB200_NO_BM256") != nullptr;
+    if (!no256 && g.clip_rows == 0 && g.M >= 256) return launch<240, 3, 2>(g, s);
+    return launch<240, 2>(g, s);
+  }
   return launch<160, 3>(g, s);
 }

@@ -68,6 +68,24 @@ def wav_first() -> bool:
     return _WAV_FIRST
 
 
+_DREAL_AT = os.environ.get('TGB200_DREAL_AT', 'gru1')
+
+
+def d_real_at() -> str:
+    """Where train_iter_gan forks the discriminator's pass over the REAL clips (independent of the generator): 'top' = at the start of
+    the iteration, beside the audio / text encoders; 'concat' = when the GRU input exists; 'gru0' / 'gru1' = once the generator's first /
+    second recurrent layer has been launched (the recurrence occupies 96 of 148 SMs for ~0.9 ms and nothing else is runnable then)."""
+    return _DREAL_AT
+
+
+_FLAT_PRIO = os.environ.get('TGB200_FLAT_PRIO', '0') == '1'
+
+
+def flat_prio() -> bool:
+    """A/B switch: one high priority for the capture stream and every preparation stream instead of the graded ones (engine._Overlap)."""
+    return _FLAT_PRIO
+
+
 _NCCL_GRAPH = os.environ.get('TGB200_NCCL_GRAPH', '1') == '1'
 
 

@@ -33,7 +33,18 @@ class _Overlap:
     def _stream(self, device, i):
         key = (device.index, i)
         if key not in self._streams:
-            self._streams[key] = torch.cuda.Stream(device=device)
+            # the per-block preparation streams (dropout masks, weight-normed filters of one TextEncoderTCN block) carry a few ~10 us
+            # launches each that gate a block of the longest chain in front of the GRU: at default priority they were starved for 100+ us
+            # by the wide kernels of the audio / discriminator branches (profiles/r02_timeline_step_final.txt, 57-510 us)
+            # Priorities (kernel nodes of a captured graph inherit them): the text chain's head - embedding / block-0 masks and filters - goes
+            # first, then the iteration's main chain (captured at -2, train_gan._capture_stream), then the later blocks' preparation; the
+            # audio branch, weight gradients and the discriminator's real pass keep the default.  The top of the iteration is ~150 us of
+            # bandwidth-bound kernels that each fill the GPU, so what starts first decides when the 8-GEMM text chain can start.
+            prio = -3 if i in (S_PREP[0], S_PREP0W) else (-1 if i in S_PREP else 0)
+            if config.flat_prio():
+                prio = min(prio, 0) and -1
+            hi = min(torch.cuda.Stream.priority_range())         # numerically lowest = most urgent (torch exposes 0 .. -3)
+            self._streams[key] = torch.cuda.Stream(device=device, priority=max(prio, hi))
         return self._streams[key]
 
     @contextlib.contextmanager
@@ -70,6 +81,12 @@ class _Overlap:
 
 side = _Overlap()
 S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3, S_SCALARS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+S_PREP0W = 14                  # weight-normed filters of block 0 (beside its masks on S_PREP[0])
+S_PREP = (10, 11, 12, 13)      # dropout masks + weight-normed filters of TextEncoderTCN block i live on S_PREP[i % 4], joined right before that block
+
+
+def s_prep(i):
+    return S_PREP[i % len(S_PREP)]
 
 F32 = torch.float32
 BN_EPS = 1e-5
@@ -186,8 +203,9 @@ class GruPlan:
                 # [6H, K] (both directions, adjacent in the arena) -> [K, 6H]: operand of the data-gradient GEMM
                 ops.transpose(self._w('weight_ih', l), self.ws.get(f'{self.tag}.wihT{l}', (K, 6 * H)), 6 * H, K)
 
-    def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool):
-        """x [B*T, I] -> out of the last layer [B*T, 2H].  masks[l] multiplies the output of layer l (l < L-1)."""
+    def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool, hook=None, hook_after: int = 0):
+        """x [B*T, I] -> out of the last layer [B*T, 2H].  masks[l] multiplies the output of layer l (l < L-1).
+        hook() is called once the recurrence of layer `hook_after` has been queued (work forked there runs beside the recurrence)."""
         H, ws, tag = self.H, self.ws, self.tag
         M = B * T
         gi = ws.get(f'{tag}.gi', (M, 6 * H))
@@ -210,6 +228,8 @@ class GruPlan:
             else:
                 ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
                                   out, saved, M * 2 * H, sync, B, T, H)
+            if hook is not None and l == min(hook_after, self.L - 1):
+                hook()
             if mk is not None:
                 if not tc:
                     ops.mul(out, mk, drop, M * 2 * H)
@@ -322,10 +342,10 @@ class GeneratorEngine:
     def G(self, name):
         return self.arena.gview(name)
 
-    def prep_weights(self):
-        """Per-optimiser-step derived weights: weight-norm'ed TCN filters and transposed recurrent matrices."""
+    def prep_weights(self, part: str = 'all'):
+        """Per-optimiser-step derived weights: weight-norm'ed TCN filters ('tcn') and transposed recurrent / head matrices ('rest')."""
         ws = self.ws
-        if self.use_text:
+        if self.use_text and part in ('all', 'tcn'):
             def norm_block(i):
                 for j in (1, 2):
                     q = f'text_encoder.tcn.network.{i}.conv{j}'
@@ -334,10 +354,13 @@ class GeneratorEngine:
                     wT = ws.get(f'tcn.wT{i}_{j}', (k, Cin, N)) if config.fast() else None
                     ops.weight_norm_fwd(v, self.P(q + '.weight_g'), ws.get(f'tcn.w{i}_{j}', (k, N, Cin)), wT, ws.get(f'tcn.inv{i}_{j}', (N,)),
                                         N, Cin, k)
-            norm_block(0)
-            with side.on(S_WAVW):       # filters of the later blocks: joined in text_forward before block 1
-                for i in range(1, self.n_tcn):
+            with side.on(S_PREP0W):             # block 0: beside its masks (S_PREP[0]); text_forward joins both in front of block 0
+                norm_block(0)
+            for i in range(1, self.n_tcn):      # filters of the later blocks: each joined in text_forward right before its block
+                with side.on(s_prep(i)):
                     norm_block(i)
+        if part == 'tcn':
+            return
         with side.on(S_WAV):        # not needed before the GRU / the backward pass: off the critical path (joined before the GRU input)
             if config.fast():
                 for name in ('text_encoder.decoder.weight', 'out.0.weight', 'out.2.weight'):
@@ -349,37 +372,39 @@ class GeneratorEngine:
 
     def make_masks(self, Bt, T, seed, offset_dev, sid0=0, split=False):
         """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel.
-        split=True: only the masks the first TCN block needs are drawn on the current stream; the others are drawn on
-        the weight-gradient stream (idle during the forward pass) and joined in text_forward before block 1."""
+        split=True: block i's masks (and the embedding's, with block 0) are drawn on that block's preparation stream
+        (joined in text_forward right before block i), the GRU's on the weight-gradient stream (idle during the forward
+        pass, joined in front of the GRU); split=False: everything on the current stream."""
         ws, M = self.ws, Bt * T
         masks = {}
-        jobs = []                                   # (early, buffer, numel, p, stream id)
+        jobs = []                                   # (side stream or None, buffer, numel, p, Philox stream id)
         sid = sid0
         if self.use_text:
             if self.p_emb > 0:
-                masks['emb'] = ws.get('mask.emb', (M, self.E)); jobs.append((True, masks['emb'], M * self.E, self.p_emb, sid))
+                masks['emb'] = ws.get('mask.emb', (M, self.E)); jobs.append((s_prep(0), masks['emb'], M * self.E, self.p_emb, sid))
             sid += 1
             for i in range(self.n_tcn):
                 for j in (1, 2):
                     if self.p_tcn > 0:
                         mk = ws.get(f'mask.tcn{i}_{j}', (M, self.H))
-                        jobs.append((i == 0, mk, M * self.H, self.p_tcn, sid))
+                        jobs.append((s_prep(i), mk, M * self.H, self.p_tcn, sid))
                         masks[f'tcn{i}_{j}'] = mk
                     sid += 1
         for l in range(self.L - 1):
             if self.p_gru > 0:
                 mk = ws.get(f'mask.gru{l}', (M, 2 * self.H))
-                jobs.append((False, mk, M * 2 * self.H, self.p_gru, sid))
+                jobs.append((S_WGRAD, mk, M * 2 * self.H, self.p_gru, sid))
                 masks[f'gru{l}'] = mk
             sid += 1
-        for early, mk, n, p, sd in jobs:
-            if early or not split:
+        for st, mk, n, p, sd in jobs:
+            if st is None or not split:
                 ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
         if split:
-            with side.on(S_WGRAD):
-                for early, mk, n, p, sd in jobs:
-                    if not early:
-                        ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
+            for stream in sorted({st for st, *_ in jobs if st is not None}, key=lambda x: (x == S_WGRAD, x)):
+                with side.on(stream):
+                    for st, mk, n, p, sd in jobs:
+                        if st == stream:
+                            ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
         return masks
 
     def start_wav(self, in_audio, training, n_bn_updates=1):
@@ -494,13 +519,14 @@ class GeneratorEngine:
         Ba = in_text.shape[0]
         idx_mod = Ba * T if Bt != Ba else 0
         emb = ws.get('txt.emb', (M, E))
+        side.join(s_prep(0))                       # the embedding's and block 0's dropout masks (make_masks split=True)
+        side.join(S_PREP0W)                        # block 0's weight-normed filters (prep_weights)
         ops.embedding_gather(self.P('text_encoder.embedding.weight'), in_text, idx_mod, masks.get('emb') if masks else None, emb, M, E)
         x, cin = emb, E
         k = self.tcn_k
         for i in range(self.n_tcn):
-            if i == 1:
-                side.join(S_WGRAD)                 # masks of the later blocks / the GRU drawn on the side stream (make_masks split=True)
-                side.join(S_WAVW)                  # weight-normed filters of the later blocks (prep_weights)
+            if i >= 1:
+                side.join(s_prep(i))               # this block's dropout masks (make_masks split=True) and weight-normed filters (prep_weights)
             d = 2 ** i
             q = f'text_encoder.tcn.network.{i}'
             assert cin == H, 'TemporalBlock.downsample (n_inputs != n_outputs) is not on the configured path (tcn.py:33)'
@@ -627,15 +653,23 @@ class GeneratorEngine:
                 audio_feat = self.wav_forward(in_audio, training, n_bn_updates)
         side.join(S_SPK)
         side.join(S_WAV)
-        side.join(S_WGRAD)                          # side-stream mask draws, if text_forward did not already join them
+        side.join(S_WGRAD)                          # the GRU's masks (make_masks split=True)
         side.join(S_WAVW)
+        for st in S_PREP + (S_PREP0W,):
+            side.join(st)                           # no-ops after text_forward; only live when the text branch is configured off
         in_data = ws.get('g.in', (M, self.I))
         Da = 32 if self.use_audio else 0
         Dt = 32 if self.use_text else 0
         assert Dp + Da + Dt + Z == self.I
         ops.gru_input_concat(pre_seq, audio_feat, text_feat, z, in_data, Bt, Ba, T, Dp, Da, Dt, Z)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
-        out = self.gru.forward(in_data, Bt, T, gmasks, save)
+        # work that does not depend on the generator (train_iter_gan: the discriminator's pass over the real clips) can be forked here
+        hook, at = getattr(self, 'beside_gru', None), getattr(self, 'beside_gru_at', -1)
+        self.beside_gru = None
+        if hook is not None and at < 0:
+            hook()
+            hook = None
+        out = self.gru.forward(in_data, Bt, T, gmasks, save, hook=hook, hook_after=at)
         H = self.H
         hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, H // 2)); poses = ws.get('g.poses', (M, m.pose_dim))
         ops.sum_halves(out, hsum, M, H)

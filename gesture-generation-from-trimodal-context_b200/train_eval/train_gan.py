@@ -128,7 +128,7 @@ def _capture_stream(device):
     GEMMs are runnable at the same time, the block scheduler fills free SMs with the critical chain first."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     if key not in _CAPTURE_STREAMS:
-        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1 if config.flat_prio() else max(-2, min(torch.cuda.Stream.priority_range())))
     return _CAPTURE_STREAMS[key]
 
 
@@ -351,13 +351,19 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
     n_pass = len(passes)
     Bt = n_pass * B
     ig = passes.index('g')
+    off = G._noise.offset_dev(dev)
+    seed = G._noise.seed
+    # The text chain (embedding -> 8 dependent GEMMs) is the longest in front of the GRU: its masks and weight-normed filters are queued
+    # first, on their own prioritised streams (engine.py: S_PREP), then the audio chain, then everything else of the iteration's top.
+    g_masks = None
+    if G.training and not (noise is not None and noise.g_masks is not None):
+        g_masks = ge.make_masks(Bt, T, seed, off, split=True)
+    ge.prep_weights('tcn')
     if ge.use_audio and (config.wav_first() or not ge.use_text):
-        ge.start_wav(in_audio, G.training, n_pass)          # eager launches are host-bound: queue the audio chain first (side stream)
+        ge.start_wav(in_audio, G.training, n_pass)          # eager launches are host-bound: queue the audio chain early (side stream)
     pre_seq = ws.get('ti.pre', (B, T, Dm + 1))
     ops.make_pre_seq(target, pre_seq, B, T, Dm, args.n_pre_poses)
 
-    off = G._noise.offset_dev(dev)
-    seed = G._noise.seed
     vid_all = eps_all = None
     with side.on(S_SPK):        # noise / speaker ids feed the speaker branch that ge.forward queues on the same stream
         if ge.z_mode is not None:
@@ -379,12 +385,8 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
                     ops.gather_i64(vid, perm, vid_all[i * B:(i + 1) * B], B)
                 else:
                     vid_all[i * B:(i + 1) * B].copy_(vid)
-    g_masks = None
-    if G.training:
-        if noise is not None and noise.g_masks is not None:
-            g_masks = _stack_masks(ws, noise.g_masks[-n_pass:] if len(noise.g_masks) > n_pass else noise.g_masks, B * T)
-        else:
-            g_masks = ge.make_masks(Bt, T, seed, off, split=True)
+    if G.training and noise is not None and noise.g_masks is not None:
+        g_masks = _stack_masks(ws, noise.g_masks[-n_pass:] if len(noise.g_masks) > n_pass else noise.g_masks, B * T)
 
     d_drawn = {}
     if D.training and not (noise is not None and noise.d_masks is not None):
@@ -415,13 +417,23 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         # generator passes (train_gan.py:38,41-42; BatchNorm statistics still see real before fake)
         de.arena.zero_grad()
         with side.on(S_DREAL):
-            de.prep_weights()
-            p_real = de.forward(target, D.training, d_masks_for(0))
-            ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
-            de.backward(dlogit, need_dposes=False)
+            masks_real = d_masks_for(0)
+
+        def d_real():
+            with side.on(S_DREAL):
+                de.prep_weights()
+                p_real = de.forward(target, D.training, masks_real)
+                ops.bce_sigmoid(p_real, B, 1.0, 0.0, 1.0, sc[4:], dlogit)
+                de.backward(dlogit, need_dposes=False)
+        at = config.d_real_at()
+        if at == 'top':
+            d_real()
+        else:
+            # forked from inside the generator's forward (engine.py: beside_gru): at the GRU input, or behind the first recurrent layers
+            ge.beside_gru, ge.beside_gru_at = d_real, {'concat': -1, 'gru0': 0, 'gru1': 1, 'gru2': 2}[at]
 
     # ---- all generator passes in one sweep
-    ge.prep_weights()
+    ge.prep_weights('rest')
     poses, z, mu, logvar = ge.forward(pre_seq, in_text, in_audio, vid_all, eps_all, Bt, G.training, g_masks, n_bn_updates=n_pass)
     G._noise.advance()          # after the forward has joined the side-stream mask draws that still read this iteration's offset
 

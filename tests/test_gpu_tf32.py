@@ -22,7 +22,8 @@ def _rand(*shape, dev, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 32, 32), (4352, 1800, 600), (4352, 1800, 108), (13056, 300, 300), (102, 150, 300), (4352, 32, 300),
-                                   (1000, 64, 960), (4352, 600, 1800), (300, 28, 64)])
+                                   (1000, 64, 960), (4352, 600, 1800), (300, 28, 64),
+                                   (13056, 1800, 600), (300, 1900, 64), (256, 960, 96)])      # the last three: 240-column tiles
 def test_gemm_tf32_plain(dev, M, N, K):
     from tgb200 import ops
     a = _rand(M, K, dev=dev); w = _rand(N, K, dev=dev, seed=1, scale=K ** -0.5); b = _rand(N, dev=dev, seed=2)
