@@ -11,6 +11,7 @@
 // so the shifted operand is a plain 2-D TMA load with a row offset - no im2col, no padded copy, no chomp.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -36,6 +37,9 @@ struct GemmP {
   float* C; int ldc;
   int M, N, K, taps, shift0, T;
   int clip_rows, tiles_per_clip;     // clip mode (clip_rows > 0): tile = 128 rows of one clip; C row = clip*clip_rows + t
+  int acc_taps;                      // > 1 (clip mode, taps == 1): tap j reads A rows t - j (rows outside the clip: TMA zero fill) against
+                                     // Bw rows j*N + n, every tap into the ONE accumulator - the data gradient of a strided convolution
+  long long c_clip_pitch, c_clip_len;  // acc_taps mode: clip c of C starts at C + c*c_clip_pitch and holds c_clip_len floats (a ragged last row)
   int ksplit;                        // > 1: blockIdx.z owns a contiguous share of the K blocks and ADDS its partial tile to a zeroed C with
                                      // red.global.add (long-K, few-tile problems: the GRU data gradient [4352 x 600] x K 1800 ran 57
                                      // dependent stages on 170 CTAs, 72 us for 31 us worth of operand traffic)
@@ -73,7 +77,8 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
   const int kb_per = p.ksplit > 1 ? (nkb_all + p.ksplit - 1) / p.ksplit : nkb_all;
   const int kb_lo = p.ksplit > 1 ? (int)blockIdx.z * kb_per : 0;
   const int nkb = p.ksplit > 1 ? max(0, min(kb_per, nkb_all - kb_lo)) : nkb_all;
-  const int iters = nkb * p.taps;
+  const int ntap = p.acc_taps > 1 ? p.acc_taps : p.taps;
+  const int iters = nkb * ntap;
   constexpr uint32_t TMEM_COLS_1 = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS_2 = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   const uint32_t tmem_cols = MH == 2 ? 2 * ACC_STRIDE : (p.taps == 2 ? TMEM_COLS_2 : TMEM_COLS_1);
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
         const uint32_t ph = (it / NSTAGE) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const int tap = it / nkb, kb = it - tap * nkb;
-        const int shift = (p.taps == 2 && tap == 0) ? p.shift0 : 0;
+        const int shift = p.acc_taps > 1 ? -tap : ((p.taps == 2 && tap == 0) ? p.shift0 : 0);
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + MH * A_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -122,10 +127,11 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
         const int tap = it / nkb, kb = it - tap * nkb;
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + MH * A_STAGE_BYTES;
-        const uint32_t dcol = tmem_base + (uint32_t)(tap * BN);
+        const uint32_t dcol = tmem_base + (uint32_t)(p.acc_taps > 1 ? 0 : tap * BN);
+        const uint32_t accum = (p.acc_taps > 1 ? it > 0 : kb > 0) ? 1u : 0u;
         constexpr uint32_t hi = desc_hi(1024, 2);                // SWIZZLE_128B; the 4 K-steps of a stage walk the 128-byte row: +32 B each
-        mma_tf32_seq<4, 2>(dcol, desc_lo(sa, 16), hi, desc_lo(sb, 16), hi, idesc, kb > 0 ? 1u : 0u);
-        if (MH == 2) mma_tf32_seq<4, 2>(dcol + ACC_STRIDE, desc_lo(sa + A_STAGE_BYTES, 16), hi, desc_lo(sb, 16), hi, idesc, kb > 0 ? 1u : 0u);
+        mma_tf32_seq<4, 2>(dcol, desc_lo(sa, 16), hi, desc_lo(sb, 16), hi, idesc, accum);
+        if (MH == 2) mma_tf32_seq<4, 2>(dcol + ACC_STRIDE, desc_lo(sa + A_STAGE_BYTES, 16), hi, desc_lo(sb, 16), hi, idesc, accum);
         tc_commit(&empty_bar[s]);
       }
       tc_commit(tmem_full_bar);
@@ -195,13 +201,21 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
           if (p.escale) es = __ldg(reinterpret_cast<const float4*>(p.escale + n));
           if (p.bias && (p.ksplit <= 1 || blockIdx.z == 0)) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           float* crow = p.C + (long long)row0 * p.ldc + n;
+          int cmax = 8;                                          // rows i < cmax may be stored
+          if (p.acc_taps > 1) {
+            // ragged clips: row t of clip `clip` lives at C + clip*c_clip_pitch + t*ldc and only the clip's first c_clip_len floats exist
+            const int tl = t0 + q * 32 + rsub;
+            crow = p.C + (long long)clip * p.c_clip_pitch + (long long)tl * p.ldc + n;
+            const long long left = p.c_clip_len - ((long long)tl * p.ldc + n);          // > 0 and a multiple of 4 when the vector is valid
+            cmax = left <= 0 ? 0 : (int)min((long long)8, (left - 4) / (4ll * p.ldc) + 1);
+          }
           const float* mrow = p.mask ? p.mask + (long long)row0 * p.ldmask + n : nullptr;
           const float* rrow = p.residual ? p.residual + (long long)row0 * p.ldres + n : nullptr;
           const float* srow = stg + rsub * SP + c4;
           const long long cstep = 4ll * p.ldc, mstep = 4ll * p.ldmask, rstep = 4ll * p.ldres;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (4 * i < rows_left) {
+            if (4 * i < rows_left && i < cmax) {
               float4 x = *reinterpret_cast<const float4*>(srow + i * 4 * SP);
               x.x = fmaf(x.x, es.x, bs.x); x.y = fmaf(x.y, es.y, bs.y); x.z = fmaf(x.z, es.z, bs.z); x.w = fmaf(x.w, es.w, bs.w);
               x.x = fmaxf(x.x, x.x * s1); x.y = fmaxf(x.y, x.y * s1); x.z = fmaxf(x.z, x.z * s1); x.w = fmaxf(x.w, x.w * s1);
@@ -303,16 +317,19 @@ int make_map_a(CUtensorMap* m, const float* base, long long clips, long long row
   return 0;
 }
 
+// accumulating-taps mode (tg_conv_dgrad_tf32): A rows per clip differ from the output rows per clip, C clips are ragged
+struct TapExt { int acc_taps; long long a_rows, c_clip_pitch, c_clip_len; };
+
 template <int BN, int NSTAGE, int MH = 1>
-int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
+int launch(const tg_gemm_tf32_t& g, cudaStream_t s, const TapExt* x = nullptr) {
   CUtensorMap ta, tb;
   const bool clipm = g.clip_rows > 0;
   const long long clips = clipm ? g.M / g.clip_rows : 1;
-  const long long arows = clipm ? g.clip_rows : g.a_rows;
+  const long long arows = x ? x->a_rows : (clipm ? g.clip_rows : g.a_rows);
   const long long cp = clipm ? g.a_clip_pitch : arows * (long long)g.lda;
   int rc = make_map_a(&ta, g.A, clips, arows, g.K, g.lda, cp > 0 ? cp : 4, "tg_gemm_tf32(A)");
   if (rc) return rc;
-  rc = make_map_2d(&tb, g.Bw, (long long)g.taps * g.N, g.K, g.ldb, BN, "tg_gemm_tf32(B)");
+  rc = make_map_2d(&tb, g.Bw, (long long)(x ? x->acc_taps : g.taps) * g.N, g.K, g.ldb, BN, "tg_gemm_tf32(B)");
   if (rc) return rc;
   GemmP p;
   p.trace = g_trace;
@@ -321,6 +338,9 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
   p.residual = g.residual; p.ldres = g.ldres; p.act2 = g.act2; p.accumulate = g.accumulate;
   p.clip_rows = clipm ? g.clip_rows : 0;
   p.tiles_per_clip = clipm ? tg_ceil_div(g.clip_rows, BM) : 0;
+  p.acc_taps = x ? x->acc_taps : 1;
+  p.c_clip_pitch = x ? x->c_clip_pitch : 0;
+  p.c_clip_len = x ? x->c_clip_len : 0;
   // split-K: a linear epilogue (scale / bias / mask only), vector-aligned contiguous C, few tiles and a long K loop
   p.ksplit = 1;
   {
@@ -356,6 +376,36 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s) {
 }
 
 }  // namespace
+
+// Data gradient of a strided, unpadded Conv1d as ceil(k/stride) accumulating taps (header: tg_conv_dgrad_tf32).  With t = stride*q + r:
+//   da[b, t, c] = sum_j dy[b, q - j, :] . w[:, c, r + stride*j]        (taps with r + stride*j >= k are zero rows of wd)
+// Row q of the output is the stride*Cin contiguous floats da[b, stride*q .. stride*q + stride - 1, :] of the channels-last gradient.
+extern "C" int tg_conv_dgrad_tf32(const float* dy, const float* wd, float* da, int B, int Tin, int Tout, int Cin, int N, int k, int stride,
+                                  tg_stream stream) {
+  TG_REQUIRE(dy && wd && da && B > 0 && Tin > 0 && Tout > 0 && Cin > 0 && N >= 8 && k > 0 && stride > 0, "tg_conv_dgrad_tf32");
+  TG_REQUIRE((Cin & 3) == 0 && (N & 3) == 0 && Tin >= (Tout - 1) * stride + k, "tg_conv_dgrad_tf32(shape)");
+  TG_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wd) | reinterpret_cast<uintptr_t>(da)) & 15) == 0,
+             "tg_conv_dgrad_tf32(alignment)");
+  const int Q = tg_ceil_div(Tin, stride), NP = stride * Cin;
+  tg_gemm_tf32_t g;
+  memset(&g, 0, sizeof(g));
+  g.A = dy; g.lda = N; g.a_rows = Tout;
+  g.Bw = wd; g.ldb = N;
+  g.C = da; g.ldc = NP;
+  g.M = B * Q; g.N = NP; g.K = N; g.taps = 1; g.T = 1;
+  g.clip_rows = Q; g.a_clip_pitch = (long long)Tout * N;
+  TapExt x;
+  x.acc_taps = tg_ceil_div(k, stride);
+  x.a_rows = Tout;
+  x.c_clip_pitch = (long long)Tin * Cin;
+  x.c_clip_len = (long long)Tin * Cin;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (NP <= 32) return launch<32, 4>(g, s, &x);
+  if (NP <= 64) return launch<64, 4>(g, s, &x);
+  const int p128 = tg_ceil_div(NP, 128) * 128, p160 = tg_ceil_div(NP, 160) * 160;
+  if (p160 < p128) return launch<160, 3>(g, s, &x);
+  return launch<128, 3>(g, s, &x);
+}
 
 extern "C" int tg_debug_gemm_trace(long long* device_buf) {
   g_trace = device_buf;

@@ -20,6 +20,17 @@ __global__ void window_weights_kernel(const float* __restrict__ w, float* __rest
     if (w2t) w2t[r * N + n] = v;
   }
 }
+// w [N][Cin][k] -> wd [ceil(k/stride)][stride*Cin][N]: wd[j][r*Cin + c][n] = w[n][c][r + stride*j] (0 when that tap does not exist)
+__global__ void window_dgrad_weights_kernel(const float* __restrict__ w, float* __restrict__ wd, int N, int Cin, int k, int stride) {
+  const int ntap = (k + stride - 1) / stride, NP = stride * Cin;
+  const int total = ntap * NP * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % N, rc = (i / N) % NP, j = i / (N * NP);
+    const int r = rc / Cin, c = rc - r * Cin;
+    const int tap = r + stride * j;
+    wd[i] = tap < k ? w[(n * Cin + c) * k + tap] : 0.f;
+  }
+}
 // dw [N][Cin][k] += dw2 [N][k*Cin]
 __global__ void window_wgrad_add_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int N, int Cin, int k) {
   const int total = N * Cin * k;
@@ -183,6 +194,13 @@ extern "C" int tg_window_weights(const float* w, float* w2, float* w2t, int N, i
   TG_REQUIRE(w && w2 && N > 0 && Cin > 0 && k > 0, "tg_window_weights");
   window_weights_kernel<<<ew_grid((long long)N * Cin * k), 256, 0, (cudaStream_t)stream>>>(w, w2, w2t, N, Cin, k);
   TG_CHECK_LAUNCH("tg_window_weights");
+  return 0;
+}
+
+extern "C" int tg_window_dgrad_weights(const float* w, float* wd, int N, int Cin, int k, int stride, tg_stream stream) {
+  TG_REQUIRE(w && wd && N > 0 && Cin > 0 && k > 0 && stride > 0, "tg_window_dgrad_weights");
+  window_dgrad_weights_kernel<<<ew_grid((long long)tg_ceil_div(k, stride) * stride * Cin * N), 256, 0, (cudaStream_t)stream>>>(w, wd, N, Cin, k, stride);
+  TG_CHECK_LAUNCH("tg_window_dgrad_weights");
   return 0;
 }
 

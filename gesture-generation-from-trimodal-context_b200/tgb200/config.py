@@ -78,6 +78,14 @@ def d_real_at() -> str:
     return _DREAL_AT
 
 
+_WAV_DGRAD_DIRECT = os.environ.get('TGB200_WAV_DGRAD_DIRECT', '1') == '1'
+
+
+def wav_dgrad_direct() -> bool:
+    """WavEncoder conv2-4 data gradients as accumulating-tap GEMMs (tg_conv_dgrad_tf32) instead of column GEMM + col2im."""
+    return _WAV_DGRAD_DIRECT
+
+
 _FLAT_PRIO = os.environ.get('TGB200_FLAT_PRIO', '0') == '1'
 
 

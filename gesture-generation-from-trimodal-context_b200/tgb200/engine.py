@@ -66,6 +66,7 @@ class _Overlap:
             return
         if i == S_WGRAD:
             self.join(S_BIAS)             # the bias-gradient column sums forked off the weight-gradient stream
+            self.join(S_BIAS2)
             self.join(S_WGRAD2)           # the second / third weight-gradient streams (independent filters round-robin over them)
             self.join(S_WGRAD3)
             self.join(S_SCALARS)          # the early read-back of the logged scalars (train_gan.py)
@@ -81,6 +82,7 @@ class _Overlap:
 
 side = _Overlap()
 S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3, S_SCALARS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+S_BIAS2 = 15                   # second bias-gradient stream: the column sums alternate between S_BIAS and S_BIAS2
 S_PREP0W = 14                  # weight-normed filters of block 0 (beside its masks on S_PREP[0])
 S_PREP = (10, 11, 12, 13)      # dropout masks + weight-normed filters of TextEncoderTCN block i live on S_PREP[i % 4], joined right before that block
 
@@ -135,6 +137,9 @@ def mm_nn(dY, W, Wt, dX, *, M, N, K, **epi):
         ops.linear_dgrad(dY, W, dX, M=M, K=K, N=N, **epi)
 
 
+_bias_rr = [0]
+
+
 def wgrad(X, G, dW, *, B, T, N, Cin, shift=0, ldx=None, ldg=None, ldw=None, dbias=None):
     """dW[N,Cin] += sum_{b,t} G[(b,t), :]^T X[(b,t+shift), :] (rows outside the clip are zero): tcgen05 TF32 kernel in fast mode
     when TMA can describe the operands, fp32 FFMA split-K kernel otherwise."""
@@ -145,7 +150,10 @@ def wgrad(X, G, dW, *, B, T, N, Cin, shift=0, ldx=None, ldg=None, ldw=None, dbia
         if dbias is not None:
             # ~3 us column-sum launches: on their own stream they run beside the weight-gradient GEMMs instead of between them (60 per
             # iteration; they owned 89 us of the step when serialised on the weight-gradient stream, profiles/r02_timeline_step_ownership.txt)
-            with side.on(S_BIAS):
+            # two streams, alternating: the discriminator's twelve column sums in a row outlasted its weight-gradient GEMMs by ~25 us and
+            # gated its Adam step (and, in the generator pass, the hand-over of d poses) - profiles/r02_timeline_step_3p86ms.txt, 1856-1920 us
+            _bias_rr[0] ^= 1
+            with side.on(S_BIAS2 if _bias_rr[0] else S_BIAS):
                 ops.col_sum(G, ldg, B * T, N, dbias)
         ops.wgrad_tf32(G, X, dW, B=B, T=T, N=N, Cin=Cin, shift=shift, ldg=ldg, ldx=ldx, ldw=ldw, dbias=None)
     else:
@@ -443,6 +451,10 @@ class GeneratorEngine:
                 ops.affine_lrelu(x, a, Ba * tin, cin, scale, shift, 0.3)
                 w2 = ws.get(f'wav.w2_{li}', (cout, k * cin)); w2t = ws.get(f'wav.w2t_{li}', (k * cin, cout))
                 ops.window_weights(self.P(conv + '.weight'), w2, w2t, cout, cin, k)
+                if config.wav_dgrad_direct() and cout >= 8:
+                    wd = ws.get(f'wav.wd_{li}', (-(-k // s) * s * cin, cout))
+                    with side.on(S_WAVW):           # only the backward reads it (wav_backward runs after the forward's joins)
+                        ops.window_dgrad_weights(self.P(conv + '.weight'), wd, cout, cin, k, s)
                 ops.gemm_tf32(a, w2, y, M=Ba * tout, N=cout, K=k * cin, lda=s * cin, clip_rows=tout, a_clip_pitch=tin * cin,
                               bias=self.P(conv + '.bias'))
             else:
@@ -486,10 +498,15 @@ class GeneratorEngine:
                     ops.wgrad_tf32(dy, a, dw2, B=Ba, T=tout, N=cout, Cin=k * cin, ldx=s * cin, x_clip_pitch=tin * cin,
                                    dbias=self.G(conv + '.bias'))
                     ops.window_wgrad_add(dw2, self.G(conv + '.weight'), cout, cin, k)
-                col = ws.get('wav.col', (Ba * self.wav_T[2] * self.WAV[1][2] * self.WAV[1][0],))[:Ba * tout * k * cin].view(Ba * tout, k * cin)
-                ops.gemm_tf32(dy, ws[f'wav.w2t_{li}'], col, M=Ba * tout, N=k * cin, K=cout)
                 da = ws.get(f'wav.da{li - 1}', (Ba * tin, cin))
-                ops.col2im(col, da, B=Ba, Tin=tin, Tout=tout, Cin=cin, k=k, stride=s)
+                if config.wav_dgrad_direct() and cout >= 8:
+                    # transposed convolution as ceil(k/s) accumulating GEMM taps over dy rows shifted in place by TMA: no column matrix
+                    # (the column GEMM + col2im wrote and re-read 161 MB for conv2: 188 us of the backward's critical tail)
+                    ops.conv_dgrad_tf32(dy, ws[f'wav.wd_{li}'], da, B=Ba, Tin=tin, Tout=tout, Cin=cin, N=cout, k=k, stride=s)
+                else:
+                    col = ws.get('wav.col', (Ba * self.wav_T[2] * self.WAV[1][2] * self.WAV[1][0],))[:Ba * tout * k * cin].view(Ba * tout, k * cin)
+                    ops.gemm_tf32(dy, ws[f'wav.w2t_{li}'], col, M=Ba * tout, N=k * cin, K=cout)
+                    ops.col2im(col, da, B=Ba, Tin=tin, Tout=tout, Cin=cin, k=k, stride=s)
             elif fast and cin == 1 and cout == 16 and k <= 15:
                 ops.conv1_wgrad(x, dy, self.G(conv + '.weight'), self.G(conv + '.bias'), B=Ba, Tin=tin, Tout=tout, N=cout, taps=k, stride=s,
                                 pad=pad)
@@ -703,7 +720,8 @@ class GeneratorEngine:
             # data parallel: the recurrent layers' gradients (the tail of the flat arena, 22 MB of 53) are complete once the weight-gradient
             # stream has drained what gru.backward queued on it - their all-reduce starts now, under the text / audio encoder backward
             with side.on(S_WGRAD):
-                side.join(S_BIAS)       # the bias gradients' column sums run on their own stream
+                side.join(S_BIAS)       # the bias gradients' column sums run on their own streams
+                side.join(S_BIAS2)
                 self.on_gru_grads()
         if not need_dx:
             side.join(S_WGRAD)

@@ -177,6 +177,14 @@ def window_wgrad_add(dw2, dw, N, Cin, k):
     check(_L().tg_window_wgrad_add(_p(_f32(dw2)), _p(_f32(dw)), N, Cin, k, _s()), 'tg_window_wgrad_add'); _count()
 
 
+def window_dgrad_weights(w, wd, N, Cin, k, stride):
+    check(_L().tg_window_dgrad_weights(_p(_f32(w)), _p(_f32(wd)), N, Cin, k, stride, _s()), 'tg_window_dgrad_weights'); _count()
+
+
+def conv_dgrad_tf32(dy, wd, da, *, B, Tin, Tout, Cin, N, k, stride):
+    check(_L().tg_conv_dgrad_tf32(_p(_f32(dy)), _p(_f32(wd)), _p(_f32(da)), B, Tin, Tout, Cin, N, k, stride, _s()), 'tg_conv_dgrad_tf32'); _count()
+
+
 def col2im(col, da, *, B, Tin, Tout, Cin, k, stride):
     check(_L().tg_col2im(_p(_f32(col)), _p(_f32(da)), B, Tin, Tout, Cin, k, stride, _s()), 'tg_col2im'); _count()
 

@@ -130,6 +130,16 @@ int tg_window_wgrad_add(const float* dw2, float* dw, int N, int Cin, int k, tg_s
 /* data gradient of a strided, unpadded Conv1d from the "column" matrix col [B*Tout, k*Cin] = dY @ w2:
  * da[b, s, c] = sum over (t, j) with t*stride + j == s of col[(b*Tout+t), j*Cin + c]; gather, no atomics; Cin % 4 == 0 */
 int tg_col2im(const float* col, float* da, int B, int Tin, int Tout, int Cin, int k, int stride, tg_stream stream);
+/* The same data gradient WITHOUT the column matrix (the column GEMM wrote and tg_col2im re-read 161 MB for conv2): with t = stride*q + r,
+ *   da[b, t, c] = sum_{j < ceil(k/stride)} dy[b, q - j, :] . w[:, c, r + stride*j]      (dy rows outside [0,Tout) and taps >= k are zero)
+ * i.e. one tensor-core GEMM over the rows q whose output row is the stride*Cin contiguous floats da[b, stride*q .. +stride-1, :], its
+ * ceil(k/stride) taps accumulating in one TMEM accumulator; the shifted dy rows are read in place by TMA (zero fill outside the clip).
+ * tg_window_dgrad_weights: nn.Conv1d filter w [N,Cin,k] -> wd [ceil(k/stride)][stride*Cin][N], wd[j][r*Cin+c][n] = w[n][c][r+stride*j].
+ * dy [B,Tout,N], da [B,Tin,Cin] channels-last, pad 0, Cin % 4 == 0, N % 4 == 0, N >= 8, 16-byte aligned.
+ * (autograd of F.conv1d in WavEncoder, multimodal_context_net.py:16-22) */
+int tg_window_dgrad_weights(const float* w, float* wd, int N, int Cin, int k, int stride, tg_stream stream);
+int tg_conv_dgrad_tf32(const float* dy, const float* wd, float* da, int B, int Tin, int Tout, int Cin, int N, int k, int stride,
+                       tg_stream stream);
 /* conv1 (Cin = 1, N = 16, taps <= 15) weight and bias gradient: dW[n,j] += sum dy[(b,t),n] * x[b, t*stride + j - pad];
  * dbias[n] += sum dy[(b,t),n] (dbias may be NULL) */
 int tg_conv1_wgrad(const float* x, const float* dy, float* dW, float* dbias, int B, int Tin, int Tout, int N, int taps, int stride,

@@ -1113,6 +1113,36 @@ class EmuLib:
         _arr(dw, N * Cin * k)[:] += _arr(dw2, N * Cin * k).reshape(N, k, Cin).transpose(0, 2, 1).reshape(-1)
         return 0
 
+    def tg_window_dgrad_weights(self, w, wd, N, Cin, k, stride, stream):
+        self.calls.append('tg_window_dgrad_weights')
+        ntap = -(-k // stride)
+        W = _arr(w, N * Cin * k).reshape(N, Cin, k)
+        WD = np.zeros((ntap, stride, Cin, N), np.float32)
+        for j in range(ntap):
+            for r in range(stride):
+                if r + stride * j < k:
+                    WD[j, r] = W[:, :, r + stride * j].T
+        _arr(wd, ntap * stride * Cin * N)[:] = WD.reshape(-1)
+        return 0
+
+    def tg_conv_dgrad_tf32(self, dy, wd, da, B, Tin, Tout, Cin, N, k, stride, stream):
+        self.calls.append('tg_conv_dgrad_tf32')
+        assert Cin % 4 == 0 and N % 4 == 0 and N >= 8 and Tin >= (Tout - 1) * stride + k, 'TG_REQUIRE of tg_conv_dgrad_tf32'
+        assert dy % 16 == 0 and wd % 16 == 0 and da % 16 == 0, 'TG_REQUIRE of tg_conv_dgrad_tf32(alignment)'
+        ntap = -(-k // stride)
+        Q = -(-Tin // stride)
+        DY = _tf32(_arr(dy, B * Tout * N).reshape(B, Tout, N), self.tf32_round).astype(np.float64)
+        WD = _tf32(_arr(wd, ntap * stride * Cin * N).reshape(ntap, stride * Cin, N), self.tf32_round).astype(np.float64)
+        out = np.zeros((B, Q, stride * Cin))
+        for j in range(ntap):
+            sh = np.zeros((B, Q, N))                       # dy rows q - j, zero outside [0, Tout)
+            lo, hi = j, min(Q, Tout + j)
+            if hi > lo:
+                sh[:, lo:hi] = DY[:, lo - j:hi - j]
+            out += sh @ WD[j].T
+        _arr(da, B * Tin * Cin)[:] = out.reshape(B, Q * stride, Cin)[:, :Tin].astype(np.float32).reshape(-1)
+        return 0
+
     def tg_col2im(self, col, da, B, Tin, Tout, Cin, k, stride, stream):
         self.calls.append('tg_col2im')
         assert Cin % 4 == 0 and col % 16 == 0 and da % 16 == 0, 'TG_REQUIRE of tg_col2im'

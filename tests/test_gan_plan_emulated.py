@@ -67,10 +67,11 @@ def emu_fast():
 
 def test_fast_mode_plans(emu_fast):
     """The DEFAULT (tf32) mode routes the large GEMMs, weight gradients, the generator GRU and WavEncoder conv2-4 through the
-    tensor-core entries (window views, two-tap causal GEMM, col2im, MN-major weight gradients): same goldens / oracle, other plan."""
+    tensor-core entries (window views, two-tap causal GEMM, accumulating-tap data gradients, MN-major weight gradients): same goldens /
+    oracle, other plan."""
     GP.test_fast_mode_forward_eval_vs_reference_golden(CPU)
     GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11, 2000, 50)
-    for sym in ('tg_gemm_tf32', 'tg_wgrad_tf32', 'tg_gru_layer_fwd_tf32', 'tg_gru_layer_bwd_tf32', 'tg_col2im', 'tg_conv1_wgrad'):
+    for sym in ('tg_gemm_tf32', 'tg_wgrad_tf32', 'tg_gru_layer_fwd_tf32', 'tg_gru_layer_bwd_tf32', 'tg_conv_dgrad_tf32', 'tg_conv1_wgrad'):
         assert sym in emu_fast.calls, sym
 
 

@@ -226,3 +226,27 @@ def test_conv1_wgrad(dev, B, Tin):
         torch.cuda.synchronize()
     assert rel_l2(dw - 1.0, w.grad.view(N, k)) < 1e-4, rel_l2(dw - 1.0, w.grad.view(N, k))
     assert rel_l2(db - 1.0, bb.grad) < 1e-4
+
+
+@pytest.mark.parametrize('B,Tin,cin,cout,k,s', [(3, 200, 16, 32, 15, 6), (128, 7891, 16, 32, 15, 6), (128, 1313, 32, 64, 15, 6), (128, 217, 64, 32, 15, 6),
+                                                (5, 100, 8, 16, 5, 5), (2, 61, 4, 8, 7, 3)])
+def test_conv_dgrad_tf32_matches_conv_transpose(dev, B, Tin, cin, cout, k, s):
+    """tg_conv_dgrad_tf32 (accumulating shifted taps, no column matrix) against autograd's conv1d data gradient."""
+    from tgb200 import ops
+    Tout = (Tin - k) // s + 1
+    w = _rand(cout, cin, k, dev=dev, scale=(cin * k) ** -0.5)
+    dy = _rand(B, Tout, cout, dev=dev, seed=1)
+    ntap = -(-k // s)
+    wd = torch.full((ntap * s * cin, cout), float('nan'), device=dev)
+    ops.window_dgrad_weights(w, wd, cout, cin, k, s)
+    da = torch.full((B, Tin, cin), float('nan'), device=dev)
+    guard = torch.full((64,), 7.0, device=dev)                      # allocated right behind da on most allocators; checked loosely
+    ops.conv_dgrad_tf32(dy, wd, da, B=B, Tin=Tin, Tout=Tout, Cin=cin, N=cout, k=k, stride=s)
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
+    ref = torch.nn.functional.conv_transpose1d(dy.double().transpose(1, 2), w.double(), stride=s)          # [B, cin, (Tout-1)*s + k]
+    full = torch.zeros(B, cin, Tin, dtype=torch.float64, device=dev)
+    full[:, :, :ref.shape[2]] = ref
+    assert torch.isfinite(da).all()
+    assert rel_l2(da, full.transpose(1, 2)) < TF32_TOL, rel_l2(da, full.transpose(1, 2))
+    assert (guard == 7.0).all()
