@@ -226,6 +226,8 @@ class GruPlan:
             saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
             mk = masks[l] if (masks is not None and l < self.L - 1) else None
             drop = ws.get(f'{tag}.drop{l}', (M, 2 * H)) if mk is not None else None
+            if l == 0 and mk is not None:
+                side.join(S_WGRAD)          # masks drawn beside the first input projection (PoseGenerator engine: _late_masks)
             if tc and mk is not None:
                 # the inter-layer dropout rides on the recurrence kernel's output store (was a separate 94 MB elementwise pass per layer)
                 ops.gru_layer_fwd_tf32_drop(gi, self._w('weight_hh', l), self._w('weight_hh', l, True), self._w('bias_hh', l),
@@ -407,12 +409,18 @@ class GeneratorEngine:
         for st, mk, n, p, sd in jobs:
             if st is None or not split:
                 ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
+        self._late_masks = None
         if split:
-            for stream in sorted({st for st, *_ in jobs if st is not None}, key=lambda x: (x == S_WGRAD, x)):
+            for stream in sorted({st for st, *_ in jobs if st is not None and st != S_WGRAD}):
                 with side.on(stream):
                     for st, mk, n, p, sd in jobs:
                         if st == stream:
                             ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
+            # the GRU's inter-layer masks (3 x 31 MB at batch 3 x 128) are first read by layer 0's recurrence: forward() draws them once the
+            # GRU input exists, under the first input projection, instead of at the bandwidth-saturated top of the iteration
+            late = [(mk, n, p, sd) for st, mk, n, p, sd in jobs if st == S_WGRAD]
+            if late:
+                self._late_masks = (late, seed, offset_dev)
         return masks
 
     def start_wav(self, in_audio, training, n_bn_updates=1):
@@ -681,6 +689,12 @@ class GeneratorEngine:
         ops.gru_input_concat(pre_seq, audio_feat, text_feat, z, in_data, Bt, Ba, T, Dp, Da, Dt, Z)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         # work that does not depend on the generator (train_iter_gan: the discriminator's pass over the real clips) can be forked here
+        late = getattr(self, '_late_masks', None)
+        self._late_masks = None
+        if late is not None:
+            with side.on(S_WGRAD):
+                for mk, n, p, sd in late[0]:
+                    ops.philox_dropout_mask(mk, n, p, late[1], late[2], sd)
         hook, at = getattr(self, 'beside_gru', None), getattr(self, 'beside_gru_at', -1)
         self.beside_gru = None
         if hook is not None and at < 0:
