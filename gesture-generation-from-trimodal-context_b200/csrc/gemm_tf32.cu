@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
       tap0_ok = ts >= 0 && ts < p.T;
     }
     const uint32_t lane_addr0 = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool vec_ok = (p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+    // (N need not be a multiple of 4: a lane whose four columns straddle N takes the scalar path below - the 150-wide head with a 152-float
+    // row pitch stores 37 vectors and one half-quad per row instead of 150 scalars)
+    const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                        (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.escale || (reinterpret_cast<uintptr_t>(p.escale) & 15) == 0) &&
                         (!p.mask || ((p.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) &&
                         (!p.residual || ((p.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
     // All TMA loads have landed and every MMA has retired once tmem_full_bar fires, so the pipeline stages are free:
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
       __syncwarp();
       const int n = nb + c4;                      // this lane's 4 columns
       if (BN % 32 != 0 && c0 + c4 >= BN) {        // BN = 240: the last 32-column chunk is half a tile wide
-      } else if (vec_ok) {
-        if (n < p.N) {                            // N % 4 == 0: the lane's four columns are all valid or all invalid
+      } else if (vec_ok && (n + 3 < p.N || n >= p.N)) {
+        if (n < p.N) {                            // the lane's four columns are all valid
           float4 es = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.escale) es = __ldg(reinterpret_cast<const float4*>(p.escale + n));
           if (p.bias && (p.ksplit <= 1 || blockIdx.z == 0)) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -351,6 +354,7 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s, const TapExt* x = nullptr) {
     static const bool off = getenv("TGB200_NO_SPLITK") != nullptr;
     if (!off && linear && vec && nkb_all >= 24 && tiles < 2 * tg_num_sms()) {
       int ks = (3 * tg_num_sms() + tiles - 1) / tiles;         // aim at ~3 resident CTAs' worth of tiles per SM pair
+      if (MH == 2) ks = tg_num_sms() / tiles;                  // 256-row tiles hold a whole SM: size the split for exactly one wave
       if (ks > 4) ks = 4;
       if (ks > nkb_all / 8) ks = nkb_all / 8;
       while (ks > 1 && ((nkb_all + ks - 1) / ks) * (ks - 1) >= nkb_all) --ks;      // every share non-empty
@@ -443,6 +447,17 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   // 3-4 stages keep two CTAs resident per SM (shared memory and 2 x 256 TMEM columns), so one CTA's epilogue overlaps
   // the other's main loop; the two-accumulator mode is limited to BN <= 128 for the same reason (2 x 2 x 128 = 512 columns)
   if (g.taps == 2 && bn == 160) bn = 128;
+  // long-K problems with few output tiles (the GRU data gradient [4352 x 1800] x [1800 x 600]): 256-row x 160-column tiles, one CTA per
+  // SM, split-K sized to ONE wave.  The 128-row tiles ran 1.7 waves of 2 CTAs per SM (510 CTAs) and took 63 us for ~30 us of operand
+  // traffic; the conditions mirror launch()'s split-K test (linear epilogue, vector-aligned contiguous C)
+  {
+    static const bool off = getenv("TGB200_NO_WIDE_SPLITK") != nullptr || getenv("TGB200_NO_SPLITK") != nullptr;
+    const bool linear = g.taps == 1 && g.clip_rows == 0 && g.act1 == 0 && g.act2 == 0 && !g.residual && !g.accumulate;
+    const bool vec = (g.N & 3) == 0 && g.ldc == g.N && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+                     (!g.mask || ((g.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
+    const int tiles = tg_ceil_div(g.M, 256) * tg_ceil_div(g.N, 160);
+    if (!off && linear && vec && g.N > 128 && g.M >= 256 && tg_ceil_div(g.K, BKF) >= 24 && tiles <= tg_num_sms()) return launch<160, 3, 2>(g, s);
+  }
   if (bn == 32) return launch<32, 4>(g, s);
   if (bn == 64) return launch<64, 4>(g, s);
   if (bn == 128) return launch<128, 3>(g, s);

@@ -86,6 +86,14 @@ def wav_dgrad_direct() -> bool:
     return _WAV_DGRAD_DIRECT
 
 
+_HEAD_PADDED = os.environ.get('TGB200_HEAD_PADDED', '1') == '1'
+
+
+def head_padded() -> bool:
+    """PoseGenerator output head: 152-float row pitch for the 150-wide hidden activation so its GEMMs run on the tensor cores (fast mode)."""
+    return _HEAD_PADDED
+
+
 _FLAT_PRIO = os.environ.get('TGB200_FLAT_PRIO', '0') == '1'
 
 

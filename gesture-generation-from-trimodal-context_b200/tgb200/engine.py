@@ -378,7 +378,19 @@ class GeneratorEngine:
                         continue
                     w = self.P(name)
                     ops.transpose(w, ws.get('T.' + name, (w.shape[1], w.shape[0])), w.shape[0], w.shape[1])
+                if self.head_ld() != self.H // 2:
+                    # the head's 150-wide hidden layer with a 152-float row pitch (TMA pitches are multiples of 16 bytes): padded copies of
+                    # out.2.weight [D,150] and out.0.weight^T [H,150]; the pad columns are never read (the TMA maps end at column 150)
+                    Hh, ld = self.H // 2, self.head_ld()
+                    ws.get('P.out.2.weight', (self.m.pose_dim, ld), zero=True)[:, :Hh].copy_(self.P('out.2.weight'))
+                    ws.get('PT.out.0.weight', (self.H, ld), zero=True)[:, :Hh].copy_(self.P('out.0.weight').t())
             self.gru.prep()
+
+    def head_ld(self):
+        """Row pitch of the output head's hidden activation y1 [M, H/2]: padded to a multiple of 4 floats in fast mode so that both head
+        GEMMs and the data gradient through out.0 run on the tensor cores (H/2 = 150: a 600-byte pitch is not a TMA pitch)."""
+        Hh = self.H // 2
+        return (Hh + 3) // 4 * 4 if (config.fast() and config.head_padded() and Hh >= 32) else Hh
 
     def make_masks(self, Bt, T, seed, offset_dev, sid0=0, split=False):
         """Dropout keep-masks (scaled by 1/(1-p)) for one training forward over Bt clips, from the Philox kernel.
@@ -702,10 +714,15 @@ class GeneratorEngine:
             hook = None
         out = self.gru.forward(in_data, Bt, T, gmasks, save, hook=hook, hook_after=at)
         H = self.H
-        hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, H // 2)); poses = ws.get('g.poses', (M, m.pose_dim))
+        ld = self.head_ld()
+        hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, ld), zero=True); poses = ws.get('g.poses', (M, m.pose_dim))
         ops.sum_halves(out, hsum, M, H)
-        mm_nt(hsum, self.P('out.0.weight'), y1, M=M, N=H // 2, K=H, bias=self.P('out.0.bias'))      # LeakyReLU(True) == identity
-        mm_nt(y1, self.P('out.2.weight'), poses, M=M, N=m.pose_dim, K=H // 2, bias=self.P('out.2.bias'))
+        if ld != H // 2:
+            ops.gemm_tf32(hsum, self.P('out.0.weight'), y1, M=M, N=H // 2, K=H, ldc=ld, bias=self.P('out.0.bias'))
+            ops.gemm_tf32(y1, ws['P.out.2.weight'], poses, M=M, N=m.pose_dim, K=H // 2, lda=ld, ldb=ld, bias=self.P('out.2.bias'))
+        else:
+            mm_nt(hsum, self.P('out.0.weight'), y1, M=M, N=H // 2, K=H, bias=self.P('out.0.bias'))      # LeakyReLU(True) == identity
+            mm_nt(y1, self.P('out.2.weight'), poses, M=M, N=m.pose_dim, K=H // 2, bias=self.P('out.2.bias'))
         return poses.view(Bt, T, m.pose_dim), z, mu, logvar
 
     def backward(self, d_poses, lo, hi, d_mu=None, d_logvar=None, d_z=None):
@@ -718,14 +735,23 @@ class GeneratorEngine:
         r0, r1 = lo * T, hi * T
         H, D = self.H, m.pose_dim
         d_poses = d_poses.reshape(Mb, D)
-        dy1 = ws.get('g.dy1', (Mb, H // 2)); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
+        Hh, ld = H // 2, self.head_ld()
+        dy1 = ws.get('g.dy1', (Mb, ld), zero=True); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
         side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading the scratch buffers below
-        with side.on(S_WGRAD):  # the head's weight gradients are fp32 CUDA-core kernels (150 columns: no TMA pitch): off the chain to the GRU
-            ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=H // 2, N=D)
-        ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=H // 2, N=D)          # K = 27 reduction: fp32 kernel
+        with side.on(S_WGRAD):  # the head's weight gradients are fp32 CUDA-core kernels (27 / 150 columns): off the chain to the GRU
+            ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=Hh, N=D, lda=ld)
+        ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=Hh, N=D, ldc=ld)          # K = 27 reduction: fp32 kernel
         with side.on(S_WGRAD2):
-            wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=H // 2, Cin=H, dbias=self.G('out.0.bias'))
-        mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=H // 2, K=H)
+            if ld != Hh:
+                ops.conv_wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, Tin=T, Tout=T, N=Hh, Cin=H, taps=1, lda=H, ldg=ld, ldw=H,
+                               dbias=self.G('out.0.bias'))
+            else:
+                wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=Hh, Cin=H, dbias=self.G('out.0.bias'))
+        if ld != Hh:
+            # d hsum = dy1 @ out.0.weight on the tensor cores: A = dy1 (152-float pitch, K = 150), B = the padded transpose [H, 152]
+            ops.gemm_tf32(dy1, ws['PT.out.0.weight'], dhs, M=Mb, N=H, K=Hh, lda=ld, ldb=ld)
+        else:
+            mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=Hh, K=H)
         ops.dup_halves(dhs, dout, Mb, H)
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'

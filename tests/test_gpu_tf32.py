@@ -23,7 +23,8 @@ def _rand(*shape, dev, seed=0, scale=1.0):
 
 @pytest.mark.parametrize('M,N,K', [(128, 32, 32), (4352, 1800, 600), (4352, 1800, 108), (13056, 300, 300), (102, 150, 300), (4352, 32, 300),
                                    (1000, 64, 960), (4352, 600, 1800), (300, 28, 64),
-                                   (13056, 1800, 600), (300, 1900, 64), (256, 960, 96)])      # the last three: 240-column tiles
+                                   (13056, 1800, 600), (300, 1900, 64), (256, 960, 96),       # 240-column tiles
+                                   (300, 320, 1024), (4352, 600, 1824)])                     # 256-row split-K tiles (with (4352, 600, 1800) above)
 def test_gemm_tf32_plain(dev, M, N, K):
     from tgb200 import ops
     a = _rand(M, K, dev=dev); w = _rand(N, K, dev=dev, seed=1, scale=K ** -0.5); b = _rand(N, dev=dev, seed=2)
@@ -250,3 +251,30 @@ def test_conv_dgrad_tf32_matches_conv_transpose(dev, B, Tin, cin, cout, k, s):
     assert torch.isfinite(da).all()
     assert rel_l2(da, full.transpose(1, 2)) < TF32_TOL, rel_l2(da, full.transpose(1, 2))
     assert (guard == 7.0).all()
+
+
+@pytest.mark.parametrize('M', [4352, 13056, 77])
+def test_gemm_tf32_padded_pitch_head(dev, M):
+    """The output head's 150-wide hidden layer with a 152-float row pitch: N % 4 != 0 with a vector epilogue (the last quad of a row is
+    stored as scalars, the pad columns are never written), then K = 150 read through lda = ldb = 152 (the TMA maps end at column 150)."""
+    from tgb200 import ops
+    H, Hh, ld, D = 300, 150, 152, 27
+    x = _rand(M, H, dev=dev); w0 = _rand(Hh, H, dev=dev, seed=1, scale=H ** -0.5); b0 = _rand(Hh, dev=dev, seed=2)
+    y1 = torch.full((M, ld), 7.0, device=dev)
+    ops.gemm_tf32(x, w0, y1, M=M, N=Hh, K=H, ldc=ld, bias=b0)
+    ref1 = x.double() @ w0.double().t() + b0.double()
+    assert rel_l2(y1[:, :Hh], ref1) < TF32_TOL, rel_l2(y1[:, :Hh], ref1)
+    assert (y1[:, Hh:] == 7.0).all()
+    w2p = torch.full((D, ld), float('nan'), device=dev); w2 = _rand(D, Hh, dev=dev, seed=3, scale=Hh ** -0.5); w2p[:, :Hh] = w2
+    b2 = _rand(D, dev=dev, seed=4)
+    y1[:, Hh:] = float('nan')                 # pad columns must not be read
+    poses = torch.full((M, D), float('nan'), device=dev)
+    ops.gemm_tf32(y1, w2p, poses, M=M, N=D, K=Hh, lda=ld, ldb=ld, bias=b2)
+    ref2 = y1[:, :Hh].double() @ w2.double().t() + b2.double()
+    assert rel_l2(poses, ref2) < TF32_TOL, rel_l2(poses, ref2)
+    # data gradient through out.0: dhs = dy1 @ W0 with the padded transpose as the B operand
+    w0tp = torch.full((H, ld), float('nan'), device=dev); w0tp[:, :Hh] = w0.t()
+    dhs = torch.full((M, H), float('nan'), device=dev)
+    ops.gemm_tf32(y1, w0tp, dhs, M=M, N=H, K=Hh, lda=ld, ldb=ld)
+    ref3 = y1[:, :Hh].double() @ w0.double()
+    assert rel_l2(dhs, ref3) < TF32_TOL, rel_l2(dhs, ref3)
