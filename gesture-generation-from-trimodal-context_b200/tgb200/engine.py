@@ -69,7 +69,6 @@ class _Overlap:
             self.join(S_BIAS2)
             self.join(S_WGRAD2)           # the second / third weight-gradient streams (independent filters round-robin over them)
             self.join(S_WGRAD3)
-            self.join(S_SCALARS)          # the early read-back of the logged scalars (train_gan.py)
         cur = torch.cuda.current_stream()
         key = (cur.device.index, i)
         if key not in self._active or self._streams[key] == cur:

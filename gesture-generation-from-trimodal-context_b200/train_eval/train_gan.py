@@ -484,6 +484,10 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
         ge.on_gru_grads = None
     ge.backward(d_out, ig * B, (ig + 1) * B, d_mu=dmu if do_kld else None, d_logvar=dlv if do_kld else None)
     ge.on_gru_grads = None
+    # the scalar read-back branch rejoins only here (as a member of the weight-gradient join group it made the discriminator's backward wait
+    # ~27 us for the device-to-host copy: profiles/r02_timeline_step_3p78ms.txt, 2072-2099 us)
+    from tgb200.engine import S_SCALARS
+    side.join(S_SCALARS)
     done = []
     if world > 1:
         if split and os.environ.get('TGB200_DP_PIPELINE', '0') == '1':
