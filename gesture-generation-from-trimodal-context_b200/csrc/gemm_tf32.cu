@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(MH == 2 ? 576 : 320, MH == 2 ? 1 : 2) gemm_tf3
                 x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
               }
               x.x = fmaxf(x.x, x.x * s2); x.y = fmaxf(x.y, x.y * s2); x.z = fmaxf(x.z, x.z * s2); x.w = fmaxf(x.w, x.w * s2);
-              if (p.accumulate) {
+              if (p.accumulate && p.ksplit <= 1) {              // split-K: the red.add below IS the accumulation
                 const float4 t4 = *reinterpret_cast<const float4*>(crow + i * cstep);
                 x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
               }
@@ -348,7 +348,9 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s, const TapExt* x = nullptr) {
   p.ksplit = 1;
   {
     const int tiles = tg_ceil_div(g.M, BM * MH) * tg_ceil_div(g.N, BN), nkb_all = tg_ceil_div(g.K, BKF);
-    const bool linear = g.taps == 1 && !clipm && g.act1 == 0 && g.act2 == 0 && !g.residual && !g.accumulate;
+    // (accumulate = 1 with a linear epilogue is split-K without the zero fill: the caller's C - e.g. a buffer zeroed ahead of time on a side
+    // stream - receives every partial tile by red.add.  A memset NODE between two kernels of a captured chain costs ~25 us of gaps.)
+    const bool linear = g.taps == 1 && !clipm && g.act1 == 0 && g.act2 == 0 && !g.residual;
     const bool vec = (g.N & 3) == 0 && g.ldc == g.N && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
                      (!g.mask || ((g.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
     static const bool off = getenv("TGB200_NO_SPLITK") != nullptr;
@@ -360,8 +362,10 @@ int launch(const tg_gemm_tf32_t& g, cudaStream_t s, const TapExt* x = nullptr) {
       while (ks > 1 && ((nkb_all + ks - 1) / ks) * (ks - 1) >= nkb_all) --ks;      // every share non-empty
       if (ks > 1) {
         p.ksplit = ks;
-        cudaError_t e = cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.N, s);
-        if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: memset: %s", cudaGetErrorString(e)); return -2; }
+        if (!g.accumulate) {
+          cudaError_t e = cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.N, s);
+          if (e != cudaSuccess) { tg_set_error("tg_gemm_tf32: memset: %s", cudaGetErrorString(e)); return -2; }
+        }
       }
     }
   }
@@ -452,7 +456,7 @@ extern "C" int tg_gemm_tf32(const tg_gemm_tf32_t* gp, tg_stream stream) {
   // traffic; the conditions mirror launch()'s split-K test (linear epilogue, vector-aligned contiguous C)
   {
     static const bool off = getenv("TGB200_NO_WIDE_SPLITK") != nullptr || getenv("TGB200_NO_SPLITK") != nullptr;
-    const bool linear = g.taps == 1 && g.clip_rows == 0 && g.act1 == 0 && g.act2 == 0 && !g.residual && !g.accumulate;
+    const bool linear = g.taps == 1 && g.clip_rows == 0 && g.act1 == 0 && g.act2 == 0 && !g.residual;
     const bool vec = (g.N & 3) == 0 && g.ldc == g.N && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
                      (!g.mask || ((g.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
     const int tiles = tg_ceil_div(g.M, 256) * tg_ceil_div(g.N, 160);

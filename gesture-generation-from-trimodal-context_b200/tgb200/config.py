@@ -94,6 +94,14 @@ def head_padded() -> bool:
     return _HEAD_PADDED
 
 
+_WGRAD_AFTER_DGRAD = os.environ.get('TGB200_WGRAD_AFTER_DGRAD', '1') == '1'
+
+
+def wgrad_after_dgrad() -> bool:
+    """GRU backward: fork a layer's weight-gradient GEMMs after (not before) its data-gradient GEMM (engine.GruPlan.backward)."""
+    return _WGRAD_AFTER_DGRAD
+
+
 _FLAT_PRIO = os.environ.get('TGB200_FLAT_PRIO', '0') == '1'
 
 

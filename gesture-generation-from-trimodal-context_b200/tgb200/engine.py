@@ -81,6 +81,7 @@ class _Overlap:
 
 side = _Overlap()
 S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3, S_SCALARS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+S_ZERO = 16                    # zero fills of split-K outputs, ahead of their GEMMs
 S_BIAS2 = 15                   # second bias-gradient stream: the column sums alternate between S_BIAS and S_BIAS2
 S_PREP0W = 14                  # weight-normed filters of block 0 (beside its masks on S_PREP[0])
 S_PREP = (10, 11, 12, 13)      # dropout masks + weight-normed filters of TextEncoderTCN block i live on S_PREP[i % 4], joined right before that block
@@ -210,9 +211,11 @@ class GruPlan:
                 # [6H, K] (both directions, adjacent in the arena) -> [K, 6H]: operand of the data-gradient GEMM
                 ops.transpose(self._w('weight_ih', l), self.ws.get(f'{self.tag}.wihT{l}', (K, 6 * H)), 6 * H, K)
 
-    def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool, hook=None, hook_after: int = 0):
+    def forward(self, x, B, T, masks: Optional[List[Optional[torch.Tensor]]], save: bool, hook=None, hook_after: int = 0, before_rec0=None):
         """x [B*T, I] -> out of the last layer [B*T, 2H].  masks[l] multiplies the output of layer l (l < L-1).
-        hook() is called once the recurrence of layer `hook_after` has been queued (work forked there runs beside the recurrence)."""
+        hook() is called once the recurrence of layer `hook_after` has been queued: work forked there starts when that recurrence has
+        finished, beside the next input projection.  before_rec0() is called between layer 0's projection and its recurrence: work forked
+        there runs beside the first recurrence."""
         H, ws, tag = self.H, self.ws, self.tag
         M = B * T
         gi = ws.get(f'{tag}.gi', (M, 6 * H))
@@ -225,8 +228,10 @@ class GruPlan:
             saved = ws.get(f'{tag}.saved{l}', (4, M, 2 * H)) if save else None
             mk = masks[l] if (masks is not None and l < self.L - 1) else None
             drop = ws.get(f'{tag}.drop{l}', (M, 2 * H)) if mk is not None else None
-            if l == 0 and mk is not None:
-                side.join(S_WGRAD)          # masks drawn beside the first input projection (PoseGenerator engine: _late_masks)
+            if l == 0 and before_rec0 is not None:
+                before_rec0()
+            if mk is not None and l > 0:
+                side.join(s_prep(l + 1))    # this layer's mask, drawn beside the first recurrence (PoseGenerator engine: _late_masks)
             if tc and mk is not None:
                 # the inter-layer dropout rides on the recurrence kernel's output store (was a separate 94 MB elementwise pass per layer)
                 ops.gru_layer_fwd_tf32_drop(gi, self._w('weight_hh', l), self._w('weight_hh', l, True), self._w('bias_hh', l),
@@ -273,6 +278,14 @@ class GruPlan:
         partial = ws.get(f'{tag}.partial', (max(ops.gru_bwd_tf32_scratch_floats(Bb, H) if tc else ops.gru_bwd_scratch_floats(Bb, H), 1),))
         sync = ws.get(f'{tag}.bsync', (max(ops.gru_tf32_sync_ints(Bb, H) if tc else ops.gru_sync_ints(Bb, H), 1),), torch.int32)
         dx = None
+        # The data-gradient GEMMs through W_ih are long-K, few-tile problems that run split-K with red.global.add; their outputs are zeroed
+        # HERE, on a side stream, and the GEMMs accumulate: a memset node between the recurrence and its GEMM cost ~25 us of gaps per layer
+        # on the serial chain (profiles/r02_timeline_step_3p78ms.txt, 2449-2479 us).  One buffer per layer, so all can be zeroed up front.
+        with side.on(S_ZERO):
+            for l in range(self.L - 1, -1, -1):
+                if l > 0 or need_dx:
+                    ws.get(f'{tag}.dx{l}' if l > 0 else f'{tag}.dxin', (Mb, self.I if l == 0 else 2 * H)).zero_()
+        zero_joined = False
         for l in range(self.L - 1, -1, -1):
             dgi = ws.get(f'{tag}.dgi{l}', (Mb, 6 * H))      # per layer: the weight gradients consume them on a side stream
             dgh = ws.get(f'{tag}.dgh{l}', (Mb, 6 * H))
@@ -291,12 +304,22 @@ class GruPlan:
                 inp = ws[f'{tag}.drop{l - 1}'][r0:r1]
             else:
                 inp = ws[f'{tag}.out{l - 1}'][r0:r1]
-            self.weight_grads(l, inp, dgi, dgh, out, Bb, T)
+            # The weight gradients of this layer are forked AFTER its data-gradient GEMM: queued before it, their 200+ CTAs flooded the SMs
+            # the moment the GEMM drained and the next recurrence's 8-CTA clusters waited ~20 us for room; forked here they become runnable
+            # together with the next recurrence, whose higher stream priority places its clusters first.
+            late_w = config.wgrad_after_dgrad() and (l > 0 or need_dx)
+            if not late_w:
+                self.weight_grads(l, inp, dgi, dgh, out, Bb, T)
             if l > 0 or need_dx:
-                dx = ws.get(f'{tag}.dx{l % 2}' if l > 0 else f'{tag}.dxin', (Mb, K))
+                dx = ws.get(f'{tag}.dx{l}' if l > 0 else f'{tag}.dxin', (Mb, K))
                 m = masks[l - 1][r0:r1] if (l > 0 and masks is not None and masks[l - 1] is not None) else None
                 wt = ws.t.get(f'{tag}.wihT{l}') if config.fast() else None
-                mm_nn(dgi, self._w('weight_ih', l), wt, dx, M=Mb, N=6 * H, K=K, mask=m)
+                if not zero_joined:
+                    side.join(S_ZERO)
+                    zero_joined = True
+                mm_nn(dgi, self._w('weight_ih', l), wt, dx, M=Mb, N=6 * H, K=K, mask=m, accumulate=True)
+                if late_w:
+                    self.weight_grads(l, inp, dgi, dgh, out, Bb, T)
                 dout = dx
             else:
                 dx = None
@@ -427,11 +450,14 @@ class GeneratorEngine:
                     for st, mk, n, p, sd in jobs:
                         if st == stream:
                             ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
-            # the GRU's inter-layer masks (3 x 31 MB at batch 3 x 128) are first read by layer 0's recurrence: forward() draws them once the
-            # GRU input exists, under the first input projection, instead of at the bandwidth-saturated top of the iteration
+            # the GRU's inter-layer masks (3 x 31 MB at batch 3 x 128): layer 0's here, at low urgency; the others are drawn by forward() on
+            # the SMs the first recurrence leaves idle instead of at the bandwidth-saturated top of the iteration
             late = [(mk, n, p, sd) for st, mk, n, p, sd in jobs if st == S_WGRAD]
             if late:
-                self._late_masks = (late, seed, offset_dev)
+                with side.on(s_prep(self.n_tcn - 1) if self.use_text else S_WGRAD):     # layer 0's mask: with the last TCN block's preparation
+                    mk, n, p, sd = late[0]
+                    ops.philox_dropout_mask(mk, n, p, seed, offset_dev, sd)
+                self._late_masks = (late[1:], seed, offset_dev)
         return masks
 
     def start_wav(self, in_audio, training, n_bn_updates=1):
@@ -702,16 +728,19 @@ class GeneratorEngine:
         # work that does not depend on the generator (train_iter_gan: the discriminator's pass over the real clips) can be forked here
         late = getattr(self, '_late_masks', None)
         self._late_masks = None
-        if late is not None:
-            with side.on(S_WGRAD):
-                for mk, n, p, sd in late[0]:
+
+        def draw_late():
+            # masks of layers >= 1, one stream each (the TCN blocks' preparation streams are idle by now): forked between layer 0's
+            # projection and its recurrence, so they are drawn on the SMs the first recurrence leaves idle; layer l joins only its own
+            for l, (mk, n, p, sd) in enumerate(late[0]):
+                with side.on(s_prep(l + 2)):
                     ops.philox_dropout_mask(mk, n, p, late[1], late[2], sd)
         hook, at = getattr(self, 'beside_gru', None), getattr(self, 'beside_gru_at', -1)
         self.beside_gru = None
         if hook is not None and at < 0:
             hook()
             hook = None
-        out = self.gru.forward(in_data, Bt, T, gmasks, save, hook=hook, hook_after=at)
+        out = self.gru.forward(in_data, Bt, T, gmasks, save, hook=hook, hook_after=at, before_rec0=draw_late if (late and late[0]) else None)
         H = self.H
         ld = self.head_ld()
         hsum = ws.get('g.hsum', (M, H)); y1 = ws.get('g.y1', (M, ld), zero=True); poses = ws.get('g.poses', (M, m.pose_dim))

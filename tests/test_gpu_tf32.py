@@ -45,6 +45,10 @@ def test_gemm_tf32_plain(dev, M, N, K):
     c3 = torch.full((M, N), float('nan'), device=dev)
     ops.gemm_tf32(a, w, c3, M=M, N=N, K=K, bias=b, mask=mask)
     assert rel_l2(c3, ref * mask.double()) < TF32_TOL, rel_l2(c3, ref * mask.double())
+    # the same with accumulate: split-K shapes add their partial tiles to the caller's C with red.global.add, no zero fill
+    c4 = torch.full((M, N), 0.5, device=dev)
+    ops.gemm_tf32(a, w, c4, M=M, N=N, K=K, bias=b, mask=mask, accumulate=True)
+    assert rel_l2(c4, ref * mask.double() + 0.5) < TF32_TOL, rel_l2(c4, ref * mask.double() + 0.5)
 
 
 @pytest.mark.parametrize('d', [1, 2, 4, 8])
