@@ -40,7 +40,7 @@ class _Overlap:
             # first, then the iteration's main chain (captured at -2, train_gan._capture_stream), then the later blocks' preparation; the
             # audio branch, weight gradients and the discriminator's real pass keep the default.  The top of the iteration is ~150 us of
             # bandwidth-bound kernels that each fill the GPU, so what starts first decides when the 8-GEMM text chain can start.
-            prio = -3 if i in (S_PREP[0], S_PREP0W) else (-1 if i in S_PREP else 0)
+            prio = -3 if i in (S_PREP[0], S_PREP0W, S_WAVB) else (-1 if i in S_PREP else 0)
             if config.flat_prio():
                 prio = min(prio, 0) and -1
             hi = min(torch.cuda.Stream.priority_range())         # numerically lowest = most urgent (torch exposes 0 .. -3)
@@ -81,6 +81,7 @@ class _Overlap:
 
 side = _Overlap()
 S_WGRAD, S_WAV, S_DREAL, S_WAVW, S_SPK, S_BIAS, S_WGRAD2, S_WGRAD3, S_SCALARS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+S_WAVB = 17                    # WavEncoder backward: the longest chain behind the GRU backward, highest priority
 S_ZERO = 16                    # zero fills of split-K outputs, ahead of their GEMMs
 S_BIAS2 = 15                   # second bias-gradient stream: the column sums alternate between S_BIAS and S_BIAS2
 S_PREP0W = 14                  # weight-normed filters of block 0 (beside its masks on S_PREP[0])
@@ -637,7 +638,8 @@ class GeneratorEngine:
         xl = ws[f'txt.x{self.n_tcn - 1}'][r0:r1]
         wgrad(xl, d_feat, self.G('text_encoder.decoder.weight'), B=Bb, T=T, N=32, Cin=H, dbias=self.G('text_encoder.decoder.bias'))
         dx = ws.get('txt.dA', (Mb, H)); dpre = ws.get('txt.dB', (Mb, H)); dy1 = ws.get('txt.dD', (Mb, H))
-        side.join(S_WGRAD)
+        # (no join of the weight-gradient streams here: every buffer they read is per convolution, and in train_iter_gan this point sits
+        # behind the GRU's weight gradients AND the early Adam step of the recurrent range - a join made the text chain wait ~100 us for them)
         mm_nn(d_feat, self.P('text_encoder.decoder.weight'), ws.t.get('T.text_encoder.decoder.weight') if config.fast() else None, dx,
               M=Mb, N=32, K=H)
         for i in range(self.n_tcn - 1, -1, -1):
@@ -673,6 +675,7 @@ class GeneratorEngine:
             Ba = in_text.shape[0]
             assert Bb == Ba and lo % Ba == 0
             ops.embedding_scatter_add(dx, in_text, sl(masks.get('emb')) if masks else None, self.G('text_encoder.embedding.weight'), Mb, E)
+        side.join(S_WGRAD)      # the filters' gradient chains forked above
 
     # -------------------------------------------------------------------------------------------- full forward
     def forward(self, pre_seq, in_text, in_audio, vid, eps, Bt, training, masks=None, n_bn_updates=1, save=True):
@@ -801,30 +804,37 @@ class GeneratorEngine:
         d_audio = ws.get('g.daudio', (Mb, max(Da, 1))); d_text = ws.get('g.dtext', (Mb, max(Dt, 1))); dzc = ws.get('g.dz', (Bb, max(Z, 1)))
         ops.gru_input_split_bwd(d_in, d_audio, d_text, dzc, Bb, T, Dp, Da, Dt, Z)
         if self.z_mode == 'speaker':
-            Zs = 16
-            if d_z is not None:
-                ops.add(dzc, d_z, dzc, Bb * Zs)
-            dmu = d_mu if d_mu is not None else ws.get('spk.dmu', (Bb, Zs), zero=True)
-            dlv = d_logvar if d_logvar is not None else ws.get('spk.dlv', (Bb, Zs), zero=True)
-            if d_mu is None: dmu.zero_()
-            if d_logvar is None: dlv.zero_()
-            ops.reparam_bwd(dzc, ws['spk.logvar'][lo:hi], c['eps'][lo:hi], dmu, dlv, Bb * Zs)
-            e0, e1 = ws['spk.e0'][lo:hi], ws['spk.e1'][lo:hi]
-            de1, de0 = ws.get('spk.de1', (Bb, Zs)), ws.get('spk.de0', (Bb, Zs))
-            ops.linear_wgrad(e1, dmu, self.G('speaker_mu.weight'), self.G('speaker_mu.bias'), M=Bb, K=Zs, N=Zs)
-            ops.linear_wgrad(e1, dlv, self.G('speaker_logvar.weight'), self.G('speaker_logvar.bias'), M=Bb, K=Zs, N=Zs)
-            ops.linear_dgrad(dmu, self.P('speaker_mu.weight'), de1, M=Bb, K=Zs, N=Zs)
-            ops.linear_dgrad(dlv, self.P('speaker_logvar.weight'), de1, M=Bb, K=Zs, N=Zs, accumulate=True)
-            ops.linear_wgrad(e0, de1, self.G('speaker_embedding.1.weight'), self.G('speaker_embedding.1.bias'), M=Bb, K=Zs, N=Zs)
-            ops.linear_dgrad(de1, self.P('speaker_embedding.1.weight'), de0, M=Bb, K=Zs, N=Zs)
-            ops.embedding_scatter_add(de0, c['vid'][lo:hi], None, self.G('speaker_embedding.0.weight'), Bb, Zs)
+            spk_ctx = side.on(S_SPK)        # ten ~10 us launches: on the main chain they held back the audio / text encoder backward by ~85 us
+        else:
+            spk_ctx = contextlib.nullcontext()
+        with spk_ctx:
+            if self.z_mode == 'speaker':
+                Zs = 16
+                if d_z is not None:
+                    ops.add(dzc, d_z, dzc, Bb * Zs)
+                dmu = d_mu if d_mu is not None else ws.get('spk.dmu', (Bb, Zs), zero=True)
+                dlv = d_logvar if d_logvar is not None else ws.get('spk.dlv', (Bb, Zs), zero=True)
+                if d_mu is None: dmu.zero_()
+                if d_logvar is None: dlv.zero_()
+                ops.reparam_bwd(dzc, ws['spk.logvar'][lo:hi], c['eps'][lo:hi], dmu, dlv, Bb * Zs)
+                e0, e1 = ws['spk.e0'][lo:hi], ws['spk.e1'][lo:hi]
+                de1, de0 = ws.get('spk.de1', (Bb, Zs)), ws.get('spk.de0', (Bb, Zs))
+                ops.linear_wgrad(e1, dmu, self.G('speaker_mu.weight'), self.G('speaker_mu.bias'), M=Bb, K=Zs, N=Zs)
+                ops.linear_wgrad(e1, dlv, self.G('speaker_logvar.weight'), self.G('speaker_logvar.bias'), M=Bb, K=Zs, N=Zs)
+                ops.linear_dgrad(dmu, self.P('speaker_mu.weight'), de1, M=Bb, K=Zs, N=Zs)
+                ops.linear_dgrad(dlv, self.P('speaker_logvar.weight'), de1, M=Bb, K=Zs, N=Zs, accumulate=True)
+                ops.linear_wgrad(e0, de1, self.G('speaker_embedding.1.weight'), self.G('speaker_embedding.1.bias'), M=Bb, K=Zs, N=Zs)
+                ops.linear_dgrad(de1, self.P('speaker_embedding.1.weight'), de0, M=Bb, K=Zs, N=Zs)
+                ops.embedding_scatter_add(de0, c['vid'][lo:hi], None, self.G('speaker_embedding.0.weight'), Bb, Zs)
         if self.use_audio:
             assert Bb == Ba and lo % Ba == 0
-            with side.on(S_WAV):
+            # ten dependent kernels (~340 us): longer than the text encoder's backward, so it gets the more urgent stream of the two
+            with side.on(S_WAVB):
                 self.wav_backward(d_audio, c['in_audio'])
         if self.use_text:
             self.text_backward(d_text, c['in_text'], lo, hi, T, masks)
-        side.join(S_WAV)
+        side.join(S_WAVB)
+        side.join(S_SPK)
         side.join(S_WGRAD)
 
 
