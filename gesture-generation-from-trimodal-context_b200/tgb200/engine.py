@@ -406,7 +406,9 @@ class GeneratorEngine:
                     # out.2.weight [D,150] and out.0.weight^T [H,150]; the pad columns are never read (the TMA maps end at column 150)
                     Hh, ld = self.H // 2, self.head_ld()
                     ws.get('P.out.2.weight', (self.m.pose_dim, ld), zero=True)[:, :Hh].copy_(self.P('out.2.weight'))
-                    ws.get('PT.out.0.weight', (self.H, ld), zero=True)[:, :Hh].copy_(self.P('out.0.weight').t())
+                    pt = ws.get('PT.out.0.weight', (2 * self.H, ld), zero=True)      # stacked twice: the data gradient lands in both
+                    pt[:self.H, :Hh].copy_(self.P('out.0.weight').t())             # direction halves of d out in one GEMM
+                    pt[self.H:, :Hh].copy_(self.P('out.0.weight').t())
             self.gru.prep()
 
     def head_ld(self):
@@ -769,21 +771,23 @@ class GeneratorEngine:
         Hh, ld = H // 2, self.head_ld()
         dy1 = ws.get('g.dy1', (Mb, ld), zero=True); dhs = ws.get('g.dhs', (Mb, H)); dout = ws.get('g.dout', (Mb, 2 * H))
         side.join(S_WGRAD)      # weight-gradient launches of an earlier backward may still be reading the scratch buffers below
-        with side.on(S_WGRAD):  # the head's weight gradients are fp32 CUDA-core kernels (27 / 150 columns): off the chain to the GRU
-            ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=Hh, N=D, lda=ld)
         ops.linear_dgrad(d_poses, self.P('out.2.weight'), dy1, M=Mb, K=Hh, N=D, ldc=ld)          # K = 27 reduction: fp32 kernel
-        with side.on(S_WGRAD2):
-            if ld != Hh:
-                ops.conv_wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, Tin=T, Tout=T, N=Hh, Cin=H, taps=1, lda=H, ldg=ld, ldw=H,
-                               dbias=self.G('out.0.bias'))
-            else:
-                wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=Hh, Cin=H, dbias=self.G('out.0.bias'))
         if ld != Hh:
-            # d hsum = dy1 @ out.0.weight on the tensor cores: A = dy1 (152-float pitch, K = 150), B = the padded transpose [H, 152]
-            ops.gemm_tf32(dy1, ws['PT.out.0.weight'], dhs, M=Mb, N=H, K=Hh, lda=ld, ldb=ld)
+            # d out = [d hsum, d hsum] with d hsum = dy1 @ out.0.weight, on the tensor cores: A = dy1 (152-float pitch, K = 150), B = the padded
+            # transpose stacked twice [2H, 152] - the gradient of the sum over directions rides on the GEMM instead of a duplication pass
+            ops.gemm_tf32(dy1, ws['PT.out.0.weight'], dout, M=Mb, N=2 * H, K=Hh, lda=ld, ldb=ld)
         else:
             mm_nn(dy1, self.P('out.0.weight'), ws.t.get('T.out.0.weight') if config.fast() else None, dhs, M=Mb, N=Hh, K=H)
-        ops.dup_halves(dhs, dout, Mb, H)
+            ops.dup_halves(dhs, dout, Mb, H)
+        # The head's weight gradients are fp32 CUDA-core kernels (27 / 150 columns, ~600 CTAs): forked HERE, behind the data-gradient chain,
+        # they become runnable together with the last layer's recurrence, whose more urgent stream places its clusters first; forked
+        # before it they held the SMs when the recurrence was launched and it started ~24 us late.
+        with side.on(S_WGRAD):
+            ops.linear_wgrad(ws['g.y1'][r0:r1], d_poses, self.G('out.2.weight'), self.G('out.2.bias'), M=Mb, K=Hh, N=D, lda=ld)
+        with side.on(S_WGRAD2):
+            # with the 152-float pitch of dy1 this is a tensor-core weight gradient too (was a 585-CTA fp32 kernel of ~45 us whose CTAs
+            # fragmented the GPCs exactly when the first recurrence needed 8 whole clusters)
+            wgrad(ws['g.hsum'][r0:r1], dy1, self.G('out.0.weight'), B=Bb, T=T, N=Hh, Cin=H, ldg=ld, dbias=self.G('out.0.bias'))
         gmasks = [masks.get(f'gru{l}') for l in range(self.L)] if masks else None
         need_dx = self.use_audio or self.use_text or self.z_mode == 'speaker'
         d_in = self.gru.backward(dout, ws['g.in'], Bt, lo, hi, T, gmasks, need_dx, join_first=False)      # joined above, before the head's forks

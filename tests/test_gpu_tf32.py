@@ -277,8 +277,8 @@ def test_gemm_tf32_padded_pitch_head(dev, M):
     ref2 = y1[:, :Hh].double() @ w2.double().t() + b2.double()
     assert rel_l2(poses, ref2) < TF32_TOL, rel_l2(poses, ref2)
     # data gradient through out.0: dhs = dy1 @ W0 with the padded transpose as the B operand
-    w0tp = torch.full((H, ld), float('nan'), device=dev); w0tp[:, :Hh] = w0.t()
-    dhs = torch.full((M, H), float('nan'), device=dev)
-    ops.gemm_tf32(y1, w0tp, dhs, M=M, N=H, K=Hh, lda=ld, ldb=ld)
+    w0tp = torch.full((2 * H, ld), float('nan'), device=dev); w0tp[:H, :Hh] = w0.t(); w0tp[H:, :Hh] = w0.t()      # stacked twice, as the engine does
+    dout = torch.full((M, 2 * H), float('nan'), device=dev)
+    ops.gemm_tf32(y1, w0tp, dout, M=M, N=2 * H, K=Hh, lda=ld, ldb=ld)
     ref3 = y1[:, :Hh].double() @ w0.double()
-    assert rel_l2(dhs, ref3) < TF32_TOL, rel_l2(dhs, ref3)
+    assert rel_l2(dout[:, :H], ref3) < TF32_TOL and rel_l2(dout[:, H:], ref3) < TF32_TOL, (rel_l2(dout[:, :H], ref3), rel_l2(dout[:, H:], ref3))
