@@ -231,6 +231,8 @@ class GruPlan:
             drop = ws.get(f'{tag}.drop{l}', (M, 2 * H)) if mk is not None else None
             if l == 0 and before_rec0 is not None:
                 before_rec0()
+            if hook is not None and hook_after >= 100 and l == hook_after - 100:
+                hook()                      # 'preN': forked between layer N's projection and its recurrence (runnable together with it)
             if mk is not None and l > 0:
                 side.join(s_prep(l + 1))    # this layer's mask, drawn beside the first recurrence (PoseGenerator engine: _late_masks)
             if tc and mk is not None:
@@ -243,7 +245,7 @@ class GruPlan:
             else:
                 ops.gru_layer_fwd(gi, ws[f'{tag}.whhT{l}_0'], ws[f'{tag}.whhT{l}_1'], self._w('bias_hh', l), self._w('bias_hh', l, True),
                                   out, saved, M * 2 * H, sync, B, T, H)
-            if hook is not None and l == min(hook_after, self.L - 1):
+            if hook is not None and hook_after < 100 and l == min(hook_after, self.L - 1):
                 hook()
             if mk is not None:
                 if not tc:

@@ -430,7 +430,7 @@ def _step_segments(args, epoch, in_text, in_audio, target, vid, G, D, pose_dec_o
             d_real()
         else:
             # forked from inside the generator's forward (engine.py: beside_gru): at the GRU input, or behind the first recurrent layers
-            ge.beside_gru, ge.beside_gru_at = d_real, {'concat': -1, 'gru0': 0, 'gru1': 1, 'gru2': 2}[at]
+            ge.beside_gru, ge.beside_gru_at = d_real, {'concat': -1, 'gru0': 0, 'gru1': 1, 'gru2': 2, 'pre0': 100, 'pre1': 101, 'pre2': 102, 'pre3': 103}[at]
 
     # ---- all generator passes in one sweep
     ge.prep_weights('rest')
