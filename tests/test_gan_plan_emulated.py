@@ -289,3 +289,12 @@ def run_train_variant(dev, ctx, zm, tol=1e-4):
 @pytest.mark.parametrize('ctx,zm', [('audio', 'speaker'), ('text', 'random'), ('none', None), ('both', 'random'), ('none', 'speaker')])
 def test_train_iter_gan_constructor_variants(emu_fp32, ctx, zm):
     run_train_variant(CPU, ctx, zm)
+
+
+@pytest.mark.parametrize('at', ['top', 'concat', 'gru0', 'gru2', 'pre1'])
+def test_discriminator_real_pass_placements_are_equivalent(emu_fast, monkeypatch, at):
+    """train_iter_gan forks D(real) from inside the generator's forward by default ('gru1'); every other placement (config.d_real_at) is
+    the same arithmetic - BatchNorm statistics still see real before fake, D's gradients are the same sum - and meets the same goldens."""
+    from tgb200 import config
+    monkeypatch.setattr(config, '_DREAL_AT', at)
+    GP.test_fast_mode_train_iter_full_size_vs_oracle(CPU, 4, 11, 2000, 50)
