@@ -361,6 +361,31 @@ __global__ void relu_mask_bwd_v4_kernel(const float4* __restrict__ dy, const flo
     dx[i] = v;
   }
 }
+// TemporalBlock backward head when the block output was produced by conv2's epilogue (xo = relu(y2 + x), y2 = relu(conv2 + b) * m2 never
+// stored): dpre = dxo * (xo > 0), dc2 = dpre * m2 * (y2 > 0) with y2 > 0 read off as xo - x > 0 (exact whenever dpre != 0: there xo = y2 + x)
+__device__ __forceinline__ void tcn_res_bwd_one(float g, float o, float xi, float m, float& dp, float& dc) {
+  dp = o > 0.f ? g : 0.f;
+  dc = (o - xi > 0.f) ? dp * m : 0.f;
+}
+__global__ void tcn_res_bwd_kernel(const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ x,
+                                   const float* __restrict__ mask, float* __restrict__ dpre, float* __restrict__ dc2, long long n) {
+  GRID_STRIDE(i, n) {
+    float dp, dc;
+    tcn_res_bwd_one(dxo[i], xo[i], x[i], mask ? mask[i] : 1.f, dp, dc);
+    dpre[i] = dp; dc2[i] = dc;
+  }
+}
+__global__ void tcn_res_bwd_v4_kernel(const float4* __restrict__ dxo, const float4* __restrict__ xo, const float4* __restrict__ x,
+                                      const float4* __restrict__ mask, float4* __restrict__ dpre, float4* __restrict__ dc2, long long n4) {
+  GRID_STRIDE(i, n4) {
+    const float4 g = dxo[i], o = xo[i], xi = x[i];
+    const float4 m = mask ? mask[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 dp, dc;
+    tcn_res_bwd_one(g.x, o.x, xi.x, m.x, dp.x, dc.x); tcn_res_bwd_one(g.y, o.y, xi.y, m.y, dp.y, dc.y);
+    tcn_res_bwd_one(g.z, o.z, xi.z, m.z, dp.z, dc.z); tcn_res_bwd_one(g.w, o.w, xi.w, m.w, dp.w, dc.w);
+    dpre[i] = dp; dc2[i] = dc;
+  }
+}
 __global__ void sum_halves_v4_kernel(const float4* __restrict__ x, float4* __restrict__ o, long long M, int H4) {
   const long long n = M * H4;
   GRID_STRIDE(i, n) {
@@ -722,6 +747,17 @@ extern "C" int tg_relu_mask_bwd(const float* dy, const float* y, const float* ma
   else
     relu_mask_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, mask, dx, n);
   TG_CHECK_LAUNCH("tg_relu_mask_bwd"); return 0;
+}
+extern "C" int tg_tcn_res_bwd(const float* dxo, const float* xo, const float* x, const float* mask, float* dpre, float* dc2, long long n,
+                              tg_stream stream) {
+  TG_REQUIRE(dxo && xo && x && dpre && dc2 && n > 0, "tg_tcn_res_bwd");
+  if ((n & 3) == 0 && (((uintptr_t)dxo | (uintptr_t)xo | (uintptr_t)x | (uintptr_t)mask | (uintptr_t)dpre | (uintptr_t)dc2) & 15) == 0)
+    tcn_res_bwd_v4_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dxo), reinterpret_cast<const float4*>(xo), reinterpret_cast<const float4*>(x),
+        reinterpret_cast<const float4*>(mask), reinterpret_cast<float4*>(dpre), reinterpret_cast<float4*>(dc2), n / 4);
+  else
+    tcn_res_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dxo, xo, x, mask, dpre, dc2, n);
+  TG_CHECK_LAUNCH("tg_tcn_res_bwd"); return 0;
 }
 extern "C" int tg_sum_halves(const float* x, float* out, long long M, int H, tg_stream stream) {
   if ((H & 3) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0)

@@ -102,6 +102,14 @@ def wgrad_after_dgrad() -> bool:
     return _WGRAD_AFTER_DGRAD
 
 
+_TCN_FUSED_ADD = os.environ.get('TGB200_TCN_FUSED_ADD', '1') == '1'
+
+
+def tcn_fused_add() -> bool:
+    """Fast mode: TemporalBlock's residual add + final ReLU ride on conv2's GEMM epilogue (y2 is not stored; backward: tg_tcn_res_bwd)."""
+    return _TCN_FUSED_ADD
+
+
 _FLAT_PRIO = os.environ.get('TGB200_FLAT_PRIO', '0') == '1'
 
 

@@ -591,6 +591,7 @@ class GeneratorEngine:
         ops.embedding_gather(self.P('text_encoder.embedding.weight'), in_text, idx_mod, masks.get('emb') if masks else None, emb, M, E)
         x, cin = emb, E
         k = self.tcn_k
+        fused = self._tcn_fused = bool(config.fast() and config.tcn_fused_add())
         for i in range(self.n_tcn):
             if i >= 1:
                 side.join(s_prep(i))               # this block's dropout masks (make_masks split=True) and weight-normed filters (prep_weights)
@@ -601,8 +602,13 @@ class GeneratorEngine:
             m1 = masks.get(f'tcn{i}_1') if masks else None
             m2 = masks.get(f'tcn{i}_2') if masks else None
             self._tcn_conv(x, ws[f'tcn.w{i}_1'], self.P(q + '.conv1.bias'), y1, Bt, T, cin, H, k, d, act1=ops.ACT_RELU, mask=m1)
-            self._tcn_conv(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), y2, Bt, T, H, H, k, d, act1=ops.ACT_RELU, mask=m2)
-            ops.add(y2, x, xo, M * H, relu=True)
+            if fused:
+                # xo = relu(relu(conv2 + b) * m2 + x) in conv2's epilogue: no y2 round trip, no add kernel on the 8-GEMM chain
+                self._tcn_conv(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), xo, Bt, T, H, H, k, d, act1=ops.ACT_RELU, mask=m2, residual=x,
+                               act2=ops.ACT_RELU)
+            else:
+                self._tcn_conv(y1, ws[f'tcn.w{i}_2'], self.P(q + '.conv2.bias'), y2, Bt, T, H, H, k, d, act1=ops.ACT_RELU, mask=m2)
+                ops.add(y2, x, xo, M * H, relu=True)
             x, cin = xo, H
         feat = ws.get('txt.feat', (M, 32))
         mm_nt(x, self.P('text_encoder.decoder.weight'), feat, M=M, N=32, K=H, bias=self.P('text_encoder.decoder.bias'))
@@ -655,8 +661,11 @@ class GeneratorEngine:
             m1 = sl(masks.get(f'tcn{i}_1')) if masks else None
             m2 = sl(masks.get(f'tcn{i}_2')) if masks else None
             dc2 = ws.get(f'txt.dc2_{i}', (Mb, H)); dc1 = ws.get(f'txt.dc1_{i}', (Mb, H))   # per conv: read by the side stream
-            ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                      # through the block's final ReLU
-            ops.relu_mask_bwd(dpre, y2, m2, dc2, Mb * H)                       # dropout2 + relu2
+            if getattr(self, '_tcn_fused', False):
+                ops.tcn_res_bwd(dx, xo, xin, m2, dpre, dc2, Mb * H)            # final ReLU, dropout2 + relu2 in one pass (y2 was not stored)
+            else:
+                ops.relu_mask_bwd(dx, xo, None, dpre, Mb * H)                  # through the block's final ReLU
+                ops.relu_mask_bwd(dpre, y2, m2, dc2, Mb * H)                   # dropout2 + relu2
             wT = lambda j: ws.t.get(f'tcn.wT{i}_{j}') if config.fast() else None
             # each filter's gradient chain (zero, two tap GEMMs, weight-norm backward: ~50 us of small launches) on one of three streams:
             # serialised on a single stream the eight chains outlasted the data-gradient chain by ~120 us at the end of the iteration

@@ -254,6 +254,10 @@ def relu_mask_bwd(dy, y, mask, dx, n):
     check(_L().tg_relu_mask_bwd(_p(dy), _p(y), _p(mask), _p(dx), n, _s()), 'tg_relu_mask_bwd'); _count()
 
 
+def tcn_res_bwd(dxo, xo, x, mask, dpre, dc2, n):
+    check(_L().tg_tcn_res_bwd(_p(dxo), _p(xo), _p(x), _p(mask), _p(dpre), _p(dc2), n, _s()), 'tg_tcn_res_bwd'); _count()
+
+
 def sum_halves(x, out, M, H):
     check(_L().tg_sum_halves(_p(x), _p(out), M, H, _s()), 'tg_sum_halves'); _count()
 

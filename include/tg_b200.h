@@ -192,6 +192,10 @@ int tg_mul(const float* a, const float* b, float* out, long long n, tg_stream st
 /* out = a + b, optionally followed by ReLU (TemporalBlock residual, tcn.py:46) */
 int tg_add(const float* a, const float* b, float* out, long long n, int relu, tg_stream stream);
 int tg_relu_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, tg_stream stream);
+/* TemporalBlock backward head (tcn.py:28-29,46) for the fast-mode forward that folds the residual add + final ReLU into conv2's GEMM epilogue
+ * (xo = relu(y2 + x) with y2 = relu(conv2 + b) * mask never stored):  dpre = dxo * (xo > 0);  dc2 = dpre * mask * (xo - x > 0).
+ * Where dpre != 0, xo = y2 + x, so xo - x > 0 is y2 > 0 (up to the rounding of that one addition); mask may be NULL (eval). */
+int tg_tcn_res_bwd(const float* dxo, const float* xo, const float* x, const float* mask, float* dpre, float* dc2, long long n, tg_stream stream);
 /* out[m, 0..H) = x[m, 0..H) + x[m, H..2H)  (sum of GRU directions, multimodal_context_net.py:156,243) and its backward */
 int tg_sum_halves(const float* x, float* out, long long M, int H, tg_stream stream);
 int tg_dup_halves(const float* d, float* dx, long long M, int H, tg_stream stream);

@@ -274,6 +274,15 @@ class EmuLib:
         _arr(dx, n)[:] = v
         return 0
 
+    def tg_tcn_res_bwd(self, dxo, xo, x, mask, dpre, dc2, n, stream):
+        self.calls.append('tg_tcn_res_bwd')
+        XO, X = _arr(xo, n), _arr(x, n)
+        dp = np.where(XO > 0, _arr(dxo, n), np.float32(0))
+        dc = np.where(XO - X > 0, dp * (_arr(mask, n) if mask else np.float32(1)), np.float32(0))
+        _arr(dpre, n)[:] = dp
+        _arr(dc2, n)[:] = dc
+        return 0
+
     def tg_sum_halves(self, x, out, M, H, stream):
         self.calls.append('tg_sum_halves')
         X = _arr(x, M * 2 * H).reshape(M, 2 * H)

@@ -66,6 +66,21 @@ def test_gemm_tf32_causal_two_tap(dev, B, d):
     xr = x.double().transpose(1, 2).requires_grad_(True)
     ref = torch.relu(F.conv1d(xr, w.double(), b.double(), padding=d, dilation=d)[:, :, :-d])
     assert rel_l2(y.view(B, T, C), ref.transpose(1, 2)) < TF32_TOL
+    # TemporalBlock tail in the epilogue (tcn.py:28-29,46): xo = relu(relu(conv + b) * mask + residual), and its backward head
+    mask = (torch.rand(B * T, C, device=dev) > 0.3).float() / 0.7
+    res = _rand(B * T, C, dev=dev, seed=4)
+    xo = torch.full((B * T, C), float('nan'), device=dev)
+    ops.gemm_tf32(x.view(B * T, C), wt.view(2 * C, C), xo, M=B * T, N=C, K=C, taps=2, shift0=-d, T=T, bias=b, act1=ops.ACT_RELU, mask=mask,
+                  residual=res, act2=ops.ACT_RELU)
+    y2 = ref.detach().transpose(1, 2).reshape(B * T, C) * mask.double()
+    assert rel_l2(xo, torch.relu(y2 + res.double())) < TF32_TOL
+    g = _rand(B * T, C, dev=dev, seed=5)
+    dpre = torch.full((B * T, C), float('nan'), device=dev); dc2 = torch.full((B * T, C), float('nan'), device=dev)
+    ops.tcn_res_bwd(g, xo, res, mask, dpre, dc2, B * T * C)
+    y2_gpu = (y * mask)                                     # what the un-fused plan would have stored
+    assert torch.equal(dpre, g * (xo > 0))
+    want = dpre * mask * (y2_gpu > 0)
+    assert (dc2 != want).float().mean().item() < 1e-4        # identical except where y2 is absorbed by the rounding of y2 + x
     dy = _rand(B, T, C, dev=dev, seed=3)
     ref.backward(dy.double().transpose(1, 2))
     dc = (dy * (ref.transpose(1, 2) > 0)).float().contiguous()
