@@ -41,8 +41,8 @@ class _Overlap:
             # audio branch, weight gradients and the discriminator's real pass keep the default.  The top of the iteration is ~150 us of
             # bandwidth-bound kernels that each fill the GPU, so what starts first decides when the 8-GEMM text chain can start.
             prio = -3 if i in (S_PREP[0], S_PREP0W, S_WAVB) else (-1 if i in S_PREP else 0)
-            if config.flat_prio():
-                prio = min(prio, 0) and -1
+            if config.flat_prio() and prio < 0:
+                prio = -1
             hi = min(torch.cuda.Stream.priority_range())         # numerically lowest = most urgent (torch exposes 0 .. -3)
             self._streams[key] = torch.cuda.Stream(device=device, priority=max(prio, hi))
         return self._streams[key]
