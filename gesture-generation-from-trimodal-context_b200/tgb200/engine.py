@@ -231,7 +231,7 @@ class GruPlan:
             drop = ws.get(f'{tag}.drop{l}', (M, 2 * H)) if mk is not None else None
             if l == 0 and before_rec0 is not None:
                 before_rec0()
-            if hook is not None and hook_after >= 100 and l == hook_after - 100:
+            if hook is not None and hook_after >= 100 and l == min(hook_after - 100, self.L - 1):
                 hook()                      # 'preN': forked between layer N's projection and its recurrence (runnable together with it)
             if mk is not None and l > 0:
                 side.join(s_prep(l + 1))    # this layer's mask, drawn beside the first recurrence (PoseGenerator engine: _late_masks)
